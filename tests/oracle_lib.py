@@ -1,0 +1,114 @@
+"""ctypes bindings of the CPU oracle (oracle/liborc.so) and, when present, the reference levmar built
+unchanged into oracle/_ref/.  TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+
+STEREO19, IMAGE8 = 19, 8
+DER, DIF = 0, 1
+MATH_DET, MATH_LIBM = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_longlong)
+FUNC_T = C.CFUNCTYPE(None, _dp, _dp, C.c_int, C.c_int, C.c_void_p)
+
+
+def build_oracle(with_ref: bool = True) -> None:
+    subprocess.run(["make", "-s", "-C", ORC_DIR], check=True)
+    if with_ref and os.path.isdir("/root/reference/levmar-2.5"):
+        subprocess.run(["make", "-s", "-C", ORC_DIR, "ref"], check=True)
+
+
+def _ptr(a, typ):
+    if a is None:
+        return None
+    return a.ctypes.data_as(typ)
+
+
+_FIT_ARGS = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _lp, _ip, C.c_int, _dp, _dp, _ip, _ip, C.c_int]
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(ORC_DIR, "liborc.so")
+        if not os.path.exists(path):
+            build_oracle(with_ref=True)
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L = self.lib
+        L.orc_fit_batch.argtypes = _FIT_ARGS
+        L.orc_fit_batch.restype = C.c_int
+        L.orc_lu_solve.argtypes = [_dp, _dp, _dp, C.c_int]
+        L.orc_lu_solve.restype = C.c_int
+        L.orc_residual_sqnorm.argtypes = [_dp, _dp, _dp, C.c_int]
+        L.orc_residual_sqnorm.restype = C.c_double
+        L.orc_ata_blocked.argtypes = [_dp, _dp, C.c_int, C.c_int]
+        L.orc_kat_problem.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _ip, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.orc_kat_problem.restype = C.c_int
+        L.orc_lm_der.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_void_p, C.c_void_p]
+        L.orc_lm_der.restype = C.c_int
+        L.orc_lm_dif.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_void_p, C.c_void_p]
+        L.orc_lm_dif.restype = C.c_int
+        L.orc_stereo19_postfit.argtypes = [_dp]
+        self.ref = None
+        self.levmar = None
+        rpath = os.path.join(ORC_DIR, "_ref", "liborc_refshim.so")
+        lpath = os.path.join(ORC_DIR, "_ref", "liblevmar_ref.so")
+        if os.path.exists(rpath) and os.path.exists(lpath):
+            self.levmar = C.CDLL(lpath, mode=C.RTLD_GLOBAL)
+            self.ref = C.CDLL(rpath)
+            self.ref.ref_fit_batch.argtypes = _FIT_ARGS
+            self.ref.ref_fit_batch.restype = C.c_int
+            lv = self.levmar
+            lv.dlevmar_der.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_void_p]
+            lv.dlevmar_der.restype = C.c_int
+            lv.dlevmar_dif.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_void_p]
+            lv.dlevmar_dif.restype = C.c_int
+            lv.dAx_eq_b_LU_noLapack.argtypes = [_dp, _dp, _dp, C.c_int]
+            lv.dAx_eq_b_LU_noLapack.restype = C.c_int
+            lv.dlevmar_chkjac.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int, C.c_void_p, _dp]
+            lv.dlevmar_L2nrmxmy.argtypes = [_dp, _dp, _dp, C.c_int]
+            lv.dlevmar_L2nrmxmy.restype = C.c_double
+            lv.dlevmar_trans_mat_mat_mult.argtypes = [_dp, _dp, C.c_int, C.c_int]
+
+    # ---- batched fits ---------------------------------------------------------------------------
+    def fit_batch(self, model, variant, p0, meas, off, counts, opts, itmax=1000, t=None, math_mode=MATH_DET,
+                  nthreads=1, use_ref=False):
+        """Runs B fits; returns dict(p, info, ret, extra).  use_ref=True routes the LM core through the
+        reference's own dlevmar_der/dlevmar_dif (oracle/_ref)."""
+        B = len(off) - 1
+        m = 19 if model == STEREO19 else 8
+        p = np.ascontiguousarray(p0, dtype=np.float64).reshape(B, m).copy()
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        opts_a = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        t_a = None if t is None else np.ascontiguousarray(t, dtype=np.float64)
+        info = np.zeros((B, 10))
+        ret = np.zeros(B, dtype=np.int32)
+        extra = np.zeros((B, 2), dtype=np.int32)
+        fn = self.ref.ref_fit_batch if use_ref else self.lib.orc_fit_batch
+        rc = fn(model, variant, math_mode, B, _ptr(p, _dp), _ptr(meas, _dp), _ptr(t_a, _dp), _ptr(off, _lp),
+                _ptr(counts, _ip), itmax, _ptr(opts_a, _dp), _ptr(info, _dp), _ptr(ret, _ip), _ptr(extra, _ip),
+                nthreads)
+        if rc != 0:
+            raise ValueError("oracle rejected the arguments")
+        return {"p": p, "info": info, "ret": ret, "extra": extra}
+
+
+_ORACLE = None
+
+
+def oracle() -> Oracle:
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE
