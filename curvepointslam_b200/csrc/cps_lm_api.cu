@@ -1,0 +1,332 @@
+// cps_lm_api.cu -- host side of the batched LM fits: context, launch geometry, the C ABI of
+// include/cps_lm.h.  Compiled with -fmad=false together with the kernels (see cps_lm_kernel.cuh).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/cps_lm.h"
+#include "cps_common.h"
+#include "cps_lm_kernel.cuh"
+
+namespace cps {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+}  // namespace cps
+
+struct cps_lm_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  unsigned int* d_queue = nullptr;
+  double* d_jstore = nullptr;
+  size_t jstore_bytes = 0;
+  // staging for the host-buffer entry points
+  char* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  int last_grid = 0, last_block = 0, last_smem = 0;
+  long long launches = 0;
+};
+
+extern "C" const char* cps_last_error(void) { return cps::g_last_error.c_str(); }
+
+extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
+  if (!out) return CPS_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cps::set_last_error("no CUDA device: libcps has no CPU path");
+    return CPS_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(device));
+  cps_lm_ctx* c = new cps_lm_ctx();
+  c->device = device;
+  CPS_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CPS_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CPS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CPS_CUDA(cudaMalloc(&c->d_queue, sizeof(unsigned int)));
+  *out = c;
+  return CPS_OK;
+}
+
+extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_queue);
+  cudaFree(c->d_jstore);
+  cudaFree(c->d_stage);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int cps_lm_sync(cps_lm_ctx* c) {
+  if (!c) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaStreamSynchronize(c->stream));
+  return CPS_OK;
+}
+
+extern "C" int cps_lm_launch_stats(cps_lm_ctx* c, int* grid, int* block, int* smem_bytes, long long* launches) {
+  if (!c) return CPS_ERR_INVALID;
+  if (grid) *grid = c->last_grid;
+  if (block) *block = c->last_block;
+  if (smem_bytes) *smem_bytes = c->last_smem;
+  if (launches) *launches = c->launches;
+  return CPS_OK;
+}
+
+namespace {
+
+template <int MODEL, bool DIF>
+int launch_fit(cps_lm_ctx* c, cps::LmLaunch& L, cudaStream_t st) {
+  using MD = cps::Model<MODEL>;
+  auto kern = cps::lm_fit_kernel<MODEL, DIF>;
+  const int per_warp = cps::lm_warp_smem_doubles(MD::M, MD::SCRATCH, L.n_max, DIF) * (int)sizeof(double);
+  // pick the warps-per-CTA that keeps the most warps resident per SM
+  int best_w = 0, best_resident = 0, best_blocks = 0;
+  for (int wpc = cps::kWarpsPerCta; wpc >= 1; --wpc) {
+    const int smem = per_warp * wpc;
+    if (smem > c->max_smem_optin) continue;
+    if (!cps::cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                      "cudaFuncSetAttribute"))
+      return CPS_ERR_CUDA;
+    int blocks = 0;
+    if (!cps::cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, wpc * 32, smem),
+                      "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+      return CPS_ERR_CUDA;
+    if (blocks * wpc > best_resident) {
+      best_resident = blocks * wpc;
+      best_w = wpc;
+      best_blocks = blocks;
+    }
+  }
+  if (best_w == 0) {
+    cps::set_last_error("a fit with this many measurements does not fit in shared memory");
+    return CPS_ERR_INVALID;
+  }
+  const int smem = per_warp * best_w;
+  CPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  long long need_ctas = ((long long)L.B + best_w - 1) / best_w;
+  int grid = (int)std::min<long long>(need_ctas, (long long)c->sm_count * best_blocks);
+  if (grid < 1) grid = 1;
+  if (DIF) {
+    const size_t need = (size_t)grid * best_w * MD::M * (size_t)L.n_max * sizeof(double);
+    if (need > c->jstore_bytes) {
+      CPS_CUDA(cudaStreamSynchronize(st));
+      cudaFree(c->d_jstore);
+      c->d_jstore = nullptr;
+      c->jstore_bytes = 0;
+      CPS_CUDA(cudaMalloc(&c->d_jstore, need));
+      c->jstore_bytes = need;
+    }
+    L.jstore = c->d_jstore;
+  } else {
+    L.jstore = nullptr;
+  }
+  L.queue = c->d_queue;
+  CPS_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned int), st));
+  kern<<<grid, best_w * 32, smem, st>>>(L);
+  CPS_CUDA(cudaGetLastError());
+  c->last_grid = grid;
+  c->last_block = best_w * 32;
+  c->last_smem = smem;
+  c->launches += 1;
+  return CPS_OK;
+}
+
+int fill_opts(cps::LmLaunch& L, const double* opts, int variant) {
+  // lm_core.c:135-141 / :510-517; defaults levmar.h:87-93
+  if (opts) {
+    L.tau = opts[0]; L.eps1 = opts[1]; L.eps2 = opts[2]; L.eps2_sq = opts[2] * opts[2]; L.eps3 = opts[3];
+    L.delta = 1E-06; L.forward = 1;
+    if (variant == CPS_LM_DIF) {
+      L.delta = opts[4];
+      if (L.delta < 0.0) { L.delta = -L.delta; L.forward = 0; }
+    }
+  } else {
+    L.tau = 1E-03; L.eps1 = 1E-17; L.eps2 = 1E-17; L.eps2_sq = 1E-17 * 1E-17; L.eps3 = 1E-17;
+    L.delta = 1E-06; L.forward = 1;
+  }
+  return CPS_OK;
+}
+
+}  // namespace
+
+extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int B, double* d_p,
+                                      const double* d_meas, const double* d_t, const long long* d_off,
+                                      const int* d_counts, int n_max, int itmax, const double* opts,
+                                      double* d_info, int* d_ret, int* d_extra, void* stream) {
+  if (!c || B < 0 || !d_p || !d_meas || !d_off || !d_counts || !d_info || !d_ret || n_max < 2 || itmax < 0)
+    return CPS_ERR_INVALID;
+  if (model != CPS_MODEL_STEREO19 && model != CPS_MODEL_IMAGE8) return CPS_ERR_UNSUPPORTED;
+  if (variant != CPS_LM_DER && variant != CPS_LM_DIF) return CPS_ERR_INVALID;
+  if (B == 0) return CPS_OK;
+  CPS_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  cps::LmLaunch L;
+  std::memset(&L, 0, sizeof L);
+  L.B = B;
+  L.n_max = (n_max + 1) & ~1;
+  L.itmax = itmax;
+  fill_opts(L, opts, variant);
+  L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;
+  L.info = d_info; L.ret = d_ret; L.extra = d_extra;
+  if (model == CPS_MODEL_STEREO19)
+    return variant == CPS_LM_DER ? launch_fit<19, false>(c, L, st) : launch_fit<19, true>(c, L, st);
+  return variant == CPS_LM_DER ? launch_fit<8, false>(c, L, st) : launch_fit<8, true>(c, L, st);
+}
+
+namespace {
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, const double* meas, const double* t,
+                     const long long* off, const int* counts, int itmax, const double* opts, double* info,
+                     int* ret, int* extra) {
+  if (!c || B < 0 || !p || !meas || !off || !counts || !info || !ret || itmax < 0) return CPS_ERR_INVALID;
+  if (model != CPS_MODEL_STEREO19 && model != CPS_MODEL_IMAGE8) return CPS_ERR_UNSUPPORTED;
+  if (B == 0) return CPS_OK;
+  const int m = (model == CPS_MODEL_STEREO19) ? 19 : 8;
+  const int nseg = (model == CPS_MODEL_STEREO19) ? 4 : 1;
+  long long n_max = 2;
+  for (int f = 0; f < B; ++f) {
+    const long long n = off[f + 1] - off[f];
+    if (n < 0) return CPS_ERR_INVALID;
+    n_max = std::max(n_max, n);
+  }
+  if (off[0] < 0) return CPS_ERR_INVALID;
+  const long long total = off[B];
+  CPS_CUDA(cudaSetDevice(c->device));
+  // one staging block: p | meas | t | off | counts | info | ret | extra
+  size_t o_p = 0, o_meas = align256(o_p + sizeof(double) * (size_t)B * m);
+  size_t o_t = align256(o_meas + sizeof(double) * (size_t)total);
+  size_t o_off = align256(o_t + (t ? sizeof(double) * (size_t)(total / 2 + 1) : 0));
+  size_t o_cnt = align256(o_off + sizeof(long long) * (size_t)(B + 1));
+  size_t o_info = align256(o_cnt + sizeof(int) * (size_t)B * nseg);
+  size_t o_ret = align256(o_info + sizeof(double) * (size_t)B * 10);
+  size_t o_ext = align256(o_ret + sizeof(int) * (size_t)B);
+  size_t bytes = align256(o_ext + sizeof(int) * (size_t)B * 2);
+  if (bytes > c->stage_bytes) {
+    CPS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    c->stage_bytes = 0;
+    CPS_CUDA(cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+  }
+  char* d = c->d_stage;
+  cudaStream_t st = c->stream;
+  CPS_CUDA(cudaMemcpyAsync(d + o_p, p, sizeof(double) * (size_t)B * m, cudaMemcpyHostToDevice, st));
+  CPS_CUDA(cudaMemcpyAsync(d + o_meas, meas + off[0], sizeof(double) * (size_t)(total - off[0]),
+                           cudaMemcpyHostToDevice, st));
+  if (t)
+    CPS_CUDA(cudaMemcpyAsync(d + o_t, t + off[0] / 2, sizeof(double) * (size_t)((total - off[0]) / 2),
+                             cudaMemcpyHostToDevice, st));
+  // offsets are rebased so that the staged block starts at 0
+  std::vector<long long> off0((size_t)B + 1);
+  for (int f = 0; f <= B; ++f) off0[f] = off[f] - off[0];
+  CPS_CUDA(cudaMemcpyAsync(d + o_off, off0.data(), sizeof(long long) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
+  CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts, sizeof(int) * (size_t)B * nseg, cudaMemcpyHostToDevice, st));
+  int rc = cps_lm_fit_batched_dev(c, model, variant, B, (double*)(d + o_p), (const double*)(d + o_meas),
+                                  t ? (const double*)(d + o_t) : nullptr, (const long long*)(d + o_off),
+                                  (const int*)(d + o_cnt), (int)std::min<long long>(n_max, 1 << 30), itmax, opts,
+                                  (double*)(d + o_info), (int*)(d + o_ret), extra ? (int*)(d + o_ext) : nullptr,
+                                  (void*)st);
+  if (rc != CPS_OK) return rc;
+  CPS_CUDA(cudaMemcpyAsync(p, d + o_p, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
+  CPS_CUDA(cudaMemcpyAsync(info, d + o_info, sizeof(double) * (size_t)B * 10, cudaMemcpyDeviceToHost, st));
+  CPS_CUDA(cudaMemcpyAsync(ret, d + o_ret, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (extra) CPS_CUDA(cudaMemcpyAsync(extra, d + o_ext, sizeof(int) * (size_t)B * 2, cudaMemcpyDeviceToHost, st));
+  CPS_CUDA(cudaStreamSynchronize(st));
+  return CPS_OK;
+}
+
+}  // namespace
+
+extern "C" int cps_dlevmar_der_batched(cps_lm_ctx* c, int model, int B, double* p, const double* meas,
+                                       const double* t, const long long* off, const int* counts, int itmax,
+                                       const double* opts, double* info, int* ret, int* extra) {
+  return fit_batched_host(c, model, CPS_LM_DER, B, p, meas, t, off, counts, itmax, opts, info, ret, extra);
+}
+
+extern "C" int cps_dlevmar_dif_batched(cps_lm_ctx* c, int model, int B, double* p, const double* meas,
+                                       const double* t, const long long* off, const int* counts, int itmax,
+                                       const double* opts, double* info, int* ret, int* extra) {
+  return fit_batched_host(c, model, CPS_LM_DIF, B, p, meas, t, off, counts, itmax, opts, info, ret, extra);
+}
+
+// ---- same-signature shims ---------------------------------------------------------------------------
+// The callbacks are tokens: the device model is selected by comparing pointers; calling them is an error.
+extern "C" void cps_modelfunc(double*, double*, int, int, void*) {
+  cps::set_last_error("cps_modelfunc is a device-model token and is never executed on the host");
+}
+extern "C" void cps_jacmodelfunc(double*, double*, int, int, void*) {
+  cps::set_last_error("cps_jacmodelfunc is a device-model token and is never executed on the host");
+}
+extern "C" void cps_modelfunc_image8(double*, double*, int, int, void*) {
+  cps::set_last_error("cps_modelfunc_image8 is a device-model token and is never executed on the host");
+}
+extern "C" void cps_jacmodelfunc_image8(double*, double*, int, int, void*) {
+  cps::set_last_error("cps_jacmodelfunc_image8 is a device-model token and is never executed on the host");
+}
+
+namespace {
+cps_lm_ctx* shim_ctx() {
+  static thread_local cps_lm_ctx* ctx = nullptr;
+  if (!ctx) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cps_lm_create(&ctx, dev) != CPS_OK) ctx = nullptr;
+  }
+  return ctx;
+}
+
+int shim_fit(int variant, void (*func)(double*, double*, int, int, void*),
+             void (*jacf)(double*, double*, int, int, void*), double* p, double* x, int m, int n, int itmax,
+             double* opts, double* info, double* work, double* covar, void* adata) {
+  int model;
+  if (func == cps_modelfunc && m == 19) model = CPS_MODEL_STEREO19;
+  else if (func == cps_modelfunc_image8 && m == 8) model = CPS_MODEL_IMAGE8;
+  else {
+    cps::set_last_error("unknown model callback: the device path has no CPU fallback for host callbacks");
+    return CPS_ERR_UNSUPPORTED;
+  }
+  if (variant == CPS_LM_DER) {
+    if ((model == CPS_MODEL_STEREO19 && jacf != cps_jacmodelfunc) ||
+        (model == CPS_MODEL_IMAGE8 && jacf != cps_jacmodelfunc_image8)) {
+      cps::set_last_error("unknown Jacobian callback");
+      return CPS_ERR_UNSUPPORTED;
+    }
+  }
+  if (work || covar) {
+    cps::set_last_error("work/covar must be NULL (the reference passes NULL, curveFittingClass.cpp:681)");
+    return CPS_ERR_UNSUPPORTED;
+  }
+  if (!p || !x || !adata || n < 0) return CPS_ERR_INVALID;
+  cps_lm_ctx* c = shim_ctx();
+  if (!c) return CPS_ERR_CUDA;
+  const cps_mydata* d = (const cps_mydata*)adata;
+  int counts[4] = {d->num_left1, d->num_left2, d->num_right1, d->num_right2};  // measurement order, :99-117
+  if (model == CPS_MODEL_IMAGE8) counts[0] = n / 2;
+  long long off[2] = {0, n};
+  int ret = 0;
+  double linfo[CPS_LM_INFO_SZ];
+  int rc = fit_batched_host(c, model, variant, 1, p, x, d->t, off, counts, itmax, opts, linfo, &ret, nullptr);
+  if (rc != CPS_OK) return rc;
+  if (info) std::memcpy(info, linfo, sizeof linfo);
+  return ret;
+}
+}  // namespace
+
+extern "C" int cps_dlevmar_der(void (*func)(double*, double*, int, int, void*),
+                               void (*jacf)(double*, double*, int, int, void*), double* p, double* x, int m, int n,
+                               int itmax, double* opts, double* info, double* work, double* covar, void* adata) {
+  return shim_fit(CPS_LM_DER, func, jacf, p, x, m, n, itmax, opts, info, work, covar, adata);
+}
+
+extern "C" int cps_dlevmar_dif(void (*func)(double*, double*, int, int, void*), double* p, double* x, int m, int n,
+                               int itmax, double* opts, double* info, double* work, double* covar, void* adata) {
+  return shim_fit(CPS_LM_DIF, func, nullptr, p, x, m, n, itmax, opts, info, work, covar, adata);
+}

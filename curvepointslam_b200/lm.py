@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's curve-fitting operator surface over libcps.so.
+
+Reference interface mirrored here (names, argument meaning, error behaviour):
+  * levmar's ``dlevmar_der`` / ``dlevmar_dif`` (levmar-2.5/levmar.h:98-107) -> batched calls with the same
+    ``p`` in/out, ``opts``, ``info[10]`` and return-value conventions;
+  * ``CurveFittingClass::fit_curve`` (curveFittingClass.cpp:408-724; declaration curveFittingClass.h:82):
+    the reference's live options ``{1e-10, 1e-10, 1e-10, 1e-20, 1e-5}``, ``itmax=1000``, ``dlevmar_dif``
+    (:661-681), ``fitting_error = info[1]`` (:683) and the post-fit sign/angle normalisation (:684-711).
+All arithmetic of the fits happens in the CUDA kernels; this file only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+STEREO19, IMAGE8 = 19, 8
+DER, DIF = 0, 1
+REFERENCE_OPTS = (1e-10, 1e-10, 1e-10, 1e-20, 1e-6 * 1e1)  # curveFittingClass.cpp:661-662
+REFERENCE_ITMAX = 1000  # curveFittingClass.cpp:681
+PI = 3.1415926535  # common.h:114
+
+
+def _vp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class LmContext:
+    """One CUDA stream + workspace (cps_lm_ctx).  Not thread-safe; make one per thread."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().cps_lm_create(C.byref(self._h), device), "cps_lm_create")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            _lib.lib().cps_lm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host buffers ---------------------------------------------------------------------------------
+    def fit_batched(self, model: int, variant: int, p0, meas, off, counts, opts=REFERENCE_OPTS,
+                    itmax: int = REFERENCE_ITMAX, t=None):
+        """B fits from host arrays.  Returns dict(p [B,m], info [B,10], ret [B], extra [B,2])."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        B = len(off) - 1
+        m = 19 if model == STEREO19 else 8
+        p = np.ascontiguousarray(p0, dtype=np.float64).reshape(B, m).copy()
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        t_a = None if t is None else np.ascontiguousarray(t, dtype=np.float64)
+        opts_a = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        info = np.zeros((B, 10))
+        ret = np.zeros(B, dtype=np.int32)
+        extra = np.zeros((B, 2), dtype=np.int32)
+        fn = _lib.lib().cps_dlevmar_der_batched if variant == DER else _lib.lib().cps_dlevmar_dif_batched
+        rc = fn(self._h, model, B, _vp(p), _vp(meas), _vp(t_a), _vp(off), _vp(counts), itmax, _vp(opts_a),
+                _vp(info), _vp(ret), _vp(extra))
+        _lib.check(rc, "cps_dlevmar_*_batched")
+        return {"p": p, "info": info, "ret": ret, "extra": extra}
+
+    # -- device buffers (raw pointers, e.g. torch tensors' data_ptr()) ---------------------------------
+    def fit_batched_dev(self, model: int, variant: int, B: int, d_p: int, d_meas: int, d_t: int | None,
+                        d_off: int, d_counts: int, n_max: int, d_info: int, d_ret: int, d_extra: int | None,
+                        opts=REFERENCE_OPTS, itmax: int = REFERENCE_ITMAX, stream: int | None = None):
+        opts_a = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        rc = _lib.lib().cps_lm_fit_batched_dev(self._h, model, variant, B, d_p, d_meas, d_t, d_off, d_counts,
+                                               n_max, itmax, _vp(opts_a), d_info, d_ret, d_extra, stream)
+        _lib.check(rc, "cps_lm_fit_batched_dev")
+
+    def sync(self):
+        _lib.check(_lib.lib().cps_lm_sync(self._h), "cps_lm_sync")
+
+    def launch_stats(self):
+        g, b, s, n = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        _lib.lib().cps_lm_launch_stats(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(n))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "launches": n.value}
+
+
+def postfit_normalise(p: np.ndarray) -> np.ndarray:
+    """fit_curve's post-fit sign/angle normalisation (curveFittingClass.cpp:684-711), vectorised over fits;
+    including the reference's ``params[18] += PI`` in the second branch."""
+    p = np.array(p, dtype=np.float64, copy=True).reshape(-1, 19)
+    flip = p[:, 18] > 0.0
+    p[flip, 1:16:2] *= -1.0
+    p[flip, 16] *= -1.0
+    p[flip, 17] += PI
+    p[flip, 18] *= -1.0
+    b2 = p[:, 16] < -PI / 2.0
+    p[b2, 1:16:2] *= -1.0
+    p[b2, 17] = -PI - p[b2, 17]
+    p[b2, 18] += PI
+    for col in (16, 17):
+        for _ in range(64):
+            hi = p[:, col] > PI
+            lo = p[:, col] < -PI
+            if not (hi.any() or lo.any()):
+                break
+            p[hi, col] -= 2 * PI
+            p[lo, col] += 2 * PI
+    return p
+
+
+class CurveFittingClass:
+    """Mirror of the reference class for the fit path (curveFittingClass.h:77-121).
+
+    ``fit_curve(L, R)`` takes the two left-image and two right-image contour segments as [k,2] arrays of
+    (x, y) pixels (the reference's 2k x 1 interleaved ``CvMat``s, curveFittingClass.cpp:435-489) and the
+    initial parameters; ``fit_curves_batched`` is the same for many frames at once."""
+
+    def __init__(self, ctx: LmContext | None = None, variant: int = DIF):
+        self.ctx = ctx or LmContext()
+        self.variant = variant
+        self.fitting_error = 0.0
+        self.info = None
+
+    def fit_curves_batched(self, params0, frames):
+        """frames: list of (L0, L1, R0, R1) arrays [k,2]; params0 [B,19] initial parameters."""
+        B = len(frames)
+        pieces, counts = [], np.zeros((B, 4), dtype=np.int32)
+        for b, (l0, l1, r0, r1) in enumerate(frames):
+            for s, seg in enumerate((l0, l1, r0, r1)):  # [L c1 | L c2 | R c1 | R c2]
+                a = np.asarray(seg, dtype=np.float64).reshape(-1, 2)
+                counts[b, s] = a.shape[0]
+                pieces.append(a.reshape(-1))
+        meas = np.concatenate(pieces) if pieces else np.zeros(0)
+        off = np.concatenate([[0], np.cumsum(2 * counts.sum(axis=1))]).astype(np.int64)
+        r = self.ctx.fit_batched(STEREO19, self.variant, params0, meas, off, counts)
+        self.info = r["info"]
+        return postfit_normalise(r["p"]), r["info"][:, 1].copy(), r
+
+    def fit_curve(self, params0, L, R):
+        p, err, _ = self.fit_curves_batched(np.asarray(params0, dtype=np.float64).reshape(1, 19),
+                                            [(L[0], L[1], R[0], R[1])])
+        self.fitting_error = float(err[0])
+        return p[0]

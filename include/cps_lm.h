@@ -1,0 +1,114 @@
+/*
+ * cps_lm.h -- C ABI of the batched Bezier Levenberg-Marquardt fits (libcps.so, CUDA, sm_100a).
+ *
+ * Replaces, for B independent fits at a time, the reference's per-frame call
+ *     dlevmar_dif(modelfunc, params, final_meas, m, num_meas, 1000, opts, info, NULL, NULL, &funcdata)
+ * (curveFittingClass.cpp:681; ABI levmar-2.5/levmar.h:98-107) and its commented-out sibling
+ * dlevmar_der (:682).  Device code cannot call host callbacks, so the model is named by an id instead
+ * of a function pointer; everything else -- p in/out, opts[5], info[10], return value -- has the
+ * reference's meaning (levmar.h:87-93, lm_core.c:396-409,422):
+ *     info[0] ||e||^2 at the initial p     info[5] iterations
+ *     info[1] ||e||^2 at the final p       info[6] stop reason 1..7
+ *     info[2] ||J^T e||_inf                info[7] function evaluations
+ *     info[3] ||dp||^2                     info[8] Jacobian evaluations
+ *     info[4] mu / max diag(J^T J)         info[9] linear systems solved
+ *     ret[f]  iterations, or -1 when the reason is 4 or 7 (LM_ERROR), or a CPS_FIT_* code below
+ * There is no CPU fallback: without a CUDA device every entry point returns CPS_ERR_CUDA.
+ */
+#ifndef CPS_LM_H
+#define CPS_LM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* model ids */
+#define CPS_MODEL_STEREO19 19 /* modelfunc, curveFittingClass.cpp:82-119: 2 ground curves + theta, phi, z  */
+#define CPS_MODEL_IMAGE8 8    /* Bernstein evaluation alone, curveFittingClass.cpp:1057-1073: one contour   */
+/* LM variants */
+#define CPS_LM_DER 0 /* analytic Jacobian, dlevmar_der lm_core.c:60-423 */
+#define CPS_LM_DIF 1 /* secant / finite differences, dlevmar_dif lm_core.c:429-828 (the reference's live call) */
+
+/* library status codes (return values of the entry points) */
+#define CPS_OK 0
+#define CPS_ERR_INVALID (-1)     /* bad argument                                            */
+#define CPS_ERR_CUDA (-2)        /* CUDA runtime error or no device; see cps_last_error()   */
+#define CPS_ERR_UNSUPPORTED (-3) /* callback / model the device path does not know          */
+#define CPS_ERR_NOMEM (-4)
+
+/* per-fit codes written to ret[] besides the reference's own values */
+#define CPS_FIT_LM_ERROR (-1)  /* the reference's LM_ERROR: n < m, or stop reason 4 / 7 */
+#define CPS_FIT_TOO_LARGE (-2) /* more measurements than n_max                          */
+#define CPS_FIT_BAD_COUNTS (-3)/* segment sizes do not add up to the measurement count  */
+
+#define CPS_LM_INFO_SZ 10 /* LM_INFO_SZ, levmar.h:85 */
+#define CPS_LM_OPTS_SZ 5  /* LM_OPTS_SZ, levmar.h:84 */
+
+typedef struct cps_lm_ctx cps_lm_ctx; /* owns a stream, the fit queue and the device workspace; one per thread */
+
+int cps_lm_create(cps_lm_ctx **out, int device);
+void cps_lm_destroy(cps_lm_ctx *ctx);
+const char *cps_last_error(void);
+
+/*
+ * B fits with HOST buffers (copies in, kernel, copies out, synchronous).
+ *   p      [B][m]     in: initial parameters, out: fitted parameters
+ *   meas   [off[B]]   concatenated (x,y) contour samples; fit f owns doubles off[f]..off[f+1];
+ *                     Stereo19 segment order [left c1 | left c2 | right c1 | right c2] (fit_curve :435-489)
+ *   t      [off[B]/2] curve parameter of every sample, or NULL: derive it from the image rows exactly
+ *                     like fit_curve (:451-511)
+ *   counts [B][4] (Stereo19) or [B][1] (Image8): points per segment
+ *   opts   [5] {tau, eps1, eps2, eps3, delta} or NULL for the reference defaults (levmar.h:87-93);
+ *          delta < 0 selects central differences (dif only)
+ *   info   [B][10], ret [B], extra [B][2] = (J^T J rebuilds, secant updates) or NULL
+ */
+int cps_dlevmar_der_batched(cps_lm_ctx *ctx, int model, int B, double *p, const double *meas, const double *t,
+                            const long long *off, const int *counts, int itmax, const double *opts,
+                            double *info, int *ret, int *extra);
+int cps_dlevmar_dif_batched(cps_lm_ctx *ctx, int model, int B, double *p, const double *meas, const double *t,
+                            const long long *off, const int *counts, int itmax, const double *opts,
+                            double *info, int *ret, int *extra);
+
+/*
+ * Same with DEVICE buffers already resident in HBM; asynchronous on `stream` (a cudaStream_t passed
+ * as void*, NULL = the context's own stream).  n_max = an even upper bound on off[f+1]-off[f].
+ */
+int cps_lm_fit_batched_dev(cps_lm_ctx *ctx, int model, int variant, int B, double *d_p, const double *d_meas,
+                           const double *d_t, const long long *d_off, const int *d_counts, int n_max, int itmax,
+                           const double *opts, double *d_info, int *d_ret, int *d_extra, void *stream);
+int cps_lm_sync(cps_lm_ctx *ctx);
+/* geometry of the last launch and the number of kernel launches issued through this context */
+int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
+
+/*
+ * Same-signature shims for code that calls levmar one fit at a time (curveFittingClass.cpp:679-682).
+ * `func` must be cps_modelfunc (m=19) or cps_modelfunc_image8 (m=8) and, for _der, `jacf` must be
+ * cps_jacmodelfunc / cps_jacmodelfunc_image8: these are tokens that select the device model, they are
+ * never executed.  Any other callback returns CPS_ERR_UNSUPPORTED (there is no CPU path).  `adata`
+ * points to the reference's struct mydata (curveFittingClass.h:22-31), restated below.  `work` and
+ * `covar` must be NULL (the reference passes NULL for both).
+ */
+struct cps_mydata {
+  double *orig_meas;
+  double *t;
+  int *curve_num;
+  int num_left1;
+  int num_right1;
+  int num_left2;
+  int num_right2;
+  void *disp;
+};
+void cps_modelfunc(double *p, double *hx, int m, int n, void *adata);
+void cps_jacmodelfunc(double *p, double *jac, int m, int n, void *adata);
+void cps_modelfunc_image8(double *p, double *hx, int m, int n, void *adata);
+void cps_jacmodelfunc_image8(double *p, double *jac, int m, int n, void *adata);
+int cps_dlevmar_der(void (*func)(double *, double *, int, int, void *),
+                    void (*jacf)(double *, double *, int, int, void *), double *p, double *x, int m, int n,
+                    int itmax, double *opts, double *info, double *work, double *covar, void *adata);
+int cps_dlevmar_dif(void (*func)(double *, double *, int, int, void *), double *p, double *x, int m, int n,
+                    int itmax, double *opts, double *info, double *work, double *covar, void *adata);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
