@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- batched Bezier LM fits/s on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--variant der|dif] [--fits B] [--impl b200|reference]
+
+A step = one pass of the hot path over one batch of synthetic stereo contours: B fits of the m=19 model
+(4 contour segments x 64 points each, n=512), i.e. 4*B contours.  Default B = 262144 fits = 1Mi contours per
+GPU (BASELINE.json configs[1], the top of the 1k-1M sweep); inputs (1.07 GB) are larger than L2.
+`value` times the kernel path with inputs resident in HBM; `e2e` times the C-ABI host-buffer call
+(pinned host memory, H2D and D2H inside).  --impl reference times the reference's own levmar (oracle/_ref,
+built from /root/reference) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_PTS = 64
+M = 19
+N_MEAS = 8 * K_PTS
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="der", choices=["der", "dif"])
+    ap.add_argument("--fits", type=int, default=262144, help="fits per GPU per step (4 contours each)")
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path: levmar-2.5 compiled unchanged (oracle/_ref) driven
+    by the restated model, all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import DER, DIF, STEREO19, oracle
+    from curvepointslam_b200 import lm, synth
+    o = oracle()
+    use_ref = o.ref is not None
+    cores = os.cpu_count() or 1
+    variant = DER if args.variant == "der" else DIF
+    per_fit_core_s = 0.6e-3 if variant == DER else 5.5e-3
+    sample = int(max(256, min(args.fits, 1.5 * cores / per_fit_core_s)))  # about 1.5 s per step
+    sample = (sample // 64) * 64
+    b = synth.make_stereo19_batch_fast(sample, K=K_PTS, seed=args.seed, first=0)
+    opts = list(lm.REFERENCE_OPTS)
+    run = lambda: o.fit_batch(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], opts, nthreads=cores,
+                              use_ref=use_ref)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    kind = "reference" if use_ref else "port"
+    line = {
+        "impl": "reference", "metric": "bezier_lm_fits_per_sec", "value": val, "unit": "fits/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.fits),
+        "cpu_baseline": {"value": val, "unit": "fits/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} fits per step of the same synthetic workload, levmar-2.5 "
+                                   f"dlevmar_{args.variant} built from /root/reference (oracle/_ref) + restated model"
+                         if use_ref else f"{sample} fits per step, oracle port (oracle/_ref not built)"},
+        "e2e": {"value": val, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, fits):
+    return {"workload": f"batched Bezier LM fit, m=19 stereo-pair model, {fits} fits/GPU/step = {4 * fits} contours "
+                        f"x {K_PTS} pts (n={N_MEAS}), levmar dlevmar_{args.variant}, opts of curveFittingClass.cpp:661",
+            "fits_per_gpu": fits, "contours_per_gpu": 4 * fits, "points_per_contour": K_PTS, "variant": args.variant,
+            "l2": "inputs larger than L2 (no flush needed)" if fits * N_MEAS * 8 > 126e6 else "L2 flushed between steps"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from curvepointslam_b200 import _lib, flops, lm, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    variant = lm.DER if args.variant == "der" else lm.DIF
+    B = args.fits
+    ctx = lm.LmContext(local)
+
+    # ---- synthetic shard of this rank (weak scaling: B fits per GPU) ---------------------------------
+    b = synth.make_stereo19_batch_fast(B, K=K_PTS, seed=args.seed, first=rank * B)
+    h_meas = torch.from_numpy(b["meas"]).pin_memory()
+    h_p0 = torch.from_numpy(b["p0"]).pin_memory()
+    h_off = torch.from_numpy(b["off"]).pin_memory()
+    h_cnt = torch.from_numpy(b["counts"]).pin_memory()
+    d_meas, d_p0, d_off, d_cnt = (x.to(dev) for x in (h_meas, h_p0, h_off, h_cnt))
+    d_p = torch.empty_like(d_p0)
+    d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+    d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_extra = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    gathered = [torch.empty_like(d_p) for _ in range(world)] if world > 1 else None
+    flush = None
+    if B * N_MEAS * 8 <= 126e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)  # every launch, copy and event of the timed region is on this stream
+    torch.cuda.set_stream(stream)
+
+    def step_resident(ev=None):
+        if flush is not None:
+            flush.zero_()
+        d_p.copy_(d_p0)
+        if ev:
+            ev[0].record(stream)
+        ctx.fit_batched_dev(M, variant, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(),
+                            d_cnt.data_ptr(), N_MEAS, d_info.data_ptr(), d_ret.data_ptr(), d_extra.data_ptr(),
+                            stream=stream.cuda_stream)
+        if ev:
+            ev[1].record(stream)
+        if world > 1:  # the only exchange of the path: gather of the fitted control points
+            dist.all_gather(gathered, d_p)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_resident(kev[i])
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = [a.elapsed_time(bb) for a, bb in kev]
+    launches_value = args.steps  # one fit kernel per step (plus one 4-byte memset node)
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside) -----------------------------
+    h_p = torch.empty_like(h_p0)
+    h_info = torch.zeros((B, 10), dtype=torch.float64).pin_memory()
+    h_ret = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_p = h_p.pin_memory()
+    fn = _lib.lib().cps_dlevmar_der_batched if variant == lm.DER else _lib.lib().cps_dlevmar_dif_batched
+    opts = np.array(lm.REFERENCE_OPTS)
+
+    def step_e2e():
+        h_p.copy_(h_p0)
+        rc = fn(ctx._h, M, B, h_p.data_ptr(), h_meas.data_ptr(), None, h_off.data_ptr(), h_cnt.data_ptr(),
+                lm.REFERENCE_ITMAX, opts.ctypes.data, h_info.data_ptr(), h_ret.data_ptr(), None)
+        _lib.check(rc, "cps_dlevmar_*_batched")
+        if world > 1:
+            d_p.copy_(h_p, non_blocking=True)
+            dist.all_gather(gathered, d_p)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    tt = torch.tensor([ms_total, e2e_s * 1e3, sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kernel_ms_avg = (float(x) for x in tt.cpu())
+
+    # ---- roofline numerators from the per-fit counters of the last resident step --------------------
+    info = d_info.cpu().numpy()
+    extra = d_extra.cpu().numpy()
+    nfev, njev, nlss = info[:, 7].sum(), info[:, 8].sum(), info[:, 9].sum()
+    if variant == lm.DER:
+        fl = flops.fit_flops_der(N_MEAS, M, nfev, njev, nlss)
+    else:
+        fl = flops.fit_flops_dif(N_MEAS, M, nfev, njev, nlss, extra[:, 0].sum(), extra[:, 1].sum())
+    reasons, rc_counts = np.unique(info[:, 6], return_counts=True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk_fma, pk_ma = _lib.C.c_double(), _lib.C.c_double()
+    _lib.check(_lib.lib().cps_measure_fp64_peak(local, _lib.C.byref(pk_fma), _lib.C.byref(pk_ma)), "fp64 peak")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    achieved_tf = fl / (kernel_ms_avg * 1e-3) / 1e12
+    value = B * world * args.steps / (ms_total * 1e-3)
+    e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
+    h2d = h_meas.numel() * 8 + h_p0.numel() * 8 + h_off.numel() * 8 + h_cnt.numel() * 4
+    d2h = h_p.numel() * 8 + h_info.numel() * 8 + h_ret.numel() * 4
+    line = {
+        "metric": "bezier_lm_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, B),
+        "contours_per_sec": 4 * value,
+        "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": f"cps_dlevmar_{args.variant}_batched (include/cps_lm.h), pinned host buffers, "
+                       "chunked copy/compute pipeline"},
+        "gpu_launches": launches_value,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "fp64", "kernel": f"lm_fit_kernel<19,{'true' if variant == lm.DIF else 'false'}>",
+            "achieved": achieved_tf, "peak": pk_fma.value, "unit": "TFLOP/s", "frac": achieved_tf / pk_fma.value,
+            "peak_source": "measured live by cps_measure_fp64_peak (DFMA stream; MEASURED_PEAKS.json has no FP64 "
+                           "entry); a kernel that may not fuse multiply-adds (bit-exact parity) tops out at "
+                           f"{pk_ma.value:.2f} TFLOP/s",
+            "peak_unfused": pk_ma.value,
+            "flops_per_fit": fl / B, "kernel_ms": kernel_ms_avg,
+            "hbm": {"achieved": flops.fit_bytes(N_MEAS, M) * B / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "note": "algorithmic bytes; the path is FP64-bound, not HBM-bound"},
+            "traffic": None,
+        },
+        "fit_stats": {"iters_mean": float(info[:, 5].mean()), "nfev_mean": float(nfev / B),
+                      "njev_mean": float(njev / B), "nlss_mean": float(nlss / B),
+                      "stop_reasons": {str(int(r)): int(c) for r, c in zip(reasons, rc_counts)}},
+    }
+
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import DER, DIF, STEREO19, oracle
+        o = oracle()
+        use_ref = o.ref is not None
+        cores = os.cpu_count() or 1
+        per_fit_core_s = 0.6e-3 if variant == lm.DER else 5.5e-3
+        sample = int(max(256, min(B, 12.0 * cores / per_fit_core_s)))
+        sample = (sample // 64) * 64
+        sl = slice(0, sample * N_MEAS)
+        t0 = time.perf_counter()
+        cpu = o.fit_batch(STEREO19, DER if variant == lm.DER else DIF, b["p0"][:sample], b["meas"][sl],
+                          b["off"][:sample + 1], b["counts"][:sample], list(lm.REFERENCE_OPTS), nthreads=cores,
+                          use_ref=use_ref)
+        dt = time.perf_counter() - t0
+        # the same sample must agree bit for bit with what the GPU produced for those fits
+        gp = d_p.cpu().numpy()[:sample]
+        same = bool(np.array_equal(gp.view(np.int64), cpu["p"].view(np.int64)))
+        line["cpu_baseline"] = {"value": sample / dt, "unit": "fits/s", "cores": cores,
+                                "kind": "reference" if use_ref else "port",
+                                "sample": f"first {sample} fits of rank 0's batch, "
+                                          + ("levmar-2.5 from /root/reference (oracle/_ref) + restated model"
+                                             if use_ref else "oracle port"),
+                                "seconds": dt, "gpu_bit_identical_on_sample": same}
+    if not args.no_extras:
+        try:
+            from curvepointslam_b200 import bench_extras
+            line["extras"] = bench_extras.run(local)
+        except Exception as ex:  # extras never take the headline down
+            line["extras"] = {"error": repr(ex)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,17 +14,26 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 }  // namespace cps
 
-struct cps_lm_ctx {
-  int device = 0;
-  int sm_count = 0;
-  int max_smem_optin = 0;
+// One pipeline slot: a stream with its own fit queue, secant-Jacobian workspace and staging block, so
+// that the host-buffer entry points can copy chunk i+1 while chunk i computes.
+struct cps_lm_slot {
   cudaStream_t stream = nullptr;
   unsigned int* d_queue = nullptr;
   double* d_jstore = nullptr;
   size_t jstore_bytes = 0;
-  // staging for the host-buffer entry points
   char* d_stage = nullptr;
   size_t stage_bytes = 0;
+  std::vector<long long> off0;  // rebased offsets of the chunk in flight (must outlive the async copy)
+};
+
+constexpr int kSlots = 2;
+constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
+
+struct cps_lm_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cps_lm_slot slot[kSlots];
   int last_grid = 0, last_block = 0, last_smem = 0;
   long long launches = 0;
 };
@@ -45,8 +54,10 @@ extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
   c->device = device;
   CPS_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   CPS_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  CPS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CPS_CUDA(cudaMalloc(&c->d_queue, sizeof(unsigned int)));
+  for (int i = 0; i < kSlots; ++i) {
+    CPS_CUDA(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
+    CPS_CUDA(cudaMalloc(&c->slot[i].d_queue, sizeof(unsigned int)));
+  }
   *out = c;
   return CPS_OK;
 }
@@ -54,17 +65,20 @@ extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
 extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_queue);
-  cudaFree(c->d_jstore);
-  cudaFree(c->d_stage);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  for (int i = 0; i < kSlots; ++i) {
+    cps_lm_slot& s = c->slot[i];
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFree(s.d_queue);
+    cudaFree(s.d_jstore);
+    cudaFree(s.d_stage);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
   delete c;
 }
 
 extern "C" int cps_lm_sync(cps_lm_ctx* c) {
   if (!c) return CPS_ERR_INVALID;
-  CPS_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
   return CPS_OK;
 }
 
@@ -80,7 +94,7 @@ extern "C" int cps_lm_launch_stats(cps_lm_ctx* c, int* grid, int* block, int* sm
 namespace {
 
 template <int MODEL, bool DIF>
-int launch_fit(cps_lm_ctx* c, cps::LmLaunch& L, cudaStream_t st) {
+int launch_fit(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st) {
   using MD = cps::Model<MODEL>;
   auto kern = cps::lm_fit_kernel<MODEL, DIF>;
   const int per_warp = cps::lm_warp_smem_doubles(MD::M, MD::SCRATCH, L.n_max, DIF) * (int)sizeof(double);
@@ -113,20 +127,21 @@ int launch_fit(cps_lm_ctx* c, cps::LmLaunch& L, cudaStream_t st) {
   if (grid < 1) grid = 1;
   if (DIF) {
     const size_t need = (size_t)grid * best_w * MD::M * (size_t)L.n_max * sizeof(double);
-    if (need > c->jstore_bytes) {
+    if (need > sl.jstore_bytes) {
       CPS_CUDA(cudaStreamSynchronize(st));
-      cudaFree(c->d_jstore);
-      c->d_jstore = nullptr;
-      c->jstore_bytes = 0;
-      CPS_CUDA(cudaMalloc(&c->d_jstore, need));
-      c->jstore_bytes = need;
+      CPS_CUDA(cudaStreamSynchronize(sl.stream));
+      cudaFree(sl.d_jstore);
+      sl.d_jstore = nullptr;
+      sl.jstore_bytes = 0;
+      CPS_CUDA(cudaMalloc(&sl.d_jstore, need));
+      sl.jstore_bytes = need;
     }
-    L.jstore = c->d_jstore;
+    L.jstore = sl.d_jstore;
   } else {
     L.jstore = nullptr;
   }
-  L.queue = c->d_queue;
-  CPS_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned int), st));
+  L.queue = sl.d_queue;
+  CPS_CUDA(cudaMemsetAsync(sl.d_queue, 0, sizeof(unsigned int), st));
   kern<<<grid, best_w * 32, smem, st>>>(L);
   CPS_CUDA(cudaGetLastError());
   c->last_grid = grid;
@@ -154,6 +169,24 @@ int fill_opts(cps::LmLaunch& L, const double* opts, int variant) {
 
 }  // namespace
 
+namespace {
+int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, double* d_p, const double* d_meas,
+            const double* d_t, const long long* d_off, const int* d_counts, int n_max, int itmax,
+            const double* opts, double* d_info, int* d_ret, int* d_extra, cudaStream_t st) {
+  cps::LmLaunch L;
+  std::memset(&L, 0, sizeof L);
+  L.B = B;
+  L.n_max = (n_max + 1) & ~1;
+  L.itmax = itmax;
+  fill_opts(L, opts, variant);
+  L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;
+  L.info = d_info; L.ret = d_ret; L.extra = d_extra;
+  if (model == CPS_MODEL_STEREO19)
+    return variant == CPS_LM_DER ? launch_fit<19, false>(c, sl, L, st) : launch_fit<19, true>(c, sl, L, st);
+  return variant == CPS_LM_DER ? launch_fit<8, false>(c, sl, L, st) : launch_fit<8, true>(c, sl, L, st);
+}
+}  // namespace
+
 extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int B, double* d_p,
                                       const double* d_meas, const double* d_t, const long long* d_off,
                                       const int* d_counts, int n_max, int itmax, const double* opts,
@@ -164,24 +197,18 @@ extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int
   if (variant != CPS_LM_DER && variant != CPS_LM_DIF) return CPS_ERR_INVALID;
   if (B == 0) return CPS_OK;
   CPS_CUDA(cudaSetDevice(c->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-  cps::LmLaunch L;
-  std::memset(&L, 0, sizeof L);
-  L.B = B;
-  L.n_max = (n_max + 1) & ~1;
-  L.itmax = itmax;
-  fill_opts(L, opts, variant);
-  L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;
-  L.info = d_info; L.ret = d_ret; L.extra = d_extra;
-  if (model == CPS_MODEL_STEREO19)
-    return variant == CPS_LM_DER ? launch_fit<19, false>(c, L, st) : launch_fit<19, true>(c, L, st);
-  return variant == CPS_LM_DER ? launch_fit<8, false>(c, L, st) : launch_fit<8, true>(c, L, st);
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
+  return fit_dev(c, c->slot[0], model, variant, B, d_p, d_meas, d_t, d_off, d_counts, n_max, itmax, opts, d_info,
+                 d_ret, d_extra, st);
 }
 
 namespace {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Host buffers: the batch is cut into chunks of kChunkFits fits; chunk i+1 is copied (and its results of
+// chunk i-1 copied back) on the other slot's stream while chunk i computes.  Pinned host memory makes the
+// copies truly asynchronous; pageable memory works but serialises.
 int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, const double* meas, const double* t,
                      const long long* off, const int* counts, int itmax, const double* opts, double* info,
                      int* ret, int* extra) {
@@ -191,55 +218,61 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   const int m = (model == CPS_MODEL_STEREO19) ? 19 : 8;
   const int nseg = (model == CPS_MODEL_STEREO19) ? 4 : 1;
   long long n_max = 2;
+  if (off[0] < 0) return CPS_ERR_INVALID;
   for (int f = 0; f < B; ++f) {
     const long long n = off[f + 1] - off[f];
     if (n < 0) return CPS_ERR_INVALID;
     n_max = std::max(n_max, n);
   }
-  if (off[0] < 0) return CPS_ERR_INVALID;
-  const long long total = off[B];
+  if (n_max > (1 << 24)) return CPS_ERR_INVALID;
   CPS_CUDA(cudaSetDevice(c->device));
-  // one staging block: p | meas | t | off | counts | info | ret | extra
-  size_t o_p = 0, o_meas = align256(o_p + sizeof(double) * (size_t)B * m);
-  size_t o_t = align256(o_meas + sizeof(double) * (size_t)total);
-  size_t o_off = align256(o_t + (t ? sizeof(double) * (size_t)(total / 2 + 1) : 0));
-  size_t o_cnt = align256(o_off + sizeof(long long) * (size_t)(B + 1));
-  size_t o_info = align256(o_cnt + sizeof(int) * (size_t)B * nseg);
-  size_t o_ret = align256(o_info + sizeof(double) * (size_t)B * 10);
-  size_t o_ext = align256(o_ret + sizeof(int) * (size_t)B);
-  size_t bytes = align256(o_ext + sizeof(int) * (size_t)B * 2);
-  if (bytes > c->stage_bytes) {
-    CPS_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_stage);
-    c->d_stage = nullptr;
-    c->stage_bytes = 0;
-    CPS_CUDA(cudaMalloc(&c->d_stage, bytes));
-    c->stage_bytes = bytes;
-  }
-  char* d = c->d_stage;
-  cudaStream_t st = c->stream;
-  CPS_CUDA(cudaMemcpyAsync(d + o_p, p, sizeof(double) * (size_t)B * m, cudaMemcpyHostToDevice, st));
-  CPS_CUDA(cudaMemcpyAsync(d + o_meas, meas + off[0], sizeof(double) * (size_t)(total - off[0]),
-                           cudaMemcpyHostToDevice, st));
-  if (t)
-    CPS_CUDA(cudaMemcpyAsync(d + o_t, t + off[0] / 2, sizeof(double) * (size_t)((total - off[0]) / 2),
+  int chunk_idx = 0;
+  for (int f0 = 0; f0 < B; f0 += kChunkFits, ++chunk_idx) {
+    const int nb = std::min(kChunkFits, B - f0);
+    cps_lm_slot& sl = c->slot[chunk_idx % kSlots];
+    cudaStream_t st = sl.stream;
+    const long long base = off[f0], total = off[f0 + nb] - base;
+    // one staging block: p | meas | t | off | counts | info | ret | extra
+    size_t o_p = 0, o_meas = align256(o_p + sizeof(double) * (size_t)nb * m);
+    size_t o_t = align256(o_meas + sizeof(double) * (size_t)total);
+    size_t o_off = align256(o_t + (t ? sizeof(double) * (size_t)(total / 2 + 1) : 0));
+    size_t o_cnt = align256(o_off + sizeof(long long) * (size_t)(nb + 1));
+    size_t o_info = align256(o_cnt + sizeof(int) * (size_t)nb * nseg);
+    size_t o_ret = align256(o_info + sizeof(double) * (size_t)nb * 10);
+    size_t o_ext = align256(o_ret + sizeof(int) * (size_t)nb);
+    size_t bytes = align256(o_ext + sizeof(int) * (size_t)nb * 2);
+    // the slot's previous chunk must have drained before its staging block / offsets are reused
+    CPS_CUDA(cudaStreamSynchronize(st));
+    if (bytes > sl.stage_bytes) {
+      cudaFree(sl.d_stage);
+      sl.d_stage = nullptr;
+      sl.stage_bytes = 0;
+      CPS_CUDA(cudaMalloc(&sl.d_stage, bytes));
+      sl.stage_bytes = bytes;
+    }
+    char* d = sl.d_stage;
+    sl.off0.resize((size_t)nb + 1);
+    for (int f = 0; f <= nb; ++f) sl.off0[f] = off[f0 + f] - base;
+    CPS_CUDA(cudaMemcpyAsync(d + o_p, p + (size_t)f0 * m, sizeof(double) * (size_t)nb * m, cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + o_meas, meas + base, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, st));
+    if (t)
+      CPS_CUDA(cudaMemcpyAsync(d + o_t, t + base / 2, sizeof(double) * (size_t)(total / 2), cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + o_off, sl.off0.data(), sizeof(long long) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts + (size_t)f0 * nseg, sizeof(int) * (size_t)nb * nseg,
                              cudaMemcpyHostToDevice, st));
-  // offsets are rebased so that the staged block starts at 0
-  std::vector<long long> off0((size_t)B + 1);
-  for (int f = 0; f <= B; ++f) off0[f] = off[f] - off[0];
-  CPS_CUDA(cudaMemcpyAsync(d + o_off, off0.data(), sizeof(long long) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
-  CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts, sizeof(int) * (size_t)B * nseg, cudaMemcpyHostToDevice, st));
-  int rc = cps_lm_fit_batched_dev(c, model, variant, B, (double*)(d + o_p), (const double*)(d + o_meas),
-                                  t ? (const double*)(d + o_t) : nullptr, (const long long*)(d + o_off),
-                                  (const int*)(d + o_cnt), (int)std::min<long long>(n_max, 1 << 30), itmax, opts,
-                                  (double*)(d + o_info), (int*)(d + o_ret), extra ? (int*)(d + o_ext) : nullptr,
-                                  (void*)st);
-  if (rc != CPS_OK) return rc;
-  CPS_CUDA(cudaMemcpyAsync(p, d + o_p, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
-  CPS_CUDA(cudaMemcpyAsync(info, d + o_info, sizeof(double) * (size_t)B * 10, cudaMemcpyDeviceToHost, st));
-  CPS_CUDA(cudaMemcpyAsync(ret, d + o_ret, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (extra) CPS_CUDA(cudaMemcpyAsync(extra, d + o_ext, sizeof(int) * (size_t)B * 2, cudaMemcpyDeviceToHost, st));
-  CPS_CUDA(cudaStreamSynchronize(st));
+    int rc = fit_dev(c, sl, model, variant, nb, (double*)(d + o_p), (const double*)(d + o_meas),
+                     t ? (const double*)(d + o_t) : nullptr, (const long long*)(d + o_off), (const int*)(d + o_cnt),
+                     (int)n_max, itmax, opts, (double*)(d + o_info), (int*)(d + o_ret),
+                     extra ? (int*)(d + o_ext) : nullptr, st);
+    if (rc != CPS_OK) return rc;
+    CPS_CUDA(cudaMemcpyAsync(p + (size_t)f0 * m, d + o_p, sizeof(double) * (size_t)nb * m, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(info + (size_t)f0 * 10, d + o_info, sizeof(double) * (size_t)nb * 10,
+                             cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(ret + f0, d + o_ret, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    if (extra)
+      CPS_CUDA(cudaMemcpyAsync(extra + (size_t)f0 * 2, d + o_ext, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
   return CPS_OK;
 }
 

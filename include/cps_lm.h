@@ -71,7 +71,7 @@ int cps_dlevmar_dif_batched(cps_lm_ctx *ctx, int model, int B, double *p, const 
 
 /*
  * Same with DEVICE buffers already resident in HBM; asynchronous on `stream` (a cudaStream_t passed
- * as void*, NULL = the context's own stream).  n_max = an even upper bound on off[f+1]-off[f].
+ * as void*; NULL = the CUDA default stream, as in any CUDA call).  n_max = an even upper bound on off[f+1]-off[f].
  */
 int cps_lm_fit_batched_dev(cps_lm_ctx *ctx, int model, int variant, int B, double *d_p, const double *d_meas,
                            const double *d_t, const long long *d_off, const int *d_counts, int n_max, int itmax,
@@ -107,6 +107,10 @@ int cps_dlevmar_der(void (*func)(double *, double *, int, int, void *),
                     int itmax, double *opts, double *info, double *work, double *covar, void *adata);
 int cps_dlevmar_dif(void (*func)(double *, double *, int, int, void *), double *p, double *x, int m, int n,
                     int itmax, double *opts, double *info, double *work, double *covar, void *adata);
+
+/* FP64 roofline denominators measured on the device: a DFMA stream and a DMUL+DADD stream (TFLOP/s,
+ * a multiply-add pair counted as 2 flop in both). */
+int cps_measure_fp64_peak(int device, double *tflops_fma, double *tflops_muladd);
 
 #ifdef __cplusplus
 }
