@@ -1,0 +1,783 @@
+// cps_ekf.cu -- EKF predict / measurement update on a device-resident dense covariance (sm_100a, FP64).
+//
+// Computes what KalmanFilter::UpdateNCurvesAndPoints (kalmanClass.cpp:669-945), UpdatePoints (:948-1126)
+// and PredictKF (:161-272) compute, re-designed around the fact that the update is bandwidth bound:
+//   * H has at most 6 + 8n + 3n_pts non-zero columns, so P H^T touches N x (that many) entries of P, not
+//     N^2 (the reference multiplies the dense M x N H three times);
+//   * S^-1 is an M x M problem solved by one thread block (Cholesky; the reference's cvInvert(CV_SVD) of a
+//     well-conditioned SPD matrix agrees to cond(S)*eps);
+//   * P <- 1/2[(P - K S K^T) + (P - K S K^T)^T] is ONE streaming pass: every thread block owns a pair of
+//     mirrored 64x64 tiles (I,J)/(J,I), reads each P entry once, writes each once (16 N^2 bytes, the
+//     minimum for a dense in/out covariance), and forms the rank-M correction from K and K S^T tiles that
+//     stay in L2/shared memory.  The correction K_I (S K_J^T) is computed once per pair and used for both
+//     mirrored tiles: K S K^T is symmetric in exact arithmetic and the reference averages the two roundings
+//     anyway (cvAddWeighted(P,0.5,P^T,0.5)), so the result differs by O(eps) per entry, inside the 1e-9
+//     tolerance of the parity tests, and is exactly symmetric like the reference's.
+// The reference allocates 14 temporaries (three of them N x N) per call; here nothing is allocated per call.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/cps_ekf.h"
+#include "cps_common.h"
+#include "cps_ekf_internal.h"
+
+namespace {
+
+constexpr int MAXM = CPS_EKF_MAX_MEAS;
+constexpr int MAXNC = 6 + MAXM;  // compact columns of H: 6 pose columns + landmark columns
+constexpr int TILE = 64;
+constexpr double kPI = 3.1415926535;  // common.h:114
+
+// constants of kalmanClass.h:17-36
+constexpr double MEAS_COV = 0.5, PT_MEAS_COV = 5.0, PHI_MEAS_COV = 0.1, THETA_MEAS_COV = 0.1, Z_MEAS_COV = 0.2;
+constexpr double VX_COV = 0.01, VY_COV = 0.01, VZ_COV = 0.5, WX_COV = 0.01, WY_COV = 0.01, WZ_COV = 0.01;
+constexpr double DT = 0.2;
+
+// layout of d_small (doubles)
+constexpr int SM_HC = 0;                       // [MAXM][MAXNC] compact H
+constexpr int SM_S = SM_HC + MAXM * MAXNC;     // [MAXM][MAXM]
+constexpr int SM_SINV = SM_S + MAXM * MAXM;    // [MAXM][MAXM]
+constexpr int SM_NU = SM_SINV + MAXM * MAXM;   // [MAXM] innovation z - zhat
+constexpr int SM_R = SM_NU + MAXM;             // [MAXM] diagonal of R
+constexpr int SM_IN = SM_R + MAXM;             // staged inputs: z[MAXM] | A[16*MAXM/8] 
+constexpr int SM_TOTAL = SM_IN + MAXM + 16 * (MAXM / 8 + 1);
+
+struct UpdateDesc {
+  int N, ld;      // state dimension, leading dimension of P
+  int n, n_pts;   // curves and points measured
+  int M, nc;      // measurement size, compact columns
+};
+
+// generate_Rbe (common.h:174-186), row-major, with the reference's sign in entry [6]
+__device__ void rbe(double phi, double theta, double psi, double* R) {
+  R[0] = cos(psi) * cos(theta);
+  R[3] = cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+  R[6] = cos(psi) * sin(theta) * cos(phi) - sin(psi) * sin(phi);
+  R[1] = sin(psi) * cos(theta);
+  R[4] = sin(psi) * sin(theta) * sin(phi) + cos(psi) * cos(phi);
+  R[7] = sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+  R[2] = -sin(theta);
+  R[5] = cos(theta) * sin(phi);
+  R[8] = cos(theta) * cos(phi);
+}
+
+// get_Rbe_derivs (kalmanClass.cpp:1275-1298) including its typo: R_be_theta(1,1) is written twice and
+// (2,1) is never set
+__device__ void rbe_derivs(double phi, double theta, double psi, double* Rp, double* Rt, double* Rs) {
+  for (int i = 0; i < 9; ++i) { Rp[i] = 0.0; Rt[i] = 0.0; Rs[i] = 0.0; }
+  Rp[3] = cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi);
+  Rp[6] = -cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+  Rp[4] = sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+  Rp[7] = -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi);
+  Rp[5] = cos(theta) * cos(phi);
+  Rp[8] = -cos(theta) * sin(phi);
+  Rt[0] = -cos(psi) * sin(theta);
+  Rt[3] = cos(psi) * cos(theta) * sin(phi);
+  Rt[6] = cos(psi) * cos(theta) * cos(phi);
+  Rt[1] = -sin(psi) * sin(theta);
+  Rt[4] = sin(psi) * cos(theta) * cos(phi);  // second write wins
+  Rt[2] = -cos(theta);
+  Rt[5] = -sin(theta) * sin(phi);
+  Rt[8] = -sin(theta) * cos(phi);
+  Rs[0] = -sin(psi) * cos(theta);
+  Rs[3] = -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi);
+  Rs[6] = -sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+  Rs[1] = cos(psi) * cos(theta);
+  Rs[4] = cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+  Rs[7] = cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi);
+}
+
+// ---- kernel 1: compact H, innovation and R from the current state (one block) ----------------------------
+// Compact columns: 0..5 = pose columns 0..5; then 8 per measured curve; then 3 per measured point.
+// in: small[SM_IN..] = z (M) followed by the A matrices (16 n); cols_in = landmark first-state indices.
+__global__ void ekf_build_kernel(UpdateDesc d, const double* __restrict__ x, double* __restrict__ small,
+                                 int* __restrict__ cols, const int* __restrict__ land_cols) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* Hc = small + SM_HC;
+  double* nu = small + SM_NU;
+  double* Rd = small + SM_R;
+  const double* z = small + SM_IN;
+  const double* A = small + SM_IN + MAXM;
+  const int cms = d.n > 0 || d.n_pts >= 0 ? 0 : 0;
+  (void)cms;
+  const bool curves_call = (d.M != 3 * d.n_pts);  // UpdateNCurvesAndPoints has the 3 direct pose rows
+  const int curve_meas = curves_call ? 8 * d.n + 3 : 0;
+  for (int i = tid; i < d.M * d.nc; i += nt) Hc[i] = 0.0;
+  for (int c = tid; c < d.nc; c += nt) {
+    int col;
+    if (c < 6) col = c;
+    else if (c < 6 + 8 * d.n) col = land_cols[(c - 6) / 8] + (c - 6) % 8;
+    else col = land_cols[d.n + (c - 6 - 8 * d.n) / 3] + (c - 6 - 8 * d.n) % 3;
+    cols[c] = col;
+  }
+  __syncthreads();
+  const double Tx = x[0], Ty = x[1], psi = x[5];
+  const double cpsi = cos(psi), spsi = sin(psi);
+  // curve rows, kalmanClass.cpp:741-787, and their predicted measurement (GetPredictedMeasurement :1162-1199)
+  for (int k = tid; k < d.n; k += nt) {
+    const int c0 = land_cols[k];
+    const double* Ak = A + 16 * k;
+    double ax[4], ay[4];
+    for (int i = 0; i < 4; ++i) {
+      double sx = 0.0, sy = 0.0;
+      for (int j = 0; j < 4; ++j) {
+        sx += Ak[4 * i + j] * x[c0 + j];
+        sy += Ak[4 * i + j] * x[c0 + 4 + j];
+      }
+      ax[i] = sx - Tx;
+      ay[i] = sy - Ty;
+    }
+    for (int i = 0; i < 4; ++i) {
+      double* hx = Hc + (8 * k + i) * d.nc;      // x rows:  cos*A | sin*A
+      double* hy = Hc + (8 * k + 4 + i) * d.nc;  // y rows: -sin*A | cos*A
+      for (int j = 0; j < 4; ++j) {
+        hx[6 + 8 * k + j] = cpsi * Ak[4 * i + j];
+        hx[6 + 8 * k + 4 + j] = spsi * Ak[4 * i + j];
+        hy[6 + 8 * k + j] = -spsi * Ak[4 * i + j];
+        hy[6 + 8 * k + 4 + j] = cpsi * Ak[4 * i + j];
+      }
+      hx[0] = -cpsi; hx[1] = -spsi;
+      hy[0] = spsi;  hy[1] = -cpsi;
+      hx[5] = -spsi * ax[i] + cpsi * ay[i];  // Rotderiv * (A x - T)
+      hy[5] = -cpsi * ax[i] - spsi * ay[i];
+      nu[8 * k + i] = z[8 * k + i] - (cpsi * ax[i] + spsi * ay[i]);
+      nu[8 * k + 4 + i] = z[8 * k + 4 + i] - (-spsi * ax[i] + cpsi * ay[i]);
+    }
+  }
+  if (curves_call && tid == 0) {  // direct rows: height, phi, theta (:790-792) with R of :705-707
+    for (int q = 0; q < 3; ++q) {
+      Hc[(8 * d.n + q) * d.nc + 2 + q] = 1.0;
+      nu[8 * d.n + q] = z[8 * d.n + q] - x[2 + q];
+    }
+  }
+  for (int i = tid; i < d.M; i += nt) {
+    double r = MEAS_COV * MEAS_COV;
+    if (!curves_call || i >= curve_meas) r = PT_MEAS_COV * PT_MEAS_COV;
+    else if (i == 8 * d.n) r = Z_MEAS_COV * Z_MEAS_COV;
+    else if (i == 8 * d.n + 1) r = PHI_MEAS_COV * PHI_MEAS_COV;
+    else if (i == 8 * d.n + 2) r = THETA_MEAS_COV * THETA_MEAS_COV;
+    Rd[i] = r;
+  }
+  // point rows, kalmanClass.cpp:815-851 / :1016-1050
+  if (d.n_pts > 0) {
+    double R_be[9], Rd3[3][9];
+    rbe(x[3], x[4], x[5], R_be);
+    rbe_derivs(x[3], x[4], x[5], Rd3[0], Rd3[1], Rd3[2]);
+    for (int k = tid; k < d.n_pts; k += nt) {
+      const int c0 = land_cols[d.n + k];
+      const int row0 = curve_meas + 3 * k, cc = 6 + 8 * d.n + 3 * k;
+      double xe[3];
+      for (int i = 0; i < 3; ++i) xe[i] = x[c0 + i] - x[i];
+      for (int i = 0; i < 3; ++i) {
+        double* h = Hc + (row0 + i) * d.nc;
+        double zh = 0.0;
+        for (int j = 0; j < 3; ++j) {
+          zh += R_be[3 * i + j] * xe[j];
+          h[j] = -R_be[3 * i + j];
+          h[cc + j] = R_be[3 * i + j];
+          double dd = 0.0;
+          for (int q = 0; q < 3; ++q) dd += Rd3[j][3 * i + q] * xe[q];
+          h[3 + j] = dd;
+        }
+        nu[row0 + i] = z[row0 + i] - zh;
+      }
+    }
+  }
+}
+
+// ---- kernel 2: T = P H^T through the compact columns (one warp per state row) -----------------------------
+__global__ void __launch_bounds__(256) ekf_pht_kernel(UpdateDesc d, const double* __restrict__ P,
+                                                      const double* __restrict__ small, const int* __restrict__ cols,
+                                                      double* __restrict__ T) {
+  extern __shared__ double sh[];
+  double* Hc = sh;                        // [M][nc]
+  double* prow = sh + d.M * d.nc;         // [8 warps][nc]
+  int* scols = (int*)(prow + 8 * d.nc);
+  for (int i = threadIdx.x; i < d.M * d.nc; i += blockDim.x) Hc[i] = small[SM_HC + i];
+  for (int i = threadIdx.x; i < d.nc; i += blockDim.x) scols[i] = cols[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* pr = prow + w * d.nc;
+  for (int row = blockIdx.x * 8 + w; row < d.N; row += gridDim.x * 8) {
+    for (int c = lane; c < d.nc; c += 32) pr[c] = P[(size_t)row * d.ld + scols[c]];
+    __syncwarp();
+    for (int r = lane; r < d.M; r += 32) {
+      const double* h = Hc + r * d.nc;
+      double s = 0.0;
+      for (int c = 0; c < d.nc; ++c) s += pr[c] * h[c];
+      T[(size_t)row * MAXM + r] = s;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- kernel 3: S = H T + R, S^-1 by Cholesky (one block) ---------------------------------------------------
+__global__ void __launch_bounds__(256) ekf_s_kernel(UpdateDesc d, const double* __restrict__ T,
+                                                    double* __restrict__ small, const int* __restrict__ cols,
+                                                    int* __restrict__ flag) {
+  extern __shared__ double sh[];
+  const int M = d.M;
+  double* L = sh;           // [M][M] Cholesky factor, then L^-1
+  double* S = sh + M * M;   // [M][M]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* Hc = small + SM_HC;
+  for (int e = tid; e < M * M; e += nt) {
+    const int r = e / M, s = e - r * M;
+    double acc = 0.0;
+    for (int c = 0; c < d.nc; ++c) {
+      const double h = Hc[r * d.nc + c];
+      if (h != 0.0) acc += h * T[(size_t)cols[c] * MAXM + s];
+    }
+    if (r == s) acc += small[SM_R + r];
+    S[e] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < M * M; e += nt) {
+    const int r = e / M, s = e - r * M;
+    small[SM_S + r * MAXM + s] = S[e];
+    L[e] = (s <= r) ? 0.5 * (S[e] + S[s * M + r]) : 0.0;  // factor the symmetric part
+  }
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int k = 0; k < M; ++k) {
+    __shared__ double piv;
+    if (tid == 0) {
+      const double v = L[k * M + k];
+      if (!(v > 0.0)) *flag = 1;
+      piv = sqrt(v);
+      L[k * M + k] = piv;
+    }
+    __syncthreads();
+    for (int i = k + 1 + tid; i < M; i += nt) L[i * M + k] /= piv;
+    __syncthreads();
+    const int rem = M - k - 1;
+    for (int e = tid; e < rem * rem; e += nt) {
+      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      if (j <= i) L[i * M + j] -= L[i * M + k] * L[j * M + k];
+    }
+    __syncthreads();
+  }
+  // invert L in place column by column (thread per column): X = L^-1, lower triangular
+  double* X = S;  // reuse
+  for (int c = tid; c < M; c += nt) {
+    for (int i = 0; i < M; ++i) {
+      if (i < c) { X[i * M + c] = 0.0; continue; }
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= L[i * M + k] * X[k * M + c];
+      X[i * M + c] = s / L[i * M + i];
+    }
+  }
+  __syncthreads();
+  // S^-1 = X^T X
+  for (int e = tid; e < M * M; e += nt) {
+    const int r = e / M, s = e - r * M;
+    double acc = 0.0;
+    for (int k = (r > s ? r : s); k < M; ++k) acc += X[k * M + r] * X[k * M + s];
+    small[SM_SINV + r * MAXM + s] = acc;
+  }
+}
+
+// ---- kernel 4: K = T S^-1, Yt = K S^T, x += K nu (one warp per state row) ----------------------------------
+__global__ void __launch_bounds__(256) ekf_gain_kernel(UpdateDesc d, const double* __restrict__ T,
+                                                       const double* __restrict__ small, double* __restrict__ Kt,
+                                                       double* __restrict__ Yt, double* __restrict__ x, int ldk) {
+  extern __shared__ double sh[];
+  const int M = d.M;
+  double* Sinv = sh;              // [M][M]
+  double* S = sh + M * M;         // [M][M]
+  double* nu = S + M * M;         // [M]
+  double* rowbuf = nu + M;        // [8 warps][2][M]
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int r = e / M, s = e - r * M;
+    Sinv[e] = small[SM_SINV + r * MAXM + s];
+    S[e] = small[SM_S + r * MAXM + s];
+  }
+  for (int e = threadIdx.x; e < M; e += blockDim.x) nu[e] = small[SM_NU + e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* trow = rowbuf + w * 2 * M;
+  double* krow = trow + M;
+  for (int row = blockIdx.x * 8 + w; row < d.N; row += gridDim.x * 8) {
+    for (int r = lane; r < M; r += 32) trow[r] = T[(size_t)row * MAXM + r];
+    __syncwarp();
+    for (int s = lane; s < M; s += 32) {
+      double acc = 0.0;
+      for (int r = 0; r < M; ++r) acc += trow[r] * Sinv[r * M + s];
+      krow[s] = acc;
+      Kt[(size_t)s * ldk + row] = acc;
+    }
+    __syncwarp();
+    double dx = 0.0;
+    for (int r = lane; r < M; r += 32) {
+      double acc = 0.0;
+      for (int s = 0; s < M; ++s) acc += krow[s] * S[r * M + s];
+      Yt[(size_t)r * ldk + row] = acc;
+      dx += krow[r] * nu[r];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dx += __shfl_xor_sync(0xffffffffu, dx, o);
+    if (lane == 0) {
+      double v = x[row] + dx;
+      if (row >= 3 && row <= 5) {  // kalmanClass.cpp:902-913
+        while (v > kPI) v -= 2 * kPI;
+        while (v < -kPI) v += 2 * kPI;
+      }
+      x[row] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- kernel 5: P <- sym(P - K S K^T), one block per mirrored tile pair --------------------------------------
+// 256 threads, thread (tx,ty) owns the 4x4 micro-tile rows I*64+4ty.., cols J*64+4tx.. of tile (I,J) and its
+// mirror image in tile (J,I).  Warps are 8 (tx) x 4 (ty) threads so that the per-step shared-memory reads are
+// 1 + 2 wavefronts (K is read by 4 distinct ty, Y by 8 distinct tx).
+__global__ void __launch_bounds__(256, 2) ekf_cov_kernel(double* __restrict__ P, int ld, int M,
+                                                          const double* __restrict__ Kt, const double* __restrict__ Yt,
+                                                          int ldk, int ntiles) {
+  extern __shared__ double sh[];
+  double* Ks = sh;             // [M][64]  K rows of tile I
+  double* Ys = sh + M * TILE;  // [M][64]  (K S^T) rows of tile J
+  // pair index -> (I <= J)
+  const long long pidx = blockIdx.x;
+  int J = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
+  while ((long long)(J + 1) * (J + 2) / 2 <= pidx) ++J;
+  while ((long long)J * (J + 1) / 2 > pidx) --J;
+  const int I = (int)(pidx - (long long)J * (J + 1) / 2);
+  (void)ntiles;
+
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int tx = (w & 1) * 8 + (l & 7);
+  const int ty = (w >> 1) * 4 + (l >> 3);
+  const int i0 = I * TILE + 4 * ty, j0 = J * TILE + 4 * tx;
+  const bool diag = (I == J);
+  const bool active = !diag || tx >= ty;
+
+  // issue the P loads first so they overlap the K/Y staging
+  double pij[4][4], pji[4][4];
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double2* s0 = reinterpret_cast<const double2*>(P + (size_t)(i0 + a) * ld + j0);
+      const double2 v0 = s0[0], v1 = s0[1];
+      pij[a][0] = v0.x; pij[a][1] = v0.y; pij[a][2] = v1.x; pij[a][3] = v1.y;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const double2* s0 = reinterpret_cast<const double2*>(P + (size_t)(j0 + b) * ld + i0);
+      const double2 v0 = s0[0], v1 = s0[1];
+      pji[b][0] = v0.x; pji[b][1] = v0.y; pji[b][2] = v1.x; pji[b][3] = v1.y;
+    }
+  }
+  for (int e = t; e < M * (TILE / 2); e += 256) {
+    const int r = e / (TILE / 2), c = (e % (TILE / 2)) * 2;
+    *reinterpret_cast<double2*>(Ks + r * TILE + c) =
+        *reinterpret_cast<const double2*>(Kt + (size_t)r * ldk + I * TILE + c);
+    *reinterpret_cast<double2*>(Ys + r * TILE + c) =
+        *reinterpret_cast<const double2*>(Yt + (size_t)r * ldk + J * TILE + c);
+  }
+  __syncthreads();
+  if (!active) return;
+
+  double wacc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) wacc[a][b] = 0.0;
+#pragma unroll 5
+  for (int r = 0; r < M; ++r) {
+    const double2 k0 = *reinterpret_cast<const double2*>(Ks + r * TILE + 4 * ty);
+    const double2 k1 = *reinterpret_cast<const double2*>(Ks + r * TILE + 4 * ty + 2);
+    const double2 y0 = *reinterpret_cast<const double2*>(Ys + r * TILE + 4 * tx);
+    const double2 y1 = *reinterpret_cast<const double2*>(Ys + r * TILE + 4 * tx + 2);
+    const double kk[4] = {k0.x, k0.y, k1.x, k1.y};
+    const double yy[4] = {y0.x, y0.y, y1.x, y1.y};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) wacc[a][b] = fma(kk[a], yy[b], wacc[a][b]);
+  }
+  double out[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) out[a][b] = 0.5 * (pij[a][b] + pji[b][a]) - wacc[a][b];
+  if (diag && tx == ty) {  // the micro-tile straddles the diagonal: make it exactly symmetric
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < a; ++b) out[a][b] = out[b][a];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double2* dst = reinterpret_cast<double2*>(P + (size_t)(i0 + a) * ld + j0);
+    dst[0] = make_double2(out[a][0], out[a][1]);
+    dst[1] = make_double2(out[a][2], out[a][3]);
+  }
+  if (!(diag && tx == ty)) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double2* dst = reinterpret_cast<double2*>(P + (size_t)(j0 + b) * ld + i0);
+      dst[0] = make_double2(out[0][b], out[1][b]);
+      dst[1] = make_double2(out[2][b], out[3][b]);
+    }
+  }
+}
+
+// ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
+// Pri <- F Pri, mirrored; Prr <- F Prr F^T + Q; x[0..5] += x[6..11] DT.  F = I + DT*[0 I6; 0 0].
+__global__ void __launch_bounds__(256) ekf_predict_cross_kernel(double* __restrict__ P, int ld, int N) {
+  const int j = 12 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  double col[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) col[i] = P[(size_t)i * ld + j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) col[i] = col[i] + DT * col[i + 6];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    P[(size_t)i * ld + j] = col[i];
+    P[(size_t)j * ld + i] = col[i];
+  }
+}
+
+__global__ void ekf_predict_pose_kernel(double* __restrict__ P, int ld, double* __restrict__ x) {
+  __shared__ double Prr[144], Tm[144], Q[144], F[144];
+  const int t = threadIdx.x;  // 144 threads
+  const int i = t / 12, j = t % 12;
+  F[t] = (i == j) ? 1.0 : ((j == i + 6 && i < 6) ? DT : 0.0);
+  Prr[t] = P[(size_t)i * ld + j];
+  Q[t] = 0.0;
+  __syncthreads();
+  if (t == 0) {
+    const double phi = x[3], theta = x[4], psi = x[5];
+    double Reb[9], t33[9], t33b[9];
+    Reb[0] = cos(psi) * cos(theta);
+    Reb[1] = cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+    Reb[2] = cos(psi) * sin(theta) * cos(phi) - sin(psi) * sin(phi);
+    Reb[3] = sin(psi) * cos(theta);
+    Reb[4] = sin(psi) * sin(theta) * sin(phi) + cos(psi) * cos(phi);
+    Reb[5] = sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+    Reb[6] = -sin(theta);
+    Reb[7] = cos(theta) * sin(phi);
+    Reb[8] = cos(theta) * cos(phi);
+    const double v2[3] = {VX_COV * VX_COV, VY_COV * VY_COV, VZ_COV * VZ_COV};
+    const double w2[3] = {WX_COV * WX_COV, WY_COV * WY_COV, WZ_COV * WZ_COV};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) t33b[3 * a + b] = Reb[3 * a + b] * v2[b];  // Reb diag(v^2)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += t33b[3 * a + k] * Reb[3 * b + k];  // * Reb^T
+        t33[3 * a + b] = s;
+      }
+    const double dt3 = DT * DT * DT, dt2 = DT * DT;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        Q[12 * a + b] = dt3 * t33[3 * a + b];
+        Q[12 * a + b + 6] = dt2 * t33[3 * a + b];
+        Q[12 * (b + 6) + a] = dt2 * t33[3 * a + b];
+        Q[12 * (a + 6) + b + 6] = DT * t33[3 * a + b];
+        const double wv = (a == b) ? w2[a] : 0.0;
+        Q[12 * (a + 3) + b + 3] = dt3 * wv;
+        Q[12 * (a + 3) + b + 9] = dt2 * wv;
+        Q[12 * (b + 9) + a + 3] = dt2 * wv;
+        Q[12 * (a + 9) + b + 9] = DT * wv;
+      }
+  }
+  __syncthreads();
+  double s = 0.0;
+  for (int k = 0; k < 12; ++k) s += F[12 * i + k] * Prr[12 * k + j];
+  Tm[t] = s;
+  __syncthreads();
+  s = 0.0;
+  for (int k = 0; k < 12; ++k) s += Tm[12 * i + k] * F[12 * j + k];
+  P[(size_t)i * ld + j] = s + Q[t];
+  if (t < 6) x[t] += x[t + 6] * DT;
+}
+
+// P = scale * G G^T + diag * I (benchmark-size synthetic covariances)
+__global__ void __launch_bounds__(256) ekf_lowrank_kernel(double* __restrict__ P, int ld, int N, const double* __restrict__ G,
+                                                          int r, double scale, double dg) {
+  __shared__ double Ga[16][65], Gb[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < r; k0 += 64) {
+    const int kn = min(64, r - k0);
+    for (int e = threadIdx.x; e < 16 * kn; e += 256) {
+      const int rr = e / kn, kk = e % kn;
+      const int gi = blockIdx.y * 16 + rr, gj = blockIdx.x * 16 + rr;
+      Ga[rr][kk] = (gi < N) ? G[(size_t)gi * r + k0 + kk] : 0.0;
+      Gb[rr][kk] = (gj < N) ? G[(size_t)gj * r + k0 + kk] : 0.0;
+    }
+    __syncthreads();
+    for (int k = 0; k < kn; ++k) acc += Ga[ty][k] * Gb[tx][k];
+    __syncthreads();
+  }
+  if (i < N && j < N) {
+    // symmetric by construction: both (i,j) and (j,i) sum the same products in the same order
+    P[(size_t)i * ld + j] = scale * acc + ((i == j) ? dg : 0.0);
+  }
+}
+
+int round_up(int v, int q) { return (v + q - 1) / q * q; }
+
+}  // namespace
+
+// =================================== C ABI ===================================
+extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
+  if (!out || capacity < CPS_ROBOT_STATE_SIZE) return CPS_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cps::set_last_error("no CUDA device: libcps has no CPU path");
+    return CPS_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(device));
+  cps_ekf* h = new cps_ekf();
+  h->device = device;
+  h->cap = round_up(capacity, TILE);
+  CPS_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CPS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t cap = (size_t)h->cap;
+  if (cudaMalloc(&h->d_P, cap * cap * sizeof(double)) != cudaSuccess) {
+    cps::set_last_error("cudaMalloc of the covariance failed");
+    cudaGetLastError();
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return CPS_ERR_NOMEM;
+  }
+  CPS_CUDA(cudaMalloc(&h->d_x, cap * sizeof(double)));
+  CPS_CUDA(cudaMalloc(&h->d_T, cap * MAXM * sizeof(double)));
+  CPS_CUDA(cudaMalloc(&h->d_Kt, cap * MAXM * sizeof(double)));
+  CPS_CUDA(cudaMalloc(&h->d_Yt, cap * MAXM * sizeof(double)));
+  CPS_CUDA(cudaMalloc(&h->d_small, SM_TOTAL * sizeof(double)));
+  CPS_CUDA(cudaMalloc(&h->d_cols, (MAXNC + MAXM) * sizeof(int)));
+  CPS_CUDA(cudaMalloc(&h->d_flag, sizeof(int)));
+  h->pinned_bytes = (MAXM + 16 * (MAXM / 8 + 1)) * sizeof(double) + MAXM * sizeof(int);
+  CPS_CUDA(cudaMallocHost(&h->h_pinned, h->pinned_bytes));
+  CPS_CUDA(cudaMemsetAsync(h->d_P, 0, cap * cap * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemsetAsync(h->d_x, 0, cap * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemsetAsync(h->d_Kt, 0, cap * MAXM * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemsetAsync(h->d_Yt, 0, cap * MAXM * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+  for (auto& e : h->ev) CPS_CUDA(cudaEventCreate(&e));
+  for (auto& e : h->gev) CPS_CUDA(cudaEventCreate(&e));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * MAXM * MAXM * (int)sizeof(double)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (2 * MAXM * MAXM + MAXM + 16 * MAXM) * (int)sizeof(double)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * MAXM * TILE * (int)sizeof(double)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (MAXM * MAXNC + 8 * MAXNC) * (int)sizeof(double) + MAXNC * (int)sizeof(int)));
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return CPS_OK;
+}
+
+extern "C" void cps_ekf_destroy(cps_ekf* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_P); cudaFree(h->d_x); cudaFree(h->d_T); cudaFree(h->d_Kt); cudaFree(h->d_Yt);
+  cudaFree(h->d_small); cudaFree(h->d_cols); cudaFree(h->d_flag);
+  cudaFree(h->d_pack); cudaFree(h->d_pcols); cudaFree(h->d_gz); cudaFree(h->d_gidx); cudaFree(h->d_gd2);
+  cudaFree(h->d_part_d2); cudaFree(h->d_part_idx);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->gev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int cps_ekf_sync(cps_ekf* h) {
+  if (!h) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  int flag = 0;
+  CPS_CUDA(cudaMemcpy(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cps::set_last_error("innovation covariance S is not positive definite");
+    CPS_CUDA(cudaMemset(h->d_flag, 0, sizeof(int)));
+    return CPS_ERR_INVALID;
+  }
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_set_state(cps_ekf* h, const double* x, const double* P, int N, const int* curve_inds,
+                                 int num_curves, const int* point_inds, int num_points) {
+  if (!h || !x || N < CPS_ROBOT_STATE_SIZE || N > h->cap || num_curves < 0 || num_points < 0) return CPS_ERR_INVALID;
+  if ((num_curves && !curve_inds) || (num_points && !point_inds)) return CPS_ERR_INVALID;
+  for (int k = 0; k < num_curves; ++k)
+    if (curve_inds[k] < 0 || curve_inds[k] + 8 > N) return CPS_ERR_INVALID;
+  for (int k = 0; k < num_points; ++k)
+    if (point_inds[k] < 0 || point_inds[k] + 3 > N) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  const size_t cap = (size_t)h->cap;
+  CPS_CUDA(cudaMemsetAsync(h->d_P, 0, cap * cap * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemsetAsync(h->d_x, 0, cap * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+  if (P)
+    CPS_CUDA(cudaMemcpy2DAsync(h->d_P, cap * sizeof(double), P, (size_t)N * sizeof(double), (size_t)N * sizeof(double),
+                               N, cudaMemcpyHostToDevice, h->stream));
+  h->N = N;
+  h->curve_inds.assign(curve_inds, curve_inds + num_curves);
+  h->point_inds.assign(point_inds, point_inds + num_points);
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_set_cov_lowrank(cps_ekf* h, const double* G, int r, double scale, double diag) {
+  if (!h || !G || r <= 0 || h->N <= 0) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  double* dG = nullptr;
+  CPS_CUDA(cudaMalloc(&dG, sizeof(double) * (size_t)h->N * r));
+  CPS_CUDA(cudaMemcpyAsync(dG, G, sizeof(double) * (size_t)h->N * r, cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((h->N + 15) / 16, (h->N + 15) / 16);
+  ekf_lowrank_kernel<<<grid, 256, 0, h->stream>>>(h->d_P, h->cap, h->N, dG, r, scale, diag);
+  CPS_CUDA(cudaGetLastError());
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(dG);
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_dims(cps_ekf* h, int* N, int* num_curves, int* num_points) {
+  if (!h) return CPS_ERR_INVALID;
+  if (N) *N = h->N;
+  if (num_curves) *num_curves = (int)h->curve_inds.size();
+  if (num_points) *num_points = (int)h->point_inds.size();
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_get_state(cps_ekf* h, double* x_out) {
+  if (!h || !x_out) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaMemcpyAsync(x_out, h->d_x, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
+  return cps_ekf_sync(h);
+}
+
+extern "C" int cps_ekf_get_cov_block(cps_ekf* h, int r0, int c0, int nr, int nc, double* out) {
+  if (!h || !out || r0 < 0 || c0 < 0 || nr < 0 || nc < 0 || r0 + nr > h->N || c0 + nc > h->N) return CPS_ERR_INVALID;
+  if (nr == 0 || nc == 0) return CPS_OK;
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaMemcpy2DAsync(out, (size_t)nc * sizeof(double), h->d_P + (size_t)r0 * h->cap + c0,
+                             (size_t)h->cap * sizeof(double), (size_t)nc * sizeof(double), nr, cudaMemcpyDeviceToHost,
+                             h->stream));
+  return cps_ekf_sync(h);
+}
+
+extern "C" int cps_ekf_get_cov(cps_ekf* h, double* P_out) {
+  if (!h) return CPS_ERR_INVALID;
+  return cps_ekf_get_cov_block(h, 0, 0, h->N, h->N, P_out);
+}
+
+extern "C" int cps_ekf_predict(cps_ekf* h) {
+  if (!h || h->N < CPS_ROBOT_STATE_SIZE) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  // the pose block reads x before it is advanced; the cross block does not read x
+  if (h->N > 12) {
+    ekf_predict_cross_kernel<<<(h->N - 12 + 255) / 256, 256, 0, h->stream>>>(h->d_P, h->cap, h->N);
+    h->launches++;
+  }
+  ekf_predict_pose_kernel<<<1, 144, 0, h->stream>>>(h->d_P, h->cap, h->d_x);
+  h->launches++;
+  CPS_CUDA(cudaGetLastError());
+  CPS_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  CPS_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  CPS_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  h->timing_valid = true;
+  return CPS_OK;
+}
+
+namespace {
+int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* curve_num, const double* point_meas,
+               const int* point_nums, int n_pts, bool curves_call) {
+  const int M = (curves_call ? 8 * n + 3 : 0) + 3 * n_pts;
+  if (M <= 0 || M > MAXM) {
+    cps::set_last_error("measurement vector empty or larger than CPS_EKF_MAX_MEAS");
+    return CPS_ERR_INVALID;
+  }
+  for (int k = 0; k < n; ++k)
+    if (curve_num[k] < 0 || curve_num[k] >= (int)h->curve_inds.size()) return CPS_ERR_INVALID;
+  for (int k = 0; k < n_pts; ++k)
+    if (point_nums[k] < 0 || point_nums[k] >= (int)h->point_inds.size()) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  // the previous update's staging must have been consumed before the pinned block is rewritten
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  double* hz = (double*)h->h_pinned;
+  double* hA = hz + MAXM;
+  int* hcols = (int*)(hA + 16 * (MAXM / 8 + 1));
+  std::memset(hz, 0, sizeof(double) * MAXM);
+  if (curves_call) {
+    std::memcpy(hz, z, sizeof(double) * (8 * n + 3));
+    std::memcpy(hA, A, sizeof(double) * 16 * n);
+  }
+  if (n_pts) std::memcpy(hz + (curves_call ? 8 * n + 3 : 0), point_meas, sizeof(double) * 3 * n_pts);
+  for (int k = 0; k < n; ++k) hcols[k] = h->curve_inds[curve_num[k]];
+  for (int k = 0; k < n_pts; ++k) hcols[n + k] = h->point_inds[point_nums[k]];
+  UpdateDesc d;
+  d.N = h->N; d.ld = h->cap; d.n = n; d.n_pts = n_pts; d.M = M; d.nc = 6 + 8 * n + 3 * n_pts;
+  cudaStream_t st = h->stream;
+  CPS_CUDA(cudaMemcpyAsync(h->d_small + SM_IN, hz, sizeof(double) * (MAXM + 16 * (size_t)n), cudaMemcpyHostToDevice, st));
+  int* d_land = h->d_cols + MAXNC;
+  if (n + n_pts)
+    CPS_CUDA(cudaMemcpyAsync(d_land, hcols, sizeof(int) * (n + n_pts), cudaMemcpyHostToDevice, st));
+  CPS_CUDA(cudaEventRecord(h->ev[0], st));
+  ekf_build_kernel<<<1, 128, 0, st>>>(d, h->d_x, h->d_small, h->d_cols, d_land);
+  const int row_blocks = std::min((d.N + 7) / 8, h->sm_count * 8);
+  const size_t sh_pht = (size_t)(d.M * d.nc + 8 * d.nc) * sizeof(double) + d.nc * sizeof(int);
+  ekf_pht_kernel<<<row_blocks, 256, sh_pht, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_T);
+  ekf_s_kernel<<<1, 256, 2 * (size_t)M * M * sizeof(double), st>>>(d, h->d_T, h->d_small, h->d_cols, h->d_flag);
+  const size_t sh_gain = (size_t)(2 * M * M + M + 16 * M) * sizeof(double);
+  ekf_gain_kernel<<<row_blocks, 256, sh_gain, st>>>(d, h->d_T, h->d_small, h->d_Kt, h->d_Yt, h->d_x, h->cap);
+  CPS_CUDA(cudaEventRecord(h->ev[2], st));
+  const int nt = (d.N + TILE - 1) / TILE;
+  const long long pairs = (long long)nt * (nt + 1) / 2;
+  ekf_cov_kernel<<<(unsigned)pairs, 256, 2 * (size_t)M * TILE * sizeof(double), st>>>(h->d_P, h->cap, M, h->d_Kt,
+                                                                                      h->d_Yt, h->cap, nt);
+  CPS_CUDA(cudaEventRecord(h->ev[3], st));
+  CPS_CUDA(cudaEventRecord(h->ev[1], st));
+  CPS_CUDA(cudaGetLastError());
+  h->launches += 5;
+  h->timing_valid = true;
+  return CPS_OK;
+}
+}  // namespace
+
+extern "C" int cps_ekf_update_curves_points(cps_ekf* h, const double* z, int n, const double* A, const int* curve_num,
+                                            const double* point_meas, const int* point_nums, int n_pts) {
+  if (!h || !z || n < 0 || n_pts < 0 || (n && (!A || !curve_num)) || (n_pts && (!point_meas || !point_nums)))
+    return CPS_ERR_INVALID;
+  return run_update(h, z, n, A, curve_num, point_meas, point_nums, n_pts, true);
+}
+
+extern "C" int cps_ekf_update_points(cps_ekf* h, const double* point_meas, const int* point_nums, int n_pts) {
+  if (!h || n_pts <= 0 || !point_meas || !point_nums) return CPS_ERR_INVALID;
+  return run_update(h, nullptr, 0, nullptr, nullptr, point_meas, point_nums, n_pts, false);
+}
+
+extern "C" int cps_ekf_last_timing(cps_ekf* h, float* total_ms, float* cov_kernel_ms, long long* launches) {
+  if (!h) return CPS_ERR_INVALID;
+  if (launches) *launches = h->launches;
+  if (!h->timing_valid) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaEventSynchronize(h->ev[1]));
+  if (total_ms) CPS_CUDA(cudaEventElapsedTime(total_ms, h->ev[0], h->ev[1]));
+  if (cov_kernel_ms) CPS_CUDA(cudaEventElapsedTime(cov_kernel_ms, h->ev[2], h->ev[3]));
+  return CPS_OK;
+}
+
+// GetSplitMatrices, kalmanClass.cpp:1144-1159
+extern "C" void cps_ekf_split_matrices(double t, double* A1, double* A2) {
+  static const double binom[4][4] = {{1, 0, 0, 0}, {1, 1, 0, 0}, {1, 2, 1, 0}, {1, 3, 3, 1}};
+  for (int i = 0; i < 16; ++i) { A1[i] = 0.0; A2[i] = 0.0; }
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j <= i; ++j) A1[i * 4 + j] = binom[i][j] * std::pow(t, j) * std::pow((1 - t), (i - j));
+    for (int j = i; j < 4; ++j) A2[4 * i + j] = binom[3 - i][j - i] * std::pow(t, (j - i)) * std::pow((1 - t), (3 - j));
+  }
+}

@@ -58,6 +58,18 @@ class Oracle:
         L.orc_lm_dif.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_void_p, C.c_void_p]
         L.orc_lm_dif.restype = C.c_int
         L.orc_stereo19_postfit.argtypes = [_dp]
+        L.orc_ekf_predict.argtypes = [_dp, _dp, C.c_int]
+        L.orc_ekf_update_curves_points.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, _dp, _ip, _dp, _ip, C.c_int,
+                                                   _dp, _dp, _dp]
+        L.orc_ekf_update_curves_points.restype = C.c_int
+        L.orc_ekf_update_points.argtypes = [_dp, _dp, C.c_int, _dp, _ip, C.c_int]
+        L.orc_ekf_update_points.restype = C.c_int
+        L.orc_ekf_split_matrices.argtypes = [C.c_double, _dp, _dp]
+        L.orc_pinv_svd.argtypes = [_dp, _dp, C.c_int]
+        L.orc_gate_mahalanobis.argtypes = [_dp, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_double, _ip, _dp,
+                                           C.c_int]
+        L.orc_gate_mahalanobis.restype = C.c_int
+        L.orc_gate_pack.argtypes = [_dp, _dp, C.c_int, _ip, C.c_int, _dp]
         self.ref = None
         self.levmar = None
         rpath = os.path.join(ORC_DIR, "_ref", "liborc_refshim.so")
@@ -102,6 +114,63 @@ class Oracle:
         if rc != 0:
             raise ValueError("oracle rejected the arguments")
         return {"p": p, "info": info, "ret": ret, "extra": extra}
+
+
+    # ---- EKF ------------------------------------------------------------------------------------
+    def ekf_predict(self, x, P):
+        x = np.array(x, dtype=np.float64)
+        P = np.array(P, dtype=np.float64, order="C")
+        self.lib.orc_ekf_predict(_ptr(x, _dp), _ptr(P, _dp), x.size)
+        return x, P
+
+    def ekf_update_curves_points(self, x, P, z, A, curve_col, point_meas=None, point_col=None, want_hsk=False):
+        x = np.array(x, dtype=np.float64)
+        P = np.array(P, dtype=np.float64, order="C")
+        N = x.size
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1, 16)
+        cc = np.ascontiguousarray(curve_col, dtype=np.int32)
+        pm = np.zeros(0) if point_meas is None else np.ascontiguousarray(point_meas, dtype=np.float64)
+        pc = np.zeros(0, dtype=np.int32) if point_col is None else np.ascontiguousarray(point_col, dtype=np.int32)
+        n, n_pts = cc.size, pc.size
+        M = 8 * n + 3 + 3 * n_pts
+        H = np.zeros((M, N)) if want_hsk else None
+        S = np.zeros((M, M)) if want_hsk else None
+        K = np.zeros((N, M)) if want_hsk else None
+        rc = self.lib.orc_ekf_update_curves_points(_ptr(x, _dp), _ptr(P, _dp), N, _ptr(z, _dp), n, _ptr(A, _dp),
+                                                   _ptr(cc, _ip), _ptr(pm, _dp), _ptr(pc, _ip), n_pts,
+                                                   _ptr(H, _dp), _ptr(S, _dp), _ptr(K, _dp))
+        assert rc == 0
+        return (x, P, H, S, K) if want_hsk else (x, P)
+
+    def ekf_update_points(self, x, P, point_meas, point_col):
+        x = np.array(x, dtype=np.float64)
+        P = np.array(P, dtype=np.float64, order="C")
+        pm = np.ascontiguousarray(point_meas, dtype=np.float64)
+        pc = np.ascontiguousarray(point_col, dtype=np.int32)
+        rc = self.lib.orc_ekf_update_points(_ptr(x, _dp), _ptr(P, _dp), x.size, _ptr(pm, _dp), _ptr(pc, _ip), pc.size)
+        assert rc == 0
+        return x, P
+
+    def gate(self, x, P, point_col, z, gate, nthreads=1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        pc = np.ascontiguousarray(point_col, dtype=np.int32)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 3)
+        idx = np.zeros(z.shape[0], dtype=np.int32)
+        d2 = np.zeros(z.shape[0])
+        rc = self.lib.orc_gate_mahalanobis(_ptr(x, _dp), _ptr(P, _dp), x.size, _ptr(pc, _ip), pc.size, _ptr(z, _dp),
+                                           z.shape[0], gate, _ptr(idx, _ip), _ptr(d2, _dp), nthreads)
+        assert rc == 0
+        return idx, d2
+
+    def gate_pack(self, x, P, point_col):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        pc = np.ascontiguousarray(point_col, dtype=np.int32)
+        pack = np.zeros((pc.size, 9))
+        self.lib.orc_gate_pack(_ptr(x, _dp), _ptr(P, _dp), x.size, _ptr(pc, _ip), pc.size, _ptr(pack, _dp))
+        return pack
 
 
 _ORACLE = None
