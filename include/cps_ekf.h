@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define CPS_ROBOT_STATE_SIZE 12 /* ROBOT_STATE_SIZE, kalmanClass.h:36 */
-#define CPS_EKF_MAX_MEAS 160    /* largest measurement vector of one update (the reference's live M is <= 35) */
+#define CPS_EKF_MAX_MEAS 104    /* largest measurement vector of one update (the reference's live M is <= 35) */
 
 typedef struct cps_ekf cps_ekf;
 

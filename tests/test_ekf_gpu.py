@@ -144,7 +144,7 @@ def _gate_inputs(L, nz, seed):
     pick = rng.integers(0, len(pi), nz)
     z = pack[pick, :3] + rng.normal(0, 5.0, (nz, 3))
     clutter = rng.random(nz) < 0.2
-    z[clutter] = rng.uniform(-50, 50, (int(clutter.sum()), 3))
+    z[clutter] = rng.uniform(-50, 50, (int(clutter.sum()), 3)) + rng.choice([-300.0, 300.0], (int(clutter.sum()), 3))
     return x, P, ci, pi, z
 
 
