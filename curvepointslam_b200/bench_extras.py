@@ -1,0 +1,160 @@
+"""Secondary measurements bench.py attaches under "extras": EKF update latency at 1k / 5k / 20k landmarks
+(BASELINE.json configs[2]) and the Mahalanobis gate at 10k measurements x 20k landmarks (configs[3]), each with
+its roofline fraction and a bounded CPU baseline.  The CPU legs import the oracle (test infrastructure) only
+as the thing being timed beside the GPU, exactly like bench.py's cpu_baseline."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import ekf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, warm: int = 3, seed: int = 0):
+    x, G, ci, pi = ekf.make_synthetic_ekf(L, d=3, seed=seed)
+    N = x.size
+    kf = ekf.KalmanFilter(capacity=N, device=device)
+    kf.set_state(x, None, ci, pi)
+    kf.set_cov_lowrank(G, 1.0 / 64.0, 0.25)
+    rng = np.random.default_rng(seed + 1)
+    A = np.stack([np.eye(4)] * 4)
+    M = 35 + 3 * n_point_meas
+    tot, cov, pred, wall = [], [], [], []
+    for it in range(warm + reps):
+        xs = kf.getCovBlock(0, 0, 1, 1)  # forces completion of the previous update (not timed)
+        del xs
+        z = np.concatenate([rng.normal(0.0, 1.0, 32), x[2:5] + rng.normal(0, 0.05, 3)])
+        pts = rng.choice(len(pi), n_point_meas, replace=False) if n_point_meas else None
+        pm = rng.normal(0.0, 5.0, 3 * n_point_meas) if n_point_meas else None
+        kf.PredictKF()
+        kf.sync()
+        tp = kf.last_timing()["total_ms"]
+        t0 = time.perf_counter()
+        kf.UpdateNCurvesAndPoints(z, 4, A, [0, 1, 2, 3], pm, pts, n_point_meas)
+        kf.sync()
+        t1 = time.perf_counter()
+        tm = kf.last_timing()
+        if it >= warm:
+            tot.append(tm["total_ms"]); cov.append(tm["cov_kernel_ms"]); pred.append(tp); wall.append((t1 - t0) * 1e3)
+    hbm, src = _peaks()
+    cov_ms = float(np.mean(cov))
+    gbs = 16.0 * N * N / (cov_ms * 1e-3) / 1e9
+    out = {"landmarks": L, "N": N, "M": M, "update_ms": float(np.mean(tot)), "cov_kernel_ms": cov_ms,
+           "predict_ms": float(np.mean(pred)), "update_e2e_ms": float(np.mean(wall)),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                        "algorithmic_bytes": 16 * N * N, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)"},
+           "flops_tflops": 2.0 * N * N * M / (cov_ms * 1e-3) / 1e12, "launches_per_update": 5,
+           "P_bytes": 8 * N * N, "l2": "P larger than L2" if 8 * N * N > 126e6 else "P fits L2 (72 MB): L2-resident"}
+    kf.close()
+    return out
+
+
+def ekf_cpu_baseline(L: int = 1000):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import oracle
+    x, G, ci, pi = ekf.make_synthetic_ekf(L, d=3, seed=0)
+    N = x.size
+    P = G @ G.T / 64.0 + 0.25 * np.eye(N)
+    rng = np.random.default_rng(1)
+    z = np.concatenate([rng.normal(0.0, 1.0, 32), x[2:5]])
+    t0 = time.perf_counter()
+    oracle().ekf_update_curves_points(x, P, z, np.stack([np.eye(4)] * 4), ci)
+    dt = time.perf_counter() - t0
+    return {"landmarks": L, "N": N, "M": 35, "update_ms": dt * 1e3, "cores": 1, "kind": "port",
+            "sample": "one dense UpdateNCurvesAndPoints restatement (oracle/orc_ekf.c), single thread as the reference is"}
+
+
+def gate_bench(device: int, L: int = 20000, nz: int = 10000, reps: int = 5, seed: int = 3):
+    import ctypes as C
+
+    from . import _lib
+    x, G, ci, pi = ekf.make_synthetic_ekf(L, d=3, seed=seed)
+    N = x.size
+    kf = ekf.KalmanFilter(capacity=N, device=device)
+    kf.set_state(x, None, ci, pi)
+    kf.set_cov_lowrank(G, 0.05 / 64.0, 0.25)
+    rng = np.random.default_rng(seed)
+    lm_xyz = x[pi[0]: pi[0] + 3 * len(pi)].reshape(-1, 3)
+    pick = rng.integers(0, len(pi), nz)
+    z = lm_xyz[pick] - x[:3] + rng.normal(0, 5.0, (nz, 3))  # roughly body-frame positions of random landmarks
+    clutter = rng.random(nz) < 0.2
+    z[clutter] = rng.uniform(-50, 50, (int(clutter.sum()), 3))
+    sweeps, packs = [], []
+    for it in range(reps + 2):
+        idx, d2 = kf.gate(z, ekf.CHI2_3DOF_99)
+        t = kf.gate_timing()
+        if it >= 2:
+            sweeps.append(t["sweep_ms"]); packs.append(t["pack_ms"])
+    pairs = float(nz) * len(pi)
+    sweep_ms = float(np.mean(sweeps))
+    pk_fma, pk_ma = C.c_double(), C.c_double()
+    _lib.lib().cps_measure_fp64_peak(device, C.byref(pk_fma), C.byref(pk_ma))
+    flops = 23.0 * pairs  # per pair: 3 sub, 12 mul, 8 add (DESIGN.md "Gate")
+    out = {"landmarks": len(pi), "measurements": nz, "pairs": pairs, "sweep_ms": sweep_ms, "pack_ms": float(np.mean(packs)),
+           "pairs_per_sec": pairs / (sweep_ms * 1e-3), "matched": int((idx >= 0).sum()),
+           "roofline": {"bound": "fp64", "achieved": flops / (sweep_ms * 1e-3) / 1e12, "peak": pk_fma.value,
+                        "peak_unfused": pk_ma.value, "unit": "TFLOP/s",
+                        "frac": flops / (sweep_ms * 1e-3) / 1e12 / pk_fma.value,
+                        "frac_of_unfused": flops / (sweep_ms * 1e-3) / 1e12 / pk_ma.value,
+                        "peak_source": "measured live (cps_measure_fp64_peak); the gate may not fuse (bit-exact indices)"}}
+    # CPU definition on a bounded sample of the measurements, all cores, and the bit-exactness of that sample
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import oracle
+    P_sub = None
+    try:
+        sample = 2000
+        # the oracle needs the dense P: only feasible for the sample if N is moderate; 60012^2 doubles = 28.8 GB
+        if N <= 16000:
+            P_full = kf.getCov()
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            io, do = oracle().gate(x, P_full, pi, z[:sample], ekf.CHI2_3DOF_99, nthreads=cores)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"pairs_per_sec": sample * len(pi) / dt, "cores": cores, "kind": "port",
+                                   "sample": f"first {sample} measurements", "indices_bit_exact": bool(np.array_equal(io, idx[:sample])),
+                                   "d2_bit_exact": bool(np.array_equal(do.view(np.int64), d2[:sample].view(np.int64)))}
+    except Exception as ex:
+        out["cpu_baseline"] = {"error": repr(ex)}
+    del P_sub
+    kf.close()
+    return out
+
+
+def run(device: int = 0):
+    res = {"ekf_update": [], "gate": None}
+    for L in (1000, 5000, 20000):
+        try:
+            res["ekf_update"].append(ekf_update_bench(device, L))
+        except Exception as ex:
+            res["ekf_update"].append({"landmarks": L, "error": repr(ex)})
+    try:
+        res["ekf_update_M65"] = ekf_update_bench(device, 5000, n_point_meas=10)
+    except Exception as ex:
+        res["ekf_update_M65"] = {"error": repr(ex)}
+    try:
+        res["ekf_cpu_baseline"] = ekf_cpu_baseline(1000)
+    except Exception as ex:
+        res["ekf_cpu_baseline"] = {"error": repr(ex)}
+    try:
+        res["gate"] = gate_bench(device, 20000, 10000)
+        res["gate_5k"] = gate_bench(device, 5000, 10000)
+    except Exception as ex:
+        res["gate"] = {"error": repr(ex)}
+    return res
+
+
+if __name__ == "__main__":
+    print(json.dumps(run(0), indent=1))

@@ -16,6 +16,7 @@
 // The reference allocates 14 temporaries (three of them N x N) per call; here nothing is allocated per call.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/cps_ekf.h"
@@ -425,6 +426,97 @@ __global__ void __launch_bounds__(256, 2) ekf_cov_kernel(double* __restrict__ P,
   }
 }
 
+// ---- kernel 5b: the same tile-pair update on the FP64 tensor cores (mma.sync.m8n8k4.f64, "DMMA") ----------
+// The CUDA-core version above is limited by shared-memory operand bandwidth (8 operand doubles per 16 FMA);
+// a DMMA instruction consumes 2 operand doubles per thread for 256 FMA per warp.  8 warps as 4 (rows) x 2
+// (cols); a warp owns 16 x 32 outputs = 2 x 4 DMMA tiles.  Fragment layout of m8n8k4 (T = lane):
+//   A (8x4, row): a = A[T/4][T%4]   B (4x8, col): b = B[T%4][T/4]   C (8x8): c0,c1 = C[T/4][2*(T%4) + {0,1}]
+// K and K S^T tiles sit in shared memory as [r][i] with a row stride of 68 doubles (68 mod 16 = 4 keeps the
+// half-warp's 16 eight-byte reads on distinct banks); rows r >= M are zero so M is padded to a multiple of 4.
+constexpr int DSTRIDE = TILE + 4;
+
+__global__ void __launch_bounds__(256, 2) ekf_cov_dmma_kernel(double* __restrict__ P, int ld, int M,
+                                                               const double* __restrict__ Kt,
+                                                               const double* __restrict__ Yt, int ldk) {
+  extern __shared__ double sh[];
+  const int Mp = (M + 3) & ~3;
+  double* Ks = sh;
+  double* Ys = sh + Mp * DSTRIDE;
+  const long long pidx = blockIdx.x;
+  int J = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
+  while ((long long)(J + 1) * (J + 2) / 2 <= pidx) ++J;
+  while ((long long)J * (J + 1) / 2 > pidx) --J;
+  const int I = (int)(pidx - (long long)J * (J + 1) / 2);
+  const bool diag = (I == J);
+
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int lr = l >> 2, lc = l & 3;
+  const int wr0 = (w >> 1) * 16, wc0 = (w & 1) * 32;  // warp tile origin inside the 64x64 tile
+  const size_t gi0 = (size_t)I * TILE + wr0 + lr;      // global row of this lane's C rows (plus 8*mi)
+  const size_t gj0 = (size_t)J * TILE + wc0 + 2 * lc;  // global col of c0 (plus 8*ni)
+
+  // prefetch the P entries: tile (I,J) as 16-byte pairs, tile (J,I) transposed as scalars
+  double2 pij[2][4];
+  double pji[2][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      pij[mi][ni] = *reinterpret_cast<const double2*>(P + (gi0 + 8 * mi) * ld + gj0 + 8 * ni);
+      pji[mi][ni][0] = P[(gj0 + 8 * ni) * ld + gi0 + 8 * mi];
+      pji[mi][ni][1] = P[(gj0 + 8 * ni + 1) * ld + gi0 + 8 * mi];
+    }
+  for (int e = t; e < Mp * (TILE / 2); e += 256) {
+    const int r = e / (TILE / 2), c = (e % (TILE / 2)) * 2;
+    double2 kv = make_double2(0.0, 0.0), yv = make_double2(0.0, 0.0);
+    if (r < M) {
+      kv = *reinterpret_cast<const double2*>(Kt + (size_t)r * ldk + (size_t)I * TILE + c);
+      yv = *reinterpret_cast<const double2*>(Yt + (size_t)r * ldk + (size_t)J * TILE + c);
+    }
+    *reinterpret_cast<double2*>(Ks + r * DSTRIDE + c) = kv;
+    *reinterpret_cast<double2*>(Ys + r * DSTRIDE + c) = yv;
+  }
+  __syncthreads();
+
+  double acc[2][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+  for (int ks = 0; ks < Mp; ks += 4) {
+    double a[2], b[4];
+    const double* kr = Ks + (ks + lc) * DSTRIDE + wr0 + lr;
+    const double* yr = Ys + (ks + lc) * DSTRIDE + wc0 + lr;
+    a[0] = kr[0];
+    a[1] = kr[8];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = yr[8 * ni];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                     : "d"(a[mi]), "d"(b[ni]));
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const size_t gi = gi0 + 8 * mi, gj = gj0 + 8 * ni;
+      const double o0 = 0.5 * (pij[mi][ni].x + pji[mi][ni][0]) - acc[mi][ni][0];
+      const double o1 = 0.5 * (pij[mi][ni].y + pji[mi][ni][1]) - acc[mi][ni][1];
+      if (!diag) {
+        *reinterpret_cast<double2*>(P + gi * ld + gj) = make_double2(o0, o1);
+        P[gj * ld + gi] = o0;
+        P[(gj + 1) * ld + gi] = o1;
+      } else {  // diagonal tile: the upper triangle (col >= row) is authoritative and mirrored
+        if (gj >= gi) { P[gi * ld + gj] = o0; if (gj != gi) P[gj * ld + gi] = o0; }
+        if (gj + 1 >= gi) { P[gi * ld + gj + 1] = o1; if (gj + 1 != gi) P[(gj + 1) * ld + gi] = o1; }
+      }
+    }
+}
+
 // ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
 // Pri <- F Pri, mirrored; Prr <- F Prr F^T + Q; x[0..5] += x[6..11] DT.  F = I + DT*[0 I6; 0 0].
 __global__ void __launch_bounds__(256) ekf_predict_cross_kernel(double* __restrict__ P, int ld, int N) {
@@ -572,6 +664,8 @@ extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
                                 (2 * MAXM * MAXM + MAXM + 16 * MAXM) * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * MAXM * TILE * (int)sizeof(double)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * MAXM * DSTRIDE * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (MAXM * MAXNC + 8 * MAXNC) * (int)sizeof(double) + MAXNC * (int)sizeof(int)));
   CPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -738,8 +832,15 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   CPS_CUDA(cudaEventRecord(h->ev[2], st));
   const int nt = (d.N + TILE - 1) / TILE;
   const long long pairs = (long long)nt * (nt + 1) / 2;
-  ekf_cov_kernel<<<(unsigned)pairs, 256, 2 * (size_t)M * TILE * sizeof(double), st>>>(h->d_P, h->cap, M, h->d_Kt,
-                                                                                      h->d_Yt, h->cap, nt);
+  static const bool use_cuda_cores = std::getenv("CPS_EKF_COV_CUDA_CORES") != nullptr;  // A/B switch for profiling
+  if (use_cuda_cores) {
+    ekf_cov_kernel<<<(unsigned)pairs, 256, 2 * (size_t)M * TILE * sizeof(double), st>>>(h->d_P, h->cap, M, h->d_Kt,
+                                                                                        h->d_Yt, h->cap, nt);
+  } else {
+    const int Mp = (M + 3) & ~3;
+    ekf_cov_dmma_kernel<<<(unsigned)pairs, 256, 2 * (size_t)Mp * DSTRIDE * sizeof(double), st>>>(
+        h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap);
+  }
   CPS_CUDA(cudaEventRecord(h->ev[3], st));
   CPS_CUDA(cudaEventRecord(h->ev[1], st));
   CPS_CUDA(cudaGetLastError());

@@ -25,6 +25,23 @@ __global__ void __launch_bounds__(256) fp64_stream_kernel(double* out, int iters
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// FP64 tensor-core stream: independent mma.sync.m8n8k4.f64 accumulations (512 flop per warp instruction)
+__global__ void __launch_bounds__(256) dmma_stream_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3 + i; c[i][1] = c[i][0] + 0.5; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <bool FMA>
 int run(double* d_out, int grid, int iters, double* tflops) {
   cudaEvent_t e0, e1;
@@ -67,4 +84,38 @@ extern "C" int cps_measure_fp64_peak(int device, double* tflops_fma, double* tfl
   if (rc == CPS_OK) rc = run<false>(d_out, grid, 4096, tflops_muladd);
   cudaFree(d_out);
   return rc;
+}
+
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4) peak in TFLOP/s
+extern "C" int cps_measure_dmma_peak(int device, double* tflops) {
+  if (!tflops) return CPS_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cps::set_last_error("no CUDA device");
+    return CPS_ERR_CUDA;
+  }
+  CPS_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  CPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int grid = sms * 8, iters = 2048;
+  double* d_out = nullptr;
+  CPS_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)grid * 256));
+  cudaEvent_t e0, e1;
+  CPS_CUDA(cudaEventCreate(&e0));
+  CPS_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CPS_CUDA(cudaEventRecord(e0));
+    dmma_stream_kernel<<<grid, 256>>>(d_out, iters, 0.999999, 1e-7);
+    CPS_CUDA(cudaEventRecord(e1));
+    CPS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CPS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = (double)grid * 8 /*warps*/ * (double)iters * 8 * 512.0 / (best * 1e-3) / 1e12;
+  return CPS_OK;
 }

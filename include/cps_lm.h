@@ -111,6 +111,8 @@ int cps_dlevmar_dif(void (*func)(double *, double *, int, int, void *), double *
 /* FP64 roofline denominators measured on the device: a DFMA stream and a DMUL+DADD stream (TFLOP/s,
  * a multiply-add pair counted as 2 flop in both). */
 int cps_measure_fp64_peak(int device, double *tflops_fma, double *tflops_muladd);
+/* FP64 tensor-core peak (mma.sync.m8n8k4.f64 stream), TFLOP/s */
+int cps_measure_dmma_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,8 @@
+"""Small EKF run used as the ncu target (N = 15012, M = 35)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from curvepointslam_b200 import bench_extras as b
+
+print(b.ekf_update_bench(0, 5000, reps=2, warm=1))

@@ -1,5 +1,18 @@
 set -x
 cd $GRAFT_REPO_ROOT
 make -s -C oracle 2>&1 | tail -2
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_der.json 2> gpurun_out/bench_der.err; tail -c 2500 gpurun_out/bench_der.json; tail -5 gpurun_out/bench_der.err
-python bench.py --variant dif --steps 3 --warmup 3 --fits 65536 > gpurun_out/bench_dif.json 2> gpurun_out/bench_dif.err; tail -c 2500 gpurun_out/bench_dif.json; tail -5 gpurun_out/bench_dif.err
+python -m pytest tests/test_ekf_gpu.py -x -q 2>&1 | tail -5
+python - <<'PY'
+from curvepointslam_b200 import bench_extras as b
+for L in (1000, 5000, 20000):
+    r = b.ekf_update_bench(0, L)
+    print('DMMA', L, 'update_ms %.4f cov_ms %.4f frac %.3f' % (r['update_ms'], r['cov_kernel_ms'], r['roofline']['frac']))
+r = b.ekf_update_bench(0, 5000, n_point_meas=10)
+print('DMMA M65', 'update_ms %.4f cov_ms %.4f frac %.3f' % (r['update_ms'], r['cov_kernel_ms'], r['roofline']['frac']))
+PY
+CPS_EKF_COV_CUDA_CORES=1 python - <<'PY'
+from curvepointslam_b200 import bench_extras as b
+for L in (5000, 20000):
+    r = b.ekf_update_bench(0, L)
+    print('CUDA-core', L, 'update_ms %.4f cov_ms %.4f frac %.3f' % (r['update_ms'], r['cov_kernel_ms'], r['roofline']['frac']))
+PY
