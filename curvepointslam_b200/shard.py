@@ -1,0 +1,31 @@
+"""Sharding of the independent curve fits over the GPUs of one box: contiguous ranges of the
+fit index, no data-path collective, one gather of the fitted parameters at the end (NCCL over NVLink on the
+GPUs; the same code runs over gloo on CPUs for the host-logic tests)."""
+from __future__ import annotations
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """[lo, hi) of the fits rank `rank` owns: contiguous, sizes differ by at most one, ranks in index order."""
+    if world <= 0 or not (0 <= rank < world) or total < 0:
+        raise ValueError("bad shard arguments")
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_fits(local_p, total: int, rank: int, world: int):
+    """All-gathers the per-rank fitted parameter blocks [b_r, m] into the global [total, m] tensor (every rank
+    gets the full result, like the reference's single address space)."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local_p
+    m = local_p.shape[1]
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width, m), dtype=local_p.dtype, device=local_p.device)
+    pad[: local_p.shape[0]] = local_p
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
