@@ -125,8 +125,9 @@ int launch_fit(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st
   long long need_ctas = ((long long)L.B + best_w - 1) / best_w;
   int grid = (int)std::min<long long>(need_ctas, (long long)c->sm_count * best_blocks);
   if (grid < 1) grid = 1;
-  if (DIF) {
-    const size_t need = (size_t)grid * best_w * MD::M * (size_t)L.n_max * sizeof(double);
+  {
+    const size_t per_warp = DIF ? (size_t)MD::M * (size_t)L.n_max : (size_t)cps::lm_der_ws_doubles(L.n_max);
+    const size_t need = (size_t)grid * best_w * per_warp * sizeof(double);
     if (need > sl.jstore_bytes) {
       CPS_CUDA(cudaStreamSynchronize(st));
       CPS_CUDA(cudaStreamSynchronize(sl.stream));
@@ -137,8 +138,6 @@ int launch_fit(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st
       sl.jstore_bytes = need;
     }
     L.jstore = sl.d_jstore;
-  } else {
-    L.jstore = nullptr;
   }
   L.queue = sl.d_queue;
   CPS_CUDA(cudaMemsetAsync(sl.d_queue, 0, sizeof(unsigned int), st));
@@ -176,7 +175,7 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
   cps::LmLaunch L;
   std::memset(&L, 0, sizeof L);
   L.B = B;
-  L.n_max = (n_max + 1) & ~1;
+  L.n_max = (n_max + 3) & ~3;
   L.itmax = itmax;
   fill_opts(L, opts, variant);
   L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;

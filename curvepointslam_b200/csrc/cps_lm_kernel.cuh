@@ -46,21 +46,51 @@ struct LmLaunch {
   double* info;             // [B][10]
   int* ret;                 // [B]
   int* extra;               // [B][2] (n_jtj, n_broyden) or nullptr
-  double* jstore;           // dif: [resident warps][M][n_max] column-major Jacobians
+  double* jstore;           // per resident warp: dif [M][n_max] column-major Jacobian; der [n_max] residual + [n_max/2] t
   unsigned int* queue;      // next fit index
 };
 
-__host__ __device__ constexpr int lm_ldt(int M) { return M | 1; }
+__host__ __device__ constexpr int lm_ldt(int M) { return M | 1; }  // tile stride of the unblocked (small-problem) path
+
+// Geometry of the blocked J^T J accumulation (see BlockAccum).  SP = the compact 12-column tile of the
+// Stereo19 analytic Jacobian (11 of 19 entries per row are non-zero); otherwise dense tiles.
+template <int M, bool SP>
+struct Blk {
+  static constexpr int NB = (M + 3) / 4;                         // groups of 4 columns
+  static constexpr int R = SP ? 6 : NB * (NB + 1) / 2;           // roles = 4x4 blocks of J^T J entries
+  static constexpr int NG = SP ? 4 : ((32 / R) >= 4 ? 4 : (32 / R));  // tiles processed at once
+  static constexpr int TC = SP ? 12 : NB * 4;                    // tile columns
+  static constexpr int LDT = SP ? TC : TC + 2;                   // even: rows stay 16-byte aligned
+  static constexpr int TILE_DOUBLES = kTileRows * LDT;
+  static constexpr int DOUBLES = NG * TILE_DOUBLES + 2 * NG * kTileRows / 2 /*row tags*/ + 32 /*item list*/;
+};
+
+__host__ __device__ constexpr int lm_tile_doubles(int M, bool sparse) {
+  return M == 19 ? (sparse ? Blk<19, true>::DOUBLES : Blk<19, false>::DOUBLES) : Blk<8, false>::DOUBLES;
+}
+
+__host__ __device__ constexpr int lm_tile_region(int M, int n_max, bool dif) {
+  return (!dif && lm_tile_doubles(M, M == 19) < n_max) ? n_max : lm_tile_doubles(M, !dif && M == 19);
+}
+
+__host__ __device__ constexpr int lm_der_ws_doubles(int n_max) { return n_max + n_max / 2; }
 
 // doubles of shared memory one warp needs
 __host__ __device__ constexpr int lm_warp_smem_doubles(int M, int scratch, int n_max, bool dif) {
-  return n_max /*x*/ + n_max / 2 /*t*/ + n_max /*e*/ + n_max /*hx*/ + (dif ? 2 * n_max : 0) +
-         kTileRows * lm_ldt(M) /*tile, reused as LU matrix*/ + M * M /*jtj*/ + 8 * 32 /*small vectors*/ + scratch;
+  // n_max is a multiple of 4 and the total is rounded to an even count so that every warp's tiles stay
+  // 16-byte aligned (the 4x4 blocks read operand pairs)
+  // The samples x stay in global memory (read once per residual, coalesced).  der: the trial residual lives in
+  // the tile region (tiles are only alive inside the normal-equation build); dif keeps hx, wrk, wrk2.
+  // der additionally keeps the accepted residual e and t in a per-warp global (L2-resident) work area: both are
+  // only streamed, lane-coalesced; e reaches the J^T e chain through the spare column of the compact tile.
+  return (((dif ? n_max / 2 + 4 * n_max : 0) + lm_tile_region(M, n_max, dif) + M * M /*jtj*/ +
+           8 * 32 /*small vectors*/ + scratch) + 1) & ~1;
 }
 
 template <int M>
 struct WarpMem {
-  double *x, *t, *e, *hx, *wrk, *wrk2, *tile, *jtj;
+  const double* x;  // the fit's samples in global memory
+  double *t, *e, *hx, *wrk, *wrk2, *tile, *jtj;
   double *p, *dp, *pdp, *jte, *diag, *pw, *xs, *scale;
   double* scratch;
 };
@@ -175,6 +205,277 @@ struct Accum {
   }
 };
 
+// ---- blocked J^T J: 4x4 register blocks, several 32-row tiles in flight ------------------------------------
+// The reference's blocked product (misc_core.c:101-126) gives every entry b_ij = sum over 32-row blocks (ascending)
+// of a partial sum that starts at 0 and runs over the block's rows (ascending).  Partial sums of different
+// blocks are independent, so NG tiles are processed at once by NG groups of lanes; within a group every lane
+// owns one 4x4 block of entries ("role": 8 operand loads feed 16 multiply-adds instead of 2 feeding 1), and the
+// partial sums are folded into the owners' accumulators in ascending block order through shuffles.
+// J^T e has no block structure in the reference (one running sum over ascending rows, lm_core.c:246-254), so it
+// stays a chain per column, lanes = columns, over the tiles in order.
+template <int M, bool SP>
+struct BlockAccum {
+  using B = Blk<M, SP>;
+  double jte;
+  int grp, role, lbase, rbase;  // tile column of the first L / R operand of this lane's block
+  bool active, is_c_role;
+
+  __device__ __forceinline__ void init(int lane) {
+    grp = lane / B::R;
+    role = lane - grp * B::R;
+    active = grp < B::NG;
+    if (!active) { grp = 0; role = 0; }
+    int bi = 0, bj = 0;
+    if (SP) {  // (g0,g0) (g1,g0) (g1,g1) (gq,g0) (gq,g1) (gq,gq); tile columns: g0 = 0..3, g1 = 4..7, gq = 8..11
+      bi = (role >= 3) ? 2 : (role >= 1 ? 1 : 0);
+      bj = (role == 2 || role == 4) ? 1 : (role == 5 ? 2 : 0);
+    } else {
+      int r = role;
+      while (r > bi) { r -= bi + 1; ++bi; }
+      bj = r;
+    }
+    lbase = 4 * bi;
+    rbase = 4 * bj;
+    is_c_role = SP && role == 5;
+  }
+  // one row of the block: 4 + 4 operands, 16 multiply-adds
+  __device__ __forceinline__ void mac_row(const double* row, double (&part)[16]) const {
+    const double2 l01 = *reinterpret_cast<const double2*>(row + lbase);
+    const double2 l23 = *reinterpret_cast<const double2*>(row + lbase + 2);
+    const double2 r01 = *reinterpret_cast<const double2*>(row + rbase);
+    const double2 r23 = *reinterpret_cast<const double2*>(row + rbase + 2);
+    const double l[4] = {l01.x, l01.y, l23.x, l23.y};
+    const double r[4] = {r01.x, r01.y, r23.x, r23.y};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) part[4 * a + b] += l[a] * r[b];
+  }
+  // partial sums of this lane's block over one tile.  `want` = row tag to accept (-1: every row); `pure` = every
+  // row of the tile carries the tag `tag0` (the usual case: a 32-row block lies inside one contour segment).
+  __device__ __forceinline__ void mac_tile(const double* tile, const int* tags, int rows, int want, bool pure, int tag0,
+                                           double (&part)[16]) const {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) part[e] = 0.0;
+    if (!SP || want < 0 || pure) {
+      if (SP && want >= 0 && tag0 != want) return;
+      int k = 0;
+      for (; k + 2 <= rows; k += 2) {
+        mac_row(tile + k * B::LDT, part);
+        mac_row(tile + (k + 1) * B::LDT, part);
+      }
+      if (k < rows) mac_row(tile + k * B::LDT, part);
+    } else {
+      for (int k = 0; k < rows; ++k)
+        if (tags[k] == want) mac_row(tile + k * B::LDT, part);
+    }
+  }
+  // output index of operand slot (group base, offset) for curve c: -1 = padding
+  __device__ __forceinline__ int out_index(int base, int off, int curve) const {
+    if (SP) {
+      if (base == 8) return off < 3 ? 16 + off : -1;
+      return 8 * curve + base + off;
+    }
+    const int v = base + off;
+    return v < M ? v : -1;
+  }
+};
+
+// item list of the compact Stereo19 path: one item per (32-row block, curve present in it), ascending blocks;
+// bit 8 = curve, bit 9 = primary (the item that also carries the block's theta/phi/z-only entries and J^T e).
+// Built once per fit by lane 0.
+__device__ __forceinline__ int build_items19(const FitGeom& g, int* items, int lane) {
+  int n_items = 0;
+  if (lane == 0) {
+    const int nblocks = (g.n + kTileRows - 1) / kTileRows;
+    for (int b = 0; b < nblocks; ++b) {
+      const int s0 = b * (kTileRows / 2), s1 = min(s0 + kTileRows / 2, g.nsamp) - 1;
+      const int seg0 = (s0 >= g.b1) + (s0 >= g.b2) + (s0 >= g.b3);
+      const int seg1 = (s1 >= g.b1) + (s1 >= g.b2) + (s1 >= g.b3);
+      const int c0 = seg0 & 1;
+      items[n_items++] = b | (c0 << 8) | (1 << 9);
+      if (seg1 != seg0) items[n_items++] = b | ((c0 ^ 1) << 8);
+    }
+  }
+  return __shfl_sync(0xffffffffu, n_items, 0);
+}
+
+// J^T J and J^T e by the blocked scheme.  STORED: rows come from the column-major secant Jacobian in global
+// memory (dif); otherwise they are evaluated from the analytic Jacobian (der), compact when SP.
+template <class MD, bool SP, bool STORED>
+__device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, const FitGeom& g,
+                                                   BlockAccum<MD::M, SP>& A, const double* J, int ld, int n_items,
+                                                   int lane) {
+  constexpr int M = MD::M;
+  using B = Blk<M, SP>;
+  double* tiles = w.tile;
+  int* tags = reinterpret_cast<int*>(w.tile + B::NG * B::TILE_DOUBLES);
+  int* items_rw = reinterpret_cast<int*>(w.tile + B::NG * B::TILE_DOUBLES + B::NG * kTileRows / 2);
+  const int* items = items_rw;
+  int* pure_flags = items_rw + 48;  // the item list holds at most 32 + 3 entries
+  (void)pure_flags;
+  if (!STORED) {
+    MD::prep_jac(w.p, w.scratch, lane);
+    __syncwarp();
+  }
+  A.jte = 0.0;
+  for (int i = lane; i < M * M; i += 32) w.jtj[i] = 0.0;  // accumulators of the owners live in the jtj array
+  const int nblocks = (g.n + kTileRows - 1) / kTileRows;
+  const int total = SP ? n_items : nblocks;
+  for (int step = 0; step * B::NG < total; ++step) {
+    // ---- produce up to NG tiles, lane = row
+#pragma unroll 1
+    for (int gi = 0; gi < B::NG; ++gi) {
+      const int it = step * B::NG + gi;
+      if (it < total) {
+        const int blk = SP ? (items[it] & 0xff) : it;
+        const int kk = blk * kTileRows;
+        const int r = kk + lane;
+        double* row = tiles + gi * B::TILE_DOUBLES + lane * B::LDT;
+        int tag = -1;
+        if (r < g.n) {
+          if constexpr (STORED) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) row[j] = J[j * ld + r];
+          } else if constexpr (SP) {
+            tag = MD::jac_row_compact(w.scratch, g, r, w.t[r >> 1], row);
+            row[11] = w.e[r];  // spare column: the residual of this row, for the J^T e chain
+            tags[gi * kTileRows + lane] = tag;
+          } else {
+            MD::jac_row(w.scratch, g, r, w.t[r >> 1], row);
+          }
+          if constexpr (!SP) {
+#pragma unroll
+            for (int j = M; j < B::TC; ++j) row[j] = 0.0;
+          }
+        }
+        if constexpr (SP) {  // "pure" tile: every row belongs to the same curve (the usual case)
+          const int t0 = __shfl_sync(0xffffffffu, tag, 0);
+          const unsigned same = __ballot_sync(0xffffffffu, tag < 0 || tag == t0);
+          if (lane == 0) pure_flags[gi] = (same == 0xffffffffu) ? 1 : 0;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- every lane: partial sums of its 4x4 block over its group's tile
+    double part[16];
+    {
+      const int it = step * B::NG + A.grp;
+      int rows = 0, want = -1;
+      if (A.active && it < total) {
+        const int item = SP ? items[it] : it;
+        const int blk = item & 0xff;
+        rows = min(kTileRows, g.n - blk * kTileRows);
+        if (SP) {
+          want = A.is_c_role ? -1 : ((item >> 8) & 1);
+          if (A.is_c_role && !((item >> 9) & 1)) rows = 0;
+        }
+      }
+      bool pure = true;
+      int tag0 = 0;
+      if constexpr (SP) {
+        tag0 = tags[A.grp * kTileRows];
+        pure = pure_flags[A.grp] != 0;
+      }
+      A.mac_tile(tiles + A.grp * B::TILE_DOUBLES, tags + A.grp * kTileRows, rows, want, pure, tag0, part);
+    }
+    // ---- fold the partial sums into the owners in ascending block order.  An owner keeps its 16 running
+    // entries in the jtj array: one load, up to NG ordered additions, one store per entry and step.
+    {
+      const int ngrp = min(B::NG, total - step * B::NG);
+      // which of this step's tiles feed this lane's entries (bit gi), and the curve they belong to
+      unsigned feed = 0;
+      if (A.active) {
+        for (int gi = 0; gi < ngrp; ++gi) {
+          bool mine;
+          if (SP) {
+            const int item = items[step * B::NG + gi];
+            mine = A.is_c_role ? (A.grp == 0 && ((item >> 9) & 1)) : (A.grp == ((item >> 8) & 1));
+          } else {
+            mine = A.grp == 0;
+          }
+          feed |= mine ? (1u << gi) : 0u;
+        }
+      }
+      const int oc = A.grp & 1;  // an owner of curve entries sits in group 0 (curve 0) or group 1 (curve 1)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = A.out_index(A.lbase, a, oc), j = A.out_index(A.rbase, b, oc);
+          const bool keep = feed != 0u && i >= 0 && j >= 0 && j <= i;
+          double acc = keep ? w.jtj[i * M + j] : 0.0;
+#pragma unroll 1
+          for (int gi = 0; gi < ngrp; ++gi) {
+            const double v = shfl_d(part[4 * a + b], gi * B::R + A.role);
+            if ((feed >> gi) & 1u) acc += v;
+          }
+          if (keep) w.jtj[i * M + j] = acc;
+        }
+    }
+    // ---- J^T e: one running sum per column over ascending rows (lanes = columns)
+#pragma unroll 1
+    for (int gi = 0; gi < B::NG; ++gi) {
+      const int it = step * B::NG + gi;
+      if (it < total) {
+        const int item = SP ? items[it] : it;
+        if (!SP || ((item >> 9) & 1)) {
+          const int blk = item & 0xff;
+          const int kk = blk * kTileRows;
+          const int rows = min(kTileRows, g.n - kk);
+          if (lane < M) {
+            const double* tile = tiles + gi * B::TILE_DOUBLES;
+            const int* tg = tags + gi * kTileRows;
+            const int col = SP ? (lane < 16 ? (lane & 7) : lane - 8) : lane;
+            const int want = (SP && lane < 16) ? (lane >> 3) : -1;
+            // four rows per trip: loads and products first, then the four chained additions.  A row of the
+            // other curve contributes +0.0 (its true entry is a structural zero; adding +-0 never changes a
+            // running sum that started at +0), which keeps the loop branch-free.
+            int k = 0;
+            for (; k + 4 <= rows; k += 4) {
+              const double t0 = tile[(k + 0) * B::LDT + col], t1 = tile[(k + 1) * B::LDT + col];
+              const double t2 = tile[(k + 2) * B::LDT + col], t3 = tile[(k + 3) * B::LDT + col];
+              double2 e01, e23;
+              if constexpr (SP) {
+                e01 = make_double2(tile[(k + 0) * B::LDT + 11], tile[(k + 1) * B::LDT + 11]);
+                e23 = make_double2(tile[(k + 2) * B::LDT + 11], tile[(k + 3) * B::LDT + 11]);
+              } else {
+                e01 = *reinterpret_cast<const double2*>(w.e + kk + k);
+                e23 = *reinterpret_cast<const double2*>(w.e + kk + k + 2);
+              }
+              double p0 = t0 * e01.x, p1 = t1 * e01.y, p2 = t2 * e23.x, p3 = t3 * e23.y;
+              if (SP && want >= 0) {
+                const int4 tg4 = *reinterpret_cast<const int4*>(tg + k);
+                p0 = (tg4.x == want) ? p0 : 0.0;
+                p1 = (tg4.y == want) ? p1 : 0.0;
+                p2 = (tg4.z == want) ? p2 : 0.0;
+                p3 = (tg4.w == want) ? p3 : 0.0;
+              }
+              A.jte += p0;
+              A.jte += p1;
+              A.jte += p2;
+              A.jte += p3;
+            }
+            for (; k < rows; ++k) {
+              if (SP && want >= 0 && tg[k] != want) continue;
+              A.jte += tile[k * B::LDT + col] * (SP ? tile[k * B::LDT + 11] : w.e[kk + k]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // mirror the lower triangle (the reference mirrors its upper triangle, misc_core.c:128-131) and publish J^T e
+  __syncwarp();
+  for (int idx = lane; idx < M * M; idx += 32) {
+    const int i = idx / M, j = idx - i * M;
+    if (j > i) w.jtj[idx] = w.jtj[j * M + i];
+  }
+  if (lane < M) w.jte[lane] = A.jte;
+  __syncwarp();
+}
+
 // analytic Jacobian evaluated tile by tile, never stored (der path)
 template <class MD>
 __device__ __forceinline__ void normal_eqs_analytic(const WarpMem<MD::M>& w, const FitGeom& g, Accum<MD::M>& A,
@@ -259,18 +560,17 @@ __device__ __forceinline__ int lu_solve(const WarpMem<M>& w, double mu, int lane
     // pivot search over rows j..M-1 in ascending order with ">=" against a running maximum from 0
     double merit = -1.0;
     if (lane >= j && lane < M) merit = scale * fabs(a[lane * LD + j]);
-    double best = 0.0;
+    // sequential semantics: the last row whose merit equals the running maximum (">="); NaN never wins.
+    // A non-negative double orders like its bit pattern, so the warp maximum is two hardware integer
+    // reductions (high word, then low word among the lanes that hold the high-word maximum).
     int besti = -1;
-    // sequential semantics: last index whose merit >= all earlier maxima and >= 0; NaN never wins
     {
-      double mx = (merit >= 0.0) ? merit : -1.0;  // NaN -> -1
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double other = shfl_d(mx, lane ^ o);
-        mx = (other > mx) ? other : mx;
-      }
-      best = mx;
-      const unsigned ballot = __ballot_sync(0xffffffffu, merit >= 0.0 && merit == best);
+      const bool valid = merit >= 0.0;
+      const unsigned long long bits = valid ? (unsigned long long)__double_as_longlong(merit) : 0ull;
+      const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+      const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned lmax = __reduce_max_sync(0xffffffffu, (hi == hmax) ? lo : 0u);
+      const unsigned ballot = __ballot_sync(0xffffffffu, valid && hi == hmax && lo == lmax);
       besti = ballot ? (31 - __clz(ballot)) : -1;
     }
     if (besti >= 0) piv = besti;
@@ -309,13 +609,19 @@ __device__ __forceinline__ int lu_solve(const WarpMem<M>& w, double mu, int lane
     }
     if (lane > j && lane < M) b -= a[lane * LD + j] * xj;
   }
-  // back substitution: row i subtracts a_ij*x_j for j = i+1..M-1 in ascending j, then divides
+  // back substitution: row i subtracts a_ij*x_j for j = i+1..M-1 in ascending j, then divides.  As soon as
+  // x_j is known every row above it turns its a_ij into the product a_ij*x_j (all lanes at once), so the
+  // serial chain of row i is plain subtractions of ready values.
   for (int i = M - 1; i >= 0; --i) {
+    double xi = 0.0;
     if (lane == i) {
       double sum = b;
-      for (int jj = i + 1; jj < M; ++jj) sum -= a[i * LD + jj] * w.xs[jj];
-      w.xs[i] = sum / a[i * LD + i];
+      for (int jj = i + 1; jj < M; ++jj) sum -= a[i * LD + jj];
+      xi = sum / a[i * LD + i];
+      w.xs[i] = xi;
     }
+    xi = shfl_d(xi, i);
+    if (lane < i) a[lane * LD + i] *= xi;
     __syncwarp();
   }
   if (lane < M) w.dp[lane] = w.xs[lane];
@@ -381,8 +687,8 @@ __device__ __forceinline__ double nielsen(double mu, double dF, double dL) {
 
 // dlevmar_der, lm_core.c:60-423
 template <class MD>
-__device__ void lm_der(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch& L, Accum<MD::M>& A, LmResult& R,
-                       int lane) {
+__device__ void lm_der(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch& L, Accum<MD::M>& A,
+                       BlockAccum<MD::M, MD::M == 19>& BA, int n_items, LmResult& R, int lane) {
   constexpr int M = MD::M;
   const bool blocked = !(g.n * M < kBlockSzSq);  // strict "<" selects the unblocked loop, lm_core.c:193
   double mu = 0.0, g_inf = 0.0, p_sq = 0.0, dp_sq = DBL_MAX;
@@ -390,13 +696,16 @@ __device__ void lm_der(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
 
   eval_func<MD>(w, g, w.p, w.hx, lane);
   nfev = 1;
-  double e_sq = residual_sqnorm(w.e, w.x, w.hx, g.n, lane);
+  double e_sq = residual_sqnorm(w.hx, w.x, w.hx, g.n, lane);  // in shared memory, then published to e
+  for (int i = lane; i < g.n; i += 32) w.e[i] = w.hx[i];
+  __syncwarp();
   const double e0 = e_sq;
   if (!isfinite(e_sq)) stop = 7;
 
   for (k = 0; k < L.itmax && !stop; ++k) {
     if (e_sq <= L.eps3) { stop = 6; break; }
-    normal_eqs_analytic<MD>(w, g, A, blocked, lane);
+    if (blocked) normal_eqs_blocked<MD, MD::M == 19, false>(w, g, BA, nullptr, 0, n_items, lane);
+    else normal_eqs_analytic<MD>(w, g, A, false, lane);
     ++njev;
     grad_stats<M>(w, p_sq, g_inf, lane);
     if (g_inf <= L.eps1) { dp_sq = 0.0; stop = 1; break; }
@@ -438,8 +747,8 @@ __device__ void lm_der(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
 
 // dlevmar_dif, lm_core.c:429-828 (secant LM; J lives column-major in `J`, leading dimension ld)
 template <class MD>
-__device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch& L, Accum<MD::M>& A, double* J,
-                       int ld, LmResult& R, int lane) {
+__device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch& L, Accum<MD::M>& A,
+                       BlockAccum<MD::M, false>& BA, double* J, int ld, LmResult& R, int lane) {
   constexpr int M = MD::M;
   const bool blocked = !(g.n * M <= kBlockSzSq);  // "<=" here, lm_core.c:585
   const int K = (M >= 10) ? M : 10;
@@ -492,7 +801,8 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
 
     if (newjac) {
       newjac = 0;
-      normal_eqs_stored<M>(w, g, J, ld, A, blocked, lane);
+      if (blocked) normal_eqs_blocked<MD, false, true>(w, g, BA, J, ld, 0, lane);
+      else normal_eqs_stored<M>(w, g, J, ld, A, false, lane);
       ++n_jtj;
       grad_stats<M>(w, p_sq, g_inf, lane);
     }
@@ -562,23 +872,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lm_fit_kernel(const LmLaunc
   double* base = smem + (size_t)wid * per_warp;
 
   WarpMem<M> w;
-  w.x = base; base += L.n_max;
-  w.t = base; base += L.n_max / 2;
-  w.e = base; base += L.n_max;
-  w.hx = base; base += L.n_max;
-  if (DIF) { w.wrk = base; base += L.n_max; w.wrk2 = base; base += L.n_max; }
-  else { w.wrk = nullptr; w.wrk2 = nullptr; }
-  w.tile = base; base += kTileRows * lm_ldt(M);
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + wid;
+  w.x = nullptr;
+  if (DIF) {
+    w.t = base; base += L.n_max / 2;
+    w.e = base; base += L.n_max;
+    w.hx = base; base += L.n_max; w.wrk = base; base += L.n_max; w.wrk2 = base; base += L.n_max;
+  } else {
+    double* ws = L.jstore + (size_t)gwarp * lm_der_ws_doubles(L.n_max);
+    w.e = ws;
+    w.t = ws + L.n_max;
+    w.wrk = nullptr; w.wrk2 = nullptr;
+  }
+  w.tile = base; base += lm_tile_region(M, L.n_max, DIF);
+  if (!DIF) w.hx = w.tile;  // trial residual: the tile region is idle outside the normal-equation build
   w.jtj = base; base += M * M;
   w.p = base; w.dp = base + 32; w.pdp = base + 64; w.jte = base + 96; w.diag = base + 128; w.pw = base + 160;
   w.xs = base + 192; w.scale = base + 224; base += 256;
   w.scratch = base;
 
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + wid;
   double* J = DIF ? (L.jstore + (size_t)gwarp * M * L.n_max) : nullptr;
 
+  constexpr bool SP = !DIF && M == 19;
   Accum<M> A;
   A.init(lane);
+  BlockAccum<M, SP> BA;
+  BA.init(lane);
 
   for (;;) {
     unsigned int f = 0;
@@ -616,8 +935,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lm_fit_kernel(const LmLaunc
     }
 
     // stage the contour samples (coalesced), the t parameter of every sample and the parameters
-    const double* xg = L.meas + o0;
-    for (int i = lane; i < g.n; i += 32) w.x[i] = xg[i];
+    w.x = L.meas + o0;
     if (lane < M) w.p[lane] = L.p[(size_t)f * M + lane];
     __syncwarp();
     if (L.t) {
@@ -644,8 +962,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lm_fit_kernel(const LmLaunc
     __syncwarp();
 
     LmResult R;
-    if (DIF) lm_dif<MD>(w, g, L, A, J, L.n_max, R, lane);
-    else lm_der<MD>(w, g, L, A, R, lane);
+    if constexpr (DIF) {
+      lm_dif<MD>(w, g, L, A, BA, J, L.n_max, R, lane);
+    } else {
+      int n_items = 0;
+      if constexpr (SP) {
+        int* items = reinterpret_cast<int*>(w.tile + Blk<M, SP>::NG * Blk<M, SP>::TILE_DOUBLES +
+                                            Blk<M, SP>::NG * kTileRows / 2);
+        n_items = build_items19(g, items, lane);
+        __syncwarp();
+      }
+      lm_der<MD>(w, g, L, A, BA, n_items, R, lane);
+    }
 
     // info[] exactly as lm_core.c:396-409 / :800-813 (the diagonal of J^T J is the un-augmented one)
     if (lane < M) L.p[(size_t)f * M + lane] = w.p[lane];

@@ -45,7 +45,7 @@ struct Trig {
   double st, ct, sp, cp, stsp, stcp, ctsp, ctcp;
 };
 
-__device__ __forceinline__ void make_trig(double theta, double phi, Trig& g) {
+__device__ __noinline__ void make_trig(double theta, double phi, Trig& g) {
   det_sincos(theta, &g.st, &g.ct);
   det_sincos(phi, &g.sp, &g.cp);
   g.stsp = g.st * g.sp;
@@ -161,6 +161,33 @@ struct Model<19> {
       for (int k = 0; k < 4; ++k) a += w[k] * D[15 * k + 2 + q];
       row[16 + q] = a;
     }
+  }
+
+  // the same row in compact form: [0..7] the 8 entries of the row's own curve, [8..10] theta/phi/z, [11] = 0;
+  // returns the curve (0/1) the row belongs to
+  __device__ static __forceinline__ int jac_row_compact(const double* scratch, const FitGeom& g, int r, double t,
+                                                        double* row) {
+    const int s = r >> 1, uv = r & 1;
+    int curve, side;
+    locate(g, s, curve, side);
+    const int coord = uv ? 2 : side;
+    double w[4];
+    bernstein3(t, w);
+    const double* D = scratch + 24 + 60 * curve + 5 * coord;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      row[2 * k] = w[k] * D[15 * k + 0];
+      row[2 * k + 1] = w[k] * D[15 * k + 1];
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a += w[k] * D[15 * k + 2 + q];
+      row[8 + q] = a;
+    }
+    row[11] = 0.0;
+    return curve;
   }
 };
 
