@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcps.so")
+LIB_PATH = os.environ.get("CPS_LIB", os.path.join(HERE, "libcps.so"))
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

@@ -1,6 +1,7 @@
 // cps_lm_api.cu -- host side of the batched LM fits: context, launch geometry, the C ABI of
 // include/cps_lm.h.  Compiled with -fmad=false together with the kernels (see cps_lm_kernel.cuh).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -120,13 +121,17 @@ int launch_fit(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st
     cps::set_last_error("a fit with this many measurements does not fit in shared memory");
     return CPS_ERR_INVALID;
   }
+  if (const char* cap = std::getenv("CPS_LM_MAX_WARPS_PER_SM")) {  // experiment knob: fewer resident warps
+    const int c = std::atoi(cap);
+    if (c > 0 && best_blocks * best_w > c) best_blocks = std::max(1, c / best_w);
+  }
   const int smem = per_warp * best_w;
   CPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long need_ctas = ((long long)L.B + best_w - 1) / best_w;
   int grid = (int)std::min<long long>(need_ctas, (long long)c->sm_count * best_blocks);
   if (grid < 1) grid = 1;
   {
-    const size_t per_warp = DIF ? (size_t)MD::M * (size_t)L.n_max : (size_t)cps::lm_der_ws_doubles(L.n_max);
+    const size_t per_warp = (size_t)cps::lm_ws_doubles(MD::M, L.n_max, DIF);
     const size_t need = (size_t)grid * best_w * per_warp * sizeof(double);
     if (need > sl.jstore_bytes) {
       CPS_CUDA(cudaStreamSynchronize(st));

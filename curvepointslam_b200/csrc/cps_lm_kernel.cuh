@@ -26,6 +26,12 @@
 
 namespace cps {
 
+#ifndef CPS_SP_NG
+#define CPS_SP_NG 4
+#endif
+#ifndef CPS_LM_MIN_BLOCKS
+#define CPS_LM_MIN_BLOCKS 3
+#endif
 constexpr int kWarpsPerCta = 4;
 constexpr int kTileRows = 32;  // the reference's __BLOCKSZ__ (misc.h:48): row blocks of J^T J partial sums
 constexpr double kEpsilon = 1E-12;          // lm.c:35
@@ -58,22 +64,28 @@ template <int M, bool SP>
 struct Blk {
   static constexpr int NB = (M + 3) / 4;                         // groups of 4 columns
   static constexpr int R = SP ? 6 : NB * (NB + 1) / 2;           // roles = 4x4 blocks of J^T J entries
-  static constexpr int NG = SP ? 4 : ((32 / R) >= 4 ? 4 : (32 / R));  // tiles processed at once
+  static constexpr int NG = SP ? CPS_SP_NG : ((32 / R) >= 4 ? 4 : (32 / R));  // tiles processed at once
   static constexpr int TC = SP ? 12 : NB * 4;                    // tile columns
   static constexpr int LDT = SP ? TC : TC + 2;                   // even: rows stay 16-byte aligned
   static constexpr int TILE_DOUBLES = kTileRows * LDT;
-  static constexpr int DOUBLES = NG * TILE_DOUBLES + 2 * NG * kTileRows / 2 /*row tags*/ + 32 /*item list*/;
+  static constexpr int DOUBLES = NG * TILE_DOUBLES + NG * kTileRows / 2 /*row tags*/ + 32 /*item list, flags*/ +
+                                 NG * kTileRows /*residuals of the tiles' rows*/;
 };
 
 __host__ __device__ constexpr int lm_tile_doubles(int M, bool sparse) {
   return M == 19 ? (sparse ? Blk<19, true>::DOUBLES : Blk<19, false>::DOUBLES) : Blk<8, false>::DOUBLES;
 }
 
+// the tile region doubles as the trial-residual buffer (tiles are only alive inside the normal-equation build)
 __host__ __device__ constexpr int lm_tile_region(int M, int n_max, bool dif) {
-  return (!dif && lm_tile_doubles(M, M == 19) < n_max) ? n_max : lm_tile_doubles(M, !dif && M == 19);
+  return lm_tile_doubles(M, !dif && M == 19) < n_max ? n_max : lm_tile_doubles(M, !dif && M == 19);
 }
 
-__host__ __device__ constexpr int lm_der_ws_doubles(int n_max) { return n_max + n_max / 2; }
+// per-warp global (L2-resident) work area, doubles: the accepted residual e and t; dif adds f(p), f(p+dp) and the
+// column-major secant Jacobian.  Everything in it is only streamed with lane-coalesced accesses.
+__host__ __device__ constexpr int lm_ws_doubles(int M, int n_max, bool dif) {
+  return n_max + n_max / 2 + (dif ? 2 * n_max + M * n_max : 0);
+}
 
 // doubles of shared memory one warp needs
 __host__ __device__ constexpr int lm_warp_smem_doubles(int M, int scratch, int n_max, bool dif) {
@@ -83,8 +95,7 @@ __host__ __device__ constexpr int lm_warp_smem_doubles(int M, int scratch, int n
   // the tile region (tiles are only alive inside the normal-equation build); dif keeps hx, wrk, wrk2.
   // der additionally keeps the accepted residual e and t in a per-warp global (L2-resident) work area: both are
   // only streamed, lane-coalesced; e reaches the J^T e chain through the spare column of the compact tile.
-  return (((dif ? n_max / 2 + 4 * n_max : 0) + lm_tile_region(M, n_max, dif) + M * M /*jtj*/ +
-           8 * 32 /*small vectors*/ + scratch) + 1) & ~1;
+  return ((lm_tile_region(M, n_max, dif) + M * M /*jtj*/ + 8 * 32 /*small vectors*/ + scratch) + 1) & ~1;
 }
 
 template <int M>
@@ -218,7 +229,8 @@ struct BlockAccum {
   using B = Blk<M, SP>;
   double jte;
   int grp, role, lbase, rbase;  // tile column of the first L / R operand of this lane's block
-  bool active, is_c_role;
+  int out0, na, nb;             // owner side: jtj index of entry (0,0) of the block, valid rows / columns
+  bool active, is_c_role, diag;
 
   __device__ __forceinline__ void init(int lane) {
     grp = lane / B::R;
@@ -237,6 +249,13 @@ struct BlockAccum {
     lbase = 4 * bi;
     rbase = 4 * bj;
     is_c_role = SP && role == 5;
+    diag = bi == bj;
+    const int oc = grp & 1;  // an owner of curve entries sits in group 0 (curve 0) or group 1 (curve 1)
+    const int ri0 = SP ? (lbase == 8 ? 16 : 8 * oc + lbase) : lbase;
+    const int rj0 = SP ? (rbase == 8 ? 16 : 8 * oc + rbase) : rbase;
+    na = SP ? (lbase == 8 ? 3 : 4) : min(4, M - lbase);
+    nb = SP ? (rbase == 8 ? 3 : 4) : min(4, M - rbase);
+    out0 = ri0 * M + rj0;
   }
   // one row of the block: 4 + 4 operands, 16 multiply-adds
   __device__ __forceinline__ void mac_row(const double* row, double (&part)[16]) const {
@@ -313,7 +332,9 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
   int* items_rw = reinterpret_cast<int*>(w.tile + B::NG * B::TILE_DOUBLES + B::NG * kTileRows / 2);
   const int* items = items_rw;
   int* pure_flags = items_rw + 48;  // the item list holds at most 32 + 3 entries
+  double* etile = w.tile + B::NG * B::TILE_DOUBLES + B::NG * kTileRows / 2 + 32;  // [NG][32] residuals, contiguous
   (void)pure_flags;
+  (void)etile;
   if (!STORED) {
     MD::prep_jac(w.p, w.scratch, lane);
     __syncwarp();
@@ -323,8 +344,22 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
   const int nblocks = (g.n + kTileRows - 1) / kTileRows;
   const int total = SP ? n_items : nblocks;
   for (int step = 0; step * B::NG < total; ++step) {
-    // ---- produce up to NG tiles, lane = row
-#pragma unroll 1
+    // ---- produce up to NG tiles, lane = row.  The t and e of all NG rows are requested first so that the
+    // L2 latencies overlap.
+    double t_pre[B::NG], e_pre[B::NG];
+    if constexpr (SP) {
+#pragma unroll
+      for (int gi = 0; gi < B::NG; ++gi) {
+        const int it = step * B::NG + gi;
+        t_pre[gi] = 0.0;
+        e_pre[gi] = 0.0;
+        if (it < total) {
+          const int r = (items[it] & 0xff) * kTileRows + lane;
+          if (r < g.n) { t_pre[gi] = w.t[r >> 1]; e_pre[gi] = w.e[r]; }
+        }
+      }
+    }
+#pragma unroll
     for (int gi = 0; gi < B::NG; ++gi) {
       const int it = step * B::NG + gi;
       if (it < total) {
@@ -338,8 +373,8 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
 #pragma unroll
             for (int j = 0; j < M; ++j) row[j] = J[j * ld + r];
           } else if constexpr (SP) {
-            tag = MD::jac_row_compact(w.scratch, g, r, w.t[r >> 1], row);
-            row[11] = w.e[r];  // spare column: the residual of this row, for the J^T e chain
+            tag = MD::jac_row_compact(w.scratch, g, r, t_pre[gi], row);
+            etile[gi * kTileRows + lane] = e_pre[gi];  // residual of this row, for the J^T e chain
             tags[gi * kTileRows + lane] = tag;
           } else {
             MD::jac_row(w.scratch, g, r, w.t[r >> 1], row);
@@ -347,6 +382,7 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
           if constexpr (!SP) {
 #pragma unroll
             for (int j = M; j < B::TC; ++j) row[j] = 0.0;
+            etile[gi * kTileRows + lane] = w.e[r];
           }
         }
         if constexpr (SP) {  // "pure" tile: every row belongs to the same curve (the usual case)
@@ -397,20 +433,19 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
           feed |= mine ? (1u << gi) : 0u;
         }
       }
-      const int oc = A.grp & 1;  // an owner of curve entries sits in group 0 (curve 0) or group 1 (curve 1)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const int i = A.out_index(A.lbase, a, oc), j = A.out_index(A.rbase, b, oc);
-          const bool keep = feed != 0u && i >= 0 && j >= 0 && j <= i;
-          double acc = keep ? w.jtj[i * M + j] : 0.0;
+          const bool keep = feed != 0u && a < A.na && b < A.nb && (!A.diag || b <= a);
+          const int idx = A.out0 + a * M + b;
+          double acc = keep ? w.jtj[idx] : 0.0;
 #pragma unroll 1
           for (int gi = 0; gi < ngrp; ++gi) {
             const double v = shfl_d(part[4 * a + b], gi * B::R + A.role);
             if ((feed >> gi) & 1u) acc += v;
           }
-          if (keep) w.jtj[i * M + j] = acc;
+          if (keep) w.jtj[idx] = acc;
         }
     }
     // ---- J^T e: one running sum per column over ascending rows (lanes = columns)
@@ -426,39 +461,34 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
           if (lane < M) {
             const double* tile = tiles + gi * B::TILE_DOUBLES;
             const int* tg = tags + gi * kTileRows;
+            const double* ev = etile + gi * kTileRows;
             const int col = SP ? (lane < 16 ? (lane & 7) : lane - 8) : lane;
             const int want = (SP && lane < 16) ? (lane >> 3) : -1;
-            // four rows per trip: loads and products first, then the four chained additions.  A row of the
-            // other curve contributes +0.0 (its true entry is a structural zero; adding +-0 never changes a
-            // running sum that started at +0), which keeps the loop branch-free.
-            int k = 0;
-            for (; k + 4 <= rows; k += 4) {
-              const double t0 = tile[(k + 0) * B::LDT + col], t1 = tile[(k + 1) * B::LDT + col];
-              const double t2 = tile[(k + 2) * B::LDT + col], t3 = tile[(k + 3) * B::LDT + col];
-              double2 e01, e23;
-              if constexpr (SP) {
-                e01 = make_double2(tile[(k + 0) * B::LDT + 11], tile[(k + 1) * B::LDT + 11]);
-                e23 = make_double2(tile[(k + 2) * B::LDT + 11], tile[(k + 3) * B::LDT + 11]);
-              } else {
-                e01 = *reinterpret_cast<const double2*>(w.e + kk + k);
-                e23 = *reinterpret_cast<const double2*>(w.e + kk + k + 2);
+            const bool pure = !SP || pure_flags[gi] != 0;
+            // a pure tile either belongs to this column's curve entirely or not at all; a mixed tile (a block
+            // that straddles two contour segments) selects row by row: a row of the other curve contributes +0.0
+            // (its true entry is a structural zero; adding +-0 never changes a running sum that started at +0)
+            if (pure) {
+              if (want < 0 || tg[0] == want) {
+                int k = 0;
+                for (; k + 4 <= rows; k += 4) {
+                  const double t0 = tile[(k + 0) * B::LDT + col], t1 = tile[(k + 1) * B::LDT + col];
+                  const double t2 = tile[(k + 2) * B::LDT + col], t3 = tile[(k + 3) * B::LDT + col];
+                  const double2 e01 = *reinterpret_cast<const double2*>(ev + k);
+                  const double2 e23 = *reinterpret_cast<const double2*>(ev + k + 2);
+                  const double p0 = t0 * e01.x, p1 = t1 * e01.y, p2 = t2 * e23.x, p3 = t3 * e23.y;
+                  A.jte += p0;
+                  A.jte += p1;
+                  A.jte += p2;
+                  A.jte += p3;
+                }
+                for (; k < rows; ++k) A.jte += tile[k * B::LDT + col] * ev[k];
               }
-              double p0 = t0 * e01.x, p1 = t1 * e01.y, p2 = t2 * e23.x, p3 = t3 * e23.y;
-              if (SP && want >= 0) {
-                const int4 tg4 = *reinterpret_cast<const int4*>(tg + k);
-                p0 = (tg4.x == want) ? p0 : 0.0;
-                p1 = (tg4.y == want) ? p1 : 0.0;
-                p2 = (tg4.z == want) ? p2 : 0.0;
-                p3 = (tg4.w == want) ? p3 : 0.0;
+            } else {
+              for (int k = 0; k < rows; ++k) {
+                if (want >= 0 && tg[k] != want) continue;
+                A.jte += tile[k * B::LDT + col] * ev[k];
               }
-              A.jte += p0;
-              A.jte += p1;
-              A.jte += p2;
-              A.jte += p3;
-            }
-            for (; k < rows; ++k) {
-              if (SP && want >= 0 && tg[k] != want) continue;
-              A.jte += tile[k * B::LDT + col] * (SP ? tile[k * B::LDT + 11] : w.e[kk + k]);
             }
           }
         }
@@ -758,7 +788,9 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
 
   eval_func<MD>(w, g, w.p, w.hx, lane);
   nfev = 1;
-  double e_sq = residual_sqnorm(w.e, w.x, w.hx, g.n, lane);
+  double e_sq = residual_sqnorm(w.wrk2, w.x, w.hx, g.n, lane);  // in shared memory, then published to e
+  for (int i = lane; i < g.n; i += 32) w.e[i] = w.wrk2[i];
+  __syncwarp();
   const double e0 = e_sq;
   if (!isfinite(e_sq)) stop = 7;
   nu = 20;  // forces a Jacobian on the first pass, lm_core.c:555
@@ -862,7 +894,7 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
 
 // ---- kernel: persistent warps pulling fits from a queue ----------------------------------------------
 template <int MODEL, bool DIF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) lm_fit_kernel(const LmLaunch L) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_kernel(const LmLaunch L) {
   using MD = Model<MODEL>;
   constexpr int M = MD::M;
   extern __shared__ double smem[];
@@ -874,24 +906,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lm_fit_kernel(const LmLaunc
   WarpMem<M> w;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + wid;
   w.x = nullptr;
+  double* ws = L.jstore + (size_t)gwarp * lm_ws_doubles(M, L.n_max, DIF);
+  w.e = ws;
+  w.t = ws + L.n_max;
+  w.tile = base; base += lm_tile_region(M, L.n_max, DIF);
+  double* J = nullptr;
   if (DIF) {
-    w.t = base; base += L.n_max / 2;
-    w.e = base; base += L.n_max;
-    w.hx = base; base += L.n_max; w.wrk = base; base += L.n_max; w.wrk2 = base; base += L.n_max;
+    w.hx = ws + L.n_max + L.n_max / 2;  // f(p)
+    w.wrk = w.hx + L.n_max;             // f(p + dp), finite-difference evaluations
+    w.wrk2 = w.tile;                    // trial residual / second central-difference evaluation
+    J = w.wrk + L.n_max;
   } else {
-    double* ws = L.jstore + (size_t)gwarp * lm_der_ws_doubles(L.n_max);
-    w.e = ws;
-    w.t = ws + L.n_max;
+    w.hx = w.tile;  // trial residual
     w.wrk = nullptr; w.wrk2 = nullptr;
   }
-  w.tile = base; base += lm_tile_region(M, L.n_max, DIF);
-  if (!DIF) w.hx = w.tile;  // trial residual: the tile region is idle outside the normal-equation build
   w.jtj = base; base += M * M;
   w.p = base; w.dp = base + 32; w.pdp = base + 64; w.jte = base + 96; w.diag = base + 128; w.pw = base + 160;
   w.xs = base + 192; w.scale = base + 224; base += 256;
   w.scratch = base;
 
-  double* J = DIF ? (L.jstore + (size_t)gwarp * M * L.n_max) : nullptr;
+
 
   constexpr bool SP = !DIF && M == 19;
   Accum<M> A;

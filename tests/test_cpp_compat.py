@@ -50,7 +50,8 @@ def test_cpp_caller_matches_oracle(tmp_path):
     xo, Po = oracle().ekf_update_curves_points(xo, Po, z, A, curve_col)
     rel = lambda a, bb: np.abs(a - bb).max() / np.abs(bb).max()
     assert rel(x, xo) < 1e-9 and rel(P, Po) < 1e-9
-    fit = oracle().fit_batch(STEREO19, DIF, b["p0"], b["meas"], b["off"], b["counts"], [1e-10, 1e-10, 1e-10, 1e-20, 1e-5])
+    # the reference writes opts[4] = LM_DIFF_DELTA*1E1 (curveFittingClass.cpp:662), which is NOT the double 1e-5
+    fit = oracle().fit_batch(STEREO19, DIF, b["p0"], b["meas"], b["off"], b["counts"], [1e-10, 1e-10, 1e-10, 1e-20, 1e-6 * 1e1])
     exp = fit["p"][0].copy()
     import ctypes as C
     oracle().lib.orc_stereo19_postfit(exp.ctypes.data_as(C.POINTER(C.c_double)))
