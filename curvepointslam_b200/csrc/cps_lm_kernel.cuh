@@ -67,7 +67,9 @@ struct Blk {
   static constexpr int NG = SP ? CPS_SP_NG : ((32 / R) >= 4 ? 4 : (32 / R));  // tiles processed at once
   static constexpr int TC = SP ? 12 : NB * 4;                    // tile columns
   static constexpr int LDT = SP ? TC : TC + 2;                   // even: rows stay 16-byte aligned
-  static constexpr int TILE_DOUBLES = kTileRows * LDT;
+  // +6 doubles (48 bytes) between tiles: lanes of neighbouring groups read the same columns of different tiles,
+  // the skew puts their 16-byte operand pairs on different banks
+  static constexpr int TILE_DOUBLES = kTileRows * LDT + 6;
   static constexpr int DOUBLES = NG * TILE_DOUBLES + NG * kTileRows / 2 /*row tags*/ + 32 /*item list, flags*/ +
                                  NG * kTileRows /*residuals of the tiles' rows*/;
 };
@@ -373,7 +375,11 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
 #pragma unroll
             for (int j = 0; j < M; ++j) row[j] = J[j * ld + r];
           } else if constexpr (SP) {
-            tag = MD::jac_row_compact(w.scratch, g, r, t_pre[gi], row);
+            double v[12];
+            tag = MD::jac_row_compact(w.scratch, g, r, t_pre[gi], v);
+#pragma unroll
+            for (int q = 0; q < 12; q += 2)  // 16-byte stores: 2-way instead of 8-way bank conflicts at this pitch
+              *reinterpret_cast<double2*>(row + q) = make_double2(v[q], v[q + 1]);
             etile[gi * kTileRows + lane] = e_pre[gi];  // residual of this row, for the J^T e chain
             tags[gi * kTileRows + lane] = tag;
           } else {
@@ -620,11 +626,15 @@ __device__ __forceinline__ int lu_solve(const WarpMem<M>& w, double mu, int lane
     if (lane == 0 && a[j * LD + j] == 0.0) a[j * LD + j] = DBL_EPSILON;
     __syncwarp();
     if (j != M - 1) {
+      // multipliers l_i = a_ij * (1/pivot) (one row per lane), then the trailing update a_ik -= l_i * u_k spread
+      // over a 4 x 8 grid of lanes: every element still receives exactly this one subtraction at step j
       const double inv = 1.0 / a[j * LD + j];
-      if (lane > j && lane < M) {
-        const double l = a[lane * LD + j] * inv;
-        a[lane * LD + j] = l;
-        for (int k = j + 1; k < M; ++k) a[lane * LD + k] -= l * a[j * LD + k];
+      if (lane > j && lane < M) a[lane * LD + j] = a[lane * LD + j] * inv;
+      __syncwarp();
+      const int li = lane >> 3, lk = lane & 7;
+      for (int k = j + 1 + lk; k < M; k += 8) {
+        const double u = a[j * LD + k];
+        for (int i = j + 1 + li; i < M; i += 4) a[i * LD + k] -= a[i * LD + j] * u;
       }
       __syncwarp();
     }
@@ -646,7 +656,13 @@ __device__ __forceinline__ int lu_solve(const WarpMem<M>& w, double mu, int lane
     double xi = 0.0;
     if (lane == i) {
       double sum = b;
-      for (int jj = i + 1; jj < M; ++jj) sum -= a[i * LD + jj];
+      int jj = i + 1;
+      for (; jj + 2 <= M; jj += 2) {
+        const double p0 = a[i * LD + jj], p1 = a[i * LD + jj + 1];
+        sum -= p0;
+        sum -= p1;
+      }
+      if (jj < M) sum -= a[i * LD + jj];
       xi = sum / a[i * LD + i];
       w.xs[i] = xi;
     }
