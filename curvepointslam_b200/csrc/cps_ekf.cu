@@ -517,6 +517,162 @@ __global__ void __launch_bounds__(256, 2) ekf_cov_dmma_kernel(double* __restrict
     }
 }
 
+// ---- kernel 5c: persistent, double-buffered version of 5b (M <= 36) -------------------------------------------
+// One block per SM walks a contiguous range of tile pairs (I-major order, so K_I stays resident while J advances).
+// The two P tiles and the Y_J tile of pair p+1 are copied global -> shared with cp.async (LDGSTS: no registers
+// held, 64 KB in flight per SM) while pair p is multiplied on the tensor cores and written back: loads, DMMA and
+// stores overlap instead of alternating.  Shared layout per stage: P_IJ [64][72] (pitch 72: the 16-byte fragment
+// reads of a quarter-warp hit distinct banks), P_JI [64][66] (pitch 66: the transposed 8-byte reads of a half-warp
+// hit distinct banks), Y_J [Mp][68]; K_I [Mp][68] single-buffered, reloaded when I changes.
+constexpr int PITCH_A = 72, PITCH_B = 66;
+constexpr int PIPE_MAX_M = 36;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void pair_from_index(long long p, int nt, int& I, int& J) {
+  // pairs in I-major order: row I holds nt - I pairs (J = I..nt-1)
+  int i = 0;
+  long long rem = p;
+  // closed form guess, then fix up
+  const double b = 2.0 * nt + 1.0;
+  i = (int)((b - sqrt(b * b - 8.0 * (double)p)) * 0.5);
+  if (i < 0) i = 0;
+  if (i > nt - 1) i = nt - 1;
+  while (i > 0 && (long long)i * nt - (long long)i * (i - 1) / 2 > p) --i;
+  while ((long long)(i + 1) * nt - (long long)(i + 1) * i / 2 <= p) ++i;
+  rem = p - ((long long)i * nt - (long long)i * (i - 1) / 2);
+  I = i;
+  J = i + (int)rem;
+}
+
+__global__ void __launch_bounds__(256, 1) ekf_cov_pipe_kernel(double* __restrict__ P, int ld, int M,
+                                                               const double* __restrict__ Kt,
+                                                               const double* __restrict__ Yt, int ldk, int nt,
+                                                               long long total_pairs) {
+  extern __shared__ double sh[];
+  const int Mp = (M + 3) & ~3;
+  const int stage_doubles = TILE * PITCH_A + TILE * PITCH_B + Mp * DSTRIDE;
+  double* Ks = sh + 2 * stage_doubles;
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int lr = l >> 2, lc = l & 3;
+  const int wr0 = (w >> 1) * 16, wc0 = (w & 1) * 32;
+
+  const long long per = (total_pairs + gridDim.x - 1) / gridDim.x;
+  const long long p_begin = (long long)blockIdx.x * per;
+  const long long p_end = min(total_pairs, p_begin + per);
+  if (p_begin >= p_end) return;
+
+  // zero the padding rows (r >= M) of K and both Y buffers once
+  for (int e = t; e < (Mp - M) * DSTRIDE; e += 256) {
+    Ks[M * DSTRIDE + e] = 0.0;
+    sh[0 * stage_doubles + TILE * PITCH_A + TILE * PITCH_B + M * DSTRIDE + e] = 0.0;
+    sh[1 * stage_doubles + TILE * PITCH_A + TILE * PITCH_B + M * DSTRIDE + e] = 0.0;
+  }
+
+  auto issue_pair = [&](int I, int J, int stage) {
+    double* pa = sh + stage * stage_doubles;
+    double* pb = pa + TILE * PITCH_A;
+    double* ys = pb + TILE * PITCH_B;
+    for (int c = t; c < TILE * 32; c += 256) {
+      const int row = c >> 5, cc = (c & 31) * 2;
+      cp_async16(pa + row * PITCH_A + cc, P + ((size_t)I * TILE + row) * ld + (size_t)J * TILE + cc);
+      if (I != J) cp_async16(pb + row * PITCH_B + cc, P + ((size_t)J * TILE + row) * ld + (size_t)I * TILE + cc);
+    }
+    for (int c = t; c < M * 32; c += 256) {
+      const int r = c >> 5, cc = (c & 31) * 2;
+      cp_async16(ys + r * DSTRIDE + cc, Yt + (size_t)r * ldk + (size_t)J * TILE + cc);
+    }
+  };
+  auto issue_k = [&](int I) {
+    for (int c = t; c < M * 32; c += 256) {
+      const int r = c >> 5, cc = (c & 31) * 2;
+      cp_async16(Ks + r * DSTRIDE + cc, Kt + (size_t)r * ldk + (size_t)I * TILE + cc);
+    }
+  };
+
+  int I, J;
+  pair_from_index(p_begin, nt, I, J);
+  int k_loaded = I;
+  issue_k(I);
+  issue_pair(I, J, 0);
+  cp_async_commit();
+
+  for (long long p = p_begin; p < p_end; ++p) {
+    const int stage = (int)((p - p_begin) & 1);
+    int In = I, Jn = J + 1;
+    if (Jn >= nt) { In = I + 1; Jn = In; }
+    const bool has_next = (p + 1 < p_end);
+    if (has_next) issue_pair(In, Jn, stage ^ 1);
+    cp_async_commit();
+    if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    if (k_loaded != I) {  // first pair of a new tile row: bring K_I in (rare: once per row)
+      issue_k(I);
+      cp_async_commit();
+      cp_async_wait<0>();
+      k_loaded = I;
+      __syncthreads();
+    }
+    const double* pa = sh + stage * stage_doubles;
+    const double* pb = pa + TILE * PITCH_A;
+    const double* ys = pb + TILE * PITCH_B;
+    const bool diag = (I == J);
+
+    double acc[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    for (int ks = 0; ks < Mp; ks += 4) {
+      double a[2], b[4];
+      const double* kr = Ks + (ks + lc) * DSTRIDE + wr0 + lr;
+      const double* yr = ys + (ks + lc) * DSTRIDE + wc0 + lr;
+      a[0] = kr[0];
+      a[1] = kr[8];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = yr[8 * ni];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                       : "d"(a[mi]), "d"(b[ni]));
+    }
+    const size_t gi0 = (size_t)I * TILE + wr0 + lr, gj0 = (size_t)J * TILE + wc0 + 2 * lc;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int ri = wr0 + lr + 8 * mi, cj = wc0 + 2 * lc + 8 * ni;  // position inside the 64x64 tile
+        const double2 pij = *reinterpret_cast<const double2*>(pa + ri * PITCH_A + cj);
+        double q0, q1;
+        if (!diag) { q0 = pb[cj * PITCH_B + ri]; q1 = pb[(cj + 1) * PITCH_B + ri]; }
+        else { q0 = pa[cj * PITCH_A + ri]; q1 = pa[(cj + 1) * PITCH_A + ri]; }
+        const double o0 = 0.5 * (pij.x + q0) - acc[mi][ni][0];
+        const double o1 = 0.5 * (pij.y + q1) - acc[mi][ni][1];
+        const size_t gi = gi0 + 8 * mi, gj = gj0 + 8 * ni;
+        if (!diag) {
+          *reinterpret_cast<double2*>(P + gi * ld + gj) = make_double2(o0, o1);
+          P[gj * ld + gi] = o0;
+          P[(gj + 1) * ld + gi] = o1;
+        } else {
+          if (gj >= gi) { P[gi * ld + gj] = o0; if (gj != gi) P[gj * ld + gi] = o0; }
+          if (gj + 1 >= gi) { P[gi * ld + gj + 1] = o1; if (gj + 1 != gi) P[(gj + 1) * ld + gi] = o1; }
+        }
+      }
+    __syncthreads();  // everyone is done with this stage before the prefetch of pair p+2 overwrites it
+    I = In;
+    J = Jn;
+  }
+}
+
 // ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
 // Pri <- F Pri, mirrored; Prr <- F Prr F^T + Q; x[0..5] += x[6..11] DT.  F = I + DT*[0 I6; 0 0].
 __global__ void __launch_bounds__(256) ekf_predict_cross_kernel(double* __restrict__ P, int ld, int N) {
@@ -664,6 +820,9 @@ extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
                                 (2 * MAXM * MAXM + MAXM + 16 * MAXM) * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * MAXM * TILE * (int)sizeof(double)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (2 * (TILE * PITCH_A + TILE * PITCH_B + PIPE_MAX_M * DSTRIDE) + PIPE_MAX_M * DSTRIDE) *
+                                    (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * MAXM * DSTRIDE * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -838,8 +997,14 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
                                                                                         h->d_Yt, h->cap, nt);
   } else {
     const int Mp = (M + 3) & ~3;
-    ekf_cov_dmma_kernel<<<(unsigned)pairs, 256, 2 * (size_t)Mp * DSTRIDE * sizeof(double), st>>>(
-        h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap);
+    static const bool no_pipe = std::getenv("CPS_EKF_COV_NO_PIPE") != nullptr;
+    if (Mp <= PIPE_MAX_M && !no_pipe && pairs >= 2LL * h->sm_count) {
+      const size_t shb = (size_t)(2 * (TILE * PITCH_A + TILE * PITCH_B + Mp * DSTRIDE) + Mp * DSTRIDE) * sizeof(double);
+      ekf_cov_pipe_kernel<<<h->sm_count, 256, shb, st>>>(h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+    } else {
+      ekf_cov_dmma_kernel<<<(unsigned)pairs, 256, 2 * (size_t)Mp * DSTRIDE * sizeof(double), st>>>(
+          h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap);
+    }
   }
   CPS_CUDA(cudaEventRecord(h->ev[3], st));
   CPS_CUDA(cudaEventRecord(h->ev[1], st));

@@ -1,5 +1,4 @@
 cd $GRAFT_REPO_ROOT
-SMALL="python bench.py --fits 16384 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
-$SMALL > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:lm_fit_kernel -s 3 -c 1 -o gpurun_out/prof_lm_der_v2 $SMALL > gpurun_out/ncu2.log 2>&1
-tail -2 gpurun_out/ncu2.log | cut -c1-200
+python scripts/ekfprof.py > gpurun_out/ekfprof_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:ekf_cov_dmma_kernel -s 1 -c 1 -o gpurun_out/prof_ekf_cov_dmma_r1 python scripts/ekfprof.py > gpurun_out/ncu3.log 2>&1
+tail -2 gpurun_out/ncu3.log | cut -c1-300

@@ -1,13 +1,15 @@
 cd $GRAFT_REPO_ROOT
 make -s -C oracle 2>&1 | tail -2
-python -m pytest tests/test_lm_gpu.py -x -q 2>&1 | tail -4
-python bench.py --fits 65536 --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/b_lu.json 2>gpurun_out/b_lu.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/b_lu.json').read().strip().splitlines()[-1])
-print('der value %.4g e2e %.4g kernel_ms %.3f frac %.4f'%(d['value'],d['e2e']['value'],d['roofline']['kernel_ms'],d['roofline']['frac']))
+python -m pytest tests/test_ekf_gpu.py -x -q 2>&1 | tail -5
+python - <<'PY'
+from curvepointslam_b200 import bench_extras as b
+for L in (1000, 5000, 20000):
+    r = b.ekf_update_bench(0, L)
+    print('PIPE', L, 'update_ms %.4f cov_ms %.4f frac %.3f' % (r['update_ms'], r['cov_kernel_ms'], r['roofline']['frac']))
 PY
-python bench.py --variant dif --fits 32768 --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/b_lu2.json 2>gpurun_out/b_lu2.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/b_lu2.json').read().strip().splitlines()[-1])
-print('dif value %.4g e2e %.4g kernel_ms %.3f frac %.4f'%(d['value'],d['e2e']['value'],d['roofline']['kernel_ms'],d['roofline']['frac']))
+CPS_EKF_COV_NO_PIPE=1 python - <<'PY'
+from curvepointslam_b200 import bench_extras as b
+for L in (5000, 20000):
+    r = b.ekf_update_bench(0, L)
+    print('DMMA-nopipe', L, 'update_ms %.4f cov_ms %.4f frac %.3f' % (r['update_ms'], r['cov_kernel_ms'], r['roofline']['frac']))
 PY
