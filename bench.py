@@ -339,7 +339,7 @@ def main():
                                 "seconds": dt, "gpu_bit_identical_on_sample": same}
     if not args.no_extras:
         try:
-            from curvepointslam_b200 import bench_extras
+            import bench_extras
             line["extras"] = bench_extras.run(local)
         except Exception as ex:  # extras never take the headline down
             line["extras"] = {"error": repr(ex)}

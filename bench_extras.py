@@ -1,7 +1,8 @@
 """Secondary measurements bench.py attaches under "extras": EKF update latency at 1k / 5k / 20k landmarks
 (BASELINE.json configs[2]) and the Mahalanobis gate at 10k measurements x 20k landmarks (configs[3]), each with
 its roofline fraction and a bounded CPU baseline.  The CPU legs import the oracle (test infrastructure) only
-as the thing being timed beside the GPU, exactly like bench.py's cpu_baseline."""
+as the thing being timed beside the GPU, exactly like bench.py's cpu_baseline (this file is part of bench.py,
+not of the product package)."""
 from __future__ import annotations
 
 import json
@@ -11,9 +12,9 @@ import time
 
 import numpy as np
 
-from . import ekf
+from curvepointslam_b200 import ekf
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
 def _peaks():
@@ -80,7 +81,7 @@ def ekf_cpu_baseline(L: int = 1000):
 def gate_bench(device: int, L: int = 20000, nz: int = 10000, reps: int = 5, seed: int = 3):
     import ctypes as C
 
-    from . import _lib
+    from curvepointslam_b200 import _lib
     x, G, ci, pi = ekf.make_synthetic_ekf(L, d=3, seed=seed)
     N = x.size
     kf = ekf.KalmanFilter(capacity=N, device=device)

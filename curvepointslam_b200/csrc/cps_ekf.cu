@@ -770,6 +770,196 @@ __global__ void __launch_bounds__(256) ekf_lowrank_kernel(double* __restrict__ P
   }
 }
 
+// ---- state augmentation ("next" rows): in place on the device-resident P ------------------------------------
+// The reference re-allocates and copies all of P (O(N^2)) for every added landmark (kalmanClass.cpp:362-389,
+// :517-535); here the new rows/columns are appended inside the capacity: O(N) work.
+constexpr double VREAL = 1.0;
+
+__global__ void ekf_first_states_kernel(double* __restrict__ x, double* __restrict__ P, int ld, const double* z19) {
+  // AddFirstStates, kalmanClass.cpp:275-311 (the 28 x 28 block was zeroed by the caller)
+  const int i = threadIdx.x;
+  if (i >= 28) return;
+  const double pose_diag[12] = {0.0000001, 0.0000001, 0.1, 0.1, 0.1, 0.0000001, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1};
+  double xv = 0.0;
+  if (i >= 12) { xv = z19[i - 12]; P[(size_t)i * ld + i] = MEAS_COV * MEAS_COV; }
+  else P[(size_t)i * ld + i] = pose_diag[i];
+  if (i == 2) xv = z19[16];
+  if (i == 3) xv = z19[17];
+  if (i == 4) xv = z19[18];
+  if (i == 6) xv = VREAL;
+  x[i] = xv;
+}
+
+// inverse of a 4x4 by Gauss-Jordan with partial pivoting (the reference's cvInvert(A, Ainv, CV_SVD) of a
+// well-conditioned split matrix)
+__device__ void inv4(const double* A, double* Ai) {
+  double m[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { m[i][j] = A[4 * i + j]; m[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(m[r][c]) > fabs(m[p][c])) p = r;
+    for (int j = 0; j < 8; ++j) { const double t = m[c][j]; m[c][j] = m[p][j]; m[p][j] = t; }
+    const double inv = 1.0 / m[c][c];
+    for (int j = 0; j < 8; ++j) m[c][j] *= inv;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const double f = m[r][c];
+        for (int j = 0; j < 8; ++j) m[r][j] -= f * m[c][j];
+      }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) Ai[4 * i + j] = m[i][4 + j];
+}
+
+// AddNewCurve, kalmanClass.cpp:314-499.  in = z (8) | A (16).  One block: thread 0 builds the small matrices
+// in shared memory, then all threads fill the new rows/columns: P[N+i][j] = (Gx P[0:12, j]) mirrored.
+__global__ void __launch_bounds__(256) ekf_add_curve_kernel(double* __restrict__ x, double* __restrict__ P, int ld,
+                                                            int N, const double* __restrict__ in) {
+  __shared__ double Gx[8][12], Gz[8][8], xnew[8], Prr[12][12];
+  const int t = threadIdx.x;
+  {
+    if (t < 144) Prr[t / 12][t % 12] = P[(size_t)(t / 12) * ld + t % 12];
+    if (t == 0) {
+      const double* z = in;
+      const double* A = in + 8;
+      const double Tx = x[0], Ty = x[1], psi = x[5];
+      const double c = cos(psi), s_ = sin(psi);
+      double Ainv[16], rz[8], rdz[8], a1[4];
+      inv4(A, Ainv);
+      // Rot = [[c I, -s I], [s I, c I]] (the transpose of the update's Rot, :333-343); Rotderiv likewise
+      for (int i = 0; i < 4; ++i) {
+        rz[i] = (c * z[i] - s_ * z[i + 4]) + Tx;
+        rz[i + 4] = (s_ * z[i] + c * z[i + 4]) + Ty;
+        rdz[i] = -s_ * z[i] - c * z[i + 4];
+        rdz[i + 4] = c * z[i] - s_ * z[i + 4];
+      }
+      for (int i = 0; i < 4; ++i) {
+        double sx = 0.0, sy = 0.0, dx = 0.0, dy = 0.0, so = 0.0;
+        for (int j = 0; j < 4; ++j) {
+          sx += Ainv[4 * i + j] * rz[j];
+          sy += Ainv[4 * i + j] * rz[j + 4];
+          dx += Ainv[4 * i + j] * rdz[j];
+          dy += Ainv[4 * i + j] * rdz[j + 4];
+          so += Ainv[4 * i + j];
+        }
+        xnew[i] = sx; xnew[i + 4] = sy; a1[i] = so;
+        for (int j = 0; j < 12; ++j) { Gx[i][j] = 0.0; Gx[i + 4][j] = 0.0; }
+        Gx[i][0] = so; Gx[i + 4][1] = so; Gx[i][5] = dx; Gx[i + 4][5] = dy;
+        for (int j = 0; j < 4; ++j) {  // Gz = Hinv Rot
+          Gz[i][j] = Ainv[4 * i + j] * c;      Gz[i][j + 4] = -Ainv[4 * i + j] * s_;
+          Gz[i + 4][j] = Ainv[4 * i + j] * s_; Gz[i + 4][j + 4] = Ainv[4 * i + j] * c;
+        }
+      }
+      (void)a1;
+    }
+    __syncthreads();
+  }
+  // cross blocks: new rows x all existing columns j in [0, N): Gx * P[0:12, j]  (for j < 12 the reference uses
+  // Gx * Prr^T, i.e. column j of Prr^T = row j of Prr)
+  for (int j = blockIdx.x * blockDim.x + t; j < N; j += gridDim.x * blockDim.x) {
+    double col[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) col[k] = (j < 12) ? Prr[j][k] : P[(size_t)k * ld + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double s_ = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) s_ += Gx[i][k] * col[k];
+      P[(size_t)(N + i) * ld + j] = s_;
+      P[(size_t)j * ld + N + i] = s_;
+    }
+  }
+  if (blockIdx.x == 0 && t < 64) {  // PN1N1 = Gx Prr Gx^T + Gz (MEAS_COV I) Gz^T   (R1 is not squared, :95-98)
+    const int i = t / 8, j = t % 8;
+    double acc = 0.0;
+    for (int a = 0; a < 12; ++a) {
+      double inner = 0.0;
+      for (int b = 0; b < 12; ++b) inner += Prr[a][b] * Gx[j][b];
+      acc += Gx[i][a] * inner;
+    }
+    double gz = 0.0;
+    for (int a = 0; a < 8; ++a) gz += Gz[i][a] * (MEAS_COV * Gz[j][a]);
+    P[(size_t)(N + i) * ld + N + j] = acc + gz;
+    if (t < 8) x[N + t] = xnew[t];
+  }
+}
+
+// AddNewPoints, kalmanClass.cpp:502-666: grid.y = point, blocks along x cover the existing columns
+__global__ void __launch_bounds__(256) ekf_add_points_kernel(double* __restrict__ x, double* __restrict__ P, int ld,
+                                                             int N, const double* __restrict__ meas, int n_pts) {
+  __shared__ double Gx[3][12], Reb[9], Prr[12][12], xnew[3];
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int o = N + 3 * n;
+  if (t < 144) Prr[t / 12][t % 12] = P[(size_t)(t / 12) * ld + t % 12];
+  if (t == 0) {
+    const double phi = x[3], theta = x[4], psi = x[5];
+    double Rd[3][9];
+    // generate_Reb common.h:189-201 and get_Reb_derivs kalmanClass.cpp:1230-1262
+    Reb[0] = cos(psi) * cos(theta);
+    Reb[1] = cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+    Reb[2] = cos(psi) * sin(theta) * cos(phi) - sin(psi) * sin(phi);
+    Reb[3] = sin(psi) * cos(theta);
+    Reb[4] = sin(psi) * sin(theta) * sin(phi) + cos(psi) * cos(phi);
+    Reb[5] = sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+    Reb[6] = -sin(theta);
+    Reb[7] = cos(theta) * sin(phi);
+    Reb[8] = cos(theta) * cos(phi);
+    double* Rp = Rd[0]; double* Rt = Rd[1]; double* Rs = Rd[2];
+    Rp[0] = 0.0; Rp[1] = cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi); Rp[2] = -cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+    Rp[3] = 0.0; Rp[4] = sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi); Rp[5] = -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi);
+    Rp[6] = 0.0; Rp[7] = cos(theta) * cos(phi); Rp[8] = -cos(theta) * sin(phi);
+    Rt[0] = -cos(psi) * sin(theta); Rt[1] = cos(psi) * cos(theta) * sin(phi); Rt[2] = cos(psi) * cos(theta) * cos(phi);
+    Rt[3] = -sin(psi) * sin(theta); Rt[4] = sin(psi) * cos(theta) * sin(phi); Rt[5] = sin(psi) * cos(theta) * cos(phi);
+    Rt[6] = -cos(theta); Rt[7] = -sin(theta) * sin(phi); Rt[8] = -sin(theta) * cos(phi);
+    Rs[0] = -sin(psi) * cos(theta); Rs[1] = -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi); Rs[2] = -sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+    Rs[3] = cos(psi) * cos(theta); Rs[4] = cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi); Rs[5] = cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi);
+    Rs[6] = 0.0; Rs[7] = 0.0; Rs[8] = 0.0;
+    const double* xb = meas + 3 * n;
+    for (int i = 0; i < 3; ++i) {
+      double s_ = 0.0;
+      for (int k = 0; k < 3; ++k) s_ += Reb[3 * i + k] * xb[k];
+      xnew[i] = s_ + x[i];
+      for (int j = 0; j < 12; ++j) Gx[i][j] = 0.0;
+      Gx[i][i] = 1.0;
+      for (int j = 0; j < 3; ++j) {
+        double d = 0.0;
+        for (int k = 0; k < 3; ++k) d += Rd[j][3 * i + k] * xb[k];
+        Gx[i][3 + j] = d;
+      }
+    }
+  }
+  __syncthreads();
+  // cross block with the states that existed before the call: j < 12 uses Gx * Prr (column j of Prr)
+  for (int j = blockIdx.x * blockDim.x + t; j < N; j += gridDim.x * blockDim.x) {
+    double col[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) col[k] = (j < 12) ? Prr[k][j] : P[(size_t)k * ld + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double s_ = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) s_ += Gx[i][k] * col[k];
+      P[(size_t)(o + i) * ld + j] = s_;
+      P[(size_t)j * ld + o + i] = s_;
+    }
+  }
+  if (blockIdx.x == 0 && t < 9) {  // PN1N1 = Gx Prr Gx^T + Reb (PT_MEAS_COV I) Reb^T  (R_pts is not squared, :99-102)
+    const int i = t / 3, j = t % 3;
+    double acc = 0.0;
+    for (int a = 0; a < 12; ++a) {
+      double inner = 0.0;
+      for (int b = 0; b < 12; ++b) inner += Prr[a][b] * Gx[j][b];
+      acc += Gx[i][a] * inner;
+    }
+    double gz = 0.0;
+    for (int a = 0; a < 3; ++a) gz += Reb[3 * i + a] * (PT_MEAS_COV * Reb[3 * j + a]);
+    P[(size_t)(o + i) * ld + o + j] = acc + gz;
+    if (t < 3) x[o + t] = xnew[t];
+  }
+}
+
 int round_up(int v, int q) { return (v + q - 1) / q * q; }
 
 }  // namespace
@@ -1035,6 +1225,80 @@ extern "C" int cps_ekf_last_timing(cps_ekf* h, float* total_ms, float* cov_kerne
   CPS_CUDA(cudaEventSynchronize(h->ev[1]));
   if (total_ms) CPS_CUDA(cudaEventElapsedTime(total_ms, h->ev[0], h->ev[1]));
   if (cov_kernel_ms) CPS_CUDA(cudaEventElapsedTime(cov_kernel_ms, h->ev[2], h->ev[3]));
+  return CPS_OK;
+}
+
+
+// ---- state augmentation ------------------------------------------------------------------------------------
+extern "C" int cps_ekf_add_first_states(cps_ekf* h, const double* z19) {
+  if (!h || !z19 || h->cap < 28) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(h->h_pinned, z19, 19 * sizeof(double));
+  const size_t cap = (size_t)h->cap;
+  CPS_CUDA(cudaMemsetAsync(h->d_P, 0, cap * cap * sizeof(double), h->stream));  // cvSetZero(P), cvSetZero(x)
+  CPS_CUDA(cudaMemsetAsync(h->d_x, 0, cap * sizeof(double), h->stream));
+  CPS_CUDA(cudaMemcpyAsync(h->d_small + SM_IN, h->h_pinned, 19 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  ekf_first_states_kernel<<<1, 32, 0, h->stream>>>(h->d_x, h->d_P, h->cap, h->d_small + SM_IN);
+  CPS_CUDA(cudaGetLastError());
+  h->launches++;
+  h->N = 28;
+  h->curve_inds = {CPS_ROBOT_STATE_SIZE, CPS_ROBOT_STATE_SIZE + 8};  // kalmanClass.cpp:307-309
+  h->point_inds.clear();
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_add_new_curve(cps_ekf* h, const double* z8, const double* A) {
+  if (!h || !z8 || !A || h->N < CPS_ROBOT_STATE_SIZE) return CPS_ERR_INVALID;
+  if (h->N + 8 > h->cap) {
+    cps::set_last_error("state capacity exhausted (cps_ekf_create capacity)");
+    return CPS_ERR_NOMEM;
+  }
+  CPS_CUDA(cudaSetDevice(h->device));
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  double* hp = (double*)h->h_pinned;
+  std::memcpy(hp, z8, 8 * sizeof(double));
+  std::memcpy(hp + 8, A, 16 * sizeof(double));
+  CPS_CUDA(cudaMemcpyAsync(h->d_small + SM_IN, hp, 24 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // reads touch rows < 12 and columns < N, writes touch rows >= N or columns >= N: blocks are independent
+  ekf_add_curve_kernel<<<std::max(1, std::min(64, (h->N + 255) / 256)), 256, 0, h->stream>>>(h->d_x, h->d_P, h->cap, h->N,
+                                                                                     h->d_small + SM_IN);
+  CPS_CUDA(cudaGetLastError());
+  h->launches++;
+  h->curve_inds.push_back(h->N);
+  h->N += 8;
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_add_new_points(cps_ekf* h, const double* meas, int n_pts) {
+  if (!h || n_pts < 0 || (n_pts && !meas) || h->N < CPS_ROBOT_STATE_SIZE) return CPS_ERR_INVALID;
+  if (n_pts == 0) return CPS_OK;
+  if (h->N + 3 * n_pts > h->cap) {
+    cps::set_last_error("state capacity exhausted (cps_ekf_create capacity)");
+    return CPS_ERR_NOMEM;
+  }
+  CPS_CUDA(cudaSetDevice(h->device));
+  double* d_meas = nullptr;
+  CPS_CUDA(cudaMalloc(&d_meas, sizeof(double) * 3 * (size_t)n_pts));
+  CPS_CUDA(cudaMemcpyAsync(d_meas, meas, sizeof(double) * 3 * (size_t)n_pts, cudaMemcpyHostToDevice, h->stream));
+  // every point reads only the pose rows/columns of the covariance as it was before the call and writes its own
+  // new rows/columns (the reference gives points added together no cross-covariance), except the mirrored pose
+  // columns P[j][o+i], j < 12, which no other point reads: one launch, grid.y = point
+  ekf_add_points_kernel<<<dim3(std::max(1, std::min(32, (h->N + 255) / 256)), n_pts), 256, 0, h->stream>>>(
+      h->d_x, h->d_P, h->cap, h->N, d_meas, n_pts);
+  CPS_CUDA(cudaGetLastError());
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_meas);
+  h->launches++;
+  for (int n = 0; n < n_pts; ++n) h->point_inds.push_back(h->N + 3 * n);
+  h->N += 3 * n_pts;
+  return CPS_OK;
+}
+
+extern "C" int cps_ekf_get_index_tables(cps_ekf* h, int* curve_inds, int* point_inds) {
+  if (!h) return CPS_ERR_INVALID;
+  if (curve_inds) std::memcpy(curve_inds, h->curve_inds.data(), sizeof(int) * h->curve_inds.size());
+  if (point_inds) std::memcpy(point_inds, h->point_inds.data(), sizeof(int) * h->point_inds.size());
   return CPS_OK;
 }
 

@@ -40,6 +40,10 @@ def _bind():
     L.cps_ekf_get_cov.argtypes = [vp, vp]
     L.cps_ekf_get_cov_block.argtypes = [vp, ci, ci, ci, ci, vp]
     L.cps_ekf_predict.argtypes = [vp]
+    L.cps_ekf_add_first_states.argtypes = [vp, vp]
+    L.cps_ekf_add_new_curve.argtypes = [vp, vp, vp]
+    L.cps_ekf_add_new_points.argtypes = [vp, vp, ci]
+    L.cps_ekf_get_index_tables.argtypes = [vp, vp, vp]
     L.cps_ekf_update_curves_points.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci]
     L.cps_ekf_update_points.argtypes = [vp, vp, vp, ci]
     L.cps_ekf_last_timing.argtypes = [vp, vp, vp, vp]
@@ -139,6 +143,30 @@ class KalmanFilter:
         pm = np.ascontiguousarray(point_meas, dtype=np.float64).reshape(-1)
         pn = np.ascontiguousarray(point_nums, dtype=np.int32)
         _lib.check(self._L.cps_ekf_update_points(self._h, _p(pm), _p(pn), n_pts), "cps_ekf_update_points")
+
+    # ---- state augmentation (kalmanClass.cpp:275-666), in place on the device ---------------------------
+    def _refresh_tables(self):
+        nc, npnt = C.c_int(), C.c_int()
+        self._L.cps_ekf_dims(self._h, None, C.byref(nc), C.byref(npnt))
+        ci, pi = np.zeros(max(nc.value, 1), dtype=np.int32), np.zeros(max(npnt.value, 1), dtype=np.int32)
+        self._L.cps_ekf_get_index_tables(self._h, _p(ci), _p(pi))
+        self.curve_inds, self.point_inds = list(map(int, ci[:nc.value])), list(map(int, pi[:npnt.value]))
+
+    def AddFirstStates(self, measurement):
+        z = np.ascontiguousarray(measurement, dtype=np.float64).reshape(-1)
+        _lib.check(self._L.cps_ekf_add_first_states(self._h, _p(z)), "cps_ekf_add_first_states")
+        self._refresh_tables()
+
+    def AddNewCurve(self, z, A):
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1)
+        Aa = np.ascontiguousarray(A, dtype=np.float64).reshape(-1)
+        _lib.check(self._L.cps_ekf_add_new_curve(self._h, _p(z), _p(Aa)), "cps_ekf_add_new_curve")
+        self._refresh_tables()
+
+    def AddNewPoints(self, measurements, n_pts):
+        m = np.ascontiguousarray(measurements, dtype=np.float64).reshape(-1)
+        _lib.check(self._L.cps_ekf_add_new_points(self._h, _p(m), int(n_pts)), "cps_ekf_add_new_points")
+        self._refresh_tables()
 
     def GetSplitMatrices(self, t):
         A1, A2 = np.zeros((4, 4)), np.zeros((4, 4))

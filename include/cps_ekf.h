@@ -52,6 +52,20 @@ int cps_ekf_get_cov_block(cps_ekf *h, int r0, int c0, int nr, int nc, double *ou
 
 int cps_ekf_predict(cps_ekf *h);
 
+/* State augmentation, in place inside the capacity (the reference re-allocates and copies P per call):
+ *   cps_ekf_add_first_states <- KalmanFilter::AddFirstStates kalmanClass.cpp:275-311  (z19 = 16 control-point
+ *                               values of the first two curves, then height, phi, theta; N becomes 28)
+ *   cps_ekf_add_new_curve    <- KalmanFilter::AddNewCurve    kalmanClass.cpp:314-499  (z8 body-frame control points,
+ *                               A the 4x4 split matrix; appends 8 states, curve_inds grows by one)
+ *   cps_ekf_add_new_points   <- KalmanFilter::AddNewPoints   kalmanClass.cpp:502-666  (3*n_pts body-frame xyz;
+ *                               appends 3 states per point)
+ * CPS_ERR_NOMEM when the capacity given to cps_ekf_create is exhausted. */
+int cps_ekf_add_first_states(cps_ekf *h, const double *z19);
+int cps_ekf_add_new_curve(cps_ekf *h, const double *z8, const double *A);
+int cps_ekf_add_new_points(cps_ekf *h, const double *meas, int n_pts);
+/* copies of the reference's curve_inds / point_inds vectors (sizes from cps_ekf_dims) */
+int cps_ekf_get_index_tables(cps_ekf *h, int *curve_inds, int *point_inds);
+
 /* z: 8n+3 values = per curve [x0..x3, y0..y3] in the body frame, then height, phi, theta (main.cpp:959-961);
  * A: n row-major 4x4 split matrices; curve_num[k] indexes curve_inds; point_meas: 3*n_pts body-frame xyz;
  * point_nums[k] indexes point_inds. */

@@ -440,3 +440,195 @@ void orc_ekf_predict(double *x, double *P, int N)
   free(Pri);
   free(Pri2);
 }
+
+/* ---- state augmentation ("next" rows of the scope table): AddFirstStates (kalmanClass.cpp:275-311),
+ * AddNewCurve (:314-499), AddNewPoints (:502-666).  The reference re-allocates and copies all of P per call;
+ * here x and P are caller-owned with capacity for the grown state, row-major with leading dimension `ld`.
+ * Reference quirks kept: R1 = MEAS_COV*I and R_pts = PT_MEAS_COV*I are NOT squared here (constructor :91-98,
+ * unlike the update's R); points added in one call get no cross-covariance among themselves (the cross block is
+ * built from the covariance as it was before the call); AddNewCurve uses Gx*Prr^T, AddNewPoints Gx*Prr. */
+#define VREAL 1.0
+
+void orc_ekf_add_first_states(double *x, double *P, int ld, const double *z19)
+{
+  static const double pose_diag[12] = {0.0000001, 0.0000001, 0.1, 0.1, 0.1, 0.0000001, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1};
+  int i, j;
+  for (i = 0; i < 28; ++i) {
+    x[i] = 0.0;
+    for (j = 0; j < 28; ++j) P[(size_t)i * ld + j] = 0.0;
+  }
+  for (i = 0; i < 16; ++i) {
+    P[(size_t)(i + 12) * ld + i + 12] = pow(MEAS_COV, 2.0);
+    x[i + 12] = z19[i];
+  }
+  x[2] = z19[16];
+  x[3] = z19[17];
+  x[4] = z19[18];
+  x[6] = VREAL;
+  for (i = 0; i < 12; ++i) P[(size_t)i * ld + i] = pose_diag[i];
+}
+
+/* returns the new state dimension N + 8 */
+int orc_ekf_add_new_curve(double *x, double *P, int ld, int N, const double *z8, const double *A)
+{
+  const double Tx = x[0], Ty = x[1], psi = x[5];
+  double Rot[64], Rotd[64], Ainv[16], Hinv[64], t81[8], t81b[8], xnew[8], ones[4] = {1, 1, 1, 1}, a1[4];
+  double Gz[64], Gx[8 * 12], Prr[144], PrrT[144], GxT[12 * 8], tmp[12 * 8], PN1N1[64], GzT[64], R1[64], t8[64], t8b[64];
+  double PN1r[8 * 12];
+  int i, j, k;
+  memset(Rot, 0, sizeof Rot);
+  memset(Rotd, 0, sizeof Rotd);
+  for (i = 0; i < 4; ++i) {
+    Rot[8 * i + i] = cos(psi);
+    Rot[8 * (i + 4) + i + 4] = cos(psi);
+    Rot[8 * (i + 4) + i] = sin(psi);
+    Rot[8 * i + i + 4] = -sin(psi);
+    Rotd[8 * i + i] = -sin(psi);
+    Rotd[8 * (i + 4) + i + 4] = -sin(psi);
+    Rotd[8 * (i + 4) + i] = cos(psi);
+    Rotd[8 * i + i + 4] = -cos(psi);
+  }
+  orc_pinv_svd(A, Ainv, 4);
+  memset(Hinv, 0, sizeof Hinv);
+  for (i = 0; i < 4; ++i)
+    for (j = 0; j < 4; ++j) {
+      Hinv[8 * i + j] = Ainv[4 * i + j];
+      Hinv[8 * (i + 4) + j + 4] = Ainv[4 * i + j];
+    }
+  gemm(Rot, z8, t81, 8, 8, 1);
+  for (i = 0; i < 4; ++i) t81[i] += Tx;
+  for (i = 4; i < 8; ++i) t81[i] += Ty;
+  gemm(Hinv, t81, xnew, 8, 8, 1);
+  gemm(Ainv, ones, a1, 4, 4, 1);
+  gemm(Hinv, Rot, Gz, 8, 8, 8);
+  gemm(Rotd, z8, t81, 8, 8, 1);
+  gemm(Hinv, t81, t81b, 8, 8, 1);
+  memset(Gx, 0, sizeof Gx);
+  for (i = 0; i < 4; ++i) {
+    Gx[12 * i + 0] = a1[i];
+    Gx[12 * (i + 4) + 1] = a1[i];
+    Gx[12 * i + 5] = t81b[i];
+    Gx[12 * (i + 4) + 5] = t81b[i + 4];
+  }
+  for (i = 0; i < 12; ++i)
+    for (j = 0; j < 12; ++j) Prr[12 * i + j] = P[(size_t)i * ld + j];
+  transpose(Gx, GxT, 8, 12);
+  gemm(Prr, GxT, tmp, 12, 12, 8);
+  gemm(Gx, tmp, PN1N1, 8, 12, 8);
+  memset(R1, 0, sizeof R1);
+  for (i = 0; i < 8; ++i) R1[9 * i] = MEAS_COV;
+  transpose(Gz, GzT, 8, 8);
+  gemm(R1, GzT, t8, 8, 8, 8);
+  gemm(Gz, t8, t8b, 8, 8, 8);
+  for (i = 0; i < 64; ++i) PN1N1[i] += t8b[i];
+  transpose(Prr, PrrT, 12, 12);
+  gemm(Gx, PrrT, PN1r, 8, 12, 12);
+  for (i = 0; i < 8; ++i) {
+    x[N + i] = xnew[i];
+    for (j = 0; j < 8; ++j) P[(size_t)(N + i) * ld + N + j] = PN1N1[8 * i + j];
+    for (j = 12; j < N; ++j) { /* PN1i = Gx * Pri */
+      double s = 0.0;
+      for (k = 0; k < 12; ++k) s += Gx[12 * i + k] * P[(size_t)k * ld + j];
+      P[(size_t)(N + i) * ld + j] = s;
+      P[(size_t)j * ld + N + i] = s;
+    }
+    for (j = 0; j < 12; ++j) {
+      P[(size_t)(N + i) * ld + j] = PN1r[12 * i + j];
+      P[(size_t)j * ld + N + i] = PN1r[12 * i + j];
+    }
+  }
+  return N + 8;
+}
+
+static void reb(double phi, double theta, double psi, double *R)
+{ /* generate_Reb, common.h:189-201 */
+  R[0] = cos(psi) * cos(theta);
+  R[1] = cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi);
+  R[2] = cos(psi) * sin(theta) * cos(phi) - sin(psi) * sin(phi);
+  R[3] = sin(psi) * cos(theta);
+  R[4] = sin(psi) * sin(theta) * sin(phi) + cos(psi) * cos(phi);
+  R[5] = sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi);
+  R[6] = -sin(theta);
+  R[7] = cos(theta) * sin(phi);
+  R[8] = cos(theta) * cos(phi);
+}
+
+static void reb_derivs(double phi, double theta, double psi, double *Rp, double *Rt, double *Rs)
+{ /* get_Reb_derivs, kalmanClass.cpp:1230-1262 */
+  S_(Rp, 0, 0, 0.0);
+  S_(Rp, 0, 1, cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi));
+  S_(Rp, 0, 2, -cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi));
+  S_(Rp, 1, 0, 0.0);
+  S_(Rp, 1, 1, sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi));
+  S_(Rp, 1, 2, -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi));
+  S_(Rp, 2, 0, 0.0);
+  S_(Rp, 2, 1, cos(theta) * cos(phi));
+  S_(Rp, 2, 2, -cos(theta) * sin(phi));
+  S_(Rt, 0, 0, -cos(psi) * sin(theta));
+  S_(Rt, 0, 1, cos(psi) * cos(theta) * sin(phi));
+  S_(Rt, 0, 2, cos(psi) * cos(theta) * cos(phi));
+  S_(Rt, 1, 0, -sin(psi) * sin(theta));
+  S_(Rt, 1, 1, sin(psi) * cos(theta) * sin(phi));
+  S_(Rt, 1, 2, sin(psi) * cos(theta) * cos(phi));
+  S_(Rt, 2, 0, -cos(theta));
+  S_(Rt, 2, 1, -sin(theta) * sin(phi));
+  S_(Rt, 2, 2, -sin(theta) * cos(phi));
+  S_(Rs, 0, 0, -sin(psi) * cos(theta));
+  S_(Rs, 0, 1, -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi));
+  S_(Rs, 0, 2, -sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi));
+  S_(Rs, 1, 0, cos(psi) * cos(theta));
+  S_(Rs, 1, 1, cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi));
+  S_(Rs, 1, 2, cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi));
+  S_(Rs, 2, 0, 0.0);
+  S_(Rs, 2, 1, 0.0);
+  S_(Rs, 2, 2, 0.0);
+}
+
+/* returns the new state dimension N + 3*n_pts */
+int orc_ekf_add_new_points(double *x, double *P, int ld, int N, const double *meas, int n_pts)
+{
+  double R_eb[9], Rd[3][9], Prr[144];
+  int n, i, j, k;
+  if (n_pts <= 0) return N;
+  reb(x[3], x[4], x[5], R_eb);
+  reb_derivs(x[3], x[4], x[5], Rd[0], Rd[1], Rd[2]);
+  for (i = 0; i < 12; ++i)
+    for (j = 0; j < 12; ++j) Prr[12 * i + j] = P[(size_t)i * ld + j];
+  for (n = 0; n < n_pts; ++n) {
+    const double *xb = meas + 3 * n;
+    const int o = N + 3 * n;
+    double t3[3], Gx[36], GxT[36], tmp[36], PN1N1[9], Rp[9], GzT[9], t33[9], t33b[9], PN1r[36];
+    gemm(R_eb, xb, t3, 3, 3, 1);
+    for (j = 0; j < 3; ++j) x[o + j] = t3[j] + x[j];
+    memset(Gx, 0, sizeof Gx);
+    Gx[0] = 1.0; Gx[12 + 1] = 1.0; Gx[24 + 2] = 1.0;
+    for (j = 0; j < 3; ++j) {
+      gemm(Rd[j], xb, t3, 3, 3, 1);
+      for (i = 0; i < 3; ++i) Gx[12 * i + j + 3] = t3[i];
+    }
+    transpose(Gx, GxT, 3, 12);
+    gemm(Prr, GxT, tmp, 12, 12, 3);
+    gemm(Gx, tmp, PN1N1, 3, 12, 3);
+    memset(Rp, 0, sizeof Rp);
+    for (i = 0; i < 3; ++i) Rp[4 * i] = PT_MEAS_COV;
+    transpose(R_eb, GzT, 3, 3);
+    gemm(Rp, GzT, t33, 3, 3, 3);
+    gemm(R_eb, t33, t33b, 3, 3, 3);
+    for (i = 0; i < 9; ++i) PN1N1[i] += t33b[i];
+    gemm(Gx, Prr, PN1r, 3, 12, 12);
+    for (i = 0; i < 3; ++i) {
+      for (j = 0; j < 3; ++j) P[(size_t)(o + i) * ld + o + j] = PN1N1[3 * i + j];
+      for (j = 12; j < N; ++j) { /* existing states as they were before the call */
+        double s = 0.0;
+        for (k = 0; k < 12; ++k) s += Gx[12 * i + k] * P[(size_t)k * ld + j];
+        P[(size_t)(o + i) * ld + j] = s;
+        P[(size_t)j * ld + o + i] = s;
+      }
+      for (j = 0; j < 12; ++j) {
+        P[(size_t)(o + i) * ld + j] = PN1r[12 * i + j];
+        P[(size_t)j * ld + o + i] = PN1r[12 * i + j];
+      }
+    }
+  }
+  return N + 3 * n_pts;
+}

@@ -42,6 +42,12 @@ int orc_ekf_update_curves_points(double *x, double *P, int N, const double *z, i
 int orc_ekf_update_points(double *x, double *P, int N, const double *point_meas, const int *point_col,
                           int n_pts);
 
+/* state augmentation (AddFirstStates :275-311, AddNewCurve :314-499, AddNewPoints :502-666) on caller-owned
+ * x / P with room for the grown state; P row-major with leading dimension ld; return the new dimension */
+void orc_ekf_add_first_states(double *x, double *P, int ld, const double *z19);
+int orc_ekf_add_new_curve(double *x, double *P, int ld, int N, const double *z8, const double *A);
+int orc_ekf_add_new_points(double *x, double *P, int ld, int N, const double *meas, int n_pts);
+
 /* helpers exported for unit tests */
 void orc_ekf_split_matrices(double t, double *A1, double *A2);
 void orc_ekf_predicted_curve(const double *x, const double *A, int curve_col, double *zhat8);

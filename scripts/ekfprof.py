@@ -3,6 +3,6 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from curvepointslam_b200 import bench_extras as b
+import bench_extras as b
 
 print(b.ekf_update_bench(0, 5000, reps=2, warm=1))

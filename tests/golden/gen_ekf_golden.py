@@ -228,6 +228,121 @@ def split_matrices(t):  # GetSplitMatrices :1144-1159
     return A1, A2
 
 
+# ---- state augmentation: AddFirstStates (:275-311), AddNewCurve (:314-499), AddNewPoints (:502-666) ----------
+def reb(phi, theta, psi):  # generate_Reb, common.h:189-201
+    return np.array([[cos(psi) * cos(theta), cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi),
+                      cos(psi) * sin(theta) * cos(phi) - sin(psi) * sin(phi)],
+                     [sin(psi) * cos(theta), sin(psi) * sin(theta) * sin(phi) + cos(psi) * cos(phi),
+                      sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi)],
+                     [-sin(theta), cos(theta) * sin(phi), cos(theta) * cos(phi)]])
+
+
+def reb_derivs(phi, theta, psi):  # get_Reb_derivs, kalmanClass.cpp:1230-1262
+    p = np.array([[0.0, cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi), -cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi)],
+                  [0.0, sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi), -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi)],
+                  [0.0, cos(theta) * cos(phi), -cos(theta) * sin(phi)]])
+    t = np.array([[-cos(psi) * sin(theta), cos(psi) * cos(theta) * sin(phi), cos(psi) * cos(theta) * cos(phi)],
+                  [-sin(psi) * sin(theta), sin(psi) * cos(theta) * sin(phi), sin(psi) * cos(theta) * cos(phi)],
+                  [-cos(theta), -sin(theta) * sin(phi), -sin(theta) * cos(phi)]])
+    s_ = np.array([[-sin(psi) * cos(theta), -sin(psi) * sin(theta) * sin(phi) - cos(psi) * cos(phi), -sin(psi) * sin(theta) * cos(phi) - cos(psi) * sin(phi)],
+                   [cos(psi) * cos(theta), cos(psi) * sin(theta) * sin(phi) - sin(psi) * cos(phi), cos(psi) * sin(theta) * cos(phi) + sin(psi) * sin(phi)],
+                   [0.0, 0.0, 0.0]])
+    return p, t, s_
+
+
+def add_first_states(z19):
+    P, x = np.zeros((28, 28)), np.zeros(28)
+    for i in range(16):
+        P[i + 12, i + 12] = MEAS_COV ** 2
+        x[i + 12] = z19[i]
+    x[2], x[3], x[4], x[6] = z19[16], z19[17], z19[18], 1.0
+    for i, v in enumerate([1e-7, 1e-7, 0.1, 0.1, 0.1, 1e-7, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1]):
+        P[i, i] = v
+    return x, P
+
+
+def add_new_curve(x, P, z8, A):
+    N = P.shape[0]
+    Tx, Ty, psi = x[0], x[1], x[5]
+    Rot, Rotd = np.zeros((8, 8)), np.zeros((8, 8))
+    for i in range(4):
+        Rot[i, i] = cos(psi); Rot[i + 4, i + 4] = cos(psi); Rot[i + 4, i] = sin(psi); Rot[i, i + 4] = -sin(psi)
+        Rotd[i, i] = -sin(psi); Rotd[i + 4, i + 4] = -sin(psi); Rotd[i + 4, i] = cos(psi); Rotd[i, i + 4] = -cos(psi)
+    Prr, Pri = P[:12, :12].copy(), P[:12, 12:].copy()
+    Pn, xn = np.zeros((N + 8, N + 8)), np.zeros(N + 8)
+    Pn[:N, :N] = P
+    xn[:N] = x
+    _, Ainv = cv2.invert(np.ascontiguousarray(A), flags=cv2.DECOMP_SVD)
+    Hinv = np.zeros((8, 8))
+    Hinv[:4, :4] = Ainv
+    Hinv[4:, 4:] = Ainv
+    t81 = mm(Rot, z8.reshape(8, 1))
+    t81[:4] += Tx
+    t81[4:] += Ty
+    xcur = mm(Hinv, t81)
+    a1 = mm(Ainv, np.ones((4, 1)))
+    Gz = mm(Hinv, Rot)
+    t81 = mm(Hinv, mm(Rotd, z8.reshape(8, 1)))
+    Gx = np.zeros((8, 12))
+    for i in range(4):
+        Gx[i, 0] = a1[i, 0]; Gx[i + 4, 1] = a1[i, 0]; Gx[i, 5] = t81[i, 0]; Gx[i + 4, 5] = t81[i + 4, 0]
+    Pcur = mm(Gx, mm(Prr, cv2.transpose(Gx)))
+    R1 = np.eye(8) * MEAS_COV
+    PN1N1 = cv2.add(Pcur, mm(Gz, mm(R1, cv2.transpose(Gz))))
+    PN1i = mm(Gx, Pri) if N > 12 else np.zeros((8, 0))
+    PN1r = mm(Gx, cv2.transpose(Prr))
+    xn[N:] = xcur.ravel()
+    Pn[N:, N:] = PN1N1
+    Pn[N:, 12:N] = PN1i
+    Pn[12:N, N:] = PN1i.T
+    Pn[N:, :12] = PN1r
+    Pn[:12, N:] = PN1r.T
+    return xn, Pn
+
+
+def add_new_points(x, P, meas):
+    N, n_pts = P.shape[0], len(meas) // 3
+    Pn, xn = np.zeros((N + 3 * n_pts, N + 3 * n_pts)), np.zeros(N + 3 * n_pts)
+    Pn[:N, :N] = P
+    xn[:N] = x
+    R_eb = reb(x[3], x[4], x[5])
+    Rd = reb_derivs(x[3], x[4], x[5])
+    Prr, Pri = P[:12, :12].copy(), P[:12, 12:].copy()
+    for n in range(n_pts):
+        xb = meas[3 * n:3 * n + 3].reshape(3, 1)
+        o = N + 3 * n
+        xn[o:o + 3] = mm(R_eb, xb).ravel() + xn[0:3]
+        Gx = np.zeros((3, 12))
+        Gx[0, 0] = Gx[1, 1] = Gx[2, 2] = 1.0
+        for j in range(3):
+            Gx[:, j + 3] = mm(Rd[j], xb).ravel()
+        PN1N1 = mm(Gx, mm(Prr, cv2.transpose(Gx)))
+        PN1N1 = cv2.add(PN1N1, mm(R_eb, mm(np.eye(3) * PT_MEAS_COV, cv2.transpose(R_eb))))
+        PN1i = mm(Gx, Pri)
+        PN1r = mm(Gx, Prr)
+        Pn[o:o + 3, o:o + 3] = PN1N1
+        Pn[o:o + 3, 12:N] = PN1i
+        Pn[12:N, o:o + 3] = PN1i.T
+        Pn[o:o + 3, :12] = PN1r
+        Pn[:12, o:o + 3] = PN1r.T
+    return xn, Pn
+
+
+def augmentation_case():
+    rng = np.random.default_rng(11)
+    z19 = np.concatenate([np.linspace(2.0, 5.0, 4), -1.2 + rng.normal(0, 0.05, 4), np.linspace(2.1, 5.2, 4),
+                          1.2 + rng.normal(0, 0.05, 4), [-1.0, 0.01, -0.02]])
+    x0, P0 = add_first_states(z19)
+    x0p, P0p = predict(x0, P0)
+    x0p[5] = 0.2  # give the heading something to rotate by
+    A1, A2 = split_matrices(0.4)
+    z8 = np.concatenate([np.linspace(3.0, 6.0, 4), -1.1 + rng.normal(0, 0.05, 4)])
+    x1, P1 = add_new_curve(x0p, P0p, z8, A2)
+    pts = rng.uniform(-5, 5, 9)
+    x2, P2 = add_new_points(x1, P1, pts)
+    return dict(z19=z19, x0=x0, P0=P0, x_in=x0p, P_in=P0p, z8=z8, A=A2, x1=x1, P1=P1, pts=pts, x2=x2, P2=P2)
+
+
 def make_case(seed, n_curves_state, n_points_state, meas_curves, meas_points, split_t):
     rng = np.random.default_rng(seed)
     N = 12 + 8 * n_curves_state + 3 * n_points_state
@@ -277,6 +392,8 @@ def main():
         out.update(A1=A1, A2=A2, split_t=np.array(0.37))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "N", c["P"].shape[0], "written")
+    np.savez_compressed(os.path.join(HERE, "ekf_augment.npz"), **augmentation_case())
+    print("ekf_augment written")
 
 
 if __name__ == "__main__":

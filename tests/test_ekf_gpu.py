@@ -164,3 +164,32 @@ def test_gate_bit_exact_indices(L, nz):
     assert np.array_equal(idx2, oracle().gate(x, P, pi, pack[:50, :3], 11.345)[0])
     assert kf.gate(np.zeros((0, 3)), 11.345, want_d2=False).size == 0
     kf.close()
+
+
+def test_augmentation_sequence_vs_golden():
+    """AddFirstStates -> (state overwritten to the golden input) -> AddNewCurve -> AddNewPoints -> update, in place
+    on the device, against the cv2 transcription of kalmanClass.cpp:275-666."""
+    g = np.load(os.path.join(HERE, "golden", "ekf_augment.npz"))
+    kf = ekf.KalmanFilter(capacity=64)
+    kf.AddFirstStates(g["z19"])
+    assert kf.N == 28 and kf.curve_inds == [12, 20] and kf.num_points == 0
+    assert np.array_equal(kf.getState(), g["x0"]) and np.array_equal(kf.getCov(), g["P0"])
+    kf.set_state(g["x_in"], g["P_in"], [12, 20], [])
+    kf.AddNewCurve(g["z8"], g["A"])
+    assert kf.N == 36 and kf.curve_inds == [12, 20, 28]
+    assert rel(kf.getState(), g["x1"]) < TOL and rel(kf.getCov(), g["P1"]) < TOL
+    kf.AddNewPoints(g["pts"], 3)
+    assert kf.N == 45 and kf.point_inds == [36, 39, 42]
+    x, P = kf.getState(), kf.getCov()
+    assert rel(x, g["x2"]) < TOL and rel(P, g["P2"]) < TOL
+    # the grown filter keeps working: predict + update of the new curve against the oracle on the same state
+    z = np.concatenate([g["z8"] + 0.05, x[2:5]])
+    kf.PredictKF()
+    kf.UpdateNCurvesAndPoints(z, 1, np.eye(4)[None], [2])
+    xo, Po = oracle().ekf_predict(x, P)
+    xo, Po = oracle().ekf_update_curves_points(xo, Po, z, np.eye(4)[None], [28])
+    assert rel(kf.getState(), xo) < TOL and rel(kf.getCov(), Po) < TOL
+    with pytest.raises(Exception):
+        for _ in range(10):
+            kf.AddNewCurve(g["z8"], g["A"])  # capacity 64 is exhausted after three more curves
+    kf.close()

@@ -122,3 +122,24 @@ def test_gate_definition_invariants():
     i1, d1 = o.gate(x, P, cols, zz, 50.0, nthreads=1)
     i4, d4 = o.gate(x, P, cols, zz, 50.0, nthreads=4)
     assert np.array_equal(i1, i4) and np.array_equal(d1, d4)
+
+
+def test_augmentation_matches_cv2_golden():
+    """AddFirstStates / AddNewCurve / AddNewPoints (kalmanClass.cpp:275-666) against the cv2 transcription."""
+    import ctypes as C
+    g = np.load(os.path.join(HERE, "golden", "ekf_augment.npz"))
+    L = oracle().lib
+    dp = C.POINTER(C.c_double)
+    L.orc_ekf_add_new_curve.restype = C.c_int
+    L.orc_ekf_add_new_points.restype = C.c_int
+    ld = 64
+    x, P = np.zeros(ld), np.zeros((ld, ld))
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+    L.orc_ekf_add_first_states(x.ctypes.data_as(dp), P.ctypes.data_as(dp), ld, c(g["z19"]))
+    assert np.array_equal(x[:28], g["x0"]) and np.array_equal(P[:28, :28], g["P0"])
+    x[:28], P[:28, :28] = g["x_in"], g["P_in"]
+    N = L.orc_ekf_add_new_curve(x.ctypes.data_as(dp), P.ctypes.data_as(dp), ld, 28, c(g["z8"]), c(g["A"]))
+    assert N == 36 and rel(x[:N], g["x1"]) < 1e-13 and rel(P[:N, :N], g["P1"]) < 1e-13
+    N = L.orc_ekf_add_new_points(x.ctypes.data_as(dp), P.ctypes.data_as(dp), ld, N, c(g["pts"]), 3)
+    assert N == 45 and rel(x[:N], g["x2"]) < 1e-13 and rel(P[:N, :N], g["P2"]) < 1e-13
+    assert np.all(P[36:39, 39:45] == 0.0)  # points added together get no cross-covariance (reference behaviour)
