@@ -70,4 +70,17 @@ __device__ __forceinline__ void det_sincos(double x, double* s, double* c) {
   }
 }
 
+// deterministic arcsine for |x| <= 0.9: six Newton steps on sin(t) = x from t0 = x (same sequence as the oracle)
+__device__ __forceinline__ double det_asin(double x) {
+  const double ax = (x >= 0.0) ? x : -x;
+  if (!(ax <= 0.9)) return asin(x);
+  double t = x, s, c;
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    det_sincos(t, &s, &c);
+    t = t - (s - x) / c;
+  }
+  return t;
+}
+
 }  // namespace cps

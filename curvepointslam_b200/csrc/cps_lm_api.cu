@@ -294,6 +294,53 @@ extern "C" int cps_dlevmar_dif_batched(cps_lm_ctx* c, int model, int B, double* 
   return fit_batched_host(c, model, CPS_LM_DIF, B, p, meas, t, off, counts, itmax, opts, info, ret, extra);
 }
 
+// ---- fit_curve's initial guess -------------------------------------------------------------------------------
+extern "C" int cps_fit_curve_init_batched_dev(cps_lm_ctx* c, int B, const double* d_meas, const long long* d_off,
+                                              const int* d_counts, double* d_p, void* stream) {
+  if (!c || B < 0 || (B && (!d_meas || !d_off || !d_counts || !d_p))) return CPS_ERR_INVALID;
+  if (B == 0) return CPS_OK;
+  CPS_CUDA(cudaSetDevice(c->device));
+  cps::lm_init_guess_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, d_meas, d_off, d_counts, d_p);
+  CPS_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return CPS_OK;
+}
+
+extern "C" int cps_fit_curve_init_batched(cps_lm_ctx* c, int B, const double* meas, const long long* off,
+                                          const int* counts, double* p_out) {
+  if (!c || B < 0 || (B && (!meas || !off || !counts || !p_out))) return CPS_ERR_INVALID;
+  if (B == 0) return CPS_OK;
+  if (off[0] < 0 || off[B] < off[0]) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(c->device));
+  cps_lm_slot& sl = c->slot[0];
+  cudaStream_t st = sl.stream;
+  const long long total = off[B] - off[0];
+  size_t o_meas = 0, o_off = align256(sizeof(double) * (size_t)total);
+  size_t o_cnt = align256(o_off + sizeof(long long) * (size_t)(B + 1));
+  size_t o_p = align256(o_cnt + sizeof(int) * (size_t)B * 4);
+  size_t bytes = align256(o_p + sizeof(double) * (size_t)B * 19);
+  CPS_CUDA(cudaStreamSynchronize(st));
+  if (bytes > sl.stage_bytes) {
+    cudaFree(sl.d_stage);
+    sl.d_stage = nullptr;
+    sl.stage_bytes = 0;
+    CPS_CUDA(cudaMalloc(&sl.d_stage, bytes));
+    sl.stage_bytes = bytes;
+  }
+  char* d = sl.d_stage;
+  sl.off0.resize((size_t)B + 1);
+  for (int f = 0; f <= B; ++f) sl.off0[f] = off[f] - off[0];
+  CPS_CUDA(cudaMemcpyAsync(d + o_meas, meas + off[0], sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, st));
+  CPS_CUDA(cudaMemcpyAsync(d + o_off, sl.off0.data(), sizeof(long long) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
+  CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts, sizeof(int) * (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  int rc = cps_fit_curve_init_batched_dev(c, B, (const double*)(d + o_meas), (const long long*)(d + o_off),
+                                          (const int*)(d + o_cnt), (double*)(d + o_p), (void*)st);
+  if (rc != CPS_OK) return rc;
+  CPS_CUDA(cudaMemcpyAsync(p_out, d + o_p, sizeof(double) * (size_t)B * 19, cudaMemcpyDeviceToHost, st));
+  CPS_CUDA(cudaStreamSynchronize(st));
+  return CPS_OK;
+}
+
 // ---- same-signature shims ---------------------------------------------------------------------------
 // The callbacks are tokens: the device model is selected by comparing pointers; calling them is an error.
 extern "C" void cps_modelfunc(double*, double*, int, int, void*) {

@@ -908,6 +908,111 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
   R.k = k; R.stop = stop; R.nfev = nfev; R.njev = njap; R.nlss = nlss; R.n_jtj = n_jtj; R.n_broyden = n_broyden;
 }
 
+// ---- fit_curve's initial guess (curveFittingClass.cpp:516-651), one thread per fit ------------------------------
+// Stereo triangulation of the start / end points of both curves, plane fit through them (normal = eigenvector of
+// the smallest eigenvalue of the centred 3x3 scatter matrix, the reference's cvSVD of the 4x3 matrix), rotation into
+// the ground frame, straight-line control points.  The sign of the reference's singular vector is
+// implementation-defined; here the normal is oriented so that d = n.c >= 0 (height parameter <= 0, the branch the
+// reference's own post-normalisation :684-702 maps every fit to).  Same operation sequence as the CPU oracle.
+__device__ __forceinline__ void triangulate(const double* m, int a, int b, double pt[3]) {
+  const double uL = m[2 * a], vL = m[2 * a + 1], uR = m[2 * b], vR = m[2 * b + 1];
+  pt[0] = CPS_FX * CPS_BASELINE / (uL - uR);
+  pt[1] = 0.5 * (pt[0] / CPS_FX * (uL - CPS_CX) - 0.5 * CPS_BASELINE) + 0.5 * (pt[0] / CPS_FX * (uR - CPS_CX) + 0.5 * CPS_BASELINE);
+  pt[2] = 0.5 * pt[0] / CPS_FY * (vL - CPS_CY) + 0.5 * pt[0] / CPS_FY * (vR - CPS_CY);
+}
+
+__global__ void __launch_bounds__(128) lm_init_guess_kernel(int B, const double* __restrict__ meas,
+                                                            const long long* __restrict__ off,
+                                                            const int* __restrict__ counts, double* __restrict__ p_out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  const double* m = meas + off[f];
+  const int nl1 = counts[4 * f], nl2 = counts[4 * f + 1], nr1 = counts[4 * f + 2], nr2 = counts[4 * f + 3];
+  const int npl = nl1 + nl2, npts = npl + nr1 + nr2;
+  double* p = p_out + (size_t)f * 19;
+  if (nl1 < 1 || nl2 < 1 || nr1 < 1 || nr2 < 1 || (long long)2 * npts != off[f + 1] - off[f]) {
+    for (int i = 0; i < 19; ++i) p[i] = __longlong_as_double(0x7ff8000000000000LL);  // no guess: NaN
+    return;
+  }
+  double s1[3], e1[3], s2[3], e2[3], c[3], M[4][3], a[3][3], V[3][3], n[3];
+  triangulate(m, 0, npl, s1);
+  triangulate(m, nl1 - 1, npl + nr1 - 1, e1);
+  triangulate(m, nl1, npl + nr1, s2);
+  triangulate(m, npl - 1, npts - 1, e2);
+  for (int j = 0; j < 3; ++j) c[j] = 0.25 * (s1[j] + s2[j] + e1[j] + e2[j]);
+  for (int j = 0; j < 3; ++j) {
+    M[0][j] = s1[j] - c[j]; M[1][j] = s2[j] - c[j]; M[2][j] = e1[j] - c[j]; M[3][j] = e2[j] - c[j];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 4; ++k) acc += M[k][i] * M[k][j];
+      a[i][j] = acc;
+      V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 8; ++sweep)
+    for (int pp = 0; pp < 2; ++pp)
+      for (int q = pp + 1; q < 3; ++q) {
+        const double apq = a[pp][q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q][q] - a[pp][pp]) / (2.0 * apq);
+        double t = 1.0 / (((theta >= 0.0) ? theta : -theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        const double cc = 1.0 / sqrt(t * t + 1.0);
+        const double ss = t * cc;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][pp], akq = a[k][q];
+          a[k][pp] = cc * akp - ss * akq;
+          a[k][q] = ss * akp + cc * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[pp][k], aqk = a[q][k];
+          a[pp][k] = cc * apk - ss * aqk;
+          a[q][k] = ss * apk + cc * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][pp], vkq = V[k][q];
+          V[k][pp] = cc * vkp - ss * vkq;
+          V[k][q] = ss * vkp + cc * vkq;
+        }
+      }
+  int best = 0;
+  if (a[1][1] < a[best][best]) best = 1;
+  if (a[2][2] < a[best][best]) best = 2;
+  for (int k = 0; k < 3; ++k) n[k] = V[k][best];
+  double d = (n[0] * c[0] + n[1] * c[1]) + n[2] * c[2];
+  if (d < 0.0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; d = -d; }
+  const double theta = -det_asin(n[0]);
+  const double phi = det_asin(n[1]);
+  double origin[3], st, ct, sp, cp, Rot[9];
+  for (int j = 0; j < 3; ++j) origin[j] = d * n[j];
+  det_sincos(theta, &st, &ct);
+  det_sincos(phi, &sp, &cp);
+  Rot[0] = ct;  Rot[1] = st * sp; Rot[2] = st * cp;
+  Rot[3] = 0.0; Rot[4] = cp;      Rot[5] = -sp;
+  Rot[6] = -st; Rot[7] = ct * sp; Rot[8] = ct * cp;
+  double* pts[4] = {s1, e1, s2, e2};
+  for (int i = 0; i < 4; ++i) {
+    double t[3], r[3];
+    for (int j = 0; j < 3; ++j) t[j] = pts[i][j] - origin[j];
+    for (int j = 0; j < 3; ++j) r[j] = (Rot[3 * j] * t[0] + Rot[3 * j + 1] * t[1]) + Rot[3 * j + 2] * t[2];
+    for (int j = 0; j < 3; ++j) pts[i][j] = r[j];
+  }
+  double cp1[8], cp2[8];
+  cp1[0] = s1[0]; cp1[1] = s1[1]; cp1[6] = e1[0]; cp1[7] = e1[1];
+  cp2[0] = s2[0]; cp2[1] = s2[1]; cp2[6] = e2[0]; cp2[7] = e2[1];
+  for (int i = 1; i < 3; ++i) {
+    cp1[2 * i] = (3 - i) * cp1[0] / 3 + i * cp1[6] / 3;
+    cp1[2 * i + 1] = (3 - i) * cp1[1] / 3 + i * cp1[7] / 3;
+    cp2[2 * i] = (3 - i) * cp2[0] / 3 + i * cp2[6] / 3;
+    cp2[2 * i + 1] = (3 - i) * cp2[1] / 3 + i * cp2[7] / 3;
+  }
+  for (int i = 0; i < 8; ++i) { p[i] = cp1[i]; p[8 + i] = cp2[i]; }
+  p[16] = theta;
+  p[17] = phi;
+  p[18] = -d;
+}
+
 // ---- kernel: persistent warps pulling fits from a queue ----------------------------------------------
 template <int MODEL, bool DIF>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_kernel(const LmLaunch L) {

@@ -76,6 +76,17 @@ class LmContext:
                                                n_max, itmax, _vp(opts_a), d_info, d_ret, d_extra, stream)
         _lib.check(rc, "cps_lm_fit_batched_dev")
 
+    def init_guess(self, meas, off, counts):
+        """fit_curve's initial guess (curveFittingClass.cpp:516-651) for B Stereo19 fits -> p [B,19]."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        B = len(off) - 1
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        p = np.zeros((B, 19))
+        _lib.check(_lib.lib().cps_fit_curve_init_batched(self._h, B, _vp(meas), _vp(off), _vp(counts), _vp(p)),
+                   "cps_fit_curve_init_batched")
+        return p
+
     def sync(self):
         _lib.check(_lib.lib().cps_lm_sync(self._h), "cps_lm_sync")
 
@@ -133,12 +144,14 @@ class CurveFittingClass:
                 pieces.append(a.reshape(-1))
         meas = np.concatenate(pieces) if pieces else np.zeros(0)
         off = np.concatenate([[0], np.cumsum(2 * counts.sum(axis=1))]).astype(np.int64)
+        if params0 is None:  # the reference ignores the incoming params and builds its own guess (:516-651)
+            params0 = self.ctx.init_guess(meas, off, counts)
         r = self.ctx.fit_batched(STEREO19, self.variant, params0, meas, off, counts)
         self.info = r["info"]
         return postfit_normalise(r["p"]), r["info"][:, 1].copy(), r
 
     def fit_curve(self, params0, L, R):
-        p, err, _ = self.fit_curves_batched(np.asarray(params0, dtype=np.float64).reshape(1, 19),
-                                            [(L[0], L[1], R[0], R[1])])
+        p0 = None if params0 is None else np.asarray(params0, dtype=np.float64).reshape(1, 19)
+        p, err, _ = self.fit_curves_batched(p0, [(L[0], L[1], R[0], R[1])])
         self.fitting_error = float(err[0])
         return p[0]

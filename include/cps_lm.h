@@ -77,6 +77,18 @@ int cps_lm_fit_batched_dev(cps_lm_ctx *ctx, int model, int variant, int B, doubl
                            const double *d_t, const long long *d_off, const int *d_counts, int n_max, int itmax,
                            const double *opts, double *d_info, int *d_ret, int *d_extra, void *stream);
 int cps_lm_sync(cps_lm_ctx *ctx);
+
+/*
+ * fit_curve's initial guess for B Stereo19 fits (curveFittingClass.cpp:516-651): stereo triangulation of the start /
+ * end points of both curves, plane fit, rotation into the ground frame, straight-line control points; writes
+ * p[B][19], the `params` the reference hands to levmar.  The reference's plane normal comes from cvSVD and its sign
+ * is implementation-defined; here it is oriented so that the height parameter is <= 0 (the branch fit_curve's own
+ * post-normalisation :684-702 maps every fit to).  Fits with an empty segment get NaN parameters.
+ */
+int cps_fit_curve_init_batched(cps_lm_ctx *ctx, int B, const double *meas, const long long *off, const int *counts,
+                               double *p_out);
+int cps_fit_curve_init_batched_dev(cps_lm_ctx *ctx, int B, const double *d_meas, const long long *d_off,
+                                   const int *d_counts, double *d_p, void *stream);
 /* geometry of the last launch and the number of kernel launches issued through this context */
 int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
 

@@ -92,4 +92,22 @@ static inline int orc_det_sincos(double x, double *s, double *c)
   }
 }
 
+/* deterministic arcsine for |x| <= 0.9: Newton on sin(t) = x with the deterministic sin/cos above, six steps
+ * from t0 = x (quadratic convergence: exact to the last bits well before the sixth step, and a fixed step count
+ * keeps the operation sequence identical everywhere).  Outside that range, or for non-finite x, falls back to
+ * libm.  Returns 1 if the deterministic path was taken. */
+static inline int orc_det_asin(double x, double *out)
+{
+  const double ax = (x >= 0.0) ? x : -x;
+  double t = x, s, c;
+  int k;
+  if (!(ax <= 0.9)) { *out = asin(x); return 0; }
+  for (k = 0; k < 6; ++k) {
+    orc_det_sincos(t, &s, &c);
+    t = t - (s - x) / c;
+  }
+  *out = t;
+  return 1;
+}
+
 #endif

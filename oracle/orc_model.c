@@ -231,6 +231,116 @@ void orc_segment_t(const double *xy, int npts, double *t_out)
   }
 }
 
+/* ---- fit_curve's initial guess, curveFittingClass.cpp:516-651 ------------------------------------------- */
+static void orc_triangulate(const double *m, int a, int b, double pt[3])
+{ /* :522-547: left sample a, right sample b (point indices into the packed measurement vector) */
+  const double uL = m[2 * a], vL = m[2 * a + 1], uR = m[2 * b], vR = m[2 * b + 1];
+  pt[0] = ORC_FX * ORC_BASELINE / (uL - uR);
+  pt[1] = 0.5 * (pt[0] / ORC_FX * (uL - ORC_CX) - 0.5 * ORC_BASELINE) + 0.5 * (pt[0] / ORC_FX * (uR - ORC_CX) + 0.5 * ORC_BASELINE);
+  pt[2] = 0.5 * pt[0] / ORC_FY * (vL - ORC_CY) + 0.5 * pt[0] / ORC_FY * (vR - ORC_CY);
+}
+
+/* eigenvector of the smallest eigenvalue of the symmetric 3x3 S = M^T M by cyclic Jacobi rotations (a fixed
+ * 8 sweeps, every operation written out: the CUDA kernel states the same sequence) */
+static void orc_smallest_eigvec3(const double S[9], double v[3])
+{
+  double a[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  int sweep, p, q, k, best;
+  for (p = 0; p < 3; ++p)
+    for (q = 0; q < 3; ++q) a[p][q] = S[3 * p + q];
+  for (sweep = 0; sweep < 8; ++sweep)
+    for (p = 0; p < 2; ++p)
+      for (q = p + 1; q < 3; ++q) {
+        const double apq = a[p][q];
+        double theta, t, c, s;
+        if (apq == 0.0) continue;
+        theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+        t = 1.0 / (((theta >= 0.0) ? theta : -theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        c = 1.0 / sqrt(t * t + 1.0);
+        s = t * c;
+        for (k = 0; k < 3; ++k) { /* A <- A J */
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+        for (k = 0; k < 3; ++k) { /* A <- J^T A */
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+        for (k = 0; k < 3; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  best = 0;
+  if (a[1][1] < a[best][best]) best = 1;
+  if (a[2][2] < a[best][best]) best = 2;
+  for (k = 0; k < 3; ++k) v[k] = V[k][best];
+}
+
+void orc_stereo19_init_guess(const double *meas, const int *counts, double *p19, int math_mode, int sign)
+{
+  const int nl1 = counts[0], nl2 = counts[1], nr1 = counts[2], nr2 = counts[3];
+  const int npl = nl1 + nl2, npts = npl + nr1 + nr2;
+  double s1[3], e1[3], s2[3], e2[3], c[3], M[4][3], S[9], n[3], d, theta, phi, origin[3], Rot[9], st, ct, sp, cp;
+  double *pts[4];
+  double cp1[8], cp2[8];
+  int i, j, k;
+  orc_triangulate(meas, 0, npl, s1);                      /* :523-525 */
+  orc_triangulate(meas, nl1 - 1, npl + nr1 - 1, e1);      /* :528-530 */
+  orc_triangulate(meas, nl1, npl + nr1, s2);              /* :537-539 */
+  orc_triangulate(meas, npl - 1, npts - 1, e2);           /* :542-544 */
+  for (j = 0; j < 3; ++j) c[j] = 0.25 * (s1[j] + s2[j] + e1[j] + e2[j]);
+  for (j = 0; j < 3; ++j) {
+    M[0][j] = s1[j] - c[j];
+    M[1][j] = s2[j] - c[j];
+    M[2][j] = e1[j] - c[j];
+    M[3][j] = e2[j] - c[j];
+  }
+  for (i = 0; i < 3; ++i)
+    for (j = 0; j < 3; ++j) {
+      double acc = 0.0;
+      for (k = 0; k < 4; ++k) acc += M[k][i] * M[k][j];
+      S[3 * i + j] = acc;
+    }
+  orc_smallest_eigvec3(S, n);
+  d = (n[0] * c[0] + n[1] * c[1]) + n[2] * c[2];
+  if ((sign >= 0 && d < 0.0) || (sign < 0 && d > 0.0)) {
+    n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2];
+    d = -d;
+  }
+  if (math_mode == ORC_MATH_LIBM) { theta = -asin(n[0]); phi = asin(n[1]); }
+  else { orc_det_asin(n[0], &theta); theta = -theta; orc_det_asin(n[1], &phi); }
+  for (j = 0; j < 3; ++j) origin[j] = d * n[j];
+  orc_sincos(theta, math_mode, &st, &ct);
+  orc_sincos(phi, math_mode, &sp, &cp);
+  Rot[0] = ct;  Rot[1] = st * sp; Rot[2] = st * cp;  /* :581-589, row-major */
+  Rot[3] = 0.0; Rot[4] = cp;      Rot[5] = -sp;
+  Rot[6] = -st; Rot[7] = ct * sp; Rot[8] = ct * cp;
+  pts[0] = s1; pts[1] = e1; pts[2] = s2; pts[3] = e2;
+  for (i = 0; i < 4; ++i) {
+    double t[3], r[3];
+    for (j = 0; j < 3; ++j) t[j] = pts[i][j] - origin[j];
+    for (j = 0; j < 3; ++j) r[j] = (Rot[3 * j] * t[0] + Rot[3 * j + 1] * t[1]) + Rot[3 * j + 2] * t[2];
+    for (j = 0; j < 3; ++j) pts[i][j] = r[j];
+  }
+  cp1[0] = s1[0]; cp1[1] = s1[1]; cp1[6] = e1[0]; cp1[7] = e1[1];
+  cp2[0] = s2[0]; cp2[1] = s2[1]; cp2[6] = e2[0]; cp2[7] = e2[1];
+  for (i = 1; i < 3; ++i) { /* :626-632 */
+    cp1[2 * i] = (3 - i) * cp1[0] / 3 + i * cp1[6] / 3;
+    cp1[2 * i + 1] = (3 - i) * cp1[1] / 3 + i * cp1[7] / 3;
+    cp2[2 * i] = (3 - i) * cp2[0] / 3 + i * cp2[6] / 3;
+    cp2[2 * i + 1] = (3 - i) * cp2[1] / 3 + i * cp2[7] / 3;
+  }
+  for (i = 0; i < 8; ++i) { p19[i] = cp1[i]; p19[8 + i] = cp2[i]; }
+  p19[16] = theta;
+  p19[17] = phi;
+  p19[18] = -d;
+}
+
 /* curveFittingClass.cpp:684-711, including the "+= PI" on the height in the second branch */
 void orc_stereo19_postfit(double *p)
 {

@@ -59,6 +59,14 @@ void orc_bernstein3(double t, int math_mode, double w[4]);
 /* t-parameterisation of one contour segment from its image rows (fit_curve:451-511) */
 void orc_segment_t(const double *xy, int npts, double *t_out);
 
+/* initial guess of fit_curve (curveFittingClass.cpp:516-651): stereo triangulation of the start / end points of
+ * both curves, plane fit (normal = right singular vector of the smallest singular value of the centred 4x3
+ * point matrix, the reference's cvSVD), rotation into the ground frame, straight-line control points.  The sign
+ * of the singular vector is implementation-defined in the reference; `sign` = +1 orients the
+ * normal so that d = n.c >= 0 (height parameter <= 0, the branch fit_curve's post-normalisation maps everything
+ * to), -1 gives the opposite orientation.  meas / counts as in orc_fit_batch. */
+void orc_stereo19_init_guess(const double *meas, const int *counts, double *p19, int math_mode, int sign);
+
 /* post-fit normalisation of the 19 parameters (fit_curve:684-711) */
 void orc_stereo19_postfit(double *p);
 

@@ -172,3 +172,34 @@ def test_same_signature_shim_and_fit_curve(ctx):
     exp = ref["p"][0].copy()
     oracle().lib.orc_stereo19_postfit(exp.ctypes.data_as(C.POINTER(C.c_double)))
     assert np.array_equal(_bits(out), _bits(exp)) and fitter.fitting_error == ref["info"][0, 1]
+
+
+def test_init_guess_bit_exact_and_feeds_the_fit(ctx):
+    """fit_curve's initial guess on the device (curveFittingClass.cpp:516-651) equals the oracle bit for bit, matches
+    the cv2 transcription up to the sign of the plane normal, and a fit started from it converges like the
+    reference's own pipeline (stop reason 2, small residual)."""
+    import ctypes as C
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lm_init_guess.npz"))
+    p_gpu = ctx.init_guess(g["meas"], g["off"], g["counts"])
+    dp = C.POINTER(C.c_double)
+    for f in range(len(g["off"]) - 1):
+        m = np.ascontiguousarray(g["meas"][g["off"][f]:g["off"][f + 1]])
+        c = np.ascontiguousarray(g["counts"][f], dtype=np.int32)
+        p = np.zeros(19)
+        oracle().lib.orc_stereo19_init_guess(m.ctypes.data_as(dp), c.ctypes.data_as(C.POINTER(C.c_int)),
+                                             p.ctypes.data_as(dp), 0, 1)
+        assert np.array_equal(_bits(p_gpu[f]), _bits(p)), f
+    b = synth.make_stereo19_batch(64, K=64, seed=41)
+    p0 = ctx.init_guess(b["meas"], b["off"], b["counts"])
+    assert np.isfinite(p0).all() and (p0[:, 18] <= 0).all()
+    gpu = ctx.fit_batched(STEREO19, DIF, p0, b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, DIF, p0, b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    assert_same_fit(gpu, cpu)
+    assert (gpu["info"][:, 6] == 2).all()
+    assert np.abs(gpu["p"][:, 18] - b["truth"][:, 18]).max() < 0.2
+    fitter = lm.CurveFittingClass(ctx, variant=DIF)
+    xy = b["meas"][:512].reshape(4, 64, 2)
+    out = fitter.fit_curve(None, [xy[0], xy[1]], [xy[2], xy[3]])  # params0=None: device builds the guess
+    assert np.allclose(out, lm.postfit_normalise(gpu["p"][:1])[0], rtol=0, atol=0)

@@ -187,3 +187,26 @@ def test_postfit_normalisation_matches_oracle():
     for row in exp:
         oracle().lib.orc_stereo19_postfit(row.ctypes.data_as(dp))
     assert np.array_equal(bits(lm.postfit_normalise(p)), bits(exp))
+
+
+def _oracle_init(meas, counts, mode, sign):
+    p = np.zeros(19)
+    m = np.ascontiguousarray(meas, dtype=np.float64)
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    oracle().lib.orc_stereo19_init_guess(m.ctypes.data_as(dp), c.ctypes.data_as(C.POINTER(C.c_int)),
+                                         p.ctypes.data_as(dp), mode, sign)
+    return p
+
+
+def test_init_guess_matches_cv2_transcription():
+    """fit_curve's initial guess (curveFittingClass.cpp:516-651) against a numpy/cv2 transcription; the sign of the
+    plane normal is implementation-defined in the reference, so either orientation of the oracle must match."""
+    g = np.load(os.path.join(HERE, "golden", "lm_init_guess.npz"))
+    for f in range(len(g["off"]) - 1):
+        meas = g["meas"][g["off"][f]:g["off"][f + 1]]
+        cands = [_oracle_init(meas, g["counts"][f], MATH_LIBM, s) for s in (1, -1)]
+        err = [np.abs(c - g["p"][f]).max() / np.abs(g["p"][f]).max() for c in cands]
+        assert min(err) < 1e-9, (f, err)
+        assert cands[0][18] <= 0.0  # sign = +1 is the orientation with a non-positive height parameter
+        det = _oracle_init(meas, g["counts"][f], MATH_DET, 1)
+        assert np.abs(det - cands[0]).max() < 1e-12
