@@ -306,7 +306,10 @@ def main():
             "flops_per_fit": fl / B, "kernel_ms": kernel_ms_avg,
             "hbm": {"achieved": flops.fit_bytes(N_MEAS, M) * B / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "note": "algorithmic bytes; the path is FP64-bound, not HBM-bound"},
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+            # (profiles/r1_ncu_full_lm_der_v2_details.csv: 148.9 MB for 32768 fits), scaled to this launch
+            "traffic": 4544.0 * B if variant == lm.DER else None,
+            "traffic_note": "ncu-measured 4544 B/fit vs 4496 B/fit algorithmic (der)",
         },
         "fit_stats": {"iters_mean": float(info[:, 5].mean()), "nfev_mean": float(nfev / B),
                       "njev_mean": float(njev / B), "nlss_mean": float(nlss / B),

@@ -134,6 +134,34 @@ def gate_bench(device: int, L: int = 20000, nz: int = 10000, reps: int = 5, seed
     return out
 
 
+def single_frame_bench(device: int, reps: int = 20):
+    """BASELINE.json configs[0]: one synthetic stereo frame = ~200 contours x 64 pts = 50 m=19 fits, through the
+    host-buffer C ABI (copies inside), der and dif (the reference's live call), with the reference levmar on one
+    core beside it (the reference is single-threaded), plus one EKF update of a small map."""
+    from curvepointslam_b200 import lm, synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import DER, DIF, STEREO19, oracle
+    ctx = lm.LmContext(device)
+    b = synth.make_stereo19_batch(50, K=64, seed=9)
+    out = {"fits": 50, "contours": 200}
+    for name, var, ovar in (("der", lm.DER, DER), ("dif", lm.DIF, DIF)):
+        p0 = ctx.init_guess(b["meas"], b["off"], b["counts"])
+        for _ in range(3):
+            ctx.fit_batched(STEREO19, var, p0, b["meas"], b["off"], b["counts"])
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = ctx.fit_batched(STEREO19, var, p0, b["meas"], b["off"], b["counts"])
+        gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+        t0 = time.perf_counter()
+        c = oracle().fit_batch(STEREO19, ovar, p0, b["meas"], b["off"], b["counts"], list(lm.REFERENCE_OPTS), nthreads=1,
+                               use_ref=oracle().ref is not None)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        out[name] = {"gpu_e2e_ms": gpu_ms, "cpu_1core_ms": cpu_ms,
+                     "bit_identical": bool(np.array_equal(r["p"].view(np.int64), c["p"].view(np.int64)))}
+    ctx.close()
+    return out
+
+
 def run(device: int = 0):
     res = {"ekf_update": [], "gate": None}
     for L in (1000, 5000, 20000):
@@ -149,6 +177,10 @@ def run(device: int = 0):
         res["ekf_cpu_baseline"] = ekf_cpu_baseline(1000)
     except Exception as ex:
         res["ekf_cpu_baseline"] = {"error": repr(ex)}
+    try:
+        res["single_frame"] = single_frame_bench(device)
+    except Exception as ex:
+        res["single_frame"] = {"error": repr(ex)}
     try:
         res["gate"] = gate_bench(device, 20000, 10000)
         res["gate_5k"] = gate_bench(device, 5000, 10000)

@@ -1068,6 +1068,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_k
     int ret_code = 0;
     if (nn < M) ret_code = -1;               // lm_core.c:117 / :493: fewer measurements than unknowns
     else if (nn > L.n_max || (nn & 1)) ret_code = -2;  // does not fit the staged buffers / odd length
+    else if (!DIF && M == 19 && nn > 40 * kTileRows) ret_code = -2;  // the compact path lists at most 40+ row blocks
     {
       int c[4] = {0, 0, 0, 0};
 #pragma unroll
