@@ -216,22 +216,42 @@ __global__ void __launch_bounds__(256) ekf_pht_kernel(UpdateDesc d, const double
 // ---- kernel 3: S = H T + R, S^-1 by Cholesky (one block) ---------------------------------------------------
 __global__ void __launch_bounds__(256) ekf_s_kernel(UpdateDesc d, const double* __restrict__ T,
                                                     double* __restrict__ small, const int* __restrict__ cols,
-                                                    int* __restrict__ flag) {
+                                                    int* __restrict__ flag, int staged) {
   extern __shared__ double sh[];
   const int M = d.M;
   double* L = sh;           // [M][M] Cholesky factor, then L^-1
   double* S = sh + M * M;   // [M][M]
   const int tid = threadIdx.x, nt = blockDim.x;
-  const double* Hc = small + SM_HC;
-  for (int e = tid; e < M * M; e += nt) {
-    const int r = e / M, s = e - r * M;
-    double acc = 0.0;
-    for (int c = 0; c < d.nc; ++c) {
-      const double h = Hc[r * d.nc + c];
-      if (h != 0.0) acc += h * T[(size_t)cols[c] * MAXM + s];
+  // S = Hc Tc + R.  When it fits, the compact H and the nc rows of T it touches are first staged in shared memory
+  // (coalesced) so that the M*M dot products do not each walk global memory.
+  if (staged) {
+    double* Hs = sh + 2 * M * M;  // [M][nc]
+    double* Ts = Hs + M * d.nc;   // [nc][M]
+    for (int e = tid; e < M * d.nc; e += nt) Hs[e] = small[SM_HC + e];
+    for (int e = tid; e < d.nc * M; e += nt) {
+      const int c = e / M, sidx = e - c * M;
+      Ts[e] = T[(size_t)cols[c] * MAXM + sidx];
     }
-    if (r == s) acc += small[SM_R + r];
-    S[e] = acc;
+    __syncthreads();
+    for (int e = tid; e < M * M; e += nt) {
+      const int r = e / M, s = e - r * M;
+      double acc = 0.0;
+      for (int c = 0; c < d.nc; ++c) acc += Hs[r * d.nc + c] * Ts[c * M + s];
+      if (r == s) acc += small[SM_R + r];
+      S[e] = acc;
+    }
+  } else {
+    const double* Hc = small + SM_HC;
+    for (int e = tid; e < M * M; e += nt) {
+      const int r = e / M, s = e - r * M;
+      double acc = 0.0;
+      for (int c = 0; c < d.nc; ++c) {
+        const double hh = Hc[r * d.nc + c];
+        if (hh != 0.0) acc += hh * T[(size_t)cols[c] * MAXM + s];
+      }
+      if (r == s) acc += small[SM_R + r];
+      S[e] = acc;
+    }
   }
   __syncthreads();
   for (int e = tid; e < M * M; e += nt) {
@@ -1005,7 +1025,7 @@ extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
   for (auto& e : h->ev) CPS_CUDA(cudaEventCreate(&e));
   for (auto& e : h->gev) CPS_CUDA(cudaEventCreate(&e));
   CPS_CUDA(cudaFuncSetAttribute(ekf_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                2 * MAXM * MAXM * (int)sizeof(double)));
+                                200 * 1024));
   CPS_CUDA(cudaFuncSetAttribute(ekf_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (2 * MAXM * MAXM + MAXM + 16 * MAXM) * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1175,7 +1195,11 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   const int row_blocks = std::min((d.N + 7) / 8, h->sm_count * 8);
   const size_t sh_pht = (size_t)(d.M * d.nc + 8 * d.nc) * sizeof(double) + d.nc * sizeof(int);
   ekf_pht_kernel<<<row_blocks, 256, sh_pht, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_T);
-  ekf_s_kernel<<<1, 256, 2 * (size_t)M * M * sizeof(double), st>>>(d, h->d_T, h->d_small, h->d_cols, h->d_flag);
+  {
+    const size_t base_b = 2 * (size_t)M * M * sizeof(double), stage_b = 2 * (size_t)M * d.nc * sizeof(double);
+    const int staged = (base_b + stage_b <= 200 * 1024) ? 1 : 0;
+    ekf_s_kernel<<<1, 256, base_b + (staged ? stage_b : 0), st>>>(d, h->d_T, h->d_small, h->d_cols, h->d_flag, staged);
+  }
   const size_t sh_gain = (size_t)(2 * M * M + M + 16 * M) * sizeof(double);
   ekf_gain_kernel<<<row_blocks, 256, sh_gain, st>>>(d, h->d_T, h->d_small, h->d_Kt, h->d_Yt, h->d_x, h->cap);
   CPS_CUDA(cudaEventRecord(h->ev[2], st));
