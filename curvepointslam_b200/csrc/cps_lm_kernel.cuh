@@ -86,7 +86,7 @@ __host__ __device__ constexpr int lm_tile_region(int M, int n_max, bool dif) {
 // per-warp global (L2-resident) work area, doubles: the accepted residual e and t; dif adds f(p), f(p+dp) and the
 // column-major secant Jacobian.  Everything in it is only streamed with lane-coalesced accesses.
 __host__ __device__ constexpr int lm_ws_doubles(int M, int n_max, bool dif) {
-  return n_max + n_max / 2 + (dif ? 2 * n_max + M * n_max : 0);
+  return n_max + n_max / 2 + (dif ? 3 * n_max + M * n_max : 0);
 }
 
 // doubles of shared memory one warp needs
@@ -103,7 +103,7 @@ __host__ __device__ constexpr int lm_warp_smem_doubles(int M, int scratch, int n
 template <int M>
 struct WarpMem {
   const double* x;  // the fit's samples in global memory
-  double *t, *e, *hx, *wrk, *wrk2, *tile, *jtj;
+  double *t, *e, *hx, *wrk, *wrk2, *dbuf, *tile, *jtj;
   double *p, *dp, *pdp, *jte, *diag, *pw, *xs, *scale;
   double* scratch;
 };
@@ -325,8 +325,8 @@ __device__ __forceinline__ int build_items19(const FitGeom& g, int* items, int l
 // memory (dif); otherwise they are evaluated from the analytic Jacobian (der), compact when SP.
 template <class MD, bool SP, bool STORED>
 __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, const FitGeom& g,
-                                                   BlockAccum<MD::M, SP>& A, const double* J, int ld, int n_items,
-                                                   int lane) {
+                                                   BlockAccum<MD::M, SP>& A, double* J, int ld, int n_items,
+                                                   int lane, bool pending = false, double pend_dp_sq = 1.0) {
   constexpr int M = MD::M;
   using B = Blk<M, SP>;
   double* tiles = w.tile;
@@ -372,8 +372,24 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
         int tag = -1;
         if (r < g.n) {
           if constexpr (STORED) {
+            double jr[M];
 #pragma unroll
-            for (int j = 0; j < M; ++j) row[j] = J[j * ld + r];
+            for (int j = 0; j < M; ++j) jr[j] = J[j * ld + r];
+            if (pending) {
+              // the deferred rank-one secant update of this row (lm_core.c:745-755), applied on its way into the
+              // tile: tmp = (f(p+dp)_r - f(p)_r - J_r.dp)/||dp||^2, J_r += tmp*dp, written back to the stored Jacobian
+              double tmp = 0.0;
+#pragma unroll
+              for (int l = 0; l < M; ++l) tmp += jr[l] * w.dp[l];
+              tmp = (w.dbuf[r] - tmp) / pend_dp_sq;
+#pragma unroll
+              for (int j = 0; j < M; ++j) {
+                jr[j] += tmp * w.dp[j];
+                J[j * ld + r] = jr[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) row[j] = jr[j];
           } else if constexpr (SP) {
             double v[12];
             tag = MD::jac_row_compact(w.scratch, g, r, t_pre[gi], v);
@@ -801,6 +817,7 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
   double mu = 0.0, g_inf = 0.0, p_sq = 0.0, dp_sq = DBL_MAX;
   int nu, stop = 0, nfev = 0, njap = 0, nlss = 0, k, n_jtj = 0, n_broyden = 0;
   int updjac = 0, updp = 1, newjac = 0;
+  bool pending = false;  // a secant update whose application is deferred to the next J^T J build
 
   eval_func<MD>(w, g, w.p, w.hx, lane);
   nfev = 1;
@@ -845,12 +862,14 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
       ++njap;
       nfev += L.forward ? M : 2 * M;
       nu = 2; updjac = 0; updp = 0; newjac = 1;
+      pending = false;  // the fresh Jacobian overwrites every entry a deferred secant update would have touched
     }
 
     if (newjac) {
       newjac = 0;
-      if (blocked) normal_eqs_blocked<MD, false, true>(w, g, BA, J, ld, 0, lane);
+      if (blocked) normal_eqs_blocked<MD, false, true>(w, g, BA, J, ld, 0, lane, pending, dp_sq);
       else normal_eqs_stored<M>(w, g, J, ld, A, false, lane);
+      pending = false;
       ++n_jtj;
       grad_stats<M>(w, p_sq, g_inf, lane);
     }
@@ -868,14 +887,44 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
       if (!isfinite(e_new)) { stop = 7; break; }
       const double dF = e_sq - e_new;
       if (updp || dF > 0.0) {
-        // rank-one secant update, lm_core.c:745-755: one Jacobian row per lane
-        for (int i = lane; i < g.n; i += 32) {
-          double tmp = 0.0;
+        if (blocked) {
+          // rank-one secant update, lm_core.c:745-755, DEFERRED: nothing reads J before the next J^T J build, which
+          // streams every row through registers anyway, so the update is applied there (one pass over the 78 KB
+          // Jacobian instead of two).  It needs f(p+dp) - f(p) of this iteration, saved now because an accepted step
+          // overwrites f(p); dp and ||dp||^2 stay untouched until the next solve, which comes after the build.
+          for (int i = lane; i < g.n; i += 32) w.dbuf[i] = w.wrk[i] - w.hx[i];
+          pending = true;
+        } else {
+        // rank-one secant update, lm_core.c:745-755: one Jacobian row per lane, two rows in flight per trip.  The row
+          // is read once into registers (all M loads of both rows are issued before anything waits on them: the
+          // Jacobian lives in L2) and written back updated.
+          for (int i0 = lane; i0 < g.n; i0 += 64) {
+            const int i1 = i0 + 32;
+            const bool two = i1 < g.n;
+            double r0[M], r1[M];
 #pragma unroll
-          for (int l = 0; l < M; ++l) tmp += J[l * ld + i] * w.dp[l];
-          tmp = (w.wrk[i] - w.hx[i] - tmp) / dp_sq;
+            for (int l = 0; l < M; ++l) {
+              r0[l] = J[l * ld + i0];
+              r1[l] = two ? J[l * ld + i1] : 0.0;
+            }
+            const double d0 = w.wrk[i0] - w.hx[i0];
+            const double d1 = two ? (w.wrk[i1] - w.hx[i1]) : 0.0;
+            double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-          for (int j = 0; j < M; ++j) J[j * ld + i] += tmp * w.dp[j];
+            for (int l = 0; l < M; ++l) {
+              const double dpl = w.dp[l];
+              t0 += r0[l] * dpl;
+              t1 += r1[l] * dpl;
+            }
+            t0 = (d0 - t0) / dp_sq;
+            t1 = (d1 - t1) / dp_sq;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+              const double dpj = w.dp[j];
+              J[j * ld + i0] = r0[j] + t0 * dpj;
+              if (two) J[j * ld + i1] = r1[j] + t1 * dpj;
+            }
+          }
         }
         __syncwarp();
         ++updjac;
@@ -1036,10 +1085,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_k
     w.hx = ws + L.n_max + L.n_max / 2;  // f(p)
     w.wrk = w.hx + L.n_max;             // f(p + dp), finite-difference evaluations
     w.wrk2 = w.tile;                    // trial residual / second central-difference evaluation
-    J = w.wrk + L.n_max;
+    w.dbuf = w.wrk + L.n_max;           // f(p+dp) - f(p) of a deferred secant update
+    J = w.dbuf + L.n_max;
   } else {
     w.hx = w.tile;  // trial residual
-    w.wrk = nullptr; w.wrk2 = nullptr;
+    w.wrk = nullptr; w.wrk2 = nullptr; w.dbuf = nullptr;
   }
   w.jtj = base; base += M * M;
   w.p = base; w.dp = base + 32; w.pdp = base + 64; w.jte = base + 96; w.diag = base + 128; w.pw = base + 160;
