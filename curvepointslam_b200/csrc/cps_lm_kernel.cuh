@@ -125,12 +125,37 @@ __device__ __forceinline__ void eval_func(const WarpMem<MD::M>& w, const FitGeom
   __syncwarp();
 }
 
+// Trial evaluation of the secant path in one pass over the samples: f(p+dp) -> fout (global), the trial residual
+// x - f(p+dp) -> eout (shared memory, fed to the norm chains without a round trip through L2), and
+// f(p+dp) - f(p) -> dout (what a deferred secant update needs; an accepted step overwrites f(p)).
+template <class MD>
+__device__ __forceinline__ void eval_trial(const WarpMem<MD::M>& w, const FitGeom& g, const double* p, double* fout,
+                                           double* eout, double* dout, const double* fold, int lane) {
+  MD::prep_func(p, w.scratch, lane);
+  __syncwarp();
+  for (int s = lane; s < g.nsamp; s += 32) {
+    double hu, hv;
+    MD::eval_sample(w.scratch, g, s, w.t[s], hu, hv);
+    const double2 xv = *reinterpret_cast<const double2*>(w.x + 2 * s);
+    const double2 fo = *reinterpret_cast<const double2*>(fold + 2 * s);
+    *reinterpret_cast<double2*>(fout + 2 * s) = make_double2(hu, hv);
+    *reinterpret_cast<double2*>(eout + 2 * s) = make_double2(xv.x - hu, xv.y - hv);
+    *reinterpret_cast<double2*>(dout + 2 * s) = make_double2(hu - fo.x, hv - fo.y);
+  }
+  __syncwarp();
+}
+
 // e = x - y, returns ||e||^2 in the summation order of dlevmar_L2nrmxmy (misc_core.c:712-798): four
 // running sums fed from the top index downwards in groups of eight, ragged tail upwards, then
 // ((s0+s1)+s2)+s3.  The four chains run on lanes 0..3.  e may alias y.
+__device__ __forceinline__ double residual_chains(const double* e, int n, int lane);
 __device__ __forceinline__ double residual_sqnorm(double* e, const double* x, const double* y, int n, int lane) {
   for (int i = lane; i < n; i += 32) e[i] = x[i] - y[i];
   __syncwarp();
+  return residual_chains(e, n, lane);
+}
+// ||e||^2 of a residual already stored (shared memory): the four reference chains on lanes 0..3
+__device__ __forceinline__ double residual_chains(const double* e, int n, int lane) {
   double s = 0.0;
   if (lane < 4) {
     const int full = (n >> 3) << 3;
@@ -881,9 +906,9 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
     if (solved) {
       const int chk = step_checks<M>(w, p_sq, L.eps2, L.eps2_sq, dp_sq, lane);
       if (chk) { stop = chk; break; }
-      eval_func<MD>(w, g, w.pdp, w.wrk, lane);
+      eval_trial<MD>(w, g, w.pdp, w.wrk, w.wrk2, w.dbuf, w.hx, lane);
       ++nfev;
-      const double e_new = residual_sqnorm(w.wrk2, w.x, w.wrk, g.n, lane);
+      const double e_new = residual_chains(w.wrk2, g.n, lane);
       if (!isfinite(e_new)) { stop = 7; break; }
       const double dF = e_sq - e_new;
       if (updp || dF > 0.0) {
@@ -892,8 +917,7 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
           // streams every row through registers anyway, so the update is applied there (one pass over the 78 KB
           // Jacobian instead of two).  It needs f(p+dp) - f(p) of this iteration, saved now because an accepted step
           // overwrites f(p); dp and ||dp||^2 stay untouched until the next solve, which comes after the build.
-          for (int i = lane; i < g.n; i += 32) w.dbuf[i] = w.wrk[i] - w.hx[i];
-          pending = true;
+          pending = true;  // f(p+dp) - f(p) was saved by eval_trial
         } else {
         // rank-one secant update, lm_core.c:745-755: one Jacobian row per lane, two rows in flight per trip.  The row
           // is read once into registers (all M loads of both rows are issued before anything waits on them: the
@@ -1118,7 +1142,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_k
     int ret_code = 0;
     if (nn < M) ret_code = -1;               // lm_core.c:117 / :493: fewer measurements than unknowns
     else if (nn > L.n_max || (nn & 1)) ret_code = -2;  // does not fit the staged buffers / odd length
-    else if (!DIF && M == 19 && nn > 40 * kTileRows) ret_code = -2;  // the compact path lists at most 40+ row blocks
+    else if (!DIF && M == 19 && nn > 40 * kTileRows) ret_code = -2;
+    else if (DIF && (o0 & 1)) ret_code = -3;  // the secant path reads (x,y) sample pairs as 16-byte words  // the compact path lists at most 40+ row blocks
     {
       int c[4] = {0, 0, 0, 0};
 #pragma unroll
