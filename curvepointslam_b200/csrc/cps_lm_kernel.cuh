@@ -399,7 +399,7 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
           if constexpr (STORED) {
             double jr[M];
 #pragma unroll
-            for (int j = 0; j < M; ++j) jr[j] = J[j * ld + r];
+            for (int j = 0; j < M; ++j) jr[j] = __ldcg(J + j * ld + r);  // streamed: keep L1 for t, x, f(p)
             if (pending) {
               // the deferred rank-one secant update of this row (lm_core.c:745-755), applied on its way into the
               // tile: tmp = (f(p+dp)_r - f(p)_r - J_r.dp)/||dp||^2, J_r += tmp*dp, written back to the stored Jacobian
@@ -410,7 +410,7 @@ __device__ __forceinline__ void normal_eqs_blocked(const WarpMem<MD::M>& w, cons
 #pragma unroll
               for (int j = 0; j < M; ++j) {
                 jr[j] += tmp * w.dp[j];
-                J[j * ld + r] = jr[j];
+                __stcg(J + j * ld + r, jr[j]);
               }
             }
 #pragma unroll
@@ -870,7 +870,7 @@ __device__ void lm_dif(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch
           __syncwarp();
           eval_func<MD>(w, g, w.pw, w.wrk, lane);
           const double inv = 1.0 / d;
-          for (int i = lane; i < g.n; i += 32) J[j * ld + i] = (w.wrk[i] - w.hx[i]) * inv;
+          for (int i = lane; i < g.n; i += 32) __stcg(J + j * ld + i, (w.wrk[i] - w.hx[i]) * inv);
         } else {
           if (lane == 0) w.pw[j] = keep - d;
           __syncwarp();
