@@ -162,6 +162,75 @@ def single_frame_bench(device: int, reps: int = 20):
     return out
 
 
+def lm_sweep(device: int):
+    """BASELINE.json configs[1]: batched Bezier LM fit sweep 1k-1M contours on one B200 (m=19 fits of 4 contours
+    each), der, through the host-buffer C ABI (copies inside the timed region)."""
+    from curvepointslam_b200 import lm, synth
+    ctx = lm.LmContext(device)
+    out = []
+    import torch
+    big = synth.make_stereo19_batch_fast(65536, K=64, seed=12)
+    for key in ("p0", "meas", "off", "counts"):  # pinned host memory, like a capture pipeline would hand over
+        big[key] = torch.from_numpy(big[key]).pin_memory().numpy()
+    for B in (256, 2048, 16384, 65536):
+        sl = slice(0, B * 512)
+        args = (lm.STEREO19, lm.DER, big["p0"][:B], big["meas"][sl], big["off"][:B + 1], big["counts"][:B])
+        for _ in range(2):
+            ctx.fit_batched(*args)
+        reps = 5 if B <= 16384 else 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.fit_batched(*args)
+        dt = (time.perf_counter() - t0) / reps
+        out.append({"fits": B, "contours": 4 * B, "e2e_ms": dt * 1e3, "fits_per_sec": B / dt})
+    ctx.close()
+    return out
+
+
+def image8_bench(device: int, B: int = 1 << 20):
+    """Per-contour image-space fits (m=8, 64 points): the "8 x 8" problem of the north star; device-resident
+    inputs, der and dif, with the reference levmar on all cores on a sample."""
+    import torch
+
+    from curvepointslam_b200 import lm, synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import DER, DIF, IMAGE8, oracle
+    ctx = lm.LmContext(device)
+    b = synth.make_image8_batch(B, K=64, seed=13)
+    dev = torch.device("cuda", device)
+    d_meas, d_p0 = torch.from_numpy(b["meas"]).to(dev), torch.from_numpy(b["p0"]).to(dev)
+    d_off, d_cnt = torch.from_numpy(b["off"]).to(dev), torch.from_numpy(b["counts"]).to(dev)
+    d_p = torch.empty_like(d_p0)
+    d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+    d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+    out = {"fits": B, "points_per_contour": 64}
+    st = torch.cuda.current_stream()
+    for name, var, ovar in (("der", lm.DER, DER), ("dif", lm.DIF, DIF)):
+        ts = []
+        for it in range(5):
+            d_p.copy_(d_p0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            ctx.fit_batched_dev(lm.IMAGE8, var, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(),
+                                d_cnt.data_ptr(), 128, d_info.data_ptr(), d_ret.data_ptr(), None,
+                                stream=st.cuda_stream)
+            e1.record(st)
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts))
+        S = 32768
+        t0 = time.perf_counter()
+        c = oracle().fit_batch(IMAGE8, ovar, b["p0"][:S], b["meas"][:S * 128], b["off"][:S + 1], b["counts"][:S],
+                               list(lm.REFERENCE_OPTS), nthreads=os.cpu_count() or 1, use_ref=oracle().ref is not None)
+        cpu_s = time.perf_counter() - t0
+        same = bool(np.array_equal(d_p[:S].cpu().numpy().view(np.int64), c["p"].view(np.int64)))
+        out[name] = {"kernel_ms": ms, "contours_per_sec": B / (ms * 1e-3), "cpu_all_cores_contours_per_sec": S / cpu_s,
+                     "cores": os.cpu_count(), "iters_mean": float(d_info[:, 5].mean().item()), "bit_identical_on_sample": same}
+    ctx.close()
+    return out
+
+
 def run(device: int = 0):
     res = {"ekf_update": [], "gate": None}
     for L in (1000, 5000, 20000):
@@ -177,6 +246,14 @@ def run(device: int = 0):
         res["ekf_cpu_baseline"] = ekf_cpu_baseline(1000)
     except Exception as ex:
         res["ekf_cpu_baseline"] = {"error": repr(ex)}
+    try:
+        res["lm_sweep_der_e2e"] = lm_sweep(device)
+    except Exception as ex:
+        res["lm_sweep_der_e2e"] = {"error": repr(ex)}
+    try:
+        res["image8"] = image8_bench(device)
+    except Exception as ex:
+        res["image8"] = {"error": repr(ex)}
     try:
         res["single_frame"] = single_frame_bench(device)
     except Exception as ex:
