@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(256) ekf_add_curve_kernel(double* __restrict__
       const double* A = in + 8;
       const double Tx = x[0], Ty = x[1], psi = x[5];
       const double c = cos(psi), s_ = sin(psi);
-      double Ainv[16], rz[8], rdz[8], a1[4];
+      double Ainv[16], rz[8], rdz[8];
       inv4(A, Ainv);
       // Rot = [[c I, -s I], [s I, c I]] (the transpose of the update's Rot, :333-343); Rotderiv likewise
       for (int i = 0; i < 4; ++i) {
@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(256) ekf_add_curve_kernel(double* __restrict__
           dy += Ainv[4 * i + j] * rdz[j + 4];
           so += Ainv[4 * i + j];
         }
-        xnew[i] = sx; xnew[i + 4] = sy; a1[i] = so;
+        xnew[i] = sx; xnew[i + 4] = sy;
         for (int j = 0; j < 12; ++j) { Gx[i][j] = 0.0; Gx[i + 4][j] = 0.0; }
         Gx[i][0] = so; Gx[i + 4][1] = so; Gx[i][5] = dx; Gx[i + 4][5] = dy;
         for (int j = 0; j < 4; ++j) {  // Gz = Hinv Rot
@@ -872,7 +872,6 @@ __global__ void __launch_bounds__(256) ekf_add_curve_kernel(double* __restrict__
           Gz[i + 4][j] = Ainv[4 * i + j] * s_; Gz[i + 4][j + 4] = Ainv[4 * i + j] * c;
         }
       }
-      (void)a1;
     }
     __syncthreads();
   }
@@ -985,17 +984,9 @@ int round_up(int v, int q) { return (v + q - 1) / q * q; }
 }  // namespace
 
 // =================================== C ABI ===================================
-extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
-  if (!out || capacity < CPS_ROBOT_STATE_SIZE) return CPS_ERR_INVALID;
-  *out = nullptr;
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
-    cps::set_last_error("no CUDA device: libcps has no CPU path");
-    return CPS_ERR_CUDA;
-  }
-  if (device < 0 || device >= count) return CPS_ERR_INVALID;
-  CPS_CUDA(cudaSetDevice(device));
-  cps_ekf* h = new cps_ekf();
+extern "C" void cps_ekf_destroy(cps_ekf* h);
+namespace {
+int ekf_create_impl(cps_ekf* h, int device, int capacity) {
   h->device = device;
   h->cap = round_up(capacity, TILE);
   CPS_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -1004,8 +995,6 @@ extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
   if (cudaMalloc(&h->d_P, cap * cap * sizeof(double)) != cudaSuccess) {
     cps::set_last_error("cudaMalloc of the covariance failed");
     cudaGetLastError();
-    cudaStreamDestroy(h->stream);
-    delete h;
     return CPS_ERR_NOMEM;
   }
   CPS_CUDA(cudaMalloc(&h->d_x, cap * sizeof(double)));
@@ -1038,9 +1027,30 @@ extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
   CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (MAXM * MAXNC + 8 * MAXNC) * (int)sizeof(double) + MAXNC * (int)sizeof(int)));
   CPS_CUDA(cudaStreamSynchronize(h->stream));
+  return CPS_OK;
+}
+}  // namespace
+
+extern "C" int cps_ekf_create(cps_ekf** out, int device, int capacity) {
+  if (!out || capacity < CPS_ROBOT_STATE_SIZE) return CPS_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cps::set_last_error("no CUDA device: libcps has no CPU path");
+    return CPS_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(device));
+  cps_ekf* h = new cps_ekf();
+  const int rc = ekf_create_impl(h, device, capacity);
+  if (rc != CPS_OK) {  // release whatever was allocated before the failure
+    cps_ekf_destroy(h);
+    return rc;
+  }
   *out = h;
   return CPS_OK;
 }
+
 
 extern "C" void cps_ekf_destroy(cps_ekf* h) {
   if (!h) return;

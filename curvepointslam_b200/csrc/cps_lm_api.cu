@@ -41,6 +41,7 @@ struct cps_lm_ctx {
 
 extern "C" const char* cps_last_error(void) { return cps::g_last_error.c_str(); }
 
+extern "C" void cps_lm_destroy(cps_lm_ctx* c);
 extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
   if (!out) return CPS_ERR_INVALID;
   *out = nullptr;
@@ -53,11 +54,19 @@ extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
   CPS_CUDA(cudaSetDevice(device));
   cps_lm_ctx* c = new cps_lm_ctx();
   c->device = device;
-  CPS_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-  CPS_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  for (int i = 0; i < kSlots; ++i) {
-    CPS_CUDA(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
-    CPS_CUDA(cudaMalloc(&c->slot[i].d_queue, sizeof(unsigned int)));
+  auto init = [&]() -> int {
+    CPS_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CPS_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    for (int i = 0; i < kSlots; ++i) {
+      CPS_CUDA(cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking));
+      CPS_CUDA(cudaMalloc(&c->slot[i].d_queue, sizeof(unsigned int)));
+    }
+    return CPS_OK;
+  };
+  const int rc = init();
+  if (rc != CPS_OK) {
+    cps_lm_destroy(c);
+    return rc;
   }
   *out = c;
   return CPS_OK;
