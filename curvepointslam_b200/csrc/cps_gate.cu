@@ -18,7 +18,7 @@
 namespace {
 
 constexpr double PT_MEAS_COV = 5.0;  // kalmanClass.h:18
-constexpr int GATE_THREADS = 256;
+constexpr int GATE_THREADS = 128;
 constexpr int GATE_TILE = 256;  // landmarks staged per shared-memory tile
 
 struct RotArgs {
@@ -77,38 +77,56 @@ __global__ void __launch_bounds__(256) gate_pack_kernel(const double* __restrict
   q[6] = c11 * idet; q[7] = c12 * idet; q[8] = c22 * idet;
 }
 
-// grid (measurement blocks, landmark chunks); partial best per (chunk, measurement)
+// grid (measurement blocks, landmark chunks); partial best per (chunk, measurement).  Every thread carries
+// GATE_MPT measurements in registers, so the 9 broadcast loads of a landmark pack feed GATE_MPT * 23 flops (with one
+// measurement per thread the sweep was limited by shared-memory wavefronts, not by the FP64 pipe).
+constexpr int GATE_MPT = 4;
+
 __global__ void __launch_bounds__(GATE_THREADS) gate_sweep_kernel(const double* __restrict__ pack, int n_land,
                                                                   const double* __restrict__ z, int nz, double gate,
                                                                   int chunk, double* __restrict__ part_d2,
                                                                   int* __restrict__ part_idx) {
   __shared__ double tile[GATE_TILE * 9];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * GATE_MPT;
   const int jlo = blockIdx.y * chunk;
   const int jhi = min(n_land, jlo + chunk);
-  double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-  if (i < nz) { z0 = z[3 * (size_t)i]; z1 = z[3 * (size_t)i + 1]; z2 = z[3 * (size_t)i + 2]; }
-  double best = gate;
-  int bi = -1;
+  double z0[GATE_MPT], z1[GATE_MPT], z2[GATE_MPT], best[GATE_MPT];
+  int bi[GATE_MPT];
+#pragma unroll
+  for (int q = 0; q < GATE_MPT; ++q) {
+    const int i = i0 + q;
+    z0[q] = z1[q] = z2[q] = 0.0;
+    if (i < nz) { z0[q] = z[3 * (size_t)i]; z1[q] = z[3 * (size_t)i + 1]; z2[q] = z[3 * (size_t)i + 2]; }
+    best[q] = gate;
+    bi[q] = -1;
+  }
   for (int j0 = jlo; j0 < jhi; j0 += GATE_TILE) {
     const int cnt = min(GATE_TILE, jhi - j0);
     __syncthreads();
     for (int e = threadIdx.x; e < cnt * 9; e += blockDim.x) tile[e] = pack[9 * (size_t)j0 + e];
     __syncthreads();
-#pragma unroll 2
     for (int jj = 0; jj < cnt; ++jj) {
-      const double* q = tile + 9 * jj;
-      const double n0 = z0 - q[0], n1 = z1 - q[1], n2 = z2 - q[2];
-      const double t0 = (q[3] * n0 + q[4] * n1) + q[5] * n2;
-      const double t1 = (q[4] * n0 + q[6] * n1) + q[7] * n2;
-      const double t2 = (q[5] * n0 + q[7] * n1) + q[8] * n2;
-      const double d2 = (n0 * t0 + n1 * t1) + n2 * t2;
-      if (d2 < best) { best = d2; bi = j0 + jj; }
+      const double* q9 = tile + 9 * jj;
+      const double c0 = q9[0], c1 = q9[1], c2 = q9[2], s00 = q9[3], s01 = q9[4], s02 = q9[5], s11 = q9[6],
+                   s12 = q9[7], s22 = q9[8];
+#pragma unroll
+      for (int q = 0; q < GATE_MPT; ++q) {
+        const double n0 = z0[q] - c0, n1 = z1[q] - c1, n2 = z2[q] - c2;
+        const double t0 = (s00 * n0 + s01 * n1) + s02 * n2;
+        const double t1 = (s01 * n0 + s11 * n1) + s12 * n2;
+        const double t2 = (s02 * n0 + s12 * n1) + s22 * n2;
+        const double d2 = (n0 * t0 + n1 * t1) + n2 * t2;
+        if (d2 < best[q]) { best[q] = d2; bi[q] = j0 + jj; }
+      }
     }
   }
-  if (i < nz) {
-    part_d2[(size_t)blockIdx.y * nz + i] = best;
-    part_idx[(size_t)blockIdx.y * nz + i] = bi;
+#pragma unroll
+  for (int q = 0; q < GATE_MPT; ++q) {
+    const int i = i0 + q;
+    if (i < nz) {
+      part_d2[(size_t)blockIdx.y * nz + i] = best[q];
+      part_idx[(size_t)blockIdx.y * nz + i] = bi[q];
+    }
   }
 }
 
@@ -187,7 +205,8 @@ extern "C" int cps_gate_mahalanobis_dev(cps_ekf* h, const double* d_z, int nz, d
     CPS_CUDA(cudaMalloc(&h->d_pcols, sizeof(int) * (size_t)std::max(n_land, 1)));
     h->pack_cap = (size_t)n_land;
   }
-  const int row_blocks = (nz + GATE_THREADS - 1) / GATE_THREADS;
+  const int row_blocks = (nz + GATE_THREADS * GATE_MPT - 1) / (GATE_THREADS * GATE_MPT);
+  const int reduce_blocks = (nz + GATE_THREADS - 1) / GATE_THREADS;
   int nchunks = std::max(1, (4 * h->sm_count + row_blocks - 1) / row_blocks);
   nchunks = std::min(nchunks, std::max(1, (n_land + GATE_TILE - 1) / GATE_TILE));
   const int chunk = std::max(1, (n_land + nchunks - 1) / nchunks);
@@ -211,7 +230,7 @@ extern "C" int cps_gate_mahalanobis_dev(cps_ekf* h, const double* d_z, int nz, d
   CPS_CUDA(cudaEventRecord(h->gev[1], st));
   gate_sweep_kernel<<<dim3(row_blocks, nchunks), GATE_THREADS, 0, st>>>(h->d_pack, n_land, d_z, nz, gate, chunk,
                                                                         h->d_part_d2, h->d_part_idx);
-  gate_reduce_kernel<<<row_blocks, GATE_THREADS, 0, st>>>(h->d_part_d2, h->d_part_idx, nchunks, nz, gate, d_idx, d_d2);
+  gate_reduce_kernel<<<reduce_blocks, GATE_THREADS, 0, st>>>(h->d_part_d2, h->d_part_idx, nchunks, nz, gate, d_idx, d_d2);
   h->launches += 2;
   CPS_CUDA(cudaEventRecord(h->gev[2], st));
   CPS_CUDA(cudaGetLastError());
