@@ -302,7 +302,7 @@ def main():
             "peak_source": "measured live by cps_measure_fp64_peak (DFMA stream; MEASURED_PEAKS.json has no FP64 "
                            "entry); a kernel that may not fuse multiply-adds (bit-exact parity) tops out at "
                            f"{pk_ma.value:.2f} TFLOP/s",
-            "peak_unfused": pk_ma.value,
+            "peak_unfused": pk_ma.value, "frac_of_unfused": achieved_tf / pk_ma.value,
             "flops_per_fit": fl / B, "kernel_ms": kernel_ms_avg,
             "hbm": {"achieved": flops.fit_bytes(N_MEAS, M) * B / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "note": "algorithmic bytes; the path is FP64-bound, not HBM-bound"},
@@ -316,7 +316,7 @@ def main():
                       "stop_reasons": {str(int(r)): int(c) for r, c in zip(reasons, rc_counts)}},
     }
 
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU leg runs at N=1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from oracle_lib import DER, DIF, STEREO19, oracle
         o = oracle()
@@ -340,7 +340,7 @@ def main():
                                           + ("levmar-2.5 from /root/reference (oracle/_ref) + restated model"
                                              if use_ref else "oracle port"),
                                 "seconds": dt, "gpu_bit_identical_on_sample": same}
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         try:
             import bench_extras
             line["extras"] = bench_extras.run(local)

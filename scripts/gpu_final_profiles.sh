@@ -1,0 +1,23 @@
+# Round-end evidence run (under gpurun): tests, bench lines, ncu launch lists and --set full captures.
+# Every ncu run is preceded by the same command line exiting 0 without ncu.
+set -x
+cd $GRAFT_REPO_ROOT
+make -s -C oracle 2>&1 | tail -2
+python -m pytest tests -q -m gpu 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 > gpurun_out/final_bench_der.json 2> gpurun_out/final_bench_der.err
+python bench.py --variant dif --steps 3 --warmup 3 --fits 65536 --no-extras > gpurun_out/final_bench_dif.json 2> gpurun_out/final_bench_dif.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_bench_reference_der.json 2>/dev/null
+python bench.py --impl reference --variant dif --steps 3 --warmup 1 > gpurun_out/final_bench_reference_dif.json 2>/dev/null
+SMALL="python bench.py --fits 32768 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
+$SMALL > gpurun_out/plain1.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/final_launches_lm_der.csv $SMALL > gpurun_out/ncu_a.log 2>&1
+$SMALL > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:lm_fit_kernel -s 3 -c 1 -o gpurun_out/final_prof_lm_der $SMALL > gpurun_out/ncu_b.log 2>&1
+SMALLD="python bench.py --variant dif --fits 8192 --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
+$SMALLD > gpurun_out/plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:lm_fit_kernel -s 3 -c 1 -o gpurun_out/final_prof_lm_dif $SMALLD > gpurun_out/ncu_c.log 2>&1
+python scripts/ekfprof.py > gpurun_out/plain4.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:ekf_cov_pipe_kernel -s 1 -c 1 -o gpurun_out/final_prof_ekf_cov python scripts/ekfprof.py > gpurun_out/ncu_d.log 2>&1
+python scripts/ekfprof.py > gpurun_out/plain5.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/final_launches_ekf.csv python scripts/ekfprof.py > gpurun_out/ncu_e.log 2>&1
+ls -la gpurun_out | tail -20
