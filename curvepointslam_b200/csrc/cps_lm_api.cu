@@ -350,6 +350,185 @@ extern "C" int cps_fit_curve_init_batched(cps_lm_ctx* c, int B, const double* me
   return CPS_OK;
 }
 
+// ---- cleanup_and_group_edges (curveFittingClass.cpp:1207-1418): contours -> packed fit inputs --------------------
+namespace {
+constexpr int kLrOffset = 0;     // LEFT_RIGHT_OFFSET, common.h:108
+constexpr int kLenCurve = 100;   // LENGTH_EACH_CURVE, common.h:112
+
+// one thread per frame walks the reference's trimming loops (integer compares on image rows, inherently serial
+// inside a frame, independent across frames); rng = kept index range per segment, cnt = points kept
+__global__ void __launch_bounds__(128) edges_trim_kernel(int F, const int* __restrict__ pts,
+                                                         const long long* __restrict__ seg_off, int reset_da,
+                                                         const double* __restrict__ tracked, int* __restrict__ rng,
+                                                         int* __restrict__ cnt, int* __restrict__ valid) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int* seg[4];
+  int size[4], r0[4], r1[4], ys[4], ye[4];
+  bool ok = true;
+  for (int s = 0; s < 4; ++s) {
+    seg[s] = pts + 2 * seg_off[4 * f + s];
+    size[s] = (int)(seg_off[4 * f + s + 1] - seg_off[4 * f + s]);
+    r0[s] = 0;
+    r1[s] = size[s] - 1;
+    if (size[s] < 10) ok = false;
+  }
+#define YAT(s, k) (seg[s][2 * (k) + 1])
+  if (ok) {
+    for (int s = 0; s < 4; ++s) { ys[s] = YAT(s, 0); ye[s] = YAT(s, size[s] - 1); }
+    for (int i = 0; i < 2 && ok; ++i) {  // align the starts of the left / right view of curve i
+      const int L = i, R = i + 2;
+      if (ys[L] > ys[R] - kLrOffset) {
+        while (ok && ys[L] > ys[R] - kLrOffset) {
+          if (++r0[L] >= size[L]) { ok = false; break; }
+          ys[L] = YAT(L, r0[L]);
+        }
+      } else if (ys[L] < ys[R] - kLrOffset) {
+        while (ok && ys[L] < ys[R] - kLrOffset) {
+          if (++r0[R] >= size[R]) { ok = false; break; }
+          ys[R] = YAT(R, r0[R]);
+        }
+      }
+    }
+    for (int i = 0; i < 2 && ok; ++i) {
+      const int L = i, R = i + 2;
+      if (ye[L] < ye[R] - kLrOffset) {
+        while (ye[L] < ye[R] - kLrOffset) {
+          if (--r1[L] < 0) { ok = false; break; }
+          ye[L] = YAT(L, r1[L]);
+        }
+      } else if (ye[L] > ye[R] - kLrOffset) {
+        while (ye[L] > ye[R] - kLrOffset) {
+          if (--r1[R] < 0) { ok = false; break; }
+          ye[R] = YAT(R, r1[R]);
+        }
+      }
+      while (ok && ye[L] < ys[L] - kLenCurve) {
+        if (--r1[L] < 0) { ok = false; break; }
+        ye[L] = YAT(L, r1[L]);
+      }
+      while (ok && ye[R] < ys[R] - kLenCurve) {
+        if (--r1[R] < 0) { ok = false; break; }
+        ye[R] = YAT(R, r1[R]);
+      }
+      const double te = tracked[2 * f + i];
+      while (ok && ye[L] > te && !reset_da) {
+        ++r0[L]; ++r1[L];
+        if (r0[L] >= size[L] || r1[L] >= size[L]) { ok = false; break; }
+        ye[L] = YAT(L, r1[L]);
+      }
+      while (ok && ye[R] > te + kLrOffset && !reset_da) {
+        ++r1[R]; ++r0[R];
+        if (r0[R] >= size[R] || r1[R] >= size[R]) { ok = false; break; }
+        ye[R] = YAT(R, r1[R]);
+      }
+    }
+    for (int i = 0; i < 2 && ok; ++i) {  // both curves of an image end on the same row
+      const int A = 2 * i, B = 2 * i + 1;
+      if (ye[A] > ye[B]) {
+        while (ye[A] > ye[B]) {
+          ++r0[A]; ++r1[A];
+          if (r0[A] >= size[A] || r1[A] >= size[A]) { ok = false; break; }
+          ye[A] = YAT(A, r1[A]);
+        }
+      } else {
+        while (ye[A] < ye[B]) {
+          ++r0[B]; ++r1[B];
+          if (r0[B] >= size[B] || r1[B] >= size[B]) { ok = false; break; }
+          ye[B] = YAT(B, r1[B]);
+        }
+      }
+    }
+  }
+#undef YAT
+  for (int s = 0; s < 4; ++s) {
+    int c = ok ? min(r1[s] - r0[s] + 1, 10000) : 0;
+    if (ok && c < 1) ok = false;
+    rng[8 * f + 2 * s] = r0[s];
+    rng[8 * f + 2 * s + 1] = r1[s];
+    cnt[4 * f + s] = c;
+  }
+  if (!ok)
+    for (int s = 0; s < 4; ++s) cnt[4 * f + s] = 0;
+  valid[f] = ok ? 1 : 0;
+}
+
+// pack the kept points as doubles in the fit's measurement order [L c1 | L c2 | R c1 | R c2] (fit_curve :435-489;
+// the reference copies into four CvMat :1395-1413)
+__global__ void __launch_bounds__(256) edges_pack_kernel(int F, const int* __restrict__ pts,
+                                                         const long long* __restrict__ seg_off,
+                                                         const int* __restrict__ rng, const int* __restrict__ cnt,
+                                                         const long long* __restrict__ off, double* __restrict__ meas) {
+  const int f = blockIdx.x;
+  if (f >= F) return;
+  int c[4], base[4];
+  int acc = 0;
+  for (int s = 0; s < 4; ++s) { c[s] = cnt[4 * f + s]; base[s] = acc; acc += c[s]; }
+  double* out = meas + off[f];
+  for (int k = threadIdx.x; k < acc; k += blockDim.x) {
+    const int s = (k >= base[1]) + (k >= base[2]) + (k >= base[3]);
+    const int idx = rng[8 * f + 2 * s] + (k - base[s]);
+    const int* p = pts + 2 * (seg_off[4 * f + s] + idx);
+    out[2 * k] = (double)p[0];
+    out[2 * k + 1] = (double)p[1];
+  }
+}
+}  // namespace
+
+extern "C" int cps_cleanup_and_group_edges_batched(cps_lm_ctx* c, int F, const int* pts, const long long* seg_off,
+                                                   int reset_data_assoc, const double* tracked_endpt_y, double* meas_out,
+                                                   long long* off_out, int* counts_out, int* valid_out) {
+  if (!c || F < 0 || (F && (!pts || !seg_off || !tracked_endpt_y || !meas_out || !off_out || !counts_out || !valid_out)))
+    return CPS_ERR_INVALID;
+  if (F == 0) { if (off_out) off_out[0] = 0; return CPS_OK; }
+  for (int k = 0; k < 4 * F; ++k)
+    if (seg_off[k + 1] < seg_off[k]) return CPS_ERR_INVALID;
+  CPS_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->slot[0].stream;
+  const long long npts = seg_off[4 * F] - seg_off[0];
+  int *d_pts = nullptr, *d_rng = nullptr, *d_cnt = nullptr, *d_valid = nullptr;
+  long long *d_seg = nullptr, *d_off = nullptr;
+  double *d_tr = nullptr, *d_meas = nullptr;
+  std::vector<long long> seg0((size_t)4 * F + 1);
+  for (int k = 0; k <= 4 * F; ++k) seg0[k] = seg_off[k] - seg_off[0];
+  auto cleanup = [&]() {
+    cudaFree(d_pts); cudaFree(d_rng); cudaFree(d_cnt); cudaFree(d_valid); cudaFree(d_seg); cudaFree(d_off);
+    cudaFree(d_tr); cudaFree(d_meas);
+  };
+  auto run = [&]() -> int {
+    CPS_CUDA(cudaMalloc(&d_pts, sizeof(int) * 2 * (size_t)std::max<long long>(npts, 1)));
+    CPS_CUDA(cudaMalloc(&d_seg, sizeof(long long) * ((size_t)4 * F + 1)));
+    CPS_CUDA(cudaMalloc(&d_tr, sizeof(double) * 2 * (size_t)F));
+    CPS_CUDA(cudaMalloc(&d_rng, sizeof(int) * 8 * (size_t)F));
+    CPS_CUDA(cudaMalloc(&d_cnt, sizeof(int) * 4 * (size_t)F));
+    CPS_CUDA(cudaMalloc(&d_valid, sizeof(int) * (size_t)F));
+    CPS_CUDA(cudaMalloc(&d_off, sizeof(long long) * ((size_t)F + 1)));
+    CPS_CUDA(cudaMemcpyAsync(d_pts, pts + 2 * seg_off[0], sizeof(int) * 2 * (size_t)npts, cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d_seg, seg0.data(), sizeof(long long) * ((size_t)4 * F + 1), cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d_tr, tracked_endpt_y, sizeof(double) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
+    edges_trim_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, d_pts, d_seg, reset_data_assoc, d_tr, d_rng, d_cnt, d_valid);
+    CPS_CUDA(cudaGetLastError());
+    CPS_CUDA(cudaMemcpyAsync(counts_out, d_cnt, sizeof(int) * 4 * (size_t)F, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(valid_out, d_valid, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaStreamSynchronize(st));
+    off_out[0] = 0;  // exclusive scan of the per-frame measurement counts (host: F integers)
+    for (int f = 0; f < F; ++f)
+      off_out[f + 1] = off_out[f] + 2LL * (counts_out[4 * f] + counts_out[4 * f + 1] + counts_out[4 * f + 2] + counts_out[4 * f + 3]);
+    const long long total = off_out[F];
+    CPS_CUDA(cudaMalloc(&d_meas, sizeof(double) * (size_t)std::max<long long>(total, 1)));
+    CPS_CUDA(cudaMemcpyAsync(d_off, off_out, sizeof(long long) * ((size_t)F + 1), cudaMemcpyHostToDevice, st));
+    edges_pack_kernel<<<F, 256, 0, st>>>(F, d_pts, d_seg, d_rng, d_cnt, d_off, d_meas);
+    CPS_CUDA(cudaGetLastError());
+    if (total) CPS_CUDA(cudaMemcpyAsync(meas_out, d_meas, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaStreamSynchronize(st));
+    c->launches += 2;
+    return CPS_OK;
+  };
+  const int rc = run();
+  cleanup();
+  return rc;
+}
+
 // ---- same-signature shims ---------------------------------------------------------------------------
 // The callbacks are tokens: the device model is selected by comparing pointers; calling them is an error.
 extern "C" void cps_modelfunc(double*, double*, int, int, void*) {

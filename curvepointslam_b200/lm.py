@@ -87,6 +87,24 @@ class LmContext:
                    "cps_fit_curve_init_batched")
         return p
 
+    def cleanup_and_group_edges(self, pts, seg_off, tracked_endpt_y, reset_data_assoc=False):
+        """CurveFittingClass::cleanup_and_group_edges (curveFittingClass.cpp:1207-1418) for F frames.
+        pts [P,2] int32 pixel (x,y); seg_off [4F+1] point offsets ([L0, L1, R0, R1] per frame); tracked_endpt_y [F,2].
+        Returns dict(meas, off, counts, valid): the inputs of fit_batched / init_guess."""
+        pts = np.ascontiguousarray(pts, dtype=np.int32).reshape(-1, 2)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        F = (len(seg_off) - 1) // 4
+        tr = np.ascontiguousarray(tracked_endpt_y, dtype=np.float64).reshape(F, 2)
+        meas = np.zeros(2 * max(len(pts), 1))
+        off = np.zeros(F + 1, dtype=np.int64)
+        counts = np.zeros((F, 4), dtype=np.int32)
+        valid = np.zeros(F, dtype=np.int32)
+        _lib.check(_lib.lib().cps_cleanup_and_group_edges_batched(self._h, F, _vp(pts), _vp(seg_off),
+                                                                  1 if reset_data_assoc else 0, _vp(tr), _vp(meas),
+                                                                  _vp(off), _vp(counts), _vp(valid)),
+                   "cps_cleanup_and_group_edges_batched")
+        return {"meas": meas[: off[F]], "off": off, "counts": counts, "valid": valid}
+
     def sync(self):
         _lib.check(_lib.lib().cps_lm_sync(self._h), "cps_lm_sync")
 

@@ -174,3 +174,47 @@ def t_from_rows(batch) -> np.ndarray:
                 out[off[b] // 2 + k0: off[b] // 2 + k0 + c] = segment_t(xy[k0:k0 + c])
             k0 += c
     return out
+
+
+def make_edge_frames(F: int, seed: int = 0, consistent: bool = False):
+    """Integer edge sequences like the reference's detector hands to cleanup_and_group_edges (featureDetector.cpp:
+    213-288: one (x, y) pixel per image row, bottom-to-top): F frames x [L0, L1, R0, R1].
+    consistent=False: image-space sequences that start and end on slightly different rows, some longer than 100 rows,
+    some too short -- exercises every trimming loop and the failure returns.
+    consistent=True: the projected synthetic ground curves sampled one point per row over a common row range, so that
+    every frame survives the trimming and can be fitted.
+    Returns pts [P,2] int32, seg_off [4F+1] int64, tracked_endpt_y [F,2]."""
+    g = _rng(seed, (3 << 40) + (1 if consistent else 0))
+    pts, seg_off, tracked = [], [0], np.zeros((F, 2))
+    base = np.concatenate([TRUTH_C1, TRUTH_C1 * np.tile([1.0, -1.0], 4)])
+    for f in range(F):
+        if consistent:
+            tr = np.empty(19)
+            tr[:16] = base + g.normal(0.0, 0.05, 16)
+            tr[16:] = (g.uniform(-0.03, 0.03), g.uniform(-0.03, 0.03), -1.0 + g.normal(0.0, 0.02))
+            img = project_control_points(tr[None])[0]  # [2 curves, 4, (uL, uR, v)]
+            w = bernstein3(np.linspace(0.0, 1.0, 400))
+            vs = [w @ img[c][:, 2] for c in (0, 1)]
+            lo = int(np.ceil(max(v.min() for v in vs))) + 1
+            hi = int(np.floor(min(v.max() for v in vs))) - 1
+            rows = np.arange(hi, lo - 1, -1)
+            for side in (0, 1):
+                for c in (0, 1):
+                    u = w @ img[c][:, side]
+                    order = np.argsort(vs[c])
+                    xs = np.rint(np.interp(rows, vs[c][order], u[order])).astype(np.int32)
+                    pts.append(np.stack([xs, rows.astype(np.int32)], axis=1))
+                    seg_off.append(seg_off[-1] + rows.size)
+            tracked[f] = (lo, lo)
+        else:
+            y0 = 228 + g.integers(-4, 5, 4)
+            length = g.integers(90, 170, 4)
+            if g.random() < 0.12:
+                length[g.integers(0, 4)] = g.integers(3, 12)
+            for s in range(4):
+                rows = np.arange(y0[s], y0[s] - length[s], -1)
+                xs = np.rint(60 + 40 * (s % 2) + 0.4 * (228 - rows) + g.normal(0.0, 0.6, rows.size)).astype(np.int32)
+                pts.append(np.stack([xs, rows.astype(np.int32)], axis=1))
+                seg_off.append(seg_off[-1] + rows.size)
+            tracked[f] = 228 - 100 + g.integers(-6, 30, 2)
+    return np.concatenate(pts).astype(np.int32), np.array(seg_off, dtype=np.int64), tracked

@@ -89,6 +89,23 @@ int cps_fit_curve_init_batched(cps_lm_ctx *ctx, int B, const double *meas, const
                                double *p_out);
 int cps_fit_curve_init_batched_dev(cps_lm_ctx *ctx, int B, const double *d_meas, const long long *d_off,
                                    const int *d_counts, double *d_p, void *stream);
+
+/*
+ * CurveFittingClass::cleanup_and_group_edges (curveFittingClass.cpp:1207-1418) for F frames: trims the four integer
+ * edge sequences of every frame (left image curves 0/1, right image curves 0/1, each bottom-to-top) so that the two
+ * views of a curve cover the same rows, no curve spans more than LENGTH_EACH_CURVE = 100 rows, nothing extends above
+ * the tracked end point (unless reset_data_assoc), and both curves of an image end on the same row; then packs the
+ * kept points as doubles in the fit's measurement order.
+ *   pts            concatenated (x,y) int pairs (the reference's std::vector<CvPoint>)
+ *   seg_off        [4F+1] point offsets, per frame [L0, L1, R0, R1]
+ *   tracked_endpt_y[F][2]
+ *   meas_out       room for 2 * (number of input points) doubles; off_out [F+1]; counts_out [F][4] -- exactly the
+ *                  meas / off / counts arguments of cps_dlevmar_*_batched
+ *   valid_out      [F] 1, or 0 where the reference returns false (such frames get zero counts)
+ */
+int cps_cleanup_and_group_edges_batched(cps_lm_ctx *ctx, int F, const int *pts, const long long *seg_off,
+                                        int reset_data_assoc, const double *tracked_endpt_y, double *meas_out,
+                                        long long *off_out, int *counts_out, int *valid_out);
 /* geometry of the last launch and the number of kernel launches issued through this context */
 int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
 

@@ -457,3 +457,106 @@ int orc_fit_batch(int model, int variant, int math_mode, int B, double *p, const
   return orc_fit_batch_impl(orc_lm_der, orc_lm_dif, model, variant, math_mode, B, p, meas, t, off,
                             counts, itmax, opts, info, ret, extra, nthreads);
 }
+
+/* ---- cleanup_and_group_edges, curveFittingClass.cpp:1207-1418 ("next" row 4) ----------------------------------
+ * Integer trimming of the four edge sequences of a frame (left image curves 0/1, right image curves 0/1, each a list
+ * of integer pixel (x,y) ordered bottom-to-top) so that the left/right views of a curve cover the same rows, no curve
+ * is longer than LENGTH_EACH_CURVE rows, nothing extends above the tracked end point, and both curves of an image
+ * end on the same row.  pts: concatenated (x,y) int pairs; seg_off[0..4]: point offsets of [L0, L1, R0, R1].
+ * Writes the kept index ranges range[4][2] (inclusive, same order) and returns 1, or returns 0 where the
+ * reference returns false.  LEFT_RIGHT_OFFSET = 0, LENGTH_EACH_CURVE = 100 (common.h:108-112). */
+#define ORC_LR_OFFSET 0
+#define ORC_LEN_CURVE 100
+
+int orc_cleanup_edges(const int *pts, const long long *seg_off, int reset_data_assoc, const double *tracked_endpt_y,
+                      int range[4][2])
+{
+  const int *seg[4];
+  int size[4], ystart[4], yend[4], i, s;
+  for (s = 0; s < 4; ++s) {
+    seg[s] = pts + 2 * seg_off[s];
+    size[s] = (int)(seg_off[s + 1] - seg_off[s]);
+    range[s][0] = 0;
+    range[s][1] = size[s] - 1;
+  }
+  if (size[0] < 10 || size[1] < 10 || size[2] < 10 || size[3] < 10) return 0;
+#define YAT(s, k) (seg[s][2 * (k) + 1])
+  for (s = 0; s < 4; ++s) { ystart[s] = YAT(s, 0); yend[s] = YAT(s, size[s] - 1); }
+  /* L = segment i, R = segment i + 2 */
+  for (i = 0; i < 2; ++i) { /* :1224-1254 align the starts */
+    const int L = i, R = i + 2;
+    if (ystart[L] > ystart[R] - ORC_LR_OFFSET) {
+      while (ystart[L] > ystart[R] - ORC_LR_OFFSET) {
+        range[L][0]++;
+        if (range[L][0] >= size[L]) return 0;
+        ystart[L] = YAT(L, range[L][0]);
+      }
+    } else if (ystart[L] < ystart[R] - ORC_LR_OFFSET) {
+      while (ystart[L] < ystart[R] - ORC_LR_OFFSET) {
+        range[R][0]++;
+        if (range[R][0] >= size[R]) return 0;
+        ystart[R] = YAT(R, range[R][0]);
+      }
+    }
+  }
+  for (i = 0; i < 2; ++i) { /* :1256-1334 */
+    const int L = i, R = i + 2;
+    if (yend[L] < yend[R] - ORC_LR_OFFSET) {
+      while (yend[L] < yend[R] - ORC_LR_OFFSET) {
+        range[L][1]--;
+        if (range[L][1] < 0) return 0;
+        yend[L] = YAT(L, range[L][1]);
+      }
+    } else if (yend[L] > yend[R] - ORC_LR_OFFSET) {
+      while (yend[L] > yend[R] - ORC_LR_OFFSET) {
+        range[R][1]--;
+        if (range[R][1] < 0) return 0;
+        yend[R] = YAT(R, range[R][1]);
+      }
+    }
+    while (yend[L] < ystart[L] - ORC_LEN_CURVE) {
+      range[L][1]--;
+      if (range[L][1] < 0) return 0;
+      yend[L] = YAT(L, range[L][1]);
+    }
+    while (yend[R] < ystart[R] - ORC_LEN_CURVE) {
+      range[R][1]--;
+      if (range[R][1] < 0) return 0;
+      yend[R] = YAT(R, range[R][1]);
+    }
+    while (yend[L] > tracked_endpt_y[i] && !reset_data_assoc) {
+      range[L][0]++;
+      range[L][1]++;
+      if (range[L][0] >= size[L] || range[L][1] >= size[L]) return 0;
+      yend[L] = YAT(L, range[L][1]);
+    }
+    while (yend[R] > tracked_endpt_y[i] + ORC_LR_OFFSET && !reset_data_assoc) {
+      range[R][1]++;
+      range[R][0]++;
+      if (range[R][0] >= size[R] || range[R][1] >= size[R]) return 0;
+      yend[R] = YAT(R, range[R][1]);
+    }
+  }
+  for (i = 0; i < 2; ++i) { /* :1335-1392 both curves of an image end on the same row (i = 0 left, 1 right image) */
+    const int A = 2 * i, B = 2 * i + 1;
+    if (yend[A] > yend[B]) {
+      while (yend[A] > yend[B]) {
+        range[A][0]++;
+        range[A][1]++;
+        if (range[A][0] >= size[A] || range[A][1] >= size[A]) return 0;
+        yend[A] = YAT(A, range[A][1]);
+      }
+    } else {
+      while (yend[A] < yend[B]) {
+        range[B][0]++;
+        range[B][1]++;
+        if (range[B][0] >= size[B] || range[B][1] >= size[B]) return 0;
+        yend[B] = YAT(B, range[B][1]);
+      }
+    }
+  }
+#undef YAT
+  for (s = 0; s < 4; ++s)
+    if (range[s][1] - range[s][0] + 1 < 1) return 0; /* cvCreateMat of a non-positive size would throw */
+  return 1;
+}

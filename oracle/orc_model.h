@@ -67,6 +67,11 @@ void orc_segment_t(const double *xy, int npts, double *t_out);
  * to), -1 gives the opposite orientation.  meas / counts as in orc_fit_batch. */
 void orc_stereo19_init_guess(const double *meas, const int *counts, double *p19, int math_mode, int sign);
 
+/* cleanup_and_group_edges (curveFittingClass.cpp:1207-1418): kept index ranges of the four edge sequences of a
+ * frame; returns 0 where the reference returns false */
+int orc_cleanup_edges(const int *pts, const long long *seg_off, int reset_data_assoc, const double *tracked_endpt_y,
+                      int range[4][2]);
+
 /* post-fit normalisation of the 19 parameters (fit_curve:684-711) */
 void orc_stereo19_postfit(double *p);
 

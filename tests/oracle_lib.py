@@ -58,6 +58,8 @@ class Oracle:
         L.orc_lm_dif.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_void_p, C.c_void_p]
         L.orc_lm_dif.restype = C.c_int
         L.orc_stereo19_postfit.argtypes = [_dp]
+        L.orc_cleanup_edges.argtypes = [_ip, _lp, C.c_int, _dp, _ip]
+        L.orc_cleanup_edges.restype = C.c_int
         L.orc_ekf_predict.argtypes = [_dp, _dp, C.c_int]
         L.orc_ekf_update_curves_points.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, _dp, _ip, _dp, _ip, C.c_int,
                                                    _dp, _dp, _dp]
@@ -115,6 +117,32 @@ class Oracle:
             raise ValueError("oracle rejected the arguments")
         return {"p": p, "info": info, "ret": ret, "extra": extra}
 
+
+    def cleanup_edges(self, pts, seg_off, tracked, reset=False):
+        """Per-frame restatement of cleanup_and_group_edges; returns dict(meas, off, counts, valid) packed like the
+        product's batched call."""
+        pts = np.ascontiguousarray(pts, dtype=np.int32).reshape(-1, 2)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        F = (len(seg_off) - 1) // 4
+        tracked = np.ascontiguousarray(tracked, dtype=np.float64).reshape(F, 2)
+        counts = np.zeros((F, 4), dtype=np.int32)
+        valid = np.zeros(F, dtype=np.int32)
+        pieces = []
+        for f in range(F):
+            so = np.ascontiguousarray(seg_off[4 * f:4 * f + 5])
+            rng = np.zeros(8, dtype=np.int32)
+            tr = np.ascontiguousarray(tracked[f])
+            ok = self.lib.orc_cleanup_edges(_ptr(pts, _ip), _ptr(so, _lp), 1 if reset else 0, _ptr(tr, _dp), _ptr(rng, _ip))
+            valid[f] = ok
+            if ok:
+                for s in range(4):
+                    c = min(int(rng[2 * s + 1] - rng[2 * s] + 1), 10000)
+                    counts[f, s] = c
+                    a = int(so[s]) + int(rng[2 * s])
+                    pieces.append(pts[a:a + c].astype(np.float64).reshape(-1))
+        meas = np.concatenate(pieces) if pieces else np.zeros(0)
+        off = np.concatenate([[0], np.cumsum(2 * counts.sum(axis=1))]).astype(np.int64)
+        return {"meas": meas, "off": off, "counts": counts, "valid": valid}
 
     # ---- EKF ------------------------------------------------------------------------------------
     def ekf_predict(self, x, P):

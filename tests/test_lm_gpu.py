@@ -203,3 +203,40 @@ def test_init_guess_bit_exact_and_feeds_the_fit(ctx):
     xy = b["meas"][:512].reshape(4, 64, 2)
     out = fitter.fit_curve(None, [xy[0], xy[1]], [xy[2], xy[3]])  # params0=None: device builds the guess
     assert np.allclose(out, lm.postfit_normalise(gpu["p"][:1])[0], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("reset", [True, False])
+def test_cleanup_and_group_edges_bit_exact(ctx, reset):
+    """cleanup_and_group_edges on the device (integer trimming + packing) equals the CPU restatement exactly, frame
+    by frame, including the frames the reference rejects."""
+    pts, so, tr = synth.make_edge_frames(300, seed=51)
+    g = ctx.cleanup_and_group_edges(pts, so, tr, reset_data_assoc=reset)
+    o = oracle().cleanup_edges(pts, so, tr, reset)
+    assert np.array_equal(g["valid"], o["valid"]) and 0 < g["valid"].sum() < 300
+    assert np.array_equal(g["counts"], o["counts"]) and np.array_equal(g["off"], o["off"])
+    assert np.array_equal(_bits(g["meas"]), _bits(o["meas"]))
+    empty = ctx.cleanup_and_group_edges(np.zeros((0, 2), dtype=np.int32), np.zeros(1, dtype=np.int64), np.zeros((0, 2)))
+    assert empty["off"].tolist() == [0]
+
+
+def test_frame_pipeline_edges_to_fit(ctx):
+    """The reference's per-frame chain main.cpp:425-445 -- cleanup_and_group_edges -> fit_curve (initial guess + LM)
+    -- entirely through the device entry points, against the same chain of CPU restatements."""
+    import ctypes as C
+    pts, so, tr = synth.make_edge_frames(24, seed=52, consistent=True)
+    g = ctx.cleanup_and_group_edges(pts, so, tr, reset_data_assoc=True)
+    assert g["valid"].all()
+    p0 = ctx.init_guess(g["meas"], g["off"], g["counts"])
+    fit = ctx.fit_batched(STEREO19, DIF, p0, g["meas"], g["off"], g["counts"], OPTS)
+    o = oracle().cleanup_edges(pts, so, tr, True)
+    dp = C.POINTER(C.c_double)
+    p0o = np.zeros((24, 19))
+    for f in range(24):
+        m = np.ascontiguousarray(o["meas"][o["off"][f]:o["off"][f + 1]])
+        c = np.ascontiguousarray(o["counts"][f], dtype=np.int32)
+        oracle().lib.orc_stereo19_init_guess(m.ctypes.data_as(dp), c.ctypes.data_as(C.POINTER(C.c_int)),
+                                             p0o[f].ctypes.data_as(dp), 0, 1)
+    cpu = oracle().fit_batch(STEREO19, DIF, p0o, o["meas"], o["off"], o["counts"], OPTS, nthreads=8)
+    assert np.array_equal(_bits(p0), _bits(p0o))
+    assert_same_fit(fit, cpu)
+    assert (fit["ret"] >= 0).all()

@@ -210,3 +210,33 @@ def test_init_guess_matches_cv2_transcription():
         assert cands[0][18] <= 0.0  # sign = +1 is the orientation with a non-positive height parameter
         det = _oracle_init(meas, g["counts"][f], MATH_DET, 1)
         assert np.abs(det - cands[0]).max() < 1e-12
+
+
+def test_cleanup_edges_hand_case():
+    """cleanup_and_group_edges (curveFittingClass.cpp:1207-1418) on a hand-made frame: the left view of curve 0 starts 3
+    rows lower and the right view ends 2 rows higher -> both are trimmed to the common rows; a sequence shorter than 10
+    points makes the reference return false."""
+    def seq(x0, y_start, n):
+        rows = np.arange(y_start, y_start - n, -1)
+        return np.stack([np.full(n, x0), rows], axis=1).astype(np.int32)
+    segs = [seq(50, 203, 150), seq(150, 200, 150), seq(40, 200, 149), seq(140, 200, 150)]  # L0 L1 R0 R1
+    pts = np.concatenate(segs)
+    so = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.int64)
+    r = oracle().cleanup_edges(pts, so, np.array([[0.0, 0.0]]), reset=True)
+    assert r["valid"][0] == 1
+    # L0 loses its 3 lowest rows (starts at 200 like R0); R0's end is pulled down to L0's; every sequence is then cut
+    # to LENGTH_EACH_CURVE = 100 rows below its start: rows 200..100, 101 points each, all ending on row 100
+    m = r["meas"].reshape(-1, 2)
+    c = r["counts"][0]
+    assert c.tolist() == [101, 101, 101, 101]
+    assert m[0].tolist() == [50.0, 200.0] and m[100].tolist() == [50.0, 100.0]
+    ends = [m[c[:k + 1].sum() - 1, 1] for k in range(4)]
+    assert ends == [100.0] * 4
+    # without slack above its end a sequence cannot slide up to meet its partner: the reference returns false
+    short = [seq(50, 203, 40), seq(150, 200, 40), seq(40, 200, 39), seq(140, 200, 40)]
+    so2 = np.concatenate([[0], np.cumsum([len(s) for s in short])]).astype(np.int64)
+    assert oracle().cleanup_edges(np.concatenate(short), so2, np.array([[0.0, 0.0]]), reset=True)["valid"][0] == 0
+    segs[1] = seq(150, 200, 9)
+    pts = np.concatenate(segs)
+    so = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.int64)
+    assert oracle().cleanup_edges(pts, so, np.array([[0.0, 0.0]]), reset=True)["valid"][0] == 0
