@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
     fn_t = C.c_void_p
     L.cps_dlevmar_der.argtypes = [fn_t, fn_t, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.cps_dlevmar_dif.argtypes = [fn_t, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.cps_closest_bezier_pt_batched.argtypes = [C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.cps_measure_fp64_peak.argtypes = [C.c_int, dp, dp]
     L.cps_measure_dmma_peak.argtypes = [C.c_int, dp]
     _lib = L

@@ -26,6 +26,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "cps_lm_api.cu": ["-fmad=false"],
     "cps_gate.cu": ["-fmad=false"],
+    "cps_closest.cu": ["-fmad=false"],
     "cps_ekf.cu": [],
     "cps_peaks.cu": [],
 }

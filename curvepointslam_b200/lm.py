@@ -114,6 +114,21 @@ class LmContext:
         return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "launches": n.value}
 
 
+def closest_bezier_pt(curves, pts, is_control_points=True, device: int = 0):
+    """closest_bezier_pt(p, pt, nearest_pt, out) of the reference (curveFittingClass.cpp:936-1043) for Q queries.
+    curves: [Q,8] (or [8] shared by all queries); pts [Q,2].  Returns (nearest [Q,2], dist [Q], t [Q], nroots [Q])."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+    Q = pts.shape[0]
+    curves = np.ascontiguousarray(curves, dtype=np.float64)
+    shared = 1 if curves.size == 8 else 0
+    nearest, out = np.zeros((Q, 2)), np.zeros((Q, 2))
+    nroots = np.zeros(Q, dtype=np.int32)
+    _lib.check(_lib.lib().cps_closest_bezier_pt_batched(device, Q, _vp(curves), 1 if is_control_points else 0, shared,
+                                                        _vp(pts), _vp(nearest), _vp(out), _vp(nroots)),
+               "cps_closest_bezier_pt_batched")
+    return nearest, out[:, 0].copy(), out[:, 1].copy(), nroots
+
+
 def postfit_normalise(p: np.ndarray) -> np.ndarray:
     """fit_curve's post-fit sign/angle normalisation (curveFittingClass.cpp:684-711), vectorised over fits;
     including the reference's ``params[18] += PI`` in the second branch."""

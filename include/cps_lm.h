@@ -137,6 +137,17 @@ int cps_dlevmar_der(void (*func)(double *, double *, int, int, void *),
 int cps_dlevmar_dif(void (*func)(double *, double *, int, int, void *), double *p, double *x, int m, int n,
                     int itmax, double *opts, double *info, double *work, double *covar, void *adata);
 
+/*
+ * Closest point on a planar cubic for Q (curve, point) queries: closest_bezier_pt(p, pt, nearest_pt, out),
+ * curveFittingClass.cpp:936-1043 (+ control2coeffs :737-749 when is_control_points != 0); callers
+ * dataAssocClass.cpp:272,366.  curves: Q x 8 doubles, or 1 x 8 shared by every query when shared_curve != 0.
+ * out[q] = {distance, t}; nearest[q] = the point (0,0 when no real root qualifies: the reference leaves it untouched);
+ * nroots[q] (may be NULL) = number of roots the solver returned, -1 if it did not converge.  The reference's root
+ * finder is GSL's gsl_poly_complex_solve; its algorithm (balanced companion matrix + Francis QR) is restated.
+ */
+int cps_closest_bezier_pt_batched(int device, int Q, const double *curves, int is_control_points, int shared_curve,
+                                  const double *pts, double *nearest, double *out, int *nroots);
+
 /* FP64 roofline denominators measured on the device: a DFMA stream and a DMUL+DADD stream (TFLOP/s,
  * a multiply-add pair counted as 2 flop in both). */
 int cps_measure_fp64_peak(int device, double *tflops_fma, double *tflops_muladd);

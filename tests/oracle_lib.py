@@ -58,6 +58,11 @@ class Oracle:
         L.orc_lm_dif.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_void_p, C.c_void_p]
         L.orc_lm_dif.restype = C.c_int
         L.orc_stereo19_postfit.argtypes = [_dp]
+        L.orc_closest_bezier_pt.argtypes = [_dp, _dp, _dp, _dp]
+        L.orc_closest_bezier_pt.restype = C.c_int
+        L.orc_control2coeffs.argtypes = [_dp, _dp]
+        L.orc_poly_roots.argtypes = [_dp, C.c_int, _dp, _dp]
+        L.orc_poly_roots.restype = C.c_int
         L.orc_cleanup_edges.argtypes = [_ip, _lp, C.c_int, _dp, _ip]
         L.orc_cleanup_edges.restype = C.c_int
         L.orc_ekf_predict.argtypes = [_dp, _dp, C.c_int]
@@ -143,6 +148,22 @@ class Oracle:
         meas = np.concatenate(pieces) if pieces else np.zeros(0)
         off = np.concatenate([[0], np.cumsum(2 * counts.sum(axis=1))]).astype(np.int64)
         return {"meas": meas, "off": off, "counts": counts, "valid": valid}
+
+    def closest(self, curves, pts, is_control_points=True):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+        Q = pts.shape[0]
+        curves = np.ascontiguousarray(curves, dtype=np.float64).reshape(-1, 8)
+        nearest, out, nroots = np.zeros((Q, 2)), np.zeros((Q, 2)), np.zeros(Q, dtype=np.int32)
+        for q in range(Q):
+            c = np.ascontiguousarray(curves[q if curves.shape[0] > 1 else 0])
+            p = np.zeros(8)
+            if is_control_points:
+                self.lib.orc_control2coeffs(_ptr(c, _dp), _ptr(p, _dp))
+            else:
+                p = c
+            pt = np.ascontiguousarray(pts[q])
+            nroots[q] = self.lib.orc_closest_bezier_pt(_ptr(p, _dp), _ptr(pt, _dp), _ptr(nearest[q], _dp), _ptr(out[q], _dp))
+        return nearest, out[:, 0].copy(), out[:, 1].copy(), nroots
 
     # ---- EKF ------------------------------------------------------------------------------------
     def ekf_predict(self, x, P):
