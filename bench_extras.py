@@ -24,8 +24,8 @@ def _peaks():
         return 6650.0, "fallback"
 
 
-def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, warm: int = 3, seed: int = 0):
-    x, G, ci, pi = ekf.make_synthetic_ekf(L, d=3, seed=seed)
+def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, warm: int = 3, seed: int = 0, d: int = 3):
+    x, G, ci, pi = ekf.make_synthetic_ekf(L, d=d, seed=seed)
     N = x.size
     kf = ekf.KalmanFilter(capacity=N, device=device)
     kf.set_state(x, None, ci, pi)
@@ -53,7 +53,7 @@ def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, 
     hbm, src = _peaks()
     cov_ms = float(np.mean(cov))
     gbs = 16.0 * N * N / (cov_ms * 1e-3) / 1e9
-    out = {"landmarks": L, "N": N, "M": M, "update_ms": float(np.mean(tot)), "cov_kernel_ms": cov_ms,
+    out = {"landmarks": L, "landmark_states": d, "N": N, "M": M, "update_ms": float(np.mean(tot)), "cov_kernel_ms": cov_ms,
            "predict_ms": float(np.mean(pred)), "update_e2e_ms": float(np.mean(wall)),
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "algorithmic_bytes": 16 * N * N, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)"},
@@ -238,6 +238,10 @@ def run(device: int = 0):
             res["ekf_update"].append(ekf_update_bench(device, L))
         except Exception as ex:
             res["ekf_update"].append({"landmarks": L, "error": repr(ex)})
+    try:  # 8-state curve landmarks: 1k and 5k curves = N 8 012 / 40 012 (12.8 GB)
+        res["ekf_update_curve_landmarks"] = [ekf_update_bench(device, L, d=8) for L in (1000, 5000)]
+    except Exception as ex:
+        res["ekf_update_curve_landmarks"] = {"error": repr(ex)}
     try:
         res["ekf_update_M65"] = ekf_update_bench(device, 5000, n_point_meas=10)
     except Exception as ex:

@@ -193,3 +193,23 @@ def test_augmentation_sequence_vs_golden():
         for _ in range(10):
             kf.AddNewCurve(g["z8"], g["A"])  # capacity 64 is exhausted after three more curves
     kf.close()
+
+
+def test_update_curve_landmarks_with_split_matrices():
+    """8-state curve landmarks (N = 12 + 8*100) measured through de Casteljau split matrices (main.cpp:715-755 feeds
+    A1/A2 of GetSplitMatrices to the update) against the dense CPU restatement."""
+    x, G, ci, pi = ekf.make_synthetic_ekf(100, d=8, seed=8)
+    N = x.size
+    P = G @ G.T / 64.0 + 0.25 * np.eye(N)
+    P = 0.5 * (P + P.T)
+    kf = ekf.KalmanFilter(capacity=N)
+    kf.set_state(x, P, ci, pi)
+    A1, A2 = kf.GetSplitMatrices(0.35)
+    A = np.stack([A1, A2, A2, A1])
+    which = [3, 17, 42, 99]
+    rng = np.random.default_rng(3)
+    z = np.concatenate([rng.normal(0, 20.0, 32), x[2:5] + rng.normal(0, 0.05, 3)])
+    kf.UpdateNCurvesAndPoints(z, 4, A, which)
+    xo, Po = oracle().ekf_update_curves_points(x, P, z, A, ci[which])
+    assert rel(kf.getState(), xo) < TOL and rel(kf.getCov(), Po) < TOL
+    kf.close()
