@@ -9,6 +9,7 @@
 #include "../../include/cps_lm.h"
 #include "cps_common.h"
 #include "cps_lm_kernel.cuh"
+#include "cps_lm_staged.cuh"
 
 namespace cps {
 static thread_local std::string g_last_error;
@@ -25,10 +26,16 @@ struct cps_lm_slot {
   char* d_stage = nullptr;
   size_t stage_bytes = 0;
   std::vector<long long> off0;  // rebased offsets of the chunk in flight (must outlive the async copy)
+  // staged (phase-split) der path: per-fit state, compaction lists, counters
+  char* d_staged = nullptr;
+  size_t staged_bytes = 0;
+  unsigned int* h_count = nullptr;  // pinned: the number of fits that go into the next round
 };
 
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
+constexpr int kStagedChunkFits = 131072;  // chunk of the staged path: its thread-per-fit kernels want >= 37 888 fits
+constexpr int kStagedMinFits = 12288;     // below this the monolithic kernel (a warp per fit) is the better shape
 
 struct cps_lm_ctx {
   int device = 0;
@@ -37,6 +44,8 @@ struct cps_lm_ctx {
   cps_lm_slot slot[kSlots];
   int last_grid = 0, last_block = 0, last_smem = 0;
   long long launches = 0;
+  int path = 0;          // CPS_LM_PATH_AUTO / _MONOLITHIC / _STAGED
+  int last_rounds = 0;   // rounds of the last staged call
 };
 
 extern "C" const char* cps_last_error(void) { return cps::g_last_error.c_str(); }
@@ -81,6 +90,8 @@ extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
     cudaFree(s.d_queue);
     cudaFree(s.d_jstore);
     cudaFree(s.d_stage);
+    cudaFree(s.d_staged);
+    if (s.h_count) cudaFreeHost(s.h_count);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   delete c;
@@ -89,6 +100,12 @@ extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
 extern "C" int cps_lm_sync(cps_lm_ctx* c) {
   if (!c) return CPS_ERR_INVALID;
   for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
+  return CPS_OK;
+}
+
+extern "C" int cps_lm_set_path(cps_lm_ctx* c, int path) {
+  if (!c || path < CPS_LM_PATH_AUTO || path > CPS_LM_PATH_STAGED) return CPS_ERR_INVALID;
+  c->path = path;
   return CPS_OK;
 }
 
@@ -164,6 +181,105 @@ int launch_fit(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st
   return CPS_OK;
 }
 
+// dlevmar_der for a large batch of Stereo19 fits as rounds of three phase kernels (cps_lm_staged.cuh).  The
+// host only sizes grids: after every round it reads one integer, the number of fits still iterating.
+int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st) {
+  using namespace cps;
+  const size_t B = (size_t)L.B;
+  auto a256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const int jac_smem = kJacTableDoubles * kJacThreads * (int)sizeof(double) + (kJacThreads / 32) * (int)sizeof(WarpTiles);
+  const int eval_smem = kEvalTableDoubles * kEvalThreads * (int)sizeof(double) + (kEvalThreads / 32) * (int)sizeof(WarpTiles);
+  CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
+  CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
+  const int solve_smem = kSolveWarpDoubles * kSolveWarps * (int)sizeof(double);
+  CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
+  CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
+  int jac_occ = 0, solve_occ = 0, eval_occ = 0;
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jac_occ, staged_jac_kernel, kJacThreads, jac_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel, kSolveWarps * 32, solve_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_occ, staged_eval_kernel<false>, kEvalThreads, eval_smem));
+  if (jac_occ < 1 || solve_occ < 1 || eval_occ < 1) {
+    cps::set_last_error("staged LM kernels do not fit on this device");
+    return CPS_ERR_CUDA;
+  }
+  const int jac_grid_max = c->sm_count * jac_occ;
+  const int ws_stride = jac_grid_max * kJacThreads;
+  // workspace layout
+  size_t o = 0;
+  const size_t o_scal = o; o = a256(o + sizeof(StagedScal) * B);
+  const size_t o_jtj = o;  o = a256(o + sizeof(double) * kLower19 * B);
+  const size_t o_jte = o;  o = a256(o + sizeof(double) * 19 * B);
+  const size_t o_pdp = o;  o = a256(o + sizeof(double) * 19 * B);
+  const size_t o_tws = o;  o = a256(o + (L.t ? 0 : sizeof(double) * (size_t)(L.n_max / 2) * B));
+  const size_t o_ws = o;   o = a256(o + sizeof(double) * kWsSlots * (size_t)ws_stride);
+  const size_t o_jl = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_el = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_s0 = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_s1 = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_cnt = o;  o = a256(o + sizeof(unsigned int) * 4);
+  if (o > sl.staged_bytes) {
+    CPS_CUDA(cudaStreamSynchronize(st));
+    CPS_CUDA(cudaStreamSynchronize(sl.stream));
+    cudaFree(sl.d_staged);
+    sl.d_staged = nullptr;
+    sl.staged_bytes = 0;
+    CPS_CUDA(cudaMalloc(&sl.d_staged, o));
+    sl.staged_bytes = o;
+  }
+  if (!sl.h_count) CPS_CUDA(cudaMallocHost(&sl.h_count, sizeof(unsigned int) * 4));
+  char* d = sl.d_staged;
+  StagedArgs A;
+  A.L = L;
+  A.scal = (StagedScal*)(d + o_scal);
+  A.jtj = (double*)(d + o_jtj);
+  A.jte = (double*)(d + o_jte);
+  A.pdp = (double*)(d + o_pdp);
+  A.tws = L.t ? nullptr : (double*)(d + o_tws);
+  A.ws = (double*)(d + o_ws);
+  A.ws_stride = ws_stride;
+  A.jac_list = (int*)(d + o_jl);
+  A.eval_list = (int*)(d + o_el);
+  A.solve_list[0] = (int*)(d + o_s0);
+  A.solve_list[1] = (int*)(d + o_s1);
+  A.cnt = (unsigned int*)(d + o_cnt);
+
+  auto grid_for = [&](size_t items, int per_block, int cap) {
+    size_t gneed = (items + per_block - 1) / per_block;
+    if (gneed < 1) gneed = 1;
+    return (int)std::min<size_t>(gneed, (size_t)cap);
+  };
+  CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 4, st));
+  staged_eval_kernel<true><<<grid_for(B, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, 0);
+  staged_jac_kernel<<<grid_for(B, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, 0);
+  CPS_CUDA(cudaGetLastError());
+  c->launches += 2;
+  int cur = 0, rounds = 0;
+  CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + cur, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CPS_CUDA(cudaStreamSynchronize(st));
+  size_t n_solve = sl.h_count[0];
+  while (n_solve > 0) {
+    const int nxt = cur ^ 1;
+    CPS_CUDA(cudaMemsetAsync(A.cnt + 1, 0, sizeof(unsigned int), st));
+    staged_solve_kernel<<<grid_for(n_solve, kSolveWarps, c->sm_count * solve_occ), kSolveWarps * 32, solve_smem, st>>>(A, cur);
+    CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int), st));
+    CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
+    staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+    staged_jac_kernel<<<grid_for(n_solve, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+    CPS_CUDA(cudaGetLastError());
+    c->launches += 3;
+    CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + nxt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaStreamSynchronize(st));
+    n_solve = sl.h_count[0];
+    cur = nxt;
+    ++rounds;
+  }
+  c->last_grid = jac_grid_max;
+  c->last_block = kJacThreads;
+  c->last_smem = jac_smem;
+  c->last_rounds = rounds;
+  return CPS_OK;
+}
+
 int fill_opts(cps::LmLaunch& L, const double* opts, int variant) {
   // lm_core.c:135-141 / :510-517; defaults levmar.h:87-93
   if (opts) {
@@ -194,6 +310,9 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
   fill_opts(L, opts, variant);
   L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;
   L.info = d_info; L.ret = d_ret; L.extra = d_extra;
+  if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
+      (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits))
+    return launch_staged_der19(c, sl, L, st);
   if (model == CPS_MODEL_STEREO19)
     return variant == CPS_LM_DER ? launch_fit<19, false>(c, sl, L, st) : launch_fit<19, true>(c, sl, L, st);
   return variant == CPS_LM_DER ? launch_fit<8, false>(c, sl, L, st) : launch_fit<8, true>(c, sl, L, st);

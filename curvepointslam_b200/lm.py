@@ -20,6 +20,7 @@ STEREO19, IMAGE8 = 19, 8
 DER, DIF = 0, 1
 REFERENCE_OPTS = (1e-10, 1e-10, 1e-10, 1e-20, 1e-6 * 1e1)  # curveFittingClass.cpp:661-662
 REFERENCE_ITMAX = 1000  # curveFittingClass.cpp:681
+PATH_AUTO, PATH_MONOLITHIC, PATH_STAGED = 0, 1, 2
 PI = 3.1415926535  # common.h:114
 
 
@@ -45,6 +46,11 @@ class LmContext:
             self.close()
         except Exception:
             pass
+
+    def set_path(self, path: int):
+        """Execution shape of dlevmar_der on Stereo19 batches (cps_lm_set_path): PATH_AUTO, PATH_MONOLITHIC (a warp
+        per fit, one kernel) or PATH_STAGED (rounds of phase kernels, a thread per fit).  Same results bit for bit."""
+        _lib.check(_lib.lib().cps_lm_set_path(self._h, int(path)), "cps_lm_set_path")
 
     # -- host buffers ---------------------------------------------------------------------------------
     def fit_batched(self, model: int, variant: int, p0, meas, off, counts, opts=REFERENCE_OPTS,

@@ -106,6 +106,18 @@ int cps_fit_curve_init_batched_dev(cps_lm_ctx *ctx, int B, const double *d_meas,
 int cps_cleanup_and_group_edges_batched(cps_lm_ctx *ctx, int F, const int *pts, const long long *seg_off,
                                         int reset_data_assoc, const double *tracked_endpt_y, double *meas_out,
                                         long long *off_out, int *counts_out, int *valid_out);
+/*
+ * Execution shape of dlevmar_der on Stereo19 batches.  Both shapes perform the reference's operation sequence
+ * and give bit-identical results; they differ in how the work is spread over the GPU:
+ *   MONOLITHIC  one persistent kernel, a warp per fit (best for a frame's worth of fits: one launch)
+ *   STAGED      rounds of three phase kernels with a thread per fit in the Jacobian / J^T J phase (best for
+ *               batches of tens of thousands of fits)
+ *   AUTO        (default) STAGED from 12 288 fits per call upwards
+ */
+#define CPS_LM_PATH_AUTO 0
+#define CPS_LM_PATH_MONOLITHIC 1
+#define CPS_LM_PATH_STAGED 2
+int cps_lm_set_path(cps_lm_ctx *ctx, int path);
 /* geometry of the last launch and the number of kernel launches issued through this context */
 int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
 

@@ -1,0 +1,110 @@
+"""GPU parity tests of the staged (phase-split, thread-per-fit) shape of dlevmar_der on Stereo19 batches
+(csrc/cps_lm_staged.cuh): bit-exact against the CPU oracle and against the monolithic kernel, on dense, ragged,
+mixed-block, tiny and degenerate inputs."""
+import numpy as np
+import pytest
+
+from curvepointslam_b200 import lm, synth
+from oracle_lib import DER, STEREO19, oracle
+from test_lm_gpu import OPTS, _bits, assert_same_fit
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sctx():
+    c = lm.LmContext(0)
+    c.set_path(lm.PATH_STAGED)
+    yield c
+    c.close()
+
+
+def test_staged_dense_bit_exact(sctx):
+    b = synth.make_stereo19_batch(300, K=64, seed=61)
+    gpu = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    assert_same_fit(gpu, cpu)
+    assert (gpu["info"][:, 6] == 2).all()
+
+
+def test_staged_ragged_and_mixed_blocks(sctx):
+    """Segment boundaries that fall inside 32-row blocks, a block holding rows of curve 1, 2 and 1 again (a 3-point
+    middle segment), the unblocked small-problem loop (n*m < 1024) and the first size above the switch."""
+    rng = np.random.default_rng(7)
+    counts = rng.integers(5, 102, size=(96, 4)).astype(np.int32)
+    counts[0] = (101, 101, 101, 101)
+    counts[1] = (3, 2, 3, 2)      # unblocked loop
+    counts[2] = (7, 7, 6, 7)      # n*m = 1026
+    counts[3] = (21, 3, 22, 30)   # rows of curve 1, curve 2, curve 1 inside one 32-row block
+    counts[4] = (10, 2, 2, 50)    # two tiny middle segments in one block
+    counts[5] = (16, 16, 16, 16)  # every boundary on a block edge
+    counts[6] = (17, 15, 33, 31)
+    counts[7] = (2, 40, 2, 40)
+    b = synth.make_stereo19_batch(96, seed=62, counts=counts, round_pixels=True)
+    gpu = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    assert_same_fit(gpu, cpu)
+
+
+def test_staged_explicit_t_opts_itmax(sctx):
+    b = synth.make_stereo19_batch(32, K=40, seed=63)
+    t = np.tile(np.linspace(0.0, 1.0, 40), 32 * 4)
+    gpu = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, t=t)
+    cpu = oracle().fit_batch(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, t=t, nthreads=8)
+    assert_same_fit(gpu, cpu)
+    for opts, itmax in [(None, 1000), (OPTS, 3), (OPTS, 1), (OPTS, 0), ([1e-3, 1e-2, 1e-15, 1e-20, 1e-6], 1000),
+                        ([1e-3, 1e-15, 1e-15, 1e+3, 1e-6], 1000)]:
+        gpu = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax)
+        cpu = oracle().fit_batch(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax)
+        assert_same_fit(gpu, cpu, check_mu=itmax > 0)
+
+
+def test_staged_edge_cases(sctx):
+    b = synth.make_stereo19_batch(4, seed=16, counts=np.array([[2, 2, 2, 2], [30, 30, 30, 30], [30, 30, 30, 30],
+                                                               [1, 1, 1, 1]], dtype=np.int32))
+    meas = b["meas"].copy()
+    o2 = b["off"][2]
+    meas[o2 + 1: o2 + 60: 2] = 200.0  # segment 0 of fit 2 becomes horizontal: t = NaN -> stop 7
+    gpu = sctx.fit_batched(STEREO19, DER, b["p0"], meas, b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, DER, b["p0"], meas, b["off"], b["counts"], OPTS)
+    assert np.array_equal(gpu["ret"], cpu["ret"])
+    assert gpu["ret"][0] == -1 and gpu["ret"][3] == -1 and gpu["ret"][2] == -1 and gpu["info"][2, 6] == 7
+    assert np.array_equal(_bits(gpu["p"][[1]]), _bits(cpu["p"][[1]]))
+    assert np.array_equal(_bits(gpu["info"][[1]]), _bits(cpu["info"][[1]]))
+    assert np.array_equal(gpu["info"][2, [5, 6, 7, 8, 9]], cpu["info"][2, [5, 6, 7, 8, 9]])
+    assert np.array_equal(_bits(gpu["p"][[0, 3]]), _bits(b["p0"][[0, 3]]))
+    # inconsistent segment sizes and an oversized fit get the documented codes, like the monolithic kernel
+    bad = synth.make_stereo19_batch(3, K=20, seed=64)
+    counts = bad["counts"].copy()
+    counts[1, 0] += 1
+    mono = lm.LmContext(0)
+    mono.set_path(lm.PATH_MONOLITHIC)
+    g1 = sctx.fit_batched(STEREO19, DER, bad["p0"], bad["meas"], bad["off"], counts, OPTS)
+    g2 = mono.fit_batched(STEREO19, DER, bad["p0"], bad["meas"], bad["off"], counts, OPTS)
+    assert g1["ret"][1] == -3 and np.array_equal(g1["ret"], g2["ret"])
+    assert np.array_equal(_bits(g1["p"]), _bits(g2["p"])) and np.array_equal(_bits(g1["info"]), _bits(g2["info"]))
+    mono.close()
+
+
+def test_staged_equals_monolithic_at_scale(sctx):
+    """40 000 fits: every fit of the staged path is bit-identical to the monolithic kernel's (which the other tests
+    pin to the oracle), a random sample is checked against the oracle directly, and AUTO picks the staged shape."""
+    B = 40000
+    b = synth.make_stereo19_batch_fast(B, K=64, seed=65)
+    mono = lm.LmContext(0)
+    mono.set_path(lm.PATH_MONOLITHIC)
+    g1 = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    g2 = mono.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    assert np.array_equal(g1["ret"], g2["ret"]) and np.array_equal(g1["extra"], g2["extra"])
+    assert np.array_equal(_bits(g1["p"]), _bits(g2["p"])) and np.array_equal(_bits(g1["info"]), _bits(g2["info"]))
+    idx = np.random.default_rng(1).choice(B, 64, replace=False)
+    sub_off = np.arange(65, dtype=np.int64) * 512
+    sub_meas = np.concatenate([b["meas"][b["off"][i]:b["off"][i + 1]] for i in idx])
+    cpu = oracle().fit_batch(STEREO19, DER, b["p0"][idx], sub_meas, sub_off, b["counts"][idx], OPTS, nthreads=8)
+    assert np.array_equal(_bits(g1["p"][idx]), _bits(cpu["p"])) and np.array_equal(_bits(g1["info"][idx]), _bits(cpu["info"]))
+    auto = lm.LmContext(0)
+    g3 = auto.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    assert np.array_equal(_bits(g3["p"]), _bits(g1["p"]))
+    assert auto.launch_stats()["launches"] > 3  # more than one kernel per chunk: the staged rounds ran
+    mono.close()
+    auto.close()
