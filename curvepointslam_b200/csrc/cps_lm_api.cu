@@ -191,12 +191,12 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   const int eval_smem = kEvalTableDoubles * kEvalThreads * (int)sizeof(double) + (kEvalThreads / 32) * (int)sizeof(WarpTiles);
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
-  const int solve_smem = kSolveWarpDoubles * kSolveWarps * (int)sizeof(double);
+  const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
   CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
   int jac_occ = 0, solve_occ = 0, eval_occ = 0;
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jac_occ, staged_jac_kernel, kJacThreads, jac_smem));
-  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel, kSolveWarps * 32, solve_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel, kSolveThreads, solve_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_occ, staged_eval_kernel<false>, kEvalThreads, eval_smem));
   if (jac_occ < 1 || solve_occ < 1 || eval_occ < 1) {
     cps::set_last_error("staged LM kernels do not fit on this device");
@@ -259,8 +259,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   size_t n_solve = sl.h_count[0];
   while (n_solve > 0) {
     const int nxt = cur ^ 1;
-    CPS_CUDA(cudaMemsetAsync(A.cnt + 1, 0, sizeof(unsigned int), st));
-    staged_solve_kernel<<<grid_for(n_solve, kSolveWarps, c->sm_count * solve_occ), kSolveWarps * 32, solve_smem, st>>>(A, cur);
+    staged_solve_kernel<<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
     CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int), st));
     CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
     staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);

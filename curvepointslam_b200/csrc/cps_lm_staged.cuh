@@ -38,10 +38,9 @@ constexpr int kEvalTableDoubles = 24;  // per thread: the 8 projected control po
 // per-thread slots of the jac kernel's global (L2-resident, [slot][thread] = coalesced) work area
 constexpr int kWsAcc = 0;     // 60 + 60 running J^T J entries of curve 1 / curve 2, then 6 theta/phi/z x theta/phi/z
 constexpr int kWsJte = 126;   // 16 J^T e chains of the control-point columns
-constexpr int kWsPend = 142;  // 2 x 60 parked block partial sums (mixed blocks only)
-constexpr int kWsSlots = 262;
-constexpr int kSolveWarps = 4;
-constexpr int kSolveWarpDoubles = 19 * 19 * 2 + 8 * 32;  // LU work matrix, J^T J, small vectors
+constexpr int kWsPend = 142;  // 2 x 60 + 6 block partial sums of a block that straddles contour segments
+constexpr int kWsPendQ = 262;
+constexpr int kWsSlots = 268;
 
 struct StagedArgs {
   LmLaunch L;
@@ -79,9 +78,16 @@ __device__ __forceinline__ void staged_finish(const StagedArgs& A, int f, const 
   if (A.L.extra) { A.L.extra[2 * f] = s.njev; A.L.extra[2 * f + 1] = 0; }
 }
 
-__device__ __forceinline__ void staged_append(int* list, unsigned int* counter, int f) {
-  const unsigned int at = atomicAdd(counter, 1u);
-  list[at] = f;
+// Appends the fits of the lanes with `pred` to a list, one atomic per warp, lanes in order: fits that sit next to each
+// other in one list sit next to each other in the next (their samples are neighbours in memory).  Call convergent.
+__device__ __forceinline__ void staged_append(int* list, unsigned int* counter, int f, bool pred) {
+  const unsigned int mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  unsigned int base = 0;
+  if (lane == (__ffs(mask) - 1)) base = atomicAdd(counter, (unsigned int)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+  if (pred) list[base + __popc(mask & ((1u << lane) - 1u))] = f;
 }
 
 __device__ __forceinline__ void staged_geom(const StagedArgs& A, int f, FitGeom& g, long long& o0) {
@@ -99,44 +105,43 @@ __device__ __forceinline__ const double* staged_t(const StagedArgs& A, int f, lo
 }
 
 
-// ---- warp-transposed staging ---------------------------------------------------------------------------
-// A thread that owns a fit streams that fit's samples, so a warp reads 32 different streams: read directly,
-// every 8-byte load would touch its own 32-byte sector.  Instead the warp moves one 32-row block (32 doubles of
-// x, 16 of t) of each of its 32 fits into shared memory with fully coalesced 256-byte loads -- lane = element,
-// loop over fits -- and every lane then reads its own row.  Row pitches 33 / 17 keep both phases conflict-free.
+// ---- staging of a fit's samples ---------------------------------------------------------------------------
+// A thread that owns a fit streams that fit's samples, so a warp reads 32 different streams; read element by
+// element, every 8-byte load would touch its own 32-byte sector and expose a global-memory latency per sample.
+// Instead every lane copies one 32-row block of its fit (32 doubles of x, 16 of t) into its own row of a
+// shared-memory tile with 16-byte cp.async (global -> shared without passing through registers, all copies of the
+// block in flight at once), prefetches the next block into the L2, and then reads the row at shared-memory
+// latency.  cp.async needs source and destination equally aligned: a stream that starts on an odd double is stored
+// one element into the row (`off`).
 struct WarpTiles {
-  double x[32][33];
-  double t[32][17];
-  const double* xp[32];
-  const double* tp[32];
-  int n[32];
-  int pad[32];
+  double x[32][34];
+  double t[32][18];
 };
 
-// The copies are cp.async (global -> shared without passing through registers): all 48 of a block are in flight
-// at once, where plain loads followed by shared stores would have to run one after the other (the compiler cannot
-// prove that the global pointers do not alias the tile).
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ void tiles_load_x(WarpTiles* wt, int b, int lane) {
-  const int idx = 32 * b + lane;
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j)
-    if (idx < wt->n[j]) cp_async8(&wt->x[j][lane], wt->xp[j] + idx);
-}
-__device__ __forceinline__ void tiles_load_t(WarpTiles* wt, int b, int lane) {
-  const int half = lane >> 4, el = lane & 15;
-  const int idx = 16 * b + el;
-#pragma unroll 8
-  for (int j2 = 0; j2 < 16; ++j2) {
-    const int fit = 2 * j2 + half;
-    if (idx < (wt->n[fit] >> 1)) cp_async8(&wt->t[fit][el], wt->tp[fit] + idx);
+// row[off + i] = src[i], i < cnt; off = parity of src's double index
+__device__ __forceinline__ void row_fill(double* row, int off, const double* src, int cnt) {
+  int i = 0;
+  if (off && cnt > 0) {
+    cp_async8(row + 1, src);
+    i = 1;
   }
+#pragma unroll 4
+  for (; i + 2 <= cnt; i += 2) cp_async16(row + off + i, src + i);
+  if (i < cnt) cp_async8(row + off + i, src + i);
 }
+__device__ __forceinline__ int ptr_parity(const double* p) { return (int)((reinterpret_cast<size_t>(p) >> 3) & 1); }
+
 __device__ __forceinline__ int seg_end(const FitGeom& g, int seg) {
   return seg == 0 ? g.b1 : (seg == 1 ? g.b2 : (seg == 2 ? g.b3 : g.nsamp));
 }
@@ -153,12 +158,13 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double* Csm = smem + tid;  // Csm[(3*cp + {uL, uR, v}) * kEvalThreads]
   WarpTiles* wt = reinterpret_cast<WarpTiles*>(smem + kEvalTableDoubles * kEvalThreads) + wid;
-  const unsigned int total = INIT ? (unsigned int)A.L.B : A.cnt[1];
+  const unsigned int total = INIT ? (unsigned int)A.L.B : A.cnt[2 + (nxt ^ 1)];  // eval list = this round's solve list
   for (unsigned int base = (blockIdx.x * (kEvalThreads / 32) + wid) * 32; base < total;
        base += gridDim.x * kEvalThreads) {
     const unsigned int item = base + lane;
     bool have = item < total;
-    const int f = have ? (INIT ? (int)item : A.eval_list[item]) : 0;
+    int f = have ? (INIT ? (int)item : A.eval_list[item]) : 0;
+    if (f < 0) { have = false; f = 0; }  // the fit stopped in the solve
     FitGeom g;
     g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;
     long long o0 = 0;
@@ -183,10 +189,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
     const bool derive_t = INIT && !A.L.t;
     const double* tp = have ? staged_t(A, f, o0) : nullptr;
     const double* pp = INIT ? A.L.p + (size_t)f * 19 : A.pdp + (size_t)f * 19;
-    __syncwarp();
-    wt->xp[lane] = x;
-    wt->tp[lane] = tp;
-    wt->n[lane] = g.n;
+    const int xoff = ptr_parity(x), toff = tp ? ptr_parity(tp) : 0;
     double firsty[4] = {0, 0, 0, 0}, spany[4] = {1, 1, 1, 1};
     if (have) {
       Trig tg;
@@ -211,11 +214,10 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
       }
     }
     const int nblk = (g.n + 31) >> 5;
-    const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);
     const int full = (g.n >> 3) << 3;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const double* xt = &wt->x[lane][0];
-    double* tt = &wt->t[lane][0];
+    const double* xt = &wt->x[lane][xoff];
+    double* tt = &wt->t[lane][toff];
     auto resid = [&](int s, double tval, double xu, double xv, double& eu, double& ev) {
       const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
       const int cb = 12 * (seg & 1), side = seg >> 1;
@@ -230,14 +232,17 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
       eu = xu - au;
       ev = xv - av;
     };
-    __syncwarp();
 #pragma unroll 1
-    for (int b = nblk_max - 1; b >= 0; --b) {
-      tiles_load_x(wt, b, lane);
-      if (!derive_t) tiles_load_t(wt, b, lane);
+    for (int b = nblk - 1; b >= 0; --b) {
+      row_fill(&wt->x[lane][0], xoff, x + 32 * b, min(32, g.n - 32 * b));
+      if (!derive_t) row_fill(&wt->t[lane][0], toff, tp + 16 * b, min(16, g.nsamp - 16 * b));
+      if (b > 0) {
+        prefetch_l2(x + 32 * (b - 1));
+        prefetch_l2(x + 32 * (b - 1) + 16);
+        if (!derive_t) prefetch_l2(tp + 16 * (b - 1));
+      }
       cp_async_wait_all();
-      __syncwarp();
-      if (b < nblk) {
+      {
         if (derive_t) {  // fit_curve:451-511: t = clamp((y - y_first)/(y_last - y_first), 0, 1) per segment
           const int s_hi = min(16 * b + 16, g.nsamp);
           for (int s = 16 * b; s < s_hi; ++s) {
@@ -269,19 +274,16 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
           s3 += eu0 * eu0;
         }
       }
-      __syncwarp();
-      if (derive_t) {  // publish the block's t, coalesced (lane = element, two fits per trip)
-        const int half = lane >> 4, el = lane & 15;
-        for (int j2 = 0; j2 < 16; ++j2) {
-          const int fit = 2 * j2 + half;
-          const int idx = 16 * b + el;
-          if (idx < (wt->n[fit] >> 1)) const_cast<double*>(wt->tp[fit])[idx] = wt->t[fit][el];
-        }
-        __syncwarp();
+      if (derive_t) {  // publish the block's t (the work area's rows start on even doubles: toff = 0)
+        double* tw = const_cast<double*>(tp) + 16 * b;
+        const int cnt = min(16, g.nsamp - 16 * b);
+        int i = 0;
+        for (; i + 2 <= cnt; i += 2) *reinterpret_cast<double2*>(tw + i) = make_double2(tt[i], tt[i + 1]);
+        if (i < cnt) tw[i] = tt[i];
       }
     }
-    if (!have) continue;
-    {
+    bool to_jac = false, to_solve = false;
+    if (have) {
       const int rem = g.n - full;  // 0, 2, 4 or 6 trailing values: at most three samples, read directly
       for (int k = 0; k < rem; k += 2) {
         const int s = (full + k) >> 1;
@@ -292,86 +294,210 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
         if (cu == 0) s0 += du; else if (cu == 1) s1 += du; else if (cu == 2) s2 += du; else s3 += du;
         if (cv == 0) s0 += dv; else if (cv == 1) s1 += dv; else if (cv == 2) s2 += dv; else s3 += dv;
       }
-    }
-    const double e_new = ((s0 + s1) + s2) + s3;
-
-    StagedScal* sp = A.scal + f;
-    if (INIT) {
-      StagedScal s;
-      s.e0 = e_new; s.e_sq = e_new; s.g_inf = 0.0; s.dp_sq = DBL_MAX; s.mu = 0.0; s.p_sq = 0.0; s.maxdiag = 0.0;
-      s.dL = 0.0; s.nu = 2; s.k = 0; s.nfev = 1; s.njev = 0; s.nlss = 0; s.pad0 = s.pad1 = s.pad2 = 0;
-      *sp = s;
-      if (!isfinite(e_new)) staged_finish(A, f, s, 7);
-      else if (!(0 < A.L.itmax)) staged_finish(A, f, s, 0);
-      else if (e_new <= A.L.eps3) staged_finish(A, f, s, 6);
-      else staged_append(A.jac_list, A.cnt + 0, f);
-      continue;
-    }
-    StagedScal s = *sp;
-    s.nfev += 1;
-    if (!isfinite(e_new)) {  // lm_core.c:352-355, inside the inner loop: the for's ++k still runs
-      s.k += 1;
-      *sp = s;
-      staged_finish(A, f, s, 7);
-      continue;
-    }
-    const double dF = s.e_sq - e_new;
-    if (s.dL > 0.0 && dF > 0.0) {
-      s.mu = nielsen(s.mu, dF, s.dL);
-      s.nu = 2;
-      double* pout = A.L.p + (size_t)f * 19;
+      const double e_new = ((s0 + s1) + s2) + s3;
+      StagedScal* sp = A.scal + f;
+      if (INIT) {
+        StagedScal s;
+        s.e0 = e_new; s.e_sq = e_new; s.g_inf = 0.0; s.dp_sq = DBL_MAX; s.mu = 0.0; s.p_sq = 0.0; s.maxdiag = 0.0;
+        s.dL = 0.0; s.nu = 2; s.k = 0; s.nfev = 1; s.njev = 0; s.nlss = 0; s.pad0 = s.pad1 = s.pad2 = 0;
+        *sp = s;
+        if (!isfinite(e_new)) staged_finish(A, f, s, 7);
+        else if (!(0 < A.L.itmax)) staged_finish(A, f, s, 0);
+        else if (e_new <= A.L.eps3) staged_finish(A, f, s, 6);
+        else to_jac = true;
+      } else {
+        StagedScal s = *sp;
+        s.nfev += 1;
+        const double dF = s.e_sq - e_new;
+        if (!isfinite(e_new)) {  // lm_core.c:352-355, inside the inner loop: the for's ++k still runs
+          s.k += 1;
+          *sp = s;
+          staged_finish(A, f, s, 7);
+        } else if (s.dL > 0.0 && dF > 0.0) {
+          s.mu = nielsen(s.mu, dF, s.dL);
+          s.nu = 2;
+          double* pout = A.L.p + (size_t)f * 19;
 #pragma unroll
-      for (int q = 0; q < 19; ++q) pout[q] = pp[q];
-      s.e_sq = e_new;
-      s.k += 1;
-      *sp = s;
-      if (s.k >= A.L.itmax) staged_finish(A, f, s, 0);
-      else if (s.e_sq <= A.L.eps3) staged_finish(A, f, s, 6);
-      else staged_append(A.jac_list, A.cnt + 0, f);
-      continue;
+          for (int q = 0; q < 19; ++q) pout[q] = pp[q];
+          s.e_sq = e_new;
+          s.k += 1;
+          *sp = s;
+          if (s.k >= A.L.itmax) staged_finish(A, f, s, 0);
+          else if (s.e_sq <= A.L.eps3) staged_finish(A, f, s, 6);
+          else to_jac = true;
+        } else {
+          s.mu *= s.nu;
+          const int nu2 = (int)((unsigned)s.nu << 1);
+          if (nu2 <= s.nu) {
+            s.k += 1;
+            *sp = s;
+            staged_finish(A, f, s, 5);
+          } else {
+            s.nu = nu2;
+            *sp = s;
+            to_solve = true;
+          }
+        }
+      }
     }
-    s.mu *= s.nu;
-    const int nu2 = (int)((unsigned)s.nu << 1);
-    if (nu2 <= s.nu) {
-      s.k += 1;
-      *sp = s;
-      staged_finish(A, f, s, 5);
-      continue;
-    }
-    s.nu = nu2;
-    *sp = s;
-    staged_append(A.solve_list[nxt], A.cnt + 2 + nxt, f);
+    __syncwarp();
+    staged_append(A.jac_list, A.cnt + 0, f, to_jac);
+    staged_append(A.solve_list[nxt], A.cnt + 2 + nxt, f, to_solve);
   }
 }
 
-// ---- solve: warp per fit ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSolveWarps * 32) staged_solve_kernel(const StagedArgs A, int cur) {
-  constexpr int M = 19;
+// ---- solve: thread per fit --------------------------------------------------------------------------------
+// (J^T J + mu I) dp = J^T e by the reference's LU (dAx_eq_b_LU_noLapack, Axb_core.c:1044-1132), step checks
+// (lm_core.c:311-331) and the predicted reduction dL (:357-360).  A warp per fit spends ten instructions of
+// bookkeeping (pivot reductions, syncs, idle lanes: 19 of 32) on every useful multiply-add of a 19x19 elimination;
+// a thread per fit spends two loads and a store.  The work matrix, the row scales and the right-hand side of a
+// thread live in shared memory, [element][thread] so that any (row, column) a thread picks -- pivoting makes the
+// row dynamic -- is conflict-free: 399 doubles per thread, 64 threads per SM.
+//
+// Same operation sequence as lu_solve of the monolithic kernel (right-looking form of the reference's Crout
+// sweep: element (i,k) receives a_ik - l_i0*u_0k - l_i1*u_1k - ... in ascending order, so every stored value is
+// bit-identical): scaled partial pivoting where the LAST maximum wins (">=", :1088) and a search that finds no
+// valid merit keeps the previous pivot row, zero pivot -> DBL_EPSILON (:1102), forward substitution that skips
+// the leading zeros of the permuted right-hand side (:1112-1121), back substitution in ascending column order.
+constexpr int kSolveThreads = 64;
+constexpr int kSolveDoubles = 19 * 19 + 19 + 19;
+
+// trailing update of W columns (k0..k0+W-1) for rows i0.. : a_ik -= l_i * u_k.  The pivot-row entries stay in
+// registers; two rows are in flight per trip (all loads first, then the arithmetic, then the stores) so that the
+// shared-memory latency of one row overlaps the other's.
+template <int W>
+__device__ __forceinline__ void lu_update_cols(double* a, int j, int k0) {
+  constexpr int M = 19, T = kSolveThreads;
+  double u[W];
+  const double* uj = a + (j * M + k0) * T;
+#pragma unroll
+  for (int c = 0; c < W; ++c) u[c] = uj[c * T];
+  int i = j + 1;
+#pragma unroll 1
+  for (; i + 2 <= M; i += 2) {
+    double* r0 = a + (i * M + k0) * T;
+    double* r1 = r0 + M * T;
+    const double l0 = a[(i * M + j) * T], l1 = a[((i + 1) * M + j) * T];
+    double x0[W], x1[W];
+#pragma unroll
+    for (int c = 0; c < W; ++c) { x0[c] = r0[c * T]; x1[c] = r1[c * T]; }
+    double p0[W], p1[W];
+#pragma unroll
+    for (int c = 0; c < W; ++c) { p0[c] = l0 * u[c]; p1[c] = l1 * u[c]; }
+#pragma unroll
+    for (int c = 0; c < W; ++c) { x0[c] -= p0[c]; x1[c] -= p1[c]; }
+#pragma unroll
+    for (int c = 0; c < W; ++c) { r0[c * T] = x0[c]; r1[c * T] = x1[c]; }
+  }
+  if (i < M) {
+    double* r0 = a + (i * M + k0) * T;
+    const double l0 = a[(i * M + j) * T];
+    double x0[W];
+#pragma unroll
+    for (int c = 0; c < W; ++c) x0[c] = r0[c * T];
+#pragma unroll
+    for (int c = 0; c < W; ++c) x0[c] -= l0 * u[c];
+#pragma unroll
+    for (int c = 0; c < W; ++c) r0[c * T] = x0[c];
+  }
+}
+
+__device__ __forceinline__ int lu_solve_thread(double* a, double* sc, double* bx, const double* lower,
+                                               const double* jte, double mu) {
+  constexpr int M = 19, T = kSolveThreads;
+#define A_(i, k) a[((i) * M + (k)) * T]
+  {  // augmented copy of the symmetric matrix and the right-hand side: the lower triangle goes global -> shared by
+     // cp.async (190 + 19 copies in flight at once, no register staging), then it is mirrored and mu joins the diagonal
+    int idx = 0;
+    for (int i = 0; i < M; ++i)
+      for (int k = 0; k <= i; ++k, ++idx) cp_async8(&A_(i, k), lower + idx);
+    for (int i = 0; i < M; ++i) cp_async8(bx + i * T, jte + i);
+    cp_async_wait_all();
+    for (int i = 0; i < M; ++i) {
+      for (int k = 0; k < i; ++k) A_(k, i) = A_(i, k);
+      A_(i, i) = A_(i, i) + mu;
+    }
+  }
+  int singular = 0;
+  for (int i = 0; i < M; ++i) {
+    double big = 0.0;
+    for (int j = 0; j < M; ++j) {
+      const double v = fabs(A_(i, j));
+      if (v > big) big = v;
+    }
+    if (big == 0.0) singular = 1;
+    else sc[i * T] = 1.0 / big;
+  }
+  if (singular) return 0;
+
+  int piv = -1;  // the reference's maxi persists across columns
+#pragma unroll 1
+  for (int j = 0; j < M; ++j) {
+    double big = 0.0;
+    for (int i = j; i < M; ++i) {
+      const double merit = sc[i * T] * fabs(A_(i, j));
+      if (merit >= big) { big = merit; piv = i; }
+    }
+    if (piv != j && piv >= 0) {
+      for (int k = 0; k < M; ++k) {
+        const double tmp = A_(piv, k);
+        A_(piv, k) = A_(j, k);
+        A_(j, k) = tmp;
+      }
+      sc[piv * T] = sc[j * T];
+      const double tb = bx[piv * T];
+      bx[piv * T] = bx[j * T];
+      bx[j * T] = tb;
+    }
+    if (A_(j, j) == 0.0) A_(j, j) = DBL_EPSILON;
+    if (j != M - 1) {
+      const double inv = 1.0 / A_(j, j);
+      for (int i = j + 1; i < M; ++i) A_(i, j) = A_(i, j) * inv;
+      int k0 = j + 1;
+      for (; k0 + 6 <= M; k0 += 6) lu_update_cols<6>(a, j, k0);
+      switch (M - k0) {
+        case 5: lu_update_cols<5>(a, j, k0); break;
+        case 4: lu_update_cols<4>(a, j, k0); break;
+        case 3: lu_update_cols<3>(a, j, k0); break;
+        case 2: lu_update_cols<2>(a, j, k0); break;
+        case 1: lu_update_cols<1>(a, j, k0); break;
+        default: break;
+      }
+    }
+  }
+  // forward substitution, column oriented (same ascending-j order per row), with the leading-zero skip
+  bool started = false;
+  for (int j = 0; j < M - 1; ++j) {
+    const double xj = bx[j * T];
+    if (!started) {
+      if (xj != 0.0) started = true;
+      else continue;
+    }
+    for (int i = j + 1; i < M; ++i) bx[i * T] -= A_(i, j) * xj;
+  }
+  for (int i = M - 1; i >= 0; --i) {
+    double sum = bx[i * T];
+    for (int jj = i + 1; jj < M; ++jj) sum -= A_(i, jj) * bx[jj * T];
+    bx[i * T] = sum / A_(i, i);
+  }
+#undef A_
+  return 1;
+}
+
+// Every entry of the solve list yields an entry of the eval list at the same position (the fit, or -1 if it stopped
+// here), which keeps neighbouring fits -- neighbouring memory -- together from kernel to kernel.
+__global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const StagedArgs A, int cur) {
+  constexpr int M = 19, T = kSolveThreads;
   extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* base = smem + (size_t)wid * kSolveWarpDoubles;
-  WarpMem<M> w;
-  w.x = nullptr; w.t = nullptr; w.e = nullptr; w.hx = nullptr; w.wrk = nullptr; w.wrk2 = nullptr; w.dbuf = nullptr;
-  w.tile = base;
-  w.jtj = base + M * M;
-  double* v = base + 2 * M * M;
-  w.p = v; w.dp = v + 32; w.pdp = v + 64; w.jte = v + 96; w.diag = v + 128; w.pw = v + 160; w.xs = v + 192;
-  w.scale = v + 224;
-  w.scratch = nullptr;
+  double* a = smem + threadIdx.x;
+  double* sc = smem + M * M * T + threadIdx.x;
+  double* bx = smem + (M * M + M) * T + threadIdx.x;
   const unsigned int total = A.cnt[2 + cur];
-  const unsigned int nwarps = gridDim.x * kSolveWarps;
-  for (unsigned int i = blockIdx.x * kSolveWarps + wid; i < total; i += nwarps) {
+  for (unsigned int i = blockIdx.x * T + threadIdx.x; i < total; i += gridDim.x * T) {
     const int f = A.solve_list[cur][i];
     const double* lower = A.jtj + (size_t)f * kLower19;
-    for (int idx = lane; idx < M * M; idx += 32) {
-      const int r = idx / M, c = idx - r * M;
-      w.jtj[idx] = (c <= r) ? lower[tri(r, c)] : lower[tri(c, r)];
-    }
-    if (lane < M) {
-      w.jte[lane] = A.jte[(size_t)f * M + lane];
-      w.p[lane] = A.L.p[(size_t)f * M + lane];
-    }
-    __syncwarp();
+    const double* jte = A.jte + (size_t)f * M;
+    const double* pp = A.L.p + (size_t)f * M;
     StagedScal* sp = A.scal + f;
     double mu = sp->mu;
     const double p_sq = sp->p_sq;
@@ -380,11 +506,16 @@ __global__ void __launch_bounds__(kSolveWarps * 32) staged_solve_kernel(const St
     int stop = 0;
     bool to_eval = false;
     for (;;) {
-      const int solved = lu_solve<M>(w, mu, lane);
+      const int solved = lu_solve_thread(a, sc, bx, lower, jte, mu);
       ++nlss;
       if (solved) {
-        const int chk = step_checks<M>(w, p_sq, A.L.eps2, A.L.eps2_sq, dp_sq, lane);
-        if (chk) { stop = chk; break; }
+        dp_sq = 0.0;
+        for (int q = 0; q < M; ++q) {
+          const double tmp = bx[q * T];
+          dp_sq += tmp * tmp;
+        }
+        if (dp_sq <= A.L.eps2_sq * p_sq) { stop = 2; break; }
+        if (dp_sq >= (p_sq + A.L.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
         to_eval = true;
         break;
       }
@@ -394,20 +525,23 @@ __global__ void __launch_bounds__(kSolveWarps * 32) staged_solve_kernel(const St
       nu = nu2;
     }
     if (to_eval) {
-      const double dL = predicted_reduction<M>(w, mu);
-      if (lane < M) A.pdp[(size_t)f * M + lane] = w.pdp[lane];
-      if (lane == 0) {
-        sp->mu = mu; sp->nu = nu; sp->nlss = nlss; sp->dp_sq = dp_sq; sp->dL = dL;
-        staged_append(A.eval_list, A.cnt + 1, f);
+      double dL = 0.0;
+      double* pdp = A.pdp + (size_t)f * M;
+      for (int q = 0; q < M; ++q) {
+        const double d = bx[q * T];
+        pdp[q] = pp[q] + d;
+        dL += d * (mu * d + jte[q]);
       }
-    } else if (lane == 0) {
+      sp->mu = mu; sp->nu = nu; sp->nlss = nlss; sp->dp_sq = dp_sq; sp->dL = dL;
+      A.eval_list[i] = f;
+    } else {
       StagedScal s = *sp;
       s.mu = mu; s.nu = nu; s.nlss = nlss; s.dp_sq = dp_sq;
       s.k += 1;  // the stop happened inside the inner loop
       *sp = s;
       staged_finish(A, f, s, stop);
+      A.eval_list[i] = -1;
     }
-    __syncwarp();
   }
 }
 
@@ -415,65 +549,133 @@ __global__ void __launch_bounds__(kSolveWarps * 32) staged_solve_kernel(const St
 // Shared memory per thread (strided by the CTA size: a warp's accesses are conflict-free):
 //   D[40]  derivative table of the current contour segment: [u-row | v-row][control point k][xe, ye, theta, phi, z]
 //   C[8]   projected control points of the segment: u of cp 0..3, v of cp 0..3
-// plus the warp's staging tiles.  Registers: the 66 partial sums of the current 32-row block and the 11 J^T e
-// chains of the current curve.  The running J^T J entries are touched once per block and live in the global work
+// plus the warp's staging tiles.  Registers: the partial sums of the current 32-row block (36 or 30 at a time) and
+// the 11 J^T e chains of the current curve.  The running J^T J entries are touched once per block and live in the global work
 // area (A.ws, [slot][thread]: coalesced, L2-resident).
-struct JacRegs {
-  double part[66];
-  double jte_cp[8];
-  double jte_q[3];
-};
-
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
 // The segment tables are re-read from shared memory for every row.  A plain load would be hoisted out of the row
-// loop (the tables are loop-invariant) into 96 registers, which the 66 partial sums need; `volatile` pins it.
+// loop (the tables are loop-invariant) into 96 registers, which the partial sums need; `volatile` pins it.
 __device__ __forceinline__ double lds_pinned(unsigned int saddr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
   return v;
 }
 
-// one Jacobian row (R = 0: the u row of the sample, 1: the v row): residual, compact row, 66 + 11 multiply-adds
-template <int R>
-__device__ __forceinline__ void jac_row_mac(unsigned int Dsa, unsigned int Csa, const double (&w)[4], double xval,
-                                            JacRegs& G) {
-  constexpr unsigned int P = kJacThreads * 8;  // byte pitch between table entries
+// A block's rows are walked twice, each time for one half of the entries (pass A / pass B below), so that the partial
+// sums in flight (36 or 30) leave registers for a second set holding the products of the next row.  The residual,
+// the Bernstein weights and the 8 control-point entries of a row are recomputed in pass B; same expressions, same
+// values.
+constexpr unsigned int kJacPitch = kJacThreads * 8;  // byte pitch between table entries
+
+// A pass is software-pipelined over rows by hand: the products of a row are formed in one loop trip and added to
+// the partial sums in the next, so that no add ever waits for its own multiply (a multiply-add pair issued back to
+// back stalls for the FP64 latency, and with two resident warps per scheduler nothing else hides it).  The row
+// index r = 2*sample + (0: u row, 1: v row) selects the half of the tables through an address offset.
+struct RowIn {
+  double w[4];
+  double e;
+};
+
+__device__ __forceinline__ void jac_row_in(unsigned int Csa, const double* xt, const double* tt, int r, RowIn& in) {
+  bernstein3(tt[(r >> 1) & 15], in.w);
+  const unsigned int c = Csa + (r & 1) * (4 * kJacPitch);
   double au = 0.0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) au += w[k] * lds_pinned(Csa + (4 * R + k) * P);
-  const double e = xval - au;
-  double v[11];
+  for (int k = 0; k < 4; ++k) au += in.w[k] * lds_pinned(c + k * kJacPitch);
+  in.e = xt[r & 31] - au;
+}
+
+__device__ __forceinline__ void jac_row_cp(unsigned int Dsa, int r, const double (&w)[4], double (&v)[8]) {
+  const unsigned int d = Dsa + (r & 1) * (20 * kJacPitch);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    v[2 * k] = w[k] * lds_pinned(Dsa + (20 * R + 5 * k + 0) * P);
-    v[2 * k + 1] = w[k] * lds_pinned(Dsa + (20 * R + 5 * k + 1) * P);
+    v[2 * k] = w[k] * lds_pinned(d + (5 * k + 0) * kJacPitch);
+    v[2 * k + 1] = w[k] * lds_pinned(d + (5 * k + 1) * kJacPitch);
   }
+}
+
+__device__ __forceinline__ void jac_products_a(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt,
+                                               int r, double (&pr)[36], double (&pe)[8]) {
+  RowIn in;
+  jac_row_in(Csa, xt, tt, r, in);
+  double v[8];
+  jac_row_cp(Dsa, r, in.w, v);
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) pr[a * (a + 1) / 2 + b] = v[a] * v[b];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) pe[a] = v[a] * in.e;
+}
+
+__device__ __forceinline__ void jac_products_b(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt,
+                                               int r, double (&pr)[30], double (&pe)[3]) {
+  RowIn in;
+  jac_row_in(Csa, xt, tt, r, in);
+  double v[8];
+  jac_row_cp(Dsa, r, in.w, v);
+  const unsigned int d = Dsa + (r & 1) * (20 * kJacPitch);
+  double vq[3];
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double a = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) a += w[k] * lds_pinned(Dsa + (20 * R + 5 * k + 2 + q) * P);
-    v[8 + q] = a;
+    for (int k = 0; k < 4; ++k) a += in.w[k] * lds_pinned(d + (5 * k + 2 + q) * kJacPitch);
+    vq[q] = a;
   }
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int q = 0; q < 3; ++q)
 #pragma unroll
-    for (int b = 0; b <= a; ++b) G.part[a * (a + 1) / 2 + b] += v[a] * v[b];
+    for (int b = 0; b < 8; ++b) pr[8 * q + b] = vq[q] * v[b];
 #pragma unroll
   for (int q = 0; q < 3; ++q)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) G.part[36 + 8 * q + b] += v[8 + q] * v[b];
+    for (int r2 = 0; r2 <= q; ++r2) pr[24 + q * (q + 1) / 2 + r2] = vq[q] * vq[r2];
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
+  for (int q = 0; q < 3; ++q) pe[q] = vq[q] * in.e;
+}
+
+// pass A: control-point x control-point entries of the row's curve (36) and their 8 J^T e chains
+__device__ __forceinline__ void jac_pass_a(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt,
+                                           int s0, int s1, double (&pa)[36], double (&jte_cp)[8]) {
+  if (s0 >= s1) return;
+  double pr[36], pe[8];
+  jac_products_a(Dsa, Csa, xt, tt, 2 * s0, pr, pe);
+#pragma unroll 1
+  for (int r = 2 * s0 + 1; r < 2 * s1; ++r) {
 #pragma unroll
-    for (int r = 0; r <= q; ++r) G.part[60 + q * (q + 1) / 2 + r] += v[8 + q] * v[8 + r];
+    for (int q = 0; q < 36; ++q) pa[q] += pr[q];
 #pragma unroll
-  for (int a = 0; a < 8; ++a) G.jte_cp[a] += v[a] * e;
+    for (int a = 0; a < 8; ++a) jte_cp[a] += pe[a];
+    jac_products_a(Dsa, Csa, xt, tt, r, pr, pe);
+  }
 #pragma unroll
-  for (int q = 0; q < 3; ++q) G.jte_q[q] += v[8 + q] * e;
+  for (int q = 0; q < 36; ++q) pa[q] += pr[q];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) jte_cp[a] += pe[a];
+}
+
+// pass B: theta/phi/z x control-point (24), theta/phi/z x theta/phi/z (6) and the 3 theta/phi/z J^T e chains
+__device__ __forceinline__ void jac_pass_b(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt,
+                                           int s0, int s1, double (&pb)[30], double (&jte_q)[3]) {
+  if (s0 >= s1) return;
+  double pr[30], pe[3];
+  jac_products_b(Dsa, Csa, xt, tt, 2 * s0, pr, pe);
+#pragma unroll 1
+  for (int r = 2 * s0 + 1; r < 2 * s1; ++r) {
+#pragma unroll
+    for (int q = 0; q < 30; ++q) pb[q] += pr[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) jte_q[q] += pe[q];
+    jac_products_b(Dsa, Csa, xt, tt, r, pr, pe);
+  }
+#pragma unroll
+  for (int q = 0; q < 30; ++q) pb[q] += pr[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) jte_q[q] += pe[q];
 }
 
 // derivative table and projected control points of one contour segment (curve, side): the four control points of
@@ -570,113 +772,134 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
     double* Jout = A.jtj + (size_t)f * kLower19;
     double* Jte = A.jte + (size_t)f * 19;
     const bool blocked = have && !(g.n * 19 < kBlockSzSq);  // strict "<", lm_core.c:193
-    __syncwarp();
-    wt->xp[lane] = x;
-    wt->tp[lane] = tp;
-    wt->n[lane] = blocked ? g.n : 0;
+    const int xoff = ptr_parity(x), toff = tp ? ptr_parity(tp) : 0;
     Trig tg;
     if (have) make_trig(pp[16], pp[17], tg);
-    JacRegs G;
+    double jte_cp[8], jte_q[3];
 #pragma unroll
-    for (int q = 0; q < 66; ++q) G.part[q] = 0.0;
+    for (int q = 0; q < 8; ++q) jte_cp[q] = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) G.jte_cp[q] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) G.jte_q[q] = 0.0;
+    for (int q = 0; q < 3; ++q) jte_q[q] = 0.0;
     if (blocked) {
 #pragma unroll 1
       for (int q = 0; q < kWsPend; ++q) __stcg(ws + q * wsn, 0.0);
     }
     const int nblk = blocked ? (g.n + 31) >> 5 : 0;
-    const int nblk_max = __reduce_max_sync(0xffffffffu, nblk);
     int cur_seg = -1, cur_curve = -1;
-    unsigned parked = 0;  // bit c: curve c has a block partial parked in the work area
-    const double* xt = &wt->x[lane][0];
-    const double* tt = &wt->t[lane][0];
-    __syncwarp();
-#pragma unroll 1
-    for (int b = 0; b < nblk_max; ++b) {
-      tiles_load_x(wt, b, lane);
-      tiles_load_t(wt, b, lane);
-      cp_async_wait_all();
-      __syncwarp();
-      if (b < nblk) {
-        int s = 16 * b;
-        const int blk_end = min(16 * b + 16, g.nsamp);
-#pragma unroll 1
-        while (s < blk_end) {
-          const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
-          if (seg != cur_seg) {
-            const int curve = seg & 1;
-            if (curve != cur_curve) {
-              if (cur_curve >= 0) {
+    const double* xt = &wt->x[lane][xoff];
+    const double* tt = &wt->t[lane][toff];
+    // entering contour segment `seg`: the J^T e chains of the control-point columns follow the curve, the tables the
+    // (curve, image side)
+    auto enter_segment = [&](int seg) {
+      const int curve = seg & 1;
+      if (curve != cur_curve) {
+        if (cur_curve >= 0) {
 #pragma unroll
-                for (int a = 0; a < 8; ++a) ws[(kWsJte + 8 * cur_curve + a) * wsn] = G.jte_cp[a];
-                if ((s & 15) != 0) {  // this block's partial of the old curve waits for the block to end
-#pragma unroll
-                  for (int q = 0; q < 60; ++q) ws[(kWsPend + 60 * cur_curve + q) * wsn] = G.part[q];
-                  parked |= 1u << cur_curve;
-                }
-              }
-#pragma unroll
-              for (int a = 0; a < 8; ++a) G.jte_cp[a] = __ldcg(ws + (kWsJte + 8 * curve + a) * wsn);
-              if (parked & (1u << curve)) {  // rows of this curve were already seen in this block
-#pragma unroll
-                for (int q = 0; q < 60; ++q) G.part[q] = __ldcg(ws + (kWsPend + 60 * curve + q) * wsn);
-                parked &= ~(1u << curve);
-              } else {
-#pragma unroll
-                for (int q = 0; q < 60; ++q) G.part[q] = 0.0;
-              }
-              cur_curve = curve;
-            }
-            jac_segment_tables(pp, tg, curve, seg >> 1, Dsm, Csm);
-            cur_seg = seg;
-          }
-          const int e_end = min(blk_end, seg_end(g, seg));
-#pragma unroll 1
-          for (; s < e_end; ++s) {
-            const int l = s & 15;
-            double w[4];
-            bernstein3(tt[l], w);
-            jac_row_mac<0>(Dsa, Csa, w, xt[2 * l], G);
-            jac_row_mac<1>(Dsa, Csa, w, xt[2 * l + 1], G);
-          }
+          for (int a = 0; a < 8; ++a) __stcg(ws + (kWsJte + 8 * cur_curve + a) * wsn, jte_cp[a]);
         }
-        // end of a 32-row block: its partial sums join the running entries (misc_core.c:118-123).  The additions are
-        // fire-and-forget reductions performed at the L2 (red.global.add.f64: the same IEEE round-to-nearest addition;
-        // one owner per address, program order per address): no load latency is exposed and the partial sums' registers
-        // are free again at once.
-        {
-          double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
 #pragma unroll
-          for (int q = 0; q < 60; ++q) {
-            red_add_f64(acc + q * wsn, G.part[q]);
-            G.part[q] = 0.0;
-          }
-          double* accq = ws + (size_t)(kWsAcc + 120) * wsn;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            red_add_f64(accq + q * wsn, G.part[60 + q]);
-            G.part[60 + q] = 0.0;
-          }
-          if (parked) {
+        for (int a = 0; a < 8; ++a) jte_cp[a] = __ldcg(ws + (kWsJte + 8 * curve + a) * wsn);
+        cur_curve = curve;
+      }
+      jac_segment_tables(pp, tg, curve, seg >> 1, Dsm, Csm);
+      cur_seg = seg;
+    };
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c)
-              if (parked & (1u << c))
-                for (int q = 0; q < 60; ++q)
-                  red_add_f64(ws + (kWsAcc + 60 * c + q) * wsn, __ldcg(ws + (kWsPend + 60 * c + q) * wsn));
-            parked = 0;
+    for (int b = 0; b < nblk; ++b) {
+      row_fill(const_cast<double*>(xt) - xoff, xoff, x + 32 * b, min(32, g.n - 32 * b));
+      row_fill(const_cast<double*>(tt) - toff, toff, tp + 16 * b, min(16, g.nsamp - 16 * b));
+      if (b + 1 < nblk) {
+        prefetch_l2(x + 32 * (b + 1));
+        prefetch_l2(x + 32 * (b + 1) + 16);
+        prefetch_l2(tp + 16 * (b + 1));
+      }
+      cp_async_wait_all();
+      {
+        const int s_lo = 16 * b, blk_end = min(16 * b + 16, g.nsamp);
+        const int seg_lo = (s_lo >= g.b1) + (s_lo >= g.b2) + (s_lo >= g.b3);
+        const int seg_hi = (blk_end - 1 >= g.b1) + (blk_end - 1 >= g.b2) + (blk_end - 1 >= g.b3);
+        if (seg_lo == seg_hi) {
+          // the block lies inside one contour segment (the usual case): partial sums start at zero in registers and join
+          // the running entries at the end of the pass (misc_core.c:118-123).  The additions are fire-and-forget
+          // reductions performed at the L2 (red.global.add.f64: the same IEEE round-to-nearest addition; one owner per
+          // address, program order per address): no load latency is exposed.
+          if (seg_lo != cur_seg) enter_segment(seg_lo);
+          double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
+          {
+            double pa[36];
+#pragma unroll
+            for (int q = 0; q < 36; ++q) pa[q] = 0.0;
+            jac_pass_a(Dsa, Csa, xt, tt, s_lo, blk_end, pa, jte_cp);
+#pragma unroll
+            for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
           }
+          {
+            double pb[30];
+#pragma unroll
+            for (int q = 0; q < 30; ++q) pb[q] = 0.0;
+            jac_pass_b(Dsa, Csa, xt, tt, s_lo, blk_end, pb, jte_q);
+#pragma unroll
+            for (int q = 0; q < 24; ++q) red_add_f64(acc + (36 + q) * wsn, pb[q]);
+            double* accq = ws + (size_t)(kWsAcc + 120) * wsn;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) red_add_f64(accq + q * wsn, pb[24 + q]);
+          }
+        } else {
+          // the block straddles segments: its partial sums are kept per curve in the work area while the pieces are
+          // walked (a curve's rows may come in two pieces: curve 1, a short curve 2, curve 1 again), and join the
+          // running entries once, at the end of the block
+#pragma unroll 1
+          for (int q = kWsPend; q < kWsSlots; ++q) __stcg(ws + q * wsn, 0.0);
+          unsigned seen = 0;
+          int s = s_lo;
+#pragma unroll 1
+          while (s < blk_end) {
+            const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
+            if (seg != cur_seg) enter_segment(seg);
+            const int e_end = min(blk_end, seg_end(g, seg));
+            double* pend = ws + (size_t)(kWsPend + 60 * cur_curve) * wsn;
+            double* pendq = ws + (size_t)kWsPendQ * wsn;
+            {
+              double pa[36];
+#pragma unroll
+              for (int q = 0; q < 36; ++q) pa[q] = __ldcg(pend + q * wsn);
+              jac_pass_a(Dsa, Csa, xt, tt, s, e_end, pa, jte_cp);
+#pragma unroll
+              for (int q = 0; q < 36; ++q) __stcg(pend + q * wsn, pa[q]);
+            }
+            {
+              double pb[30];
+#pragma unroll
+              for (int q = 0; q < 24; ++q) pb[q] = __ldcg(pend + (36 + q) * wsn);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) pb[24 + q] = __ldcg(pendq + q * wsn);
+              jac_pass_b(Dsa, Csa, xt, tt, s, e_end, pb, jte_q);
+#pragma unroll
+              for (int q = 0; q < 24; ++q) __stcg(pend + (36 + q) * wsn, pb[q]);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) __stcg(pendq + q * wsn, pb[24 + q]);
+            }
+            seen |= 1u << cur_curve;
+            s = e_end;
+          }
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c)
+            if (seen & (1u << c))
+              for (int q = 0; q < 60; ++q)
+                red_add_f64(ws + (kWsAcc + 60 * c + q) * wsn, __ldcg(ws + (kWsPend + 60 * c + q) * wsn));
+#pragma unroll 1
+          for (int q = 0; q < 6; ++q) red_add_f64(ws + (kWsAcc + 120 + q) * wsn, __ldcg(ws + (kWsPendQ + q) * wsn));
         }
       }
-      __syncwarp();
     }
-    if (!have) continue;
+    bool to_solve = false;
+    if (have) {
+    // gradient statistics, lm_core.c:256-287 (maxima do not depend on the order of the comparisons)
+    double p_sq = 0.0, g_inf = 0.0, big = -DBL_MAX;
     if (blocked) {
       if (cur_curve >= 0) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a) ws[(kWsJte + 8 * cur_curve + a) * wsn] = G.jte_cp[a];
+        for (int a = 0; a < 8; ++a) __stcg(ws + (kWsJte + 8 * cur_curve + a) * wsn, jte_cp[a]);
       }
       // the lower triangle, row-major: curve blocks, the structurally zero cross block, theta/phi/z rows.  Every
       // group is read into registers before it is written so that the loads overlap (the work area is read past the
@@ -690,6 +913,9 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
         for (int a = 0; a < 8; ++a)
 #pragma unroll
           for (int bq = 0; bq <= a; ++bq) Jout[tri(8 * c + a, 8 * c + bq)] = v[a * (a + 1) / 2 + bq];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          if (v[a * (a + 1) / 2 + a] > big) big = v[a * (a + 1) / 2 + a];
       }
 #pragma unroll
       for (int a = 0; a < 8; ++a)
@@ -709,6 +935,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
           for (int j = 0; j < 16; ++j) Jout[tri(16 + q, j)] = v[24 * (j >> 3) + 8 * q + (j & 7)];
 #pragma unroll
           for (int r = 0; r <= q; ++r) Jout[tri(16 + q, 16 + r)] = v[48 + q * (q + 1) / 2 + r];
+          if (v[48 + q * (q + 1) / 2 + q] > big) big = v[48 + q * (q + 1) / 2 + q];
         }
       }
       {
@@ -716,24 +943,30 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = __ldcg(ws + (kWsJte + q) * wsn);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) Jte[q] = v[q];
+        for (int q = 0; q < 16; ++q) {
+          Jte[q] = v[q];
+          const double tmp = fabs(v[q]);
+          if (g_inf < tmp) g_inf = tmp;
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 3; ++q) Jte[16 + q] = G.jte_q[q];
+      for (int q = 0; q < 3; ++q) {
+        Jte[16 + q] = jte_q[q];
+        const double tmp = fabs(jte_q[q]);
+        if (g_inf < tmp) g_inf = tmp;
+      }
     } else {
       jac_unblocked(pp, tg, g, x, tp, Dsm, Csm, Jout, Jte);
-    }
-
-    // gradient statistics, lm_core.c:256-287
-    double p_sq = 0.0, g_inf = 0.0, big = -DBL_MAX;
 #pragma unroll 1
-    for (int q = 0; q < 19; ++q) {
-      const double tmp = fabs(Jte[q]);
-      if (g_inf < tmp) g_inf = tmp;
-      p_sq += pp[q] * pp[q];
-      const double d = Jout[tri(q, q)];
-      if (d > big) big = d;
+      for (int q = 0; q < 19; ++q) {
+        const double tmp = fabs(Jte[q]);
+        if (g_inf < tmp) g_inf = tmp;
+        const double d = Jout[tri(q, q)];
+        if (d > big) big = d;
+      }
     }
+#pragma unroll 1
+    for (int q = 0; q < 19; ++q) p_sq += pp[q] * pp[q];
     StagedScal* sp = A.scal + f;
     StagedScal sc = *sp;
     sc.njev += 1;
@@ -744,11 +977,14 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
       sc.dp_sq = 0.0;
       *sp = sc;
       staged_finish(A, f, sc, 1);
-      continue;
+    } else {
+      if (sc.k == 0) sc.mu = A.L.tau * big;
+      *sp = sc;
+      to_solve = true;
     }
-    if (sc.k == 0) sc.mu = A.L.tau * big;
-    *sp = sc;
-    staged_append(A.solve_list[nxt], A.cnt + 2 + nxt, f);
+    }
+    __syncwarp();
+    staged_append(A.solve_list[nxt], A.cnt + 2 + nxt, f, to_solve);
   }
 }
 
