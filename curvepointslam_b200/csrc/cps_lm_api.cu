@@ -34,7 +34,6 @@ struct cps_lm_slot {
 
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
-constexpr int kStagedChunkFits = 131072;  // chunk of the staged path: its thread-per-fit kernels want >= 37 888 fits
 constexpr int kStagedMinFits = 12288;     // below this the monolithic kernel (a warp per fit) is the better shape
 
 struct cps_lm_ctx {
@@ -183,15 +182,24 @@ int launch_fit(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st
 
 // dlevmar_der for a large batch of Stereo19 fits as rounds of three phase kernels (cps_lm_staged.cuh).  The
 // host only sizes grids: after every round it reads one integer, the number of fits still iterating.
-int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st) {
+// The batch may arrive in pieces (ranges of the fit index, each guarded by an event recorded on a copy stream):
+// a piece joins the rounds as soon as its samples are on the device, so the host-buffer entry points overlap the
+// transfer of the batch with the iterations of the fits that are already there.
+struct StagedPiece {
+  int first, count;
+  cudaEvent_t ready;  // nullptr: already resident
+};
+
+int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st,
+                        const std::vector<StagedPiece>& pieces) {
   using namespace cps;
   const size_t B = (size_t)L.B;
   auto a256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const int jac_smem = kJacTableDoubles * kJacThreads * (int)sizeof(double) + (kJacThreads / 32) * (int)sizeof(WarpTiles);
   const int eval_smem = kEvalTableDoubles * kEvalThreads * (int)sizeof(double) + (kEvalThreads / 32) * (int)sizeof(WarpTiles);
+  const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
-  const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
   CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
   int jac_occ = 0, solve_occ = 0, eval_occ = 0;
@@ -242,6 +250,8 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   A.solve_list[0] = (int*)(d + o_s0);
   A.solve_list[1] = (int*)(d + o_s1);
   A.cnt = (unsigned int*)(d + o_cnt);
+  A.init_first = 0;
+  A.init_count = 0;
 
   auto grid_for = [&](size_t items, int per_block, int cap) {
     size_t gneed = (items + per_block - 1) / per_block;
@@ -249,28 +259,47 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     return (int)std::min<size_t>(gneed, (size_t)cap);
   };
   CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 4, st));
-  staged_eval_kernel<true><<<grid_for(B, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, 0);
-  staged_jac_kernel<<<grid_for(B, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, 0);
-  CPS_CUDA(cudaGetLastError());
-  c->launches += 2;
-  int cur = 0, rounds = 0;
-  CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + cur, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-  CPS_CUDA(cudaStreamSynchronize(st));
-  size_t n_solve = sl.h_count[0];
-  while (n_solve > 0) {
+  size_t next_piece = 0, n_solve = 0;
+  int cur = 1, rounds = 0;
+  for (;;) {
     const int nxt = cur ^ 1;
-    staged_solve_kernel<<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
+    if (n_solve > 0) {
+      staged_solve_kernel<<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
+      c->launches += 1;
+    }
     CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int), st));
     CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
-    staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
-    staged_jac_kernel<<<grid_for(n_solve, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+    if (n_solve > 0) {
+      staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+      c->launches += 1;
+    }
+    // pieces of the batch that have arrived start here: validation, t, e0, loop-top checks of iteration 0
+    size_t added = 0;
+    while (next_piece < pieces.size()) {
+      const StagedPiece& P = pieces[next_piece];
+      if (P.ready) {
+        if (n_solve + added > 0 && cudaEventQuery(P.ready) != cudaSuccess) break;  // not there yet: keep iterating
+        CPS_CUDA(cudaStreamWaitEvent(st, P.ready, 0));
+      }
+      if (P.count > 0) {
+        A.init_first = P.first;
+        A.init_count = P.count;
+        staged_eval_kernel<true><<<grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+        c->launches += 1;
+        added += (size_t)P.count;
+      }
+      ++next_piece;
+    }
+    if (n_solve + added == 0) break;
+    staged_jac_kernel<<<grid_for(n_solve + added, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
     CPS_CUDA(cudaGetLastError());
-    c->launches += 3;
+    c->launches += 1;
     CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + nxt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaStreamSynchronize(st));
     n_solve = sl.h_count[0];
     cur = nxt;
     ++rounds;
+    if (n_solve == 0 && next_piece == pieces.size()) break;
   }
   c->last_grid = jac_grid_max;
   c->last_block = kJacThreads;
@@ -300,7 +329,7 @@ int fill_opts(cps::LmLaunch& L, const double* opts, int variant) {
 namespace {
 int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, double* d_p, const double* d_meas,
             const double* d_t, const long long* d_off, const int* d_counts, int n_max, int itmax,
-            const double* opts, double* d_info, int* d_ret, int* d_extra, cudaStream_t st) {
+            const double* opts, double* d_info, int* d_ret, int* d_extra, cudaStream_t st, int path) {
   cps::LmLaunch L;
   std::memset(&L, 0, sizeof L);
   L.B = B;
@@ -309,9 +338,10 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
   fill_opts(L, opts, variant);
   L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;
   L.info = d_info; L.ret = d_ret; L.extra = d_extra;
-  if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
-      (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits))
-    return launch_staged_der19(c, sl, L, st);
+  if (path == CPS_LM_PATH_AUTO) path = c->path;
+  if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && path != CPS_LM_PATH_MONOLITHIC &&
+      (path == CPS_LM_PATH_STAGED || B >= kStagedMinFits))
+    return launch_staged_der19(c, sl, L, st, {StagedPiece{0, B, nullptr}});
   if (model == CPS_MODEL_STEREO19)
     return variant == CPS_LM_DER ? launch_fit<19, false>(c, sl, L, st) : launch_fit<19, true>(c, sl, L, st);
   return variant == CPS_LM_DER ? launch_fit<8, false>(c, sl, L, st) : launch_fit<8, true>(c, sl, L, st);
@@ -330,12 +360,103 @@ extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int
   CPS_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   return fit_dev(c, c->slot[0], model, variant, B, d_p, d_meas, d_t, d_off, d_counts, n_max, itmax, opts, d_info,
-                 d_ret, d_extra, st);
+                 d_ret, d_extra, st, CPS_LM_PATH_AUTO);
 }
 
 namespace {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Host buffers, staged shape: the whole batch gets one staging block; p / offsets / counts go first, then the samples
+// in pieces on the copy stream (slot 1), each followed by an event.  The rounds (slot 0's stream) pick a piece up as
+// soon as its event has fired, so the fits of the first pieces are already iterating while the rest of the batch
+// is still crossing PCIe; results come back in one copy at the end.
+int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas, const double* t, const long long* off,
+                            const int* counts, long long n_max, int itmax, const double* opts, double* info, int* ret,
+                            int* extra) {
+  constexpr int m = 19, nseg = 4;
+  cps_lm_slot& sl = c->slot[0];
+  cudaStream_t st = sl.stream, cp = c->slot[1].stream;
+  const long long base = off[0], total = off[B] - base;
+  size_t o_p = 0, o_meas = align256(o_p + sizeof(double) * (size_t)B * m);
+  size_t o_t = align256(o_meas + sizeof(double) * (size_t)total);
+  size_t o_off = align256(o_t + (t ? sizeof(double) * (size_t)(total / 2 + 1) : 0));
+  size_t o_cnt = align256(o_off + sizeof(long long) * (size_t)(B + 1));
+  size_t o_info = align256(o_cnt + sizeof(int) * (size_t)B * nseg);
+  size_t o_ret = align256(o_info + sizeof(double) * (size_t)B * 10);
+  size_t o_ext = align256(o_ret + sizeof(int) * (size_t)B);
+  const size_t bytes = align256(o_ext + sizeof(int) * (size_t)B * 2);
+  CPS_CUDA(cudaStreamSynchronize(st));
+  CPS_CUDA(cudaStreamSynchronize(cp));
+  if (bytes > sl.stage_bytes) {
+    cudaFree(sl.d_stage);
+    sl.d_stage = nullptr;
+    sl.stage_bytes = 0;
+    CPS_CUDA(cudaMalloc(&sl.d_stage, bytes));
+    sl.stage_bytes = bytes;
+  }
+  char* d = sl.d_stage;
+  sl.off0.resize((size_t)B + 1);
+  for (int f = 0; f <= B; ++f) sl.off0[f] = off[f] - base;
+  int piece = std::max(8192, (B + 15) / 16);
+  if (const char* e = std::getenv("CPS_LM_STAGED_PIECE")) {  // experiment knob
+    const int v = std::atoi(e);
+    if (v >= 1024) piece = v;
+  }
+  const int n_pieces = (B + piece - 1) / piece;
+  std::vector<StagedPiece> pieces((size_t)n_pieces);
+  std::vector<cudaEvent_t> events((size_t)n_pieces, nullptr);
+  auto destroy_events = [&]() {
+    for (cudaEvent_t e : events)
+      if (e) cudaEventDestroy(e);
+  };
+  auto run = [&]() -> int {
+    CPS_CUDA(cudaMemcpyAsync(d + o_p, p, sizeof(double) * (size_t)B * m, cudaMemcpyHostToDevice, cp));
+    CPS_CUDA(cudaMemcpyAsync(d + o_off, sl.off0.data(), sizeof(long long) * (size_t)(B + 1), cudaMemcpyHostToDevice, cp));
+    CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts, sizeof(int) * (size_t)B * nseg, cudaMemcpyHostToDevice, cp));
+    for (int k = 0; k < n_pieces; ++k) {
+      const int f0 = k * piece, f1 = std::min(B, f0 + piece);
+      const long long m0 = sl.off0[f0], m1 = sl.off0[f1];
+      if (m1 > m0) {
+        CPS_CUDA(cudaMemcpyAsync(d + o_meas + sizeof(double) * (size_t)m0, meas + base + m0,
+                                 sizeof(double) * (size_t)(m1 - m0), cudaMemcpyHostToDevice, cp));
+        if (t)
+          CPS_CUDA(cudaMemcpyAsync(d + o_t + sizeof(double) * (size_t)(m0 / 2), t + (base + m0) / 2,
+                                   sizeof(double) * (size_t)((m1 - m0) / 2), cudaMemcpyHostToDevice, cp));
+      }
+      CPS_CUDA(cudaEventCreateWithFlags(&events[k], cudaEventDisableTiming));
+      CPS_CUDA(cudaEventRecord(events[k], cp));
+      pieces[k] = StagedPiece{f0, f1 - f0, events[k]};
+    }
+    cps::LmLaunch L;
+    std::memset(&L, 0, sizeof L);
+    L.B = B;
+    L.n_max = ((int)n_max + 3) & ~3;
+    L.itmax = itmax;
+    fill_opts(L, opts, CPS_LM_DER);
+    L.p = (double*)(d + o_p);
+    L.meas = (const double*)(d + o_meas);
+    L.t = t ? (const double*)(d + o_t) : nullptr;
+    L.off = (const long long*)(d + o_off);
+    L.counts = (const int*)(d + o_cnt);
+    L.info = (double*)(d + o_info);
+    L.ret = (int*)(d + o_ret);
+    L.extra = extra ? (int*)(d + o_ext) : nullptr;
+    const int rc = launch_staged_der19(c, sl, L, st, pieces);
+    if (rc != CPS_OK) return rc;
+    CPS_CUDA(cudaMemcpyAsync(p, d + o_p, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(info, d + o_info, sizeof(double) * (size_t)B * 10, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(ret, d + o_ret, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (extra) CPS_CUDA(cudaMemcpyAsync(extra, d + o_ext, sizeof(int) * (size_t)B * 2, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaStreamSynchronize(st));
+    return CPS_OK;
+  };
+  const int rc = run();
+  cudaStreamSynchronize(cp);
+  cudaStreamSynchronize(st);
+  destroy_events();
+  return rc;
+}
 
 // Host buffers: the batch is cut into chunks of kChunkFits fits; chunk i+1 is copied (and its results of
 // chunk i-1 copied back) on the other slot's stream while chunk i computes.  Pinned host memory makes the
@@ -357,21 +478,33 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   }
   if (n_max > (1 << 24)) return CPS_ERR_INVALID;
   CPS_CUDA(cudaSetDevice(c->device));
-  int chunk_idx = 0;
-  for (int f0 = 0; f0 < B; f0 += kChunkFits, ++chunk_idx) {
-    const int nb = std::min(kChunkFits, B - f0);
-    cps_lm_slot& sl = c->slot[chunk_idx % kSlots];
+  const bool staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
+                      (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits);
+  if (staged) return fit_batched_host_staged(c, B, p, meas, t, off, counts, n_max, itmax, opts, info, ret, extra);
+  const int chunk = kChunkFits;
+  const int n_chunks = (B + chunk - 1) / chunk;
+  struct Staged {
+    int f0, nb;
+    size_t o_p, o_meas, o_t, o_off, o_cnt, o_info, o_ret, o_ext;
+  } desc[kSlots];
+  // copies of chunk ci into its slot's staging block: p | meas | t | off | counts | info | ret | extra
+  auto stage_in = [&](int ci) -> int {
+    cps_lm_slot& sl = c->slot[ci % kSlots];
+    Staged& D = desc[ci % kSlots];
     cudaStream_t st = sl.stream;
+    D.f0 = ci * chunk;
+    D.nb = std::min(chunk, B - D.f0);
+    const int f0 = D.f0, nb = D.nb;
     const long long base = off[f0], total = off[f0 + nb] - base;
-    // one staging block: p | meas | t | off | counts | info | ret | extra
-    size_t o_p = 0, o_meas = align256(o_p + sizeof(double) * (size_t)nb * m);
-    size_t o_t = align256(o_meas + sizeof(double) * (size_t)total);
-    size_t o_off = align256(o_t + (t ? sizeof(double) * (size_t)(total / 2 + 1) : 0));
-    size_t o_cnt = align256(o_off + sizeof(long long) * (size_t)(nb + 1));
-    size_t o_info = align256(o_cnt + sizeof(int) * (size_t)nb * nseg);
-    size_t o_ret = align256(o_info + sizeof(double) * (size_t)nb * 10);
-    size_t o_ext = align256(o_ret + sizeof(int) * (size_t)nb);
-    size_t bytes = align256(o_ext + sizeof(int) * (size_t)nb * 2);
+    D.o_p = 0;
+    D.o_meas = align256(D.o_p + sizeof(double) * (size_t)nb * m);
+    D.o_t = align256(D.o_meas + sizeof(double) * (size_t)total);
+    D.o_off = align256(D.o_t + (t ? sizeof(double) * (size_t)(total / 2 + 1) : 0));
+    D.o_cnt = align256(D.o_off + sizeof(long long) * (size_t)(nb + 1));
+    D.o_info = align256(D.o_cnt + sizeof(int) * (size_t)nb * nseg);
+    D.o_ret = align256(D.o_info + sizeof(double) * (size_t)nb * 10);
+    D.o_ext = align256(D.o_ret + sizeof(int) * (size_t)nb);
+    const size_t bytes = align256(D.o_ext + sizeof(int) * (size_t)nb * 2);
     // the slot's previous chunk must have drained before its staging block / offsets are reused
     CPS_CUDA(cudaStreamSynchronize(st));
     if (bytes > sl.stage_bytes) {
@@ -384,25 +517,42 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
     char* d = sl.d_stage;
     sl.off0.resize((size_t)nb + 1);
     for (int f = 0; f <= nb; ++f) sl.off0[f] = off[f0 + f] - base;
-    CPS_CUDA(cudaMemcpyAsync(d + o_p, p + (size_t)f0 * m, sizeof(double) * (size_t)nb * m, cudaMemcpyHostToDevice, st));
-    CPS_CUDA(cudaMemcpyAsync(d + o_meas, meas + base, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + D.o_p, p + (size_t)f0 * m, sizeof(double) * (size_t)nb * m, cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + D.o_meas, meas + base, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, st));
     if (t)
-      CPS_CUDA(cudaMemcpyAsync(d + o_t, t + base / 2, sizeof(double) * (size_t)(total / 2), cudaMemcpyHostToDevice, st));
-    CPS_CUDA(cudaMemcpyAsync(d + o_off, sl.off0.data(), sizeof(long long) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
-    CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts + (size_t)f0 * nseg, sizeof(int) * (size_t)nb * nseg,
+      CPS_CUDA(cudaMemcpyAsync(d + D.o_t, t + base / 2, sizeof(double) * (size_t)(total / 2), cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + D.o_off, sl.off0.data(), sizeof(long long) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d + D.o_cnt, counts + (size_t)f0 * nseg, sizeof(int) * (size_t)nb * nseg,
                              cudaMemcpyHostToDevice, st));
-    int rc = fit_dev(c, sl, model, variant, nb, (double*)(d + o_p), (const double*)(d + o_meas),
-                     t ? (const double*)(d + o_t) : nullptr, (const long long*)(d + o_off), (const int*)(d + o_cnt),
-                     (int)n_max, itmax, opts, (double*)(d + o_info), (int*)(d + o_ret),
-                     extra ? (int*)(d + o_ext) : nullptr, st);
+    return CPS_OK;
+  };
+  // kernels of chunk ci (the staged shape blocks the host while its rounds run: the other slot's copies proceed
+  // meanwhile) and the copies back
+  auto run = [&](int ci) -> int {
+    cps_lm_slot& sl = c->slot[ci % kSlots];
+    const Staged& D = desc[ci % kSlots];
+    cudaStream_t st = sl.stream;
+    char* d = sl.d_stage;
+    const int f0 = D.f0, nb = D.nb;
+    int rc = fit_dev(c, sl, model, variant, nb, (double*)(d + D.o_p), (const double*)(d + D.o_meas),
+                     t ? (const double*)(d + D.o_t) : nullptr, (const long long*)(d + D.o_off),
+                     (const int*)(d + D.o_cnt), (int)n_max, itmax, opts, (double*)(d + D.o_info), (int*)(d + D.o_ret),
+                     extra ? (int*)(d + D.o_ext) : nullptr, st, CPS_LM_PATH_MONOLITHIC);
     if (rc != CPS_OK) return rc;
-    CPS_CUDA(cudaMemcpyAsync(p + (size_t)f0 * m, d + o_p, sizeof(double) * (size_t)nb * m, cudaMemcpyDeviceToHost, st));
-    CPS_CUDA(cudaMemcpyAsync(info + (size_t)f0 * 10, d + o_info, sizeof(double) * (size_t)nb * 10,
+    CPS_CUDA(cudaMemcpyAsync(p + (size_t)f0 * m, d + D.o_p, sizeof(double) * (size_t)nb * m, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(info + (size_t)f0 * 10, d + D.o_info, sizeof(double) * (size_t)nb * 10,
                              cudaMemcpyDeviceToHost, st));
-    CPS_CUDA(cudaMemcpyAsync(ret + f0, d + o_ret, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(ret + f0, d + D.o_ret, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, st));
     if (extra)
-      CPS_CUDA(cudaMemcpyAsync(extra + (size_t)f0 * 2, d + o_ext, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, st));
+      CPS_CUDA(cudaMemcpyAsync(extra + (size_t)f0 * 2, d + D.o_ext, sizeof(int) * (size_t)nb * 2, cudaMemcpyDeviceToHost, st));
+    return CPS_OK;
+  };
+  int rc = stage_in(0);
+  for (int ci = 0; ci < n_chunks && rc == CPS_OK; ++ci) {
+    if (ci + 1 < n_chunks) rc = stage_in(ci + 1);
+    if (rc == CPS_OK) rc = run(ci);
   }
+  if (rc != CPS_OK) return rc;
   for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
   return CPS_OK;
 }

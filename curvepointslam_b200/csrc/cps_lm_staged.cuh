@@ -54,7 +54,8 @@ struct StagedArgs {
   int* jac_list;
   int* eval_list;
   int* solve_list[2];
-  unsigned int* cnt;   // [0] jac, [1] eval, [2], [3] solve lists
+  unsigned int* cnt;   // [0] jac, [1] unused, [2], [3] solve lists
+  int init_first, init_count;  // range of the fit index an INIT launch covers
 };
 
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -158,12 +159,12 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double* Csm = smem + tid;  // Csm[(3*cp + {uL, uR, v}) * kEvalThreads]
   WarpTiles* wt = reinterpret_cast<WarpTiles*>(smem + kEvalTableDoubles * kEvalThreads) + wid;
-  const unsigned int total = INIT ? (unsigned int)A.L.B : A.cnt[2 + (nxt ^ 1)];  // eval list = this round's solve list
+  const unsigned int total = INIT ? (unsigned int)A.init_count : A.cnt[2 + (nxt ^ 1)];  // eval list = this round's solve list
   for (unsigned int base = (blockIdx.x * (kEvalThreads / 32) + wid) * 32; base < total;
        base += gridDim.x * kEvalThreads) {
     const unsigned int item = base + lane;
     bool have = item < total;
-    int f = have ? (INIT ? (int)item : A.eval_list[item]) : 0;
+    int f = have ? (INIT ? A.init_first + (int)item : A.eval_list[item]) : 0;
     if (f < 0) { have = false; f = 0; }  // the fit stopped in the solve
     FitGeom g;
     g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;
@@ -365,94 +366,131 @@ constexpr int kSolveDoubles = 19 * 19 + 19 + 19;
 // trailing update of W columns (k0..k0+W-1) for rows i0.. : a_ik -= l_i * u_k.  The pivot-row entries stay in
 // registers; two rows are in flight per trip (all loads first, then the arithmetic, then the stores) so that the
 // shared-memory latency of one row overlaps the other's.
+template <int W, int NR>
+__device__ __forceinline__ void lu_update_rows(double* a, int j, int k0, int i, const double (&u)[W]) {
+  constexpr int M = 19, T = kSolveThreads;
+  double l[NR], x[NR][W];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    l[r] = a[((i + r) * M + j) * T];
+#pragma unroll
+    for (int c = 0; c < W; ++c) x[r][c] = a[((i + r) * M + k0 + c) * T];
+  }
+  double p[NR][W];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < W; ++c) p[r][c] = l[r] * u[c];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < W; ++c) x[r][c] -= p[r][c];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < W; ++c) a[((i + r) * M + k0 + c) * T] = x[r][c];
+}
+
+// trailing update of W columns (k0..k0+W-1) for the rows below j: a_ik -= l_i * u_k.  The pivot-row entries stay
+// in registers; four rows are in flight per trip (all loads first, then the arithmetic, then the stores) so that
+// the shared-memory latencies overlap.
 template <int W>
 __device__ __forceinline__ void lu_update_cols(double* a, int j, int k0) {
   constexpr int M = 19, T = kSolveThreads;
   double u[W];
-  const double* uj = a + (j * M + k0) * T;
 #pragma unroll
-  for (int c = 0; c < W; ++c) u[c] = uj[c * T];
+  for (int c = 0; c < W; ++c) u[c] = a[(j * M + k0 + c) * T];
   int i = j + 1;
 #pragma unroll 1
-  for (; i + 2 <= M; i += 2) {
-    double* r0 = a + (i * M + k0) * T;
-    double* r1 = r0 + M * T;
-    const double l0 = a[(i * M + j) * T], l1 = a[((i + 1) * M + j) * T];
-    double x0[W], x1[W];
-#pragma unroll
-    for (int c = 0; c < W; ++c) { x0[c] = r0[c * T]; x1[c] = r1[c * T]; }
-    double p0[W], p1[W];
-#pragma unroll
-    for (int c = 0; c < W; ++c) { p0[c] = l0 * u[c]; p1[c] = l1 * u[c]; }
-#pragma unroll
-    for (int c = 0; c < W; ++c) { x0[c] -= p0[c]; x1[c] -= p1[c]; }
-#pragma unroll
-    for (int c = 0; c < W; ++c) { r0[c * T] = x0[c]; r1[c * T] = x1[c]; }
-  }
-  if (i < M) {
-    double* r0 = a + (i * M + k0) * T;
-    const double l0 = a[(i * M + j) * T];
-    double x0[W];
-#pragma unroll
-    for (int c = 0; c < W; ++c) x0[c] = r0[c * T];
-#pragma unroll
-    for (int c = 0; c < W; ++c) x0[c] -= l0 * u[c];
-#pragma unroll
-    for (int c = 0; c < W; ++c) r0[c * T] = x0[c];
-  }
+  for (; i + 4 <= M; i += 4) lu_update_rows<W, 4>(a, j, k0, i, u);
+  if (i + 2 <= M) { lu_update_rows<W, 2>(a, j, k0, i, u); i += 2; }
+  if (i < M) lu_update_rows<W, 1>(a, j, k0, i, u);
 }
 
+// With one warp per scheduler nothing hides a latency but the thread's own independent work, so every phase is
+// written as "issue all loads of a batch, then the arithmetic, then the stores" over statically unrolled batches.
 __device__ __forceinline__ int lu_solve_thread(double* a, double* sc, double* bx, const double* lower,
-                                               const double* jte, double mu) {
+                                               const double* jte, double mu, double (&xout)[19]) {
   constexpr int M = 19, T = kSolveThreads;
 #define A_(i, k) a[((i) * M + (k)) * T]
-  {  // augmented copy of the symmetric matrix and the right-hand side: the lower triangle goes global -> shared by
-     // cp.async (190 + 19 copies in flight at once, no register staging), then it is mirrored and mu joins the diagonal
+  {  // augmented copy of the symmetric matrix and the right-hand side, global -> shared by cp.async (every element
+     // of the lower triangle lands in both halves; 380 copies in flight at once, no register staging); then mu
+     // joins the diagonal
     int idx = 0;
-    for (int i = 0; i < M; ++i)
-      for (int k = 0; k <= i; ++k, ++idx) cp_async8(&A_(i, k), lower + idx);
+#pragma unroll 1
+    for (int i = 0; i < M; ++i) {
+      for (int k = 0; k < i; ++k, ++idx) {
+        cp_async8(&A_(i, k), lower + idx);
+        cp_async8(&A_(k, i), lower + idx);
+      }
+      cp_async8(&A_(i, i), lower + idx);
+      ++idx;
+    }
+#pragma unroll
     for (int i = 0; i < M; ++i) cp_async8(bx + i * T, jte + i);
     cp_async_wait_all();
-    for (int i = 0; i < M; ++i) {
-      for (int k = 0; k < i; ++k) A_(k, i) = A_(i, k);
-      A_(i, i) = A_(i, i) + mu;
-    }
+    double d[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) d[i] = A_(i, i);
+#pragma unroll
+    for (int i = 0; i < M; ++i) A_(i, i) = d[i] + mu;
   }
-  int singular = 0;
-  for (int i = 0; i < M; ++i) {
-    double big = 0.0;
+  {  // row scales: 1 / max_j |a_ij|, all 19 running maxima advance together
+    double big[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) big[i] = 0.0;
+#pragma unroll 1
     for (int j = 0; j < M; ++j) {
-      const double v = fabs(A_(i, j));
-      if (v > big) big = v;
+      double v[M];
+#pragma unroll
+      for (int i = 0; i < M; ++i) v[i] = fabs(A_(i, j));
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        if (v[i] > big[i]) big[i] = v[i];
     }
-    if (big == 0.0) singular = 1;
-    else sc[i * T] = 1.0 / big;
+    int singular = 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+      if (big[i] == 0.0) singular = 1;
+    if (singular) return 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) sc[i * T] = 1.0 / big[i];
   }
-  if (singular) return 0;
 
   int piv = -1;  // the reference's maxi persists across columns
 #pragma unroll 1
   for (int j = 0; j < M; ++j) {
-    double big = 0.0;
-    for (int i = j; i < M; ++i) {
-      const double merit = sc[i * T] * fabs(A_(i, j));
-      if (merit >= big) { big = merit; piv = i; }
+    {
+      double merit[M];
+#pragma unroll
+      for (int i = 0; i < M; ++i) merit[i] = (i >= j) ? sc[i * T] * fabs(A_(i, j)) : 0.0;
+      double big = 0.0;
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        if (i >= j && merit[i] >= big) { big = merit[i]; piv = i; }
     }
     if (piv != j && piv >= 0) {
-      for (int k = 0; k < M; ++k) {
-        const double tmp = A_(piv, k);
-        A_(piv, k) = A_(j, k);
-        A_(j, k) = tmp;
-      }
+      double rp[M], rj[M];
+#pragma unroll
+      for (int k = 0; k < M; ++k) { rp[k] = A_(piv, k); rj[k] = A_(j, k); }
+#pragma unroll
+      for (int k = 0; k < M; ++k) { A_(piv, k) = rj[k]; A_(j, k) = rp[k]; }
       sc[piv * T] = sc[j * T];
-      const double tb = bx[piv * T];
-      bx[piv * T] = bx[j * T];
+      const double tb = bx[piv * T], tj = bx[j * T];
+      bx[piv * T] = tj;
       bx[j * T] = tb;
     }
     if (A_(j, j) == 0.0) A_(j, j) = DBL_EPSILON;
     if (j != M - 1) {
       const double inv = 1.0 / A_(j, j);
-      for (int i = j + 1; i < M; ++i) A_(i, j) = A_(i, j) * inv;
+      {
+        double l[M];
+#pragma unroll
+        for (int i = 1; i < M; ++i) l[i] = (i > j) ? A_(i, j) : 0.0;
+#pragma unroll
+        for (int i = 1; i < M; ++i)
+          if (i > j) A_(i, j) = l[i] * inv;
+      }
       int k0 = j + 1;
       for (; k0 + 6 <= M; k0 += 6) lu_update_cols<6>(a, j, k0);
       switch (M - k0) {
@@ -465,21 +503,36 @@ __device__ __forceinline__ int lu_solve_thread(double* a, double* sc, double* bx
       }
     }
   }
+  // the permutation is final: the right-hand side moves to registers and both substitutions are fully unrolled
+  double b[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) b[i] = bx[i * T];
   // forward substitution, column oriented (same ascending-j order per row), with the leading-zero skip
   bool started = false;
+#pragma unroll
   for (int j = 0; j < M - 1; ++j) {
-    const double xj = bx[j * T];
-    if (!started) {
-      if (xj != 0.0) started = true;
-      else continue;
+    const double xj = b[j];
+    if (!started && xj != 0.0) started = true;
+    if (started) {
+      double l[M];
+#pragma unroll
+      for (int i = j + 1; i < M; ++i) l[i] = A_(i, j);
+#pragma unroll
+      for (int i = j + 1; i < M; ++i) b[i] -= l[i] * xj;
     }
-    for (int i = j + 1; i < M; ++i) bx[i * T] -= A_(i, j) * xj;
   }
+#pragma unroll
   for (int i = M - 1; i >= 0; --i) {
-    double sum = bx[i * T];
-    for (int jj = i + 1; jj < M; ++jj) sum -= A_(i, jj) * bx[jj * T];
-    bx[i * T] = sum / A_(i, i);
+    double u[M];
+#pragma unroll
+    for (int jj = i; jj < M; ++jj) u[jj] = A_(i, jj);
+    double sum = b[i];
+#pragma unroll
+    for (int jj = i + 1; jj < M; ++jj) sum -= u[jj] * b[jj];
+    b[i] = sum / u[i];
   }
+#pragma unroll
+  for (int i = 0; i < M; ++i) xout[i] = b[i];
 #undef A_
   return 1;
 }
@@ -505,15 +558,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
     double dp_sq = sp->dp_sq;
     int stop = 0;
     bool to_eval = false;
+    double dp[M];
     for (;;) {
-      const int solved = lu_solve_thread(a, sc, bx, lower, jte, mu);
+      const int solved = lu_solve_thread(a, sc, bx, lower, jte, mu, dp);
       ++nlss;
       if (solved) {
         dp_sq = 0.0;
-        for (int q = 0; q < M; ++q) {
-          const double tmp = bx[q * T];
-          dp_sq += tmp * tmp;
-        }
+#pragma unroll
+        for (int q = 0; q < M; ++q) dp_sq += dp[q] * dp[q];
         if (dp_sq <= A.L.eps2_sq * p_sq) { stop = 2; break; }
         if (dp_sq >= (p_sq + A.L.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
         to_eval = true;
@@ -525,12 +577,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
       nu = nu2;
     }
     if (to_eval) {
+      double pv[M], gv[M];
+#pragma unroll
+      for (int q = 0; q < M; ++q) { pv[q] = pp[q]; gv[q] = jte[q]; }
       double dL = 0.0;
       double* pdp = A.pdp + (size_t)f * M;
+#pragma unroll
       for (int q = 0; q < M; ++q) {
-        const double d = bx[q * T];
-        pdp[q] = pp[q] + d;
-        dL += d * (mu * d + jte[q]);
+        pdp[q] = pv[q] + dp[q];
+        dL += dp[q] * (mu * dp[q] + gv[q]);
       }
       sp->mu = mu; sp->nu = nu; sp->nlss = nlss; sp->dp_sq = dp_sq; sp->dL = dL;
       A.eval_list[i] = f;
@@ -965,8 +1020,13 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
         if (d > big) big = d;
       }
     }
-#pragma unroll 1
-    for (int q = 0; q < 19; ++q) p_sq += pp[q] * pp[q];
+    {
+      double pv[19];
+#pragma unroll
+      for (int q = 0; q < 19; ++q) pv[q] = pp[q];
+#pragma unroll
+      for (int q = 0; q < 19; ++q) p_sq += pv[q] * pv[q];
+    }
     StagedScal* sp = A.scal + f;
     StagedScal sc = *sp;
     sc.njev += 1;
