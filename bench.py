@@ -167,6 +167,7 @@ def main():
     variant = lm.DER if args.variant == "der" else lm.DIF
     B = args.fits
     ctx = lm.LmContext(local)
+    ctx.set_profiling(True)  # CUDA-event pairs around the staged shape's kernels (about 130 events per step)
 
     # ---- synthetic shard of this rank (weak scaling: B fits per GPU) ---------------------------------
     b = synth.make_stereo19_batch_fast(B, K=K_PTS, seed=args.seed, first=rank * B)
@@ -215,6 +216,8 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ctx.get_profile(reset=True)
+    launches_before = ctx.launch_stats()["launches"]
     e0.record(stream)
     for i in range(args.steps):
         step_resident(kev[i])
@@ -222,7 +225,9 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     kernel_ms = [a.elapsed_time(bb) for a, bb in kev]
-    launches_value = args.steps  # one fit kernel per step (plus one 4-byte memset node)
+    launches_value = ctx.launch_stats()["launches"] - launches_before  # kernels of libcps.so launched in the timed region
+    prof = ctx.get_profile(reset=True)  # per-kernel CUDA-event time over the same timed region
+    staged = prof["jac"][1] > 0
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside) -----------------------------
     h_p = torch.empty_like(h_p0)
@@ -272,6 +277,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    flops_jac = njev * (flops.f_jac(N_MEAS, M) + flops.f_jtj(N_MEAS, M) + flops.f_jte(N_MEAS, M))
     pk_fma, pk_ma = _lib.C.c_double(), _lib.C.c_double()
     _lib.check(_lib.lib().cps_measure_fp64_peak(local, _lib.C.byref(pk_fma), _lib.C.byref(pk_ma)), "fp64 peak")
     peaks = {}
@@ -285,6 +291,48 @@ def main():
     e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
     h2d = h_meas.numel() * 8 + h_p0.numel() * 8 + h_off.numel() * 8 + h_cnt.numel() * 4
     d2h = h_p.numel() * 8 + h_info.numel() * 8 + h_ret.numel() * 4
+    peak_note = ("measured live by cps_measure_fp64_peak (DFMA stream; MEASURED_PEAKS.json has no FP64 entry); a kernel "
+                 f"that may not fuse multiply-adds (bit-exact parity) tops out at {pk_ma.value:.2f} TFLOP/s")
+    hbm_part = {"achieved": flops.fit_bytes(N_MEAS, M) * B / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "note": "algorithmic bytes of a whole fit over the step; the path is FP64-bound, not HBM-bound"}
+    if staged:
+        # dominant kernel of the staged shape: staged_jac_kernel (Jacobian + J^T J + J^T e of every accepted step)
+        jac_ms, jac_n = prof["jac"]
+        jac_tf = flops_jac * args.steps / (jac_ms * 1e-3) / 1e12  # the profile covers all timed steps
+        tot_prof = sum(v[0] for v in prof.values())
+        roofline = {
+            "bound": "fp64", "kernel": "staged_jac_kernel", "achieved": jac_tf, "peak": pk_fma.value, "unit": "TFLOP/s",
+            "frac": jac_tf / pk_fma.value, "peak_source": peak_note, "peak_unfused": pk_ma.value,
+            "frac_of_unfused": jac_tf / pk_ma.value,
+            "flops_per_launch": flops_jac * args.steps / max(jac_n, 1), "launches": int(jac_n),
+            "avg_launch_ms": jac_ms / max(jac_n, 1),
+            "kernel_share_of_step": {k: v[0] / tot_prof for k, v in prof.items()},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "launches_per_step": {k: v[1] / args.steps for k, v in prof.items()},
+            "whole_step": {"achieved": achieved_tf, "frac": achieved_tf / pk_fma.value,
+                           "frac_of_unfused": achieved_tf / pk_ma.value, "flops_per_fit": fl / B,
+                           "step_ms": kernel_ms_avg,
+                           "note": "all kernels of a step (solve + eval + jac rounds): every algorithmic flop of the fits "
+                                   "over the device time of the step"},
+            "hbm": hbm_part,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of staged_jac_kernel at
+            # 262144 fits (profiles/r1s_ncu_full_staged_jac_details.csv), per launch
+            "traffic": 3.44e9 * (B / 262144.0),
+            "traffic_note": "ncu: 2.41 GB read + 1.03 GB written per full-batch launch of staged_jac_kernel at 262144 "
+                            "fits (samples 1.6 GB + J^T J / work-area traffic); algorithmic 0.4 GB of J^T J output + 1.6 "
+                            "GB of samples",
+        }
+    else:
+        roofline = {
+            "bound": "fp64", "kernel": f"lm_fit_kernel<19,{'true' if variant == lm.DIF else 'false'}>",
+            "achieved": achieved_tf, "peak": pk_fma.value, "unit": "TFLOP/s", "frac": achieved_tf / pk_fma.value,
+            "peak_source": peak_note, "peak_unfused": pk_ma.value, "frac_of_unfused": achieved_tf / pk_ma.value,
+            "flops_per_fit": fl / B, "kernel_ms": kernel_ms_avg, "hbm": hbm_part,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+            # (profiles/r1_ncu_full_lm_der_v2_details.csv: 148.9 MB for 32768 fits), scaled to this launch
+            "traffic": 4544.0 * B if variant == lm.DER else None,
+            "traffic_note": "ncu-measured 4544 B/fit vs 4496 B/fit algorithmic (der)",
+        }
     line = {
         "metric": "bezier_lm_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -293,24 +341,12 @@ def main():
         "contours_per_sec": 4 * value,
         "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": f"cps_dlevmar_{args.variant}_batched (include/cps_lm.h), pinned host buffers, "
-                       "chunked copy/compute pipeline"},
+                       "the batch streams in while the fits that have arrived iterate"},
+        "execution_shape": "staged (solve / eval / jac phase kernels, thread per fit)" if staged
+                           else "monolithic (one persistent kernel, warp per fit)",
         "gpu_launches": launches_value,
         "clocks": clocks,
-        "roofline": {
-            "bound": "fp64", "kernel": f"lm_fit_kernel<19,{'true' if variant == lm.DIF else 'false'}>",
-            "achieved": achieved_tf, "peak": pk_fma.value, "unit": "TFLOP/s", "frac": achieved_tf / pk_fma.value,
-            "peak_source": "measured live by cps_measure_fp64_peak (DFMA stream; MEASURED_PEAKS.json has no FP64 "
-                           "entry); a kernel that may not fuse multiply-adds (bit-exact parity) tops out at "
-                           f"{pk_ma.value:.2f} TFLOP/s",
-            "peak_unfused": pk_ma.value, "frac_of_unfused": achieved_tf / pk_ma.value,
-            "flops_per_fit": fl / B, "kernel_ms": kernel_ms_avg,
-            "hbm": {"achieved": flops.fit_bytes(N_MEAS, M) * B / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
-                    "unit": "GB/s", "note": "algorithmic bytes; the path is FP64-bound, not HBM-bound"},
-            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-            # (profiles/r1_ncu_full_lm_der_v2_details.csv: 148.9 MB for 32768 fits), scaled to this launch
-            "traffic": 4544.0 * B if variant == lm.DER else None,
-            "traffic_note": "ncu-measured 4544 B/fit vs 4496 B/fit algorithmic (der)",
-        },
+        "roofline": roofline,
         "fit_stats": {"iters_mean": float(info[:, 5].mean()), "nfev_mean": float(nfev / B),
                       "njev_mean": float(njev / B), "nlss_mean": float(nlss / B),
                       "stop_reasons": {str(int(r)): int(c) for r, c in zip(reasons, rc_counts)}},

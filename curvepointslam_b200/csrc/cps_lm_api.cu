@@ -45,6 +45,11 @@ struct cps_lm_ctx {
   long long launches = 0;
   int path = 0;          // CPS_LM_PATH_AUTO / _MONOLITHIC / _STAGED
   int last_rounds = 0;   // rounds of the last staged call
+  // optional per-kernel timing of the staged rounds (CUDA events on the launching stream)
+  int profiling = 0;
+  double prof_ms[3] = {0, 0, 0};        // solve, eval (incl. the initial pass), jac
+  long long prof_launches[3] = {0, 0, 0};
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 extern "C" const char* cps_last_error(void) { return cps::g_last_error.c_str(); }
@@ -93,6 +98,7 @@ extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
     if (s.h_count) cudaFreeHost(s.h_count);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   delete c;
 }
 
@@ -105,6 +111,22 @@ extern "C" int cps_lm_sync(cps_lm_ctx* c) {
 extern "C" int cps_lm_set_path(cps_lm_ctx* c, int path) {
   if (!c || path < CPS_LM_PATH_AUTO || path > CPS_LM_PATH_STAGED) return CPS_ERR_INVALID;
   c->path = path;
+  return CPS_OK;
+}
+
+extern "C" int cps_lm_set_profiling(cps_lm_ctx* c, int on) {
+  if (!c) return CPS_ERR_INVALID;
+  c->profiling = on ? 1 : 0;
+  return CPS_OK;
+}
+
+extern "C" int cps_lm_get_profile(cps_lm_ctx* c, double* ms3, long long* launches3, int reset) {
+  if (!c) return CPS_ERR_INVALID;
+  for (int i = 0; i < 3; ++i) {
+    if (ms3) ms3[i] = c->prof_ms[i];
+    if (launches3) launches3[i] = c->prof_launches[i];
+    if (reset) { c->prof_ms[i] = 0.0; c->prof_launches[i] = 0; }
+  }
   return CPS_OK;
 }
 
@@ -259,18 +281,54 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     return (int)std::min<size_t>(gneed, (size_t)cap);
   };
   CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 4, st));
+  // per-kernel timing (cps_lm_set_profiling): an event pair around every launch, read after the round's sync
+  struct Span { int kind; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+  auto ev_get = [&]() -> cudaEvent_t {
+    if (ev_used == c->ev_pool.size()) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+      c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[ev_used++];
+  };
+  auto span_begin = [&](int kind) {
+    if (!c->profiling) return;
+    Span sp{kind, ev_get(), ev_get()};
+    if (sp.a && sp.b) { cudaEventRecord(sp.a, st); spans.push_back(sp); }
+  };
+  auto span_end = [&]() {
+    if (!c->profiling || spans.empty()) return;
+    cudaEventRecord(spans.back().b, st);
+  };
+  auto spans_collect = [&]() {
+    for (const Span& sp : spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+        c->prof_ms[sp.kind] += ms;
+        c->prof_launches[sp.kind] += 1;
+      }
+    }
+    spans.clear();
+    ev_used = 0;
+  };
   size_t next_piece = 0, n_solve = 0;
   int cur = 1, rounds = 0;
   for (;;) {
     const int nxt = cur ^ 1;
     if (n_solve > 0) {
+      span_begin(0);
       staged_solve_kernel<<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
+      span_end();
       c->launches += 1;
     }
     CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int), st));
     CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
     if (n_solve > 0) {
+      span_begin(1);
       staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+      span_end();
       c->launches += 1;
     }
     // pieces of the batch that have arrived start here: validation, t, e0, loop-top checks of iteration 0
@@ -284,18 +342,23 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
       if (P.count > 0) {
         A.init_first = P.first;
         A.init_count = P.count;
+        span_begin(1);
         staged_eval_kernel<true><<<grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+        span_end();
         c->launches += 1;
         added += (size_t)P.count;
       }
       ++next_piece;
     }
     if (n_solve + added == 0) break;
+    span_begin(2);
     staged_jac_kernel<<<grid_for(n_solve + added, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+    span_end();
     CPS_CUDA(cudaGetLastError());
     c->launches += 1;
     CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + nxt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaStreamSynchronize(st));
+    spans_collect();
     n_solve = sl.h_count[0];
     cur = nxt;
     ++rounds;

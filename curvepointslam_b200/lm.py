@@ -52,6 +52,16 @@ class LmContext:
         per fit, one kernel) or PATH_STAGED (rounds of phase kernels, a thread per fit).  Same results bit for bit."""
         _lib.check(_lib.lib().cps_lm_set_path(self._h, int(path)), "cps_lm_set_path")
 
+    def set_profiling(self, on: bool):
+        _lib.check(_lib.lib().cps_lm_set_profiling(self._h, 1 if on else 0), "cps_lm_set_profiling")
+
+    def get_profile(self, reset: bool = True):
+        """Accumulated CUDA-event time and launch count of the staged shape's kernels: {kernel: (ms, launches)}."""
+        ms = (C.c_double * 3)()
+        n = (C.c_longlong * 3)()
+        _lib.check(_lib.lib().cps_lm_get_profile(self._h, ms, n, 1 if reset else 0), "cps_lm_get_profile")
+        return {k: (ms[i], n[i]) for i, k in enumerate(("solve", "eval", "jac"))}
+
     # -- host buffers ---------------------------------------------------------------------------------
     def fit_batched(self, model: int, variant: int, p0, meas, off, counts, opts=REFERENCE_OPTS,
                     itmax: int = REFERENCE_ITMAX, t=None):

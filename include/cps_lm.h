@@ -118,6 +118,13 @@ int cps_cleanup_and_group_edges_batched(cps_lm_ctx *ctx, int F, const int *pts, 
 #define CPS_LM_PATH_MONOLITHIC 1
 #define CPS_LM_PATH_STAGED 2
 int cps_lm_set_path(cps_lm_ctx *ctx, int path);
+/*
+ * Per-kernel timing of the staged shape: with profiling on, every launch of its three kernels is bracketed by CUDA
+ * events on the launching stream; cps_lm_get_profile returns the accumulated milliseconds and launch counts of
+ * {solve, eval, jac} (and clears them when reset != 0).
+ */
+int cps_lm_set_profiling(cps_lm_ctx *ctx, int on);
+int cps_lm_get_profile(cps_lm_ctx *ctx, double *ms3, long long *launches3, int reset);
 /* geometry of the last launch and the number of kernel launches issued through this context */
 int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
 
