@@ -42,3 +42,10 @@ def fit_flops_dif(n, m, nfev, njap, nlss, n_jtj, n_broyden):
 def fit_bytes(n, m):
     """algorithmic HBM bytes of one fit: measurements + parameters in/out + info + segment counts"""
     return 8 * (n + m + m + 10) + 16
+
+
+def staged_jac_executed_flops(n):
+    """FP64 operations the staged shape's jac kernel really issues per Jacobian evaluation of an m=19 fit: it skips
+    the 8 structurally zero entries of every row and walks a block twice (pass A / pass B), 114 + 116 operations per
+    row (cuobjdump: 64 DMUL + 50 DADD and 65 DMUL + 51 DADD in the two row loops)."""
+    return n * (114 + 116)

@@ -8,7 +8,16 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/final_bench_der.json 2> gpurun
 python bench.py --variant dif --steps 3 --warmup 3 --fits 65536 --no-extras > gpurun_out/final_bench_dif.json 2> gpurun_out/final_bench_dif.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_bench_reference_der.json 2>/dev/null
 python bench.py --impl reference --variant dif --steps 3 --warmup 1 > gpurun_out/final_bench_reference_dif.json 2>/dev/null
-SMALL="python bench.py --fits 32768 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
+# staged shape (der, large batches): launch list of the bench command, then one full capture per kernel
+BIG="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
+$BIG > gpurun_out/plain0.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches_staged_der.csv $BIG > gpurun_out/ncu_s0.log 2>&1
+for K in jac solve eval; do
+  $BIG > gpurun_out/plain_$K.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:staged_${K}_kernel -s 2 -c 1 -o gpurun_out/final_prof_staged_$K $BIG > gpurun_out/ncu_s_$K.log 2>&1
+done
+# monolithic shape (a warp per fit): der at 8192 fits (below the switch-over), dif
+SMALL="python bench.py --fits 8192 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 $SMALL > gpurun_out/plain1.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/final_launches_lm_der.csv $SMALL > gpurun_out/ncu_a.log 2>&1
 $SMALL > gpurun_out/plain2.log 2>&1 &&
@@ -20,4 +29,4 @@ python scripts/ekfprof.py > gpurun_out/plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ekf_cov_pipe_kernel -s 1 -c 1 -o gpurun_out/final_prof_ekf_cov python scripts/ekfprof.py > gpurun_out/ncu_d.log 2>&1
 python scripts/ekfprof.py > gpurun_out/plain5.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/final_launches_ekf.csv python scripts/ekfprof.py > gpurun_out/ncu_e.log 2>&1
-ls -la gpurun_out | tail -20
+ls -la gpurun_out | tail -30
