@@ -34,7 +34,7 @@ struct cps_lm_slot {
 
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
-constexpr int kStagedMinFits = 12288;     // below this the monolithic kernel (a warp per fit) is the better shape
+constexpr int kStagedMinFits = 20480;     // below this the monolithic kernel (a warp per fit) is faster (measured crossover: 18-20 k fits)
 
 struct cps_lm_ctx {
   int device = 0;
