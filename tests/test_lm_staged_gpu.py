@@ -108,3 +108,30 @@ def test_staged_equals_monolithic_at_scale(sctx):
     assert auto.launch_stats()["launches"] > 3  # more than one kernel per chunk: the staged rounds ran
     mono.close()
     auto.close()
+
+
+def test_staged_device_entry_and_profile(sctx):
+    """cps_lm_fit_batched_dev with buffers resident in HBM (torch tensors) through the staged shape: bit-identical to
+    the host-buffer entry, and the per-kernel profile of the rounds is filled."""
+    import torch
+    B = 24000
+    b = synth.make_stereo19_batch_fast(B, K=64, seed=66)
+    dev = torch.device("cuda", 0)
+    d_meas, d_p, d_off, d_cnt = (torch.from_numpy(b[k]).to(dev) for k in ("meas", "p0", "off", "counts"))
+    d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+    d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_extra = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    sctx.set_profiling(True)
+    sctx.get_profile(reset=True)
+    sctx.fit_batched_dev(19, lm.DER, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(), d_cnt.data_ptr(), 512,
+                         d_info.data_ptr(), d_ret.data_ptr(), d_extra.data_ptr(), opts=OPTS)
+    sctx.sync()
+    torch.cuda.synchronize()
+    prof = sctx.get_profile(reset=True)
+    sctx.set_profiling(False)
+    assert prof["jac"][1] >= 5 and prof["solve"][1] >= 5 and prof["eval"][1] >= 5 and prof["jac"][0] > 0.0
+    host = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    assert np.array_equal(_bits(d_p.cpu().numpy()), _bits(host["p"]))
+    assert np.array_equal(_bits(d_info.cpu().numpy()), _bits(host["info"]))
+    assert np.array_equal(d_ret.cpu().numpy(), host["ret"]) and np.array_equal(d_extra.cpu().numpy(), host["extra"])
