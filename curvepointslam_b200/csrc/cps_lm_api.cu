@@ -34,7 +34,7 @@ struct cps_lm_slot {
 
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
-constexpr int kStagedMinFits = 20480;     // below this the monolithic kernel (a warp per fit) is faster (measured crossover: 18-20 k fits)
+constexpr int kStagedMinFits = 16384;     // below this the monolithic kernel (a warp per fit) is faster (measured crossover: 12-16 k fits)
 
 struct cps_lm_ctx {
   int device = 0;
@@ -222,10 +222,11 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
-  CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
+  CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
+  CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
   int jac_occ = 0, solve_occ = 0, eval_occ = 0;
-  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jac_occ, staged_jac_kernel, kJacThreads, jac_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jac_occ, staged_jac_kernel<false>, kJacThreads, jac_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel, kSolveThreads, solve_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_occ, staged_eval_kernel<false>, kEvalThreads, eval_smem));
   if (jac_occ < 1 || solve_occ < 1 || eval_occ < 1) {
@@ -351,11 +352,26 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
       ++next_piece;
     }
     if (n_solve + added == 0) break;
-    span_begin(2);
-    staged_jac_kernel<<<grid_for(n_solve + added, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
-    span_end();
+    // how many fits need a Jacobian: at most all that were solved plus the new arrivals; in the late rounds most
+    // fits are re-solving rejected steps and only a few accepted one, so the exact count is worth a read-back
+    size_t n_jac = n_solve + added;
+    const size_t jac_cap = (size_t)jac_grid_max * kJacThreads;
+    if (n_jac * 2 > jac_cap && n_jac <= 4 * jac_cap) {
+      CPS_CUDA(cudaMemcpyAsync(sl.h_count + 1, A.cnt + 0, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      CPS_CUDA(cudaStreamSynchronize(st));
+      n_jac = sl.h_count[1];
+      spans_collect();
+    }
+    if (n_jac > 0) {
+      span_begin(2);
+      if (n_jac * 2 <= jac_cap)  // few fits: two threads per fit
+        staged_jac_kernel<true><<<grid_for(n_jac, kJacThreads / 2, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+      else
+        staged_jac_kernel<false><<<grid_for(n_jac, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+      span_end();
+      c->launches += 1;
+    }
     CPS_CUDA(cudaGetLastError());
-    c->launches += 1;
     CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + nxt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaStreamSynchronize(st));
     spans_collect();

@@ -848,9 +848,16 @@ __device__ __noinline__ void jac_unblocked(const double* pp, const Trig& tg, con
   }
 }
 
+// SPLIT: when fewer fits than half the resident threads need a Jacobian (the late rounds of a batch, mid-size
+// batches), a fit gets two threads -- warps 0,1 of a CTA run pass A for 64 fits, warps 2,3 pass B for the same
+// fits -- which halves the latency floor of a round (one fit per thread takes 250 us however few fits there are).
+// The two halves write disjoint entries; whichever finishes second (an atomic counter in the fit's state) computes
+// the gradient statistics from the finished arrays and hands the fit on.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const StagedArgs A, int nxt) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool doA = !SPLIT || wid < 2, doB = !SPLIT || wid >= 2;
   double* Dsm = smem + tid;
   double* Csm = smem + 40 * kJacThreads + tid;
   const unsigned int Dsa = (unsigned int)__cvta_generic_to_shared(Dsm);
@@ -860,14 +867,17 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
   const size_t wsn = (size_t)A.ws_stride;
   double* ws = A.ws + gtid;
   const unsigned int total = A.cnt[0];
-  for (unsigned int base = (blockIdx.x * (kJacThreads / 32) + wid) * 32; base < total; base += gridDim.x * kJacThreads) {
+  const unsigned int warp0 = SPLIT ? (blockIdx.x * 2 + (wid & 1)) * 32 : (blockIdx.x * (kJacThreads / 32) + wid) * 32;
+  const unsigned int stride = SPLIT ? gridDim.x * (kJacThreads / 2) : gridDim.x * kJacThreads;
+  for (unsigned int base = warp0; base < total; base += stride) {
     const unsigned int item = base + lane;
-    const bool have = item < total;
+    bool have = item < total;
     const int f = have ? A.jac_list[item] : 0;
     FitGeom g;
     g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;
     long long o0 = 0;
     if (have) staged_geom(A, f, g, o0);
+    if (SPLIT && !doA && g.n * 19 < kBlockSzSq) have = false;  // a small (unblocked) fit is left to its pass-A thread
     const double* x = A.L.meas + o0;
     const double* tp = have ? staged_t(A, f, o0) : nullptr;
     const double* pp = A.L.p + (size_t)f * 19;
@@ -927,7 +937,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
           // address, program order per address): no load latency is exposed.
           if (seg_lo != cur_seg) enter_segment(seg_lo);
           double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
-          {
+          if (doA) {
             double pa[36];
 #pragma unroll
             for (int q = 0; q < 36; ++q) pa[q] = 0.0;
@@ -935,7 +945,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
 #pragma unroll
             for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
           }
-          {
+          if (doB) {
             double pb[30];
 #pragma unroll
             for (int q = 0; q < 30; ++q) pb[q] = 0.0;
@@ -961,7 +971,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
             const int e_end = min(blk_end, seg_end(g, seg));
             double* pend = ws + (size_t)(kWsPend + 60 * cur_curve) * wsn;
             double* pendq = ws + (size_t)kWsPendQ * wsn;
-            {
+            if (doA) {
               double pa[36];
 #pragma unroll
               for (int q = 0; q < 36; ++q) pa[q] = __ldcg(pend + q * wsn);
@@ -969,7 +979,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
 #pragma unroll
               for (int q = 0; q < 36; ++q) __stcg(pend + q * wsn, pa[q]);
             }
-            {
+            if (doB) {
               double pb[30];
 #pragma unroll
               for (int q = 0; q < 24; ++q) pb[q] = __ldcg(pend + (36 + q) * wsn);
@@ -1006,6 +1016,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
       // the lower triangle, row-major: curve blocks, the structurally zero cross block, theta/phi/z rows.  Every
       // group is read into registers before it is written so that the loads overlap (the work area is read past the
       // L1: its entries were updated by reductions at the L2).
+      if (doA) {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         double v[36];
@@ -1023,7 +1034,8 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
       for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int bq = 0; bq < 8; ++bq) Jout[tri(8 + a, bq)] = 0.0;
-      {
+      }
+      if (doB) {
         double v[54];
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -1040,7 +1052,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
           if (v[48 + q * (q + 1) / 2 + q] > big) big = v[48 + q * (q + 1) / 2 + q];
         }
       }
-      {
+      if (doA) {
         double v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = __ldcg(ws + (kWsJte + q) * wsn);
@@ -1051,11 +1063,13 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
           if (g_inf < tmp) g_inf = tmp;
         }
       }
+      if (doB) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        Jte[16 + q] = jte_q[q];
-        const double tmp = fabs(jte_q[q]);
-        if (g_inf < tmp) g_inf = tmp;
+        for (int q = 0; q < 3; ++q) {
+          Jte[16 + q] = jte_q[q];
+          const double tmp = fabs(jte_q[q]);
+          if (g_inf < tmp) g_inf = tmp;
+        }
       }
     } else {
       jac_unblocked(pp, tg, g, x, tp, Dsm, Csm, Jout, Jte);
@@ -1075,6 +1089,28 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
       for (int q = 0; q < 19; ++q) p_sq += pv[q] * pv[q];
     }
     StagedScal* sp = A.scal + f;
+    bool last = true;
+    if (SPLIT && blocked) {
+      // publish this half, then see whether the other half is already there
+      __threadfence();
+      last = atomicAdd(&sp->pad0, 1) == 1;
+      if (last) {
+        sp->pad0 = 0;
+        __threadfence();
+        g_inf = 0.0;
+        big = -DBL_MAX;
+        double jv[19], dv[19];
+#pragma unroll
+        for (int q = 0; q < 19; ++q) { jv[q] = __ldcg(Jte + q); dv[q] = __ldcg(Jout + tri(q, q)); }
+#pragma unroll
+        for (int q = 0; q < 19; ++q) {
+          const double tmp = fabs(jv[q]);
+          if (g_inf < tmp) g_inf = tmp;
+          if (dv[q] > big) big = dv[q];
+        }
+      }
+    }
+    if (last) {
     StagedScal sc = *sp;
     sc.njev += 1;
     sc.g_inf = g_inf;
@@ -1088,6 +1124,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
       if (sc.k == 0) sc.mu = A.L.tau * big;
       *sp = sc;
       to_solve = true;
+    }
     }
     }
     __syncwarp();

@@ -114,7 +114,7 @@ int cps_cleanup_and_group_edges_batched(cps_lm_ctx *ctx, int F, const int *pts, 
  *   MONOLITHIC  one persistent kernel, a warp per fit (best for a frame's worth of fits: one launch)
  *   STAGED      rounds of three phase kernels with a thread per fit in the Jacobian / J^T J phase (best for
  *               batches of tens of thousands of fits)
- *   AUTO        (default) STAGED from 20 480 fits per call upwards (the measured crossover on B200)
+ *   AUTO        (default) STAGED from 16 384 fits per call upwards (the measured crossover on B200)
  */
 #define CPS_LM_PATH_AUTO 0
 #define CPS_LM_PATH_MONOLITHIC 1

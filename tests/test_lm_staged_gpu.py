@@ -135,3 +135,29 @@ def test_staged_device_entry_and_profile(sctx):
     assert np.array_equal(_bits(d_p.cpu().numpy()), _bits(host["p"]))
     assert np.array_equal(_bits(d_info.cpu().numpy()), _bits(host["info"]))
     assert np.array_equal(d_ret.cpu().numpy(), host["ret"]) and np.array_equal(d_extra.cpu().numpy(), host["extra"])
+
+
+def test_staged_ragged_large_batch_both_jac_variants(sctx):
+    """The ragged / mixed-block batch replicated 250 times (24 000 fits): the early rounds run the one-thread-per-fit
+    J^T J kernel, the late rounds the two-threads-per-fit variant; every replica must equal the 96-fit batch (which
+    runs the two-thread variant throughout and is pinned to the oracle by test_staged_ragged_and_mixed_blocks)."""
+    rng = np.random.default_rng(7)
+    counts = rng.integers(5, 102, size=(96, 4)).astype(np.int32)
+    counts[0] = (101, 101, 101, 101)
+    counts[1] = (3, 2, 3, 2)
+    counts[2] = (7, 7, 6, 7)
+    counts[3] = (21, 3, 22, 30)
+    counts[4] = (10, 2, 2, 50)
+    counts[5] = (16, 16, 16, 16)
+    counts[6] = (17, 15, 33, 31)
+    counts[7] = (2, 40, 2, 40)
+    b = synth.make_stereo19_batch(96, seed=62, counts=counts, round_pixels=True)
+    small = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    R = 250
+    meas = np.tile(b["meas"], R)
+    n_per = np.diff(b["off"])
+    off = np.concatenate([[0], np.cumsum(np.tile(n_per, R))]).astype(np.int64)
+    big = sctx.fit_batched(STEREO19, DER, np.tile(b["p0"], (R, 1)), meas, off, np.tile(b["counts"], (R, 1)), OPTS)
+    assert np.array_equal(big["ret"], np.tile(small["ret"], R))
+    assert np.array_equal(_bits(big["p"]), _bits(np.tile(small["p"], (R, 1))))
+    assert np.array_equal(_bits(big["info"]), _bits(np.tile(small["info"], (R, 1))))
