@@ -1013,6 +1013,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
 #pragma unroll
         for (int a = 0; a < 8; ++a) __stcg(ws + (kWsJte + 8 * cur_curve + a) * wsn, jte_cp[a]);
       }
+      __threadfence();  // the block folds were reductions at the L2: order this thread's reads of the sums after them
       // the lower triangle, row-major: curve blocks, the structurally zero cross block, theta/phi/z rows.  Every
       // group is read into registers before it is written so that the loads overlap (the work area is read past the
       // L1: its entries were updated by reductions at the L2).
