@@ -371,9 +371,8 @@ constexpr int kSolveDoubles = 19 * 19 + 19 + 19;
 // zero in the second curve's columns: 60 % of the multiply-adds of a dense sweep touch nothing.  Skipping them is
 // exact for finite data (sums here are never -0.0, so x - (+-0) == x bit for bit); it is decided at run time from
 // the values, not assumed from the structure.
-template <int W, int NR>
+template <int M, int T, int W, int NR>
 __device__ __forceinline__ void lu_update_rows(double* a, int j, int k0, const int (&rows)[NR], const double (&u)[W]) {
-  constexpr int M = 19, T = kSolveThreads;
   double l[NR], x[NR][W];
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
@@ -398,9 +397,8 @@ __device__ __forceinline__ void lu_update_rows(double* a, int j, int k0, const i
 
 // W columns k0..k0+W-1, the rows named by `rowmask`; the pivot-row entries stay in registers; four rows are in
 // flight per trip (all loads first, then the arithmetic, then the stores) so that the shared-memory latencies overlap
-template <int W>
+template <int M, int T, int W>
 __device__ __forceinline__ void lu_update_cols(double* a, int j, int k0, unsigned int rowmask) {
-  constexpr int M = 19, T = kSolveThreads;
   double u[W];
 #pragma unroll
   for (int c = 0; c < W; ++c) u[c] = a[(j * M + k0 + c) * T];
@@ -415,38 +413,39 @@ __device__ __forceinline__ void lu_update_cols(double* a, int j, int k0, unsigne
       if (m) { m &= m - 1; ++n; }
     }
     if (n == 4) {
-      lu_update_rows<W, 4>(a, j, k0, rows, u);
+      lu_update_rows<M, T, W, 4>(a, j, k0, rows, u);
     } else {
       if (n >= 2) {
         const int r2[2] = {rows[0], rows[1]};
-        lu_update_rows<W, 2>(a, j, k0, r2, u);
+        lu_update_rows<M, T, W, 2>(a, j, k0, r2, u);
       }
       if (n & 1) {
         const int r1[1] = {n == 1 ? rows[0] : rows[2]};
-        lu_update_rows<W, 1>(a, j, k0, r1, u);
+        lu_update_rows<M, T, W, 1>(a, j, k0, r1, u);
       }
     }
   }
 }
 
 // the columns lo..hi-1 in chunks of at most six
+template <int M, int T>
 __device__ __forceinline__ void lu_update_window(double* a, int j, int lo, int hi, unsigned int rowmask) {
   int k0 = lo;
-  for (; k0 + 6 <= hi; k0 += 6) lu_update_cols<6>(a, j, k0, rowmask);
+  for (; k0 + 6 <= hi; k0 += 6) lu_update_cols<M, T, 6>(a, j, k0, rowmask);
   switch (hi - k0) {
-    case 5: lu_update_cols<5>(a, j, k0, rowmask); break;
-    case 4: lu_update_cols<4>(a, j, k0, rowmask); break;
-    case 3: lu_update_cols<3>(a, j, k0, rowmask); break;
-    case 2: lu_update_cols<2>(a, j, k0, rowmask); break;
-    case 1: lu_update_cols<1>(a, j, k0, rowmask); break;
+    case 5: lu_update_cols<M, T, 5>(a, j, k0, rowmask); break;
+    case 4: lu_update_cols<M, T, 4>(a, j, k0, rowmask); break;
+    case 3: lu_update_cols<M, T, 3>(a, j, k0, rowmask); break;
+    case 2: lu_update_cols<M, T, 2>(a, j, k0, rowmask); break;
+    case 1: lu_update_cols<M, T, 1>(a, j, k0, rowmask); break;
     default: break;
   }
 }
 
 // With one warp per scheduler nothing hides a latency but the thread's own independent work, so every phase is
 // written as "issue all loads of a batch, then the arithmetic, then the stores" over statically unrolled batches.
-__device__ __forceinline__ int lu_solve_thread(double* a, double* sc, double* bx, const double* lower,
-                                               const double* jte, double mu, double (&xout)[19]) {
+// fills the work matrix of the m=19 solve from the lower triangle in global memory
+__device__ __forceinline__ void lu_fill_global19(double* a, double* bx, const double* lower, const double* jte, double mu) {
   constexpr int M = 19, T = kSolveThreads;
 #define A_(i, k) a[((i) * M + (k)) * T]
   {  // augmented copy of the symmetric matrix and the right-hand side, global -> shared by cp.async (every element
@@ -471,7 +470,15 @@ __device__ __forceinline__ int lu_solve_thread(double* a, double* sc, double* bx
 #pragma unroll
     for (int i = 0; i < M; ++i) A_(i, i) = d[i] + mu;
   }
-  {  // row scales: 1 / max_j |a_ij|, all 19 running maxima advance together
+#undef A_
+}
+
+// factorises the M x M matrix in a[(i*M+k)*T] (shared memory, [element][thread]) and solves for the right-hand side
+// in bx[i*T]; returns 0 if a row is entirely zero
+template <int M, int T>
+__device__ __forceinline__ int lu_factor_solve(double* a, double* sc, double* bx, double (&xout)[M]) {
+#define A_(i, k) a[((i) * M + (k)) * T]
+  {  // row scales: 1 / max_j |a_ij|, all running maxima advance together
     double big[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) big[i] = 0.0;
@@ -533,20 +540,20 @@ __device__ __forceinline__ int lu_solve_thread(double* a, double* sc, double* bx
       }
       // columns right of j; if the pivot row is zero across the second curve's columns 8..15, those are left out
       bool gap = false;
-      if (j < 8) {
+      if (M == 19 && j < 8) {
         double u8[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) u8[k] = A_(j, 8 + k);
+        for (int k = 0; k < 8; ++k) u8[k] = A_(j, (8 + k) % M);
         gap = true;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (u8[k] != 0.0) gap = false;
       }
       if (gap) {
-        lu_update_window(a, j, j + 1, 8, rowmask);
-        lu_update_window(a, j, 16, M, rowmask);
+        lu_update_window<M, T>(a, j, j + 1, 8, rowmask);
+        lu_update_window<M, T>(a, j, 16, M, rowmask);
       } else {
-        lu_update_window(a, j, j + 1, M, rowmask);
+        lu_update_window<M, T>(a, j, j + 1, M, rowmask);
       }
     }
   }
@@ -607,7 +614,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
     bool to_eval = false;
     double dp[M];
     for (;;) {
-      const int solved = lu_solve_thread(a, sc, bx, lower, jte, mu, dp);
+      lu_fill_global19(a, bx, lower, jte, mu);
+      const int solved = lu_factor_solve<M, T>(a, sc, bx, dp);
       ++nlss;
       if (solved) {
         dp_sq = 0.0;

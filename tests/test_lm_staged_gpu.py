@@ -161,3 +161,20 @@ def test_staged_ragged_large_batch_both_jac_variants(sctx):
     assert np.array_equal(big["ret"], np.tile(small["ret"], R))
     assert np.array_equal(_bits(big["p"]), _bits(np.tile(small["p"], (R, 1))))
     assert np.array_equal(_bits(big["info"]), _bits(np.tile(small["info"], (R, 1))))
+
+
+@pytest.mark.parametrize("K", [64, 63, 4, 5, 100])
+def test_image8_thread_per_fit_bit_exact(sctx, K):
+    """m = 8 der through the thread-per-fit kernel (cps_lm_image8.cuh): bit-exact against the oracle on the blocked
+    path, on the reference's switch (K = 64: n*m = 1024), below it (unblocked loop) and on ragged tails."""
+    from oracle_lib import IMAGE8
+    b = synth.make_image8_batch(200, K=K, seed=71)
+    gpu = sctx.fit_batched(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    assert_same_fit(gpu, cpu)
+    if K == 64:
+        t = np.tile(np.linspace(0.0, 1.0, K), 200)
+        for opts, itmax in [(None, 1000), (OPTS, 1), (OPTS, 0)]:
+            gpu = sctx.fit_batched(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax, t=t)
+            cpu = oracle().fit_batch(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax, t=t)
+            assert_same_fit(gpu, cpu, check_mu=itmax > 0)
