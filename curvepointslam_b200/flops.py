@@ -46,6 +46,6 @@ def fit_bytes(n, m):
 
 def staged_jac_executed_flops(n):
     """FP64 operations the staged shape's jac kernel really issues per Jacobian evaluation of an m=19 fit: it skips
-    the 8 structurally zero entries of every row and walks a block twice (pass A / pass B), 114 + 116 operations per
-    row (cuobjdump: 64 DMUL + 50 DADD and 65 DMUL + 51 DADD in the two row loops)."""
-    return n * (114 + 116)
+    the 8 structurally zero entries of every row and walks a block twice (pass A / pass B): 223 + 232 operations per
+    two rows (cuobjdump of the two row loops, unrolled by two: 122 DMUL + 101 DADD and 130 DMUL + 102 DADD)."""
+    return n * 227.5

@@ -16,6 +16,10 @@ for K in jac solve eval; do
   $BIG > gpurun_out/plain_$K.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:staged_${K}_kernel -s 2 -c 1 -o gpurun_out/final_prof_staged_$K $BIG > gpurun_out/ncu_s_$K.log 2>&1
 done
+# per-contour m = 8 fits, a thread per fit
+I8="python scripts/image8_probe.py 1048576 thread"
+$I8 > gpurun_out/plain_i8.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:image8_der_kernel -s 2 -c 1 -o gpurun_out/final_prof_image8 $I8 > gpurun_out/ncu_i8.log 2>&1
 # monolithic shape (a warp per fit): der at 8192 fits (below the switch-over), dif
 SMALL="python bench.py --fits 8192 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 $SMALL > gpurun_out/plain1.log 2>&1 &&
