@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
       row_fill(const_cast<double*>(tt) - toff, toff, tp + 16 * b, min(16, g.nsamp - 16 * b));
       if (b + 1 < nblk) {
         prefetch_l2(x + 32 * (b + 1));
-        prefetch_l2(x + 32 * (b + 1) + 16);
+        if (32 * (b + 1) + 16 < g.n) prefetch_l2(x + 32 * (b + 1) + 16);
         prefetch_l2(tp + 16 * (b + 1));
       }
       cp_async_wait_all();

@@ -17,6 +17,20 @@ b = synth.make_stereo19_batch(12, seed=3, counts=counts)
 for var in (lm.DER, lm.DIF):
     r = ctx.fit_batched(lm.STEREO19, var, b["p0"], b["meas"], b["off"], b["counts"])
     print("stereo19", var, r["ret"][:4])
+# the staged shape (phase kernels) on the same ragged batch plus a mixed-block fit, and the m = 8 thread-per-fit kernel
+sctx = lm.LmContext(0)
+sctx.set_path(lm.PATH_STAGED)
+counts2 = counts.copy()
+counts2[2] = (21, 3, 22, 30)
+counts2[3] = (7, 7, 6, 7)
+b2 = synth.make_stereo19_batch(12, seed=3, counts=counts2)
+r = sctx.fit_batched(lm.STEREO19, lm.DER, b2["p0"], b2["meas"], b2["off"], b2["counts"])
+print("stereo19 staged", r["ret"][:4])
+for K in (33, 64, 70):
+    b8s = synth.make_image8_batch(40, K=K, seed=4)
+    r = sctx.fit_batched(lm.IMAGE8, lm.DER, b8s["p0"], b8s["meas"], b8s["off"], b8s["counts"])
+    print("image8 thread-per-fit", K, r["ret"][:4])
+sctx.close()
 b8 = synth.make_image8_batch(40, K=33, seed=4)
 for var in (lm.DER, lm.DIF):
     r = ctx.fit_batched(lm.IMAGE8, var, b8["p0"], b8["meas"], b8["off"], b8["counts"])
