@@ -5,21 +5,21 @@
 // one fit's 32-row blocks over lanes (tiles through shared memory, partial sums folded through shuffles).
 // With >= tens of thousands of fits in a batch there is a better source of parallelism: the fits
 // themselves.  Here every fit is a small state machine kept in HBM and a round of three kernels advances
-// all active fits by one linear solve:
+// all active fits by one linear solve, every kernel with a thread per fit:
 //
-//   solve  (warp per fit)    (J^T J + mu I) dp = J^T e by the reference's LU (lu_solve of the monolithic
-//                            kernel, unchanged), step checks, predicted reduction       lm_core.c:292-345
-//   eval   (thread per fit)  f(p+dp), ||x - f||^2 in the reference's four chains, accept / reject,
-//                            Nielsen damping, the loop-top checks of the next iteration  lm_core.c:347-388,198
-//   jac    (thread per fit)  analytic Jacobian, J^T J as per-32-row-block partial sums, J^T e, gradient
-//                            statistics, initial mu                                      lm_core.c:205-287
+//   solve  (J^T J + mu I) dp = J^T e by the reference's LU on a work matrix in shared memory, step checks,
+//          predicted reduction                                                          lm_core.c:292-345
+//   eval   f(p+dp), ||x - f||^2 in the reference's four chains, accept / reject, Nielsen damping, the
+//          loop-top checks of the next iteration                                         lm_core.c:347-388,198
+//   jac    analytic Jacobian, J^T J as per-32-row-block partial sums, J^T e, gradient statistics, initial
+//          mu (two threads per fit when few fits are left)                               lm_core.c:205-287
 //
 // A thread that owns a whole fit walks the rows in the reference's own order, so the summation orders
-// of the parity contract are simply the loop orders: no shuffles, no tiles, 66
-// independent multiply-add chains per row in registers.  Compaction lists carry the fits from kernel to
-// kernel; a rejected step goes straight back to `solve` with the old J^T J (the inner loop of
-// dlevmar_der).  The arithmetic -- every operation and its order -- is the same as in the monolithic
-// kernel, so both paths are bit-identical to the oracle and to each other (tests/test_lm_gpu.py).
+// of the parity contract are simply the loop orders: no shuffles, no tiles shared
+// between lanes, no idle lanes.  Compaction lists carry the fits from kernel to kernel; a rejected step goes
+// straight back to `solve` with the old J^T J (the inner loop of dlevmar_der).  The arithmetic -- every
+// operation and its order -- is the same as in the monolithic kernel, so both paths are bit-identical to the
+// oracle and to each other (tests/test_lm_staged_gpu.py).
 #pragma once
 #include "cps_lm_kernel.cuh"
 
