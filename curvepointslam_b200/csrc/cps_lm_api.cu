@@ -339,7 +339,9 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     while (next_piece < pieces.size()) {
       const StagedPiece& P = pieces[next_piece];
       if (P.ready) {
-        if (n_solve + added > 0 && cudaEventQuery(P.ready) != cudaSuccess) break;  // not there yet: keep iterating
+        // not there yet: keep iterating if the fits at hand fill the GPU, otherwise let the stream wait for the piece
+        // (rounds over a few thousand fits run at the latency floor of the kernels and only add launches)
+        if (n_solve + added >= (size_t)jac_grid_max * kJacThreads && cudaEventQuery(P.ready) != cudaSuccess) break;
         CPS_CUDA(cudaStreamWaitEvent(st, P.ready, 0));
       }
       if (P.count > 0) {
@@ -359,7 +361,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     size_t n_jac = n_solve + added;
     const size_t jac_cap = (size_t)jac_grid_max * kJacThreads;
     if (n_jac * 2 > jac_cap && n_jac <= 4 * jac_cap) {
-      CPS_CUDA(cudaMemcpyAsync(sl.h_count + 1, A.cnt + 0, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      staged_publish_kernel<<<1, 1, 0, st>>>(A.cnt + 0, sl.h_count + 1);
       CPS_CUDA(cudaStreamSynchronize(st));
       n_jac = sl.h_count[1];
       spans_collect();
@@ -374,7 +376,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
       c->launches += 1;
     }
     CPS_CUDA(cudaGetLastError());
-    CPS_CUDA(cudaMemcpyAsync(sl.h_count, A.cnt + 2 + nxt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    staged_publish_kernel<<<1, 1, 0, st>>>(A.cnt + 2 + nxt, sl.h_count);
     CPS_CUDA(cudaStreamSynchronize(st));
     spans_collect();
     n_solve = sl.h_count[0];
@@ -514,12 +516,16 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas,
   char* d = sl.d_stage;
   sl.off0.resize((size_t)B + 1);
   for (int f = 0; f <= B; ++f) sl.off0[f] = off[f] - base;
-  int piece = std::max(8192, (B + 15) / 16);
+  // piece sizes: small at first so that the rounds can start early, then growing to B/16
+  int piece_cap = std::max(8192, (B + 15) / 16);
   if (const char* e = std::getenv("CPS_LM_STAGED_PIECE")) {  // experiment knob
     const int v = std::atoi(e);
-    if (v >= 1024) piece = v;
+    if (v >= 1024) piece_cap = v;
   }
-  const int n_pieces = (B + piece - 1) / piece;
+  std::vector<int> bounds(1, 0);
+  for (int sz = std::min(piece_cap, std::max(2048, B / 64)); bounds.back() < B; sz = std::min(piece_cap, 2 * sz))
+    bounds.push_back(std::min(B, bounds.back() + sz));
+  const int n_pieces = (int)bounds.size() - 1;
   std::vector<StagedPiece> pieces((size_t)n_pieces);
   std::vector<cudaEvent_t> events((size_t)n_pieces, nullptr);
   auto destroy_events = [&]() {
@@ -527,12 +533,17 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas,
       if (e) cudaEventDestroy(e);
   };
   auto run = [&]() -> int {
-    CPS_CUDA(cudaMemcpyAsync(d + o_p, p, sizeof(double) * (size_t)B * m, cudaMemcpyHostToDevice, cp));
+    // the rebased offsets live in pageable memory (a copy from there blocks the host until the stream reaches it), so
+    // they go first and in one piece
     CPS_CUDA(cudaMemcpyAsync(d + o_off, sl.off0.data(), sizeof(long long) * (size_t)(B + 1), cudaMemcpyHostToDevice, cp));
-    CPS_CUDA(cudaMemcpyAsync(d + o_cnt, counts, sizeof(int) * (size_t)B * nseg, cudaMemcpyHostToDevice, cp));
     for (int k = 0; k < n_pieces; ++k) {
-      const int f0 = k * piece, f1 = std::min(B, f0 + piece);
+      const int f0 = bounds[k], f1 = bounds[k + 1];
       const long long m0 = sl.off0[f0], m1 = sl.off0[f1];
+      // the piece's parameters and segment counts, then its samples
+      CPS_CUDA(cudaMemcpyAsync(d + o_p + sizeof(double) * (size_t)f0 * m, p + (size_t)f0 * m,
+                               sizeof(double) * (size_t)(f1 - f0) * m, cudaMemcpyHostToDevice, cp));
+      CPS_CUDA(cudaMemcpyAsync(d + o_cnt + sizeof(int) * (size_t)f0 * nseg, counts + (size_t)f0 * nseg,
+                               sizeof(int) * (size_t)(f1 - f0) * nseg, cudaMemcpyHostToDevice, cp));
       if (m1 > m0) {
         CPS_CUDA(cudaMemcpyAsync(d + o_meas + sizeof(double) * (size_t)m0, meas + base + m0,
                                  sizeof(double) * (size_t)(m1 - m0), cudaMemcpyHostToDevice, cp));

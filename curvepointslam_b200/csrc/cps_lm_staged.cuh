@@ -655,6 +655,13 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
   }
 }
 
+// The host reads the list counters through pinned host memory the device writes directly (a cudaMemcpy of four
+// bytes would queue on a copy engine behind the megabytes of samples the host-buffer entry point is streaming in).
+__global__ void staged_publish_kernel(const unsigned int* __restrict__ src, volatile unsigned int* dst_host) {
+  *dst_host = *src;
+  __threadfence_system();
+}
+
 // ---- jac: thread per fit ---------------------------------------------------------------------------------
 // Shared memory per thread (strided by the CTA size: a warp's accesses are conflict-free):
 //   D[40]  derivative table of the current contour segment: [u-row | v-row][control point k][xe, ye, theta, phi, z]

@@ -21,6 +21,7 @@ h_info = torch.zeros((B, 10), dtype=torch.float64).pin_memory()
 h_ret = torch.zeros(B, dtype=torch.int32).pin_memory()
 opts = np.array(lm.REFERENCE_OPTS)
 ctx = lm.LmContext(0)
+ctx.set_profiling(True)
 fn = _lib.lib().cps_dlevmar_der_batched
 ts = []
 for it in range(6):
@@ -30,4 +31,6 @@ for it in range(6):
             opts.ctypes.data, h_info.data_ptr(), h_ret.data_ptr(), None)
     assert rc == 0
     ts.append((time.perf_counter() - t0) * 1e3)
+    prof = ctx.get_profile(reset=True)
+print("kernel time of the last call:", {k: (round(v[0], 2), v[1]) for k, v in prof.items()}, "sum %.2f ms" % sum(v[0] for v in prof.values()))
 print(f"chunk={os.environ.get('CPS_LM_STAGED_CHUNK', 'default')}: e2e {min(ts[2:]):.2f} ms = {B / min(ts[2:]) * 1e3 / 1e6:.3f} M fits/s  all {['%.1f' % t for t in ts]}")
