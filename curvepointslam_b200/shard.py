@@ -13,19 +13,30 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_fits(local_p, total: int, rank: int, world: int):
-    """All-gathers the per-rank fitted parameter blocks [b_r, m] into the global [total, m] tensor (every rank
-    gets the full result, like the reference's single address space)."""
+def gather_rows(local, total: int, rank: int, world: int):
+    """All-gathers per-rank blocks [b_r, ...] (the rows a rank owns by shard_range) into the global [total, ...] tensor;
+    every rank gets the full result, like the reference's single address space."""
     import torch
     import torch.distributed as dist
 
     if world == 1:
-        return local_p
-    m = local_p.shape[1]
+        return local
     sizes = [shard_range(total, r, world) for r in range(world)]
     width = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((width, m), dtype=local_p.dtype, device=local_p.device)
-    pad[: local_p.shape[0]] = local_p
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
+def gather_fits(local_p, total: int, rank: int, world: int):
+    """The fits' only exchange: the fitted parameter blocks [b_r, m] of all ranks -> [total, m]."""
+    return gather_rows(local_p, total, rank, world)
+
+
+def gather_gate(local_idx, total: int, rank: int, world: int):
+    """Mahalanobis gate sharded by measurement: every rank holds the landmark state (x, P: the packed
+    landmarks are 1.9 MB at 20k landmarks) and gates its contiguous range of the measurements; the association indices
+    [b_r] int32 are all-gathered (40 KB for 10k measurements)."""
+    return gather_rows(local_idx, total, rank, world)

@@ -63,3 +63,44 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     for rank in range(2):
         got = np.load(os.path.join(str(tmp_path), f"rank{rank}.npy"))
         assert got.shape == ref.shape and np.array_equal(got.view(np.int64), ref.view(np.int64))
+
+
+def _gate_problem():
+    from curvepointslam_b200 import ekf
+    x, G, ci, pi = ekf.make_synthetic_ekf(60, d=3, seed=5)
+    N = x.size
+    P = G @ G.T / 64.0 * 0.05 + 0.25 * np.eye(N)
+    P = 0.5 * (P + P.T)
+    rng = np.random.default_rng(9)
+    lm_xyz = x[pi[0]: pi[0] + 3 * len(pi)].reshape(-1, 3)
+    z = lm_xyz[rng.integers(0, len(pi), 37)] - x[:3] + rng.normal(0, 3.0, (37, 3))
+    return x, P, pi, z
+
+
+def _gate_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, P, pi, z = _gate_problem()
+    lo, hi = shard.shard_range(len(z), rank, world)
+    idx, _ = oracle().gate(x, P, pi, z[lo:hi], 11.345)
+    full = shard.gather_gate(torch.from_numpy(idx), len(z), rank, world)
+    np.save(os.path.join(out_dir, f"gate{rank}.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gate_sharded_by_measurement(tmp_path):
+    """The gate shards by measurement with the landmarks replicated: two ranks gate ragged halves and all-gather the
+    indices; every rank ends up with the single-process association."""
+    from oracle_lib import oracle
+    port = _free_port()
+    mp.spawn(_gate_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    x, P, pi, z = _gate_problem()
+    ref, _ = oracle().gate(x, P, pi, z, 11.345)
+    assert (ref >= 0).any()
+    for rank in range(2):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"gate{rank}.npy")), ref)
