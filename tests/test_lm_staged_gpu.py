@@ -178,3 +178,25 @@ def test_image8_thread_per_fit_bit_exact(sctx, K):
             gpu = sctx.fit_batched(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax, t=t)
             cpu = oracle().fit_batch(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax, t=t)
             assert_same_fit(gpu, cpu, check_mu=itmax > 0)
+
+
+def test_staged_ragged_with_explicit_t(sctx):
+    """Caller-supplied t on a ragged batch: fits whose t stream starts on an odd double (the staging tiles then hold
+    the row one element in) must give the same bits as t derived on the device and as the oracle."""
+    rng = np.random.default_rng(11)
+    counts = rng.integers(5, 60, size=(64, 4)).astype(np.int32)
+    counts[0] = (7, 8, 9, 11)  # 35 samples: the next fit's t starts on an odd index
+    b = synth.make_stereo19_batch(64, seed=67, counts=counts, round_pixels=False)
+    t = synth.t_from_rows(b)
+    assert any((int(o) // 2) % 2 == 1 for o in b["off"][:-1])
+    gpu_t = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, t=t)
+    gpu = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, t=t, nthreads=8)
+    assert_same_fit(gpu_t, cpu)
+    assert np.array_equal(_bits(gpu_t["p"]), _bits(gpu["p"])) and np.array_equal(_bits(gpu_t["info"]), _bits(gpu["info"]))
+    from oracle_lib import IMAGE8
+    b8 = synth.make_image8_batch(50, K=33, seed=68)  # 33 samples per fit: every second fit starts on an odd t index
+    t8 = np.tile(np.linspace(0.0, 1.0, 33), 50)
+    g8 = sctx.fit_batched(IMAGE8, DER, b8["p0"], b8["meas"], b8["off"], b8["counts"], OPTS, t=t8)
+    c8 = oracle().fit_batch(IMAGE8, DER, b8["p0"], b8["meas"], b8["off"], b8["counts"], OPTS, t=t8, nthreads=8)
+    assert_same_fit(g8, c8)
