@@ -200,3 +200,26 @@ def test_staged_ragged_with_explicit_t(sctx):
     g8 = sctx.fit_batched(IMAGE8, DER, b8["p0"], b8["meas"], b8["off"], b8["counts"], OPTS, t=t8)
     c8 = oracle().fit_batch(IMAGE8, DER, b8["p0"], b8["meas"], b8["off"], b8["counts"], OPTS, t=t8, nthreads=8)
     assert_same_fit(g8, c8)
+
+
+def test_staged_device_entry_unaligned_samples(sctx):
+    """Device buffers whose samples start 8 bytes off a 16-byte boundary (a view into a larger allocation): the 16-byte
+    staging copies shift the tile row by one element; results must not change."""
+    import torch
+    B = 400
+    b = synth.make_stereo19_batch_fast(B, K=64, seed=69)
+    dev = torch.device("cuda", 0)
+    big = torch.zeros(b["meas"].size + 1, dtype=torch.float64, device=dev)
+    big[1:] = torch.from_numpy(b["meas"]).to(dev)
+    assert (big.data_ptr() + 8) % 16 == 8
+    d_p, d_off, d_cnt = (torch.from_numpy(b[k]).to(dev) for k in ("p0", "off", "counts"))
+    d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+    d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    sctx.fit_batched_dev(19, lm.DER, B, d_p.data_ptr(), big.data_ptr() + 8, None, d_off.data_ptr(), d_cnt.data_ptr(), 512,
+                         d_info.data_ptr(), d_ret.data_ptr(), None, opts=OPTS)
+    sctx.sync()
+    torch.cuda.synchronize()
+    host = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    assert np.array_equal(_bits(d_p.cpu().numpy()), _bits(host["p"]))
+    assert np.array_equal(_bits(d_info.cpu().numpy()), _bits(host["info"]))
