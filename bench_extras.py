@@ -226,7 +226,7 @@ def image8_bench(device: int, B: int = 1 << 20):
         cpu_s = time.perf_counter() - t0
         same = bool(np.array_equal(d_p[:S].cpu().numpy().view(np.int64), c["p"].view(np.int64)))
         out[name] = {"kernel_ms": ms, "contours_per_sec": B / (ms * 1e-3), "cpu_all_cores_contours_per_sec": S / cpu_s,
-                     "kernel": ("image8_der_kernel (a thread per fit)" if name == "der" else "lm_fit_kernel<8,true> (a warp per fit)"),
+                     "kernel": f"image8_{name}_kernel (a thread per fit)",
                      "cores": os.cpu_count(), "iters_mean": float(d_info[:, 5].mean().item()), "bit_identical_on_sample": same}
     ctx.close()
     return out

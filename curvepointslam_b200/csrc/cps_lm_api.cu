@@ -35,7 +35,7 @@ struct cps_lm_slot {
 
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
-constexpr int kImage8ThreadMinFits = 16384;  // m = 8 der: a thread per fit from this many fits per call
+constexpr int kImage8ThreadMinFits = 16384;  // m = 8: a thread per fit from this many fits per call
 constexpr int kStagedMinFits = 16384;     // below this the monolithic kernel (a warp per fit) is faster (measured crossover: 12-16 k fits)
 
 struct cps_lm_ctx {
@@ -391,18 +391,25 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   return CPS_OK;
 }
 
-// dlevmar_der for a large batch of per-contour m = 8 fits: one kernel, a thread per fit (cps_lm_image8.cuh)
-int launch_image8_der(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st) {
+// dlevmar_der / dlevmar_dif for a large batch of per-contour m = 8 fits: one kernel, a thread per fit
+// (cps_lm_image8.cuh).  Work area: [dif: the secant Jacobians, n_max x 8 per resident thread][t of every fit unless
+// the caller supplies it]
+int launch_image8(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st, bool dif) {
   using namespace cps;
   const int smem = kI8LuDoubles * kI8Threads * (int)sizeof(double) + (kI8Threads / 32) * (int)sizeof(EvalTiles);
-  CPS_CUDA(cudaFuncSetAttribute(image8_der_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const void* fn = dif ? (const void*)image8_dif_kernel : (const void*)image8_der_kernel;
+  CPS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 0;
-  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, image8_der_kernel, kI8Threads, smem));
+  if (dif) CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, image8_dif_kernel, kI8Threads, smem));
+  else CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, image8_der_kernel, kI8Threads, smem));
   if (occ < 1) {
     cps::set_last_error("image8 kernel does not fit on this device");
     return CPS_ERR_CUDA;
   }
-  const size_t need = L.t ? 0 : sizeof(double) * (size_t)(L.n_max / 2) * (size_t)L.B;
+  const long long ctas = ((long long)L.B + kI8Threads - 1) / kI8Threads;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, (long long)c->sm_count * occ));
+  const size_t jac_bytes = dif ? sizeof(double) * 8 * (size_t)L.n_max * (size_t)grid * kI8Threads : 0;
+  const size_t need = jac_bytes + (L.t ? 0 : sizeof(double) * (size_t)(L.n_max / 2) * (size_t)L.B);
   if (need > sl.staged_bytes) {
     CPS_CUDA(cudaStreamSynchronize(st));
     CPS_CUDA(cudaStreamSynchronize(sl.stream));
@@ -412,9 +419,9 @@ int launch_image8_der(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStre
     CPS_CUDA(cudaMalloc(&sl.d_staged, need));
     sl.staged_bytes = need;
   }
-  const long long ctas = ((long long)L.B + kI8Threads - 1) / kI8Threads;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, (long long)c->sm_count * occ));
-  image8_der_kernel<<<grid, kI8Threads, smem, st>>>(L, (double*)sl.d_staged);
+  double* tws = (double*)((char*)sl.d_staged + jac_bytes);
+  if (dif) image8_dif_kernel<<<grid, kI8Threads, smem, st>>>(L, tws, (double*)sl.d_staged);
+  else image8_der_kernel<<<grid, kI8Threads, smem, st>>>(L, tws);
   CPS_CUDA(cudaGetLastError());
   c->last_grid = grid;
   c->last_block = kI8Threads;
@@ -457,9 +464,9 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
   if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && path != CPS_LM_PATH_MONOLITHIC &&
       (path == CPS_LM_PATH_STAGED || B >= kStagedMinFits))
     return launch_staged_der19(c, sl, L, st, {StagedPiece{0, B, nullptr}});
-  if (model == CPS_MODEL_IMAGE8 && variant == CPS_LM_DER && path != CPS_LM_PATH_MONOLITHIC &&
+  if (model == CPS_MODEL_IMAGE8 && path != CPS_LM_PATH_MONOLITHIC &&
       (path == CPS_LM_PATH_STAGED || B >= kImage8ThreadMinFits))
-    return launch_image8_der(c, sl, L, st);
+    return launch_image8(c, sl, L, st, variant == CPS_LM_DIF);
   if (model == CPS_MODEL_STEREO19)
     return variant == CPS_LM_DER ? launch_fit<19, false>(c, sl, L, st) : launch_fit<19, true>(c, sl, L, st);
   return variant == CPS_LM_DER ? launch_fit<8, false>(c, sl, L, st) : launch_fit<8, true>(c, sl, L, st);

@@ -368,4 +368,341 @@ __global__ void __launch_bounds__(kI8Threads, 2) image8_der_kernel(const LmLaunc
   }
 }
 
+// ---- dlevmar_dif (lm_core.c:429-828) for the m = 8 model, a thread per fit ----------------------------------------
+// The secant Jacobian of a fit (n x 8) lives in a global work area, the rows of a CTA's 128 threads interleaved in
+// 16-byte pieces so that a warp's loads and stores coalesce; everything else is
+// recomputed from the parameters on the fly: f(p) and f(p + dp) are four-term Bernstein sums, so the stored copies the
+// reference keeps (hx, wrk) are never needed -- a value recomputed from the same inputs by the same operations is the
+// same value.  The rank-one secant update (:745-755) is applied to a row on its way into the next J^T J build, like in
+// the warp-per-fit kernel; a finite-difference Jacobian (misc_core.c:135-209) in between simply overwrites the rows.
+// A pending secant update: p at the time of the trial, the trial point and the step sit in the (then idle) LU work
+// matrix in shared memory, [element][thread]: elements 0-7, 8-15, 16-23.
+struct I8Pending {
+  bool on;
+  double dp_sq;
+  const double* sh;
+};
+
+// a Jacobian row of this thread: four 16-byte pieces, [row][piece][thread] within the CTA's slice (coalesced)
+__device__ __forceinline__ double2* i8_jrow(double* J, int row) {
+  return reinterpret_cast<double2*>(J) + (size_t)row * 4 * kI8Threads;
+}
+
+__device__ __forceinline__ double i8_sum(const double (&w)[4], const double (&p)[8], int uv) {
+  double a = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a += w[k] * p[2 * k + uv];
+  return a;
+}
+
+// one row of the normal-equation build: secant update if pending, residual, accumulation into acc (36 lower entries,
+// index i(i+1)/2 + j) and the J^T e chains
+__device__ __forceinline__ void i8_dif_row(double2* q, const double (&w)[4], int uv, double xval, const double (&p)[8],
+                                           const I8Pending& P, double (&acc)[36], double (&jte)[8]) {
+  constexpr int T = kI8Threads;
+  double jr[8];
+  {
+    const double2 a0 = q[0], a1 = q[T], a2 = q[2 * T], a3 = q[3 * T];
+    jr[0] = a0.x; jr[1] = a0.y; jr[2] = a1.x; jr[3] = a1.y; jr[4] = a2.x; jr[5] = a2.y; jr[6] = a3.x; jr[7] = a3.y;
+  }
+  if (P.on) {
+    double f0 = 0.0, f1 = 0.0, dp[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f0 += w[k] * P.sh[(2 * k + uv) * T];
+      f1 += w[k] * P.sh[(8 + 2 * k + uv) * T];
+    }
+    const double d = f1 - f0;
+    double tmp = 0.0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      dp[l] = P.sh[(16 + l) * T];
+      tmp += jr[l] * dp[l];
+    }
+    tmp = (d - tmp) / P.dp_sq;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) jr[j] += tmp * dp[j];
+    q[0] = make_double2(jr[0], jr[1]);
+    q[T] = make_double2(jr[2], jr[3]);
+    q[2 * T] = make_double2(jr[4], jr[5]);
+    q[3 * T] = make_double2(jr[6], jr[7]);
+  }
+  const double e = xval - i8_sum(w, p, uv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) acc[i * (i + 1) / 2 + j] += jr[j] * jr[i];
+    jte[i] += jr[i] * e;
+  }
+}
+
+// J^T J and J^T e from the stored Jacobian.  BLOCKED: per-32-row partial sums, ascending rows (misc_core.c:101-126,
+// lm_core.c:636-644); otherwise the unblocked loop over descending rows (lm_core.c:604-628, n*m <= 1024).
+template <bool BLOCKED>
+__device__ __forceinline__ void i8_dif_normal_eqs(const I8Fit& F, const double (&p)[8], double* J, EvalTiles* wt, int lane,
+                                                  const I8Pending& P, double (&jtj)[36], double (&jte)[8]) {
+  double* xrow = &wt->x[lane][0];
+  double* trow = &wt->t[lane][0];
+  const double* xt = xrow + F.xoff;
+  const double* tt = trow + F.toff;
+#pragma unroll
+  for (int q = 0; q < 36; ++q) jtj[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) jte[q] = 0.0;
+  double part[36];
+  if (BLOCKED) {
+#pragma unroll
+    for (int q = 0; q < 36; ++q) part[q] = 0.0;
+  }
+  const int nstage = (F.n + 15) >> 4;
+#pragma unroll 1
+  for (int it = 0; it < nstage; ++it) {
+    const int b = BLOCKED ? it : nstage - 1 - it;
+    row_fill(xrow, F.xoff, F.x + 16 * b, min(16, F.n - 16 * b));
+    row_fill(trow, F.toff, F.tp + 8 * b, min(8, F.nsamp - 8 * b));
+    cp_async_wait_all();
+    const int s_lo = 8 * b, s_hi = min(8 * b + 8, F.nsamp);
+#pragma unroll 1
+    for (int is = 0; is < s_hi - s_lo; ++is) {
+      const int s = BLOCKED ? s_lo + is : s_hi - 1 - is;
+      const int l = s & 7;
+      double w[4];
+      bernstein3(tt[l], w);
+      if (BLOCKED) {
+        i8_dif_row(i8_jrow(J, 2 * s), w, 0, xt[2 * l], p, P, part, jte);
+        i8_dif_row(i8_jrow(J, 2 * s + 1), w, 1, xt[2 * l + 1], p, P, part, jte);
+      } else {
+        i8_dif_row(i8_jrow(J, 2 * s + 1), w, 1, xt[2 * l + 1], p, P, jtj, jte);
+        i8_dif_row(i8_jrow(J, 2 * s), w, 0, xt[2 * l], p, P, jtj, jte);
+      }
+    }
+    if (BLOCKED && ((b & 1) || b + 1 == nstage)) {
+#pragma unroll
+      for (int q = 0; q < 36; ++q) {
+        jtj[q] += part[q];
+        part[q] = 0.0;
+      }
+    }
+  }
+}
+
+// finite-difference Jacobian, row by row: forward (wrk - hx)/d or central (wrk2 - wrk)/(2d) per column, where the
+// perturbed evaluations differ from the base one only in the sums that contain the perturbed parameter (the others
+// reproduce the base value exactly and give +0.0)
+__device__ __forceinline__ void i8_dif_fd_jacobian(const I8Fit& F, const double (&p)[8], double* J, EvalTiles* wt, int lane,
+                                                   double delta, int forward) {
+  double* trow = &wt->t[lane][0];
+  const double* tt = trow + F.toff;
+  double dlt[8], scale[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double d = 1E-04 * p[j];
+    d = fabs(d);
+    if (d < delta) d = delta;
+    dlt[j] = d;
+    scale[j] = forward ? 1.0 / d : 0.5 / d;
+  }
+  const int nstage = (F.n + 15) >> 4;
+#pragma unroll 1
+  for (int b = 0; b < nstage; ++b) {
+    row_fill(trow, F.toff, F.tp + 8 * b, min(8, F.nsamp - 8 * b));
+    cp_async_wait_all();
+    const int s_hi = min(8 * b + 8, F.nsamp);
+#pragma unroll 1
+    for (int s = 8 * b; s < s_hi; ++s) {
+      double w[4];
+      bernstein3(tt[s & 7], w);
+#pragma unroll
+      for (int uv = 0; uv < 2; ++uv) {
+        const double base = i8_sum(w, p, uv);
+        double jr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) jr[j] = 0.0;
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+          const int j = 2 * kq + uv;
+          double hi = 0.0, lo = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double pk = p[2 * k + uv];
+            hi += w[k] * ((k == kq) ? pk + dlt[j] : pk);
+            lo += w[k] * ((k == kq) ? pk - dlt[j] : pk);
+          }
+          jr[j] = forward ? (hi - base) * scale[j] : (hi - lo) * scale[j];
+        }
+        double2* q = i8_jrow(J, 2 * s + uv);
+        q[0] = make_double2(jr[0], jr[1]);
+        q[kI8Threads] = make_double2(jr[2], jr[3]);
+        q[2 * kI8Threads] = make_double2(jr[4], jr[5]);
+        q[3 * kI8Threads] = make_double2(jr[6], jr[7]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kI8Threads, 2) image8_dif_kernel(const LmLaunch L, double* tws, double* jws) {
+  constexpr int M = 8, T = kI8Threads;
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double* a = smem + tid;
+  double* sc = smem + M * M * T + tid;
+  double* bx = smem + (M * M + M) * T + tid;
+  EvalTiles* wt = reinterpret_cast<EvalTiles*>(smem + kI8LuDoubles * T) + wid;
+  double* J = jws + (size_t)blockIdx.x * T * (size_t)L.n_max * M + 2 * tid;  // see i8_jrow
+  for (unsigned int f = blockIdx.x * T + tid; f < (unsigned int)L.B; f += gridDim.x * T) {
+    const long long o0 = L.off[f], nn = L.off[f + 1] - o0;
+    int ret_code = 0;
+    if (nn < M) ret_code = -1;  // lm_core.c:493
+    else if (nn > L.n_max || (nn & 1)) ret_code = -2;
+    else if (L.counts[f] != (int)(nn >> 1)) ret_code = -3;
+    if (ret_code != 0) {
+      for (int q = 0; q < 10; ++q) L.info[(size_t)f * 10 + q] = 0.0;
+      L.ret[f] = ret_code;
+      if (L.extra) { L.extra[2 * f] = 0; L.extra[2 * f + 1] = 0; }
+      continue;
+    }
+    I8Fit F;
+    F.x = L.meas + o0;
+    F.n = (int)nn;
+    F.nsamp = F.n >> 1;
+    F.tp = L.t ? L.t + (o0 >> 1) : tws + (size_t)f * (L.n_max >> 1);
+    F.xoff = ptr_parity(F.x);
+    F.toff = ptr_parity(F.tp);
+    double p[M];
+#pragma unroll
+    for (int q = 0; q < M; ++q) p[q] = L.p[(size_t)f * M + q];
+    const bool blocked = !(F.n * M <= kBlockSzSq);  // "<=" here, lm_core.c:585
+    const int K = 10;                                // max(m, 10)
+
+    double mu = 0.0, g_inf = 0.0, p_sq = 0.0, dp_sq = DBL_MAX, maxdiag = 0.0;
+    int nu = 20, stop = 0, nfev = 1, njap = 0, nlss = 0, n_jtj = 0, n_broyden = 0, k;
+    int updjac = 0, updp = 1, newjac = 0;
+    double e_sq;
+    if (L.t) {
+      e_sq = i8_eval_pass<false>(F, p, wt, lane, 0.0, 1.0);
+    } else {
+      const double firsty = F.x[1];
+      e_sq = i8_eval_pass<true>(F, p, wt, lane, firsty, F.x[2 * F.nsamp - 1] - firsty);
+    }
+    const double e0 = e_sq;
+    if (!isfinite(e_sq)) stop = 7;
+    double jtj[36], jte[M];
+#pragma unroll
+    for (int q = 0; q < 36; ++q) jtj[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < M; ++q) jte[q] = 0.0;
+    I8Pending P;
+    P.on = false;
+    P.dp_sq = 1.0;
+    P.sh = a;
+
+    for (k = 0; k < L.itmax && !stop; ++k) {
+      if (e_sq <= L.eps3) { stop = 6; break; }
+      if ((updp && nu > 16) || updjac == K) {
+        i8_dif_fd_jacobian(F, p, J, wt, lane, L.delta, L.forward);
+        ++njap;
+        nfev += L.forward ? M : 2 * M;
+        nu = 2; updjac = 0; updp = 0; newjac = 1;
+        P.on = false;  // the fresh Jacobian overwrites every row a deferred secant update would have touched
+      }
+      if (newjac) {
+        newjac = 0;
+        if (blocked) i8_dif_normal_eqs<true>(F, p, J, wt, lane, P, jtj, jte);
+        else i8_dif_normal_eqs<false>(F, p, J, wt, lane, P, jtj, jte);
+        P.on = false;
+        ++n_jtj;
+        p_sq = 0.0;
+        g_inf = 0.0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          const double tmp = fabs(jte[q]);
+          if (g_inf < tmp) g_inf = tmp;
+          p_sq += p[q] * p[q];
+        }
+        maxdiag = -DBL_MAX;
+#pragma unroll
+        for (int q = 0; q < M; ++q)
+          if (jtj[q * (q + 1) / 2 + q] > maxdiag) maxdiag = jtj[q * (q + 1) / 2 + q];
+      }
+      if (g_inf <= L.eps1) { dp_sq = 0.0; stop = 1; break; }
+      if (k == 0) mu = L.tau * maxdiag;
+
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          double v = (i >= c) ? jtj[i * (i + 1) / 2 + c] : jtj[c * (c + 1) / 2 + i];
+          if (i == c) v += mu;
+          a[(i * M + c) * T] = v;
+        }
+#pragma unroll
+      for (int i = 0; i < M; ++i) bx[i * T] = jte[i];
+      double dp[M];
+      const int solved = lu_factor_solve<M, T>(a, sc, bx, dp);
+      ++nlss;
+      if (solved) {
+        double pdp[M];
+        dp_sq = 0.0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          pdp[q] = p[q] + dp[q];
+          dp_sq += dp[q] * dp[q];
+        }
+        if (dp_sq <= L.eps2_sq * p_sq) { stop = 2; break; }
+        if (dp_sq >= (p_sq + L.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
+        const double e_new = i8_eval_pass<false>(F, pdp, wt, lane, 0.0, 1.0);
+        ++nfev;
+        if (!isfinite(e_new)) { stop = 7; break; }
+        const double dF = e_sq - e_new;
+        if (updp || dF > 0.0) {
+          // rank-one secant update, deferred to the next normal-equation build (nothing reads J before it)
+          P.on = true;
+          P.dp_sq = dp_sq;
+#pragma unroll
+          for (int q = 0; q < M; ++q) {
+            a[q * T] = p[q];
+            a[(8 + q) * T] = pdp[q];
+            a[(16 + q) * T] = dp[q];
+          }
+          ++updjac;
+          newjac = 1;
+          ++n_broyden;
+        }
+        double dL = 0.0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) dL += dp[q] * (mu * dp[q] + jte[q]);
+        if (dL > 0.0 && dF > 0.0) {
+          mu = nielsen(mu, dF, dL);
+          nu = 2;
+#pragma unroll
+          for (int q = 0; q < M; ++q) p[q] = pdp[q];
+          e_sq = e_new;
+          updp = 1;
+          continue;
+        }
+      }
+      mu *= nu;
+      const int nu2 = (int)((unsigned)nu << 1);
+      if (nu2 <= nu) { stop = 5; break; }
+      nu = nu2;
+    }
+    if (k >= L.itmax) stop = 3;
+#pragma unroll
+    for (int q = 0; q < M; ++q) L.p[(size_t)f * M + q] = p[q];
+    double* info = L.info + (size_t)f * 10;
+    info[0] = e0;
+    info[1] = e_sq;
+    info[2] = g_inf;
+    info[3] = dp_sq;
+    info[4] = mu / maxdiag;
+    info[5] = (double)k;
+    info[6] = (double)stop;
+    info[7] = (double)nfev;
+    info[8] = (double)njap;
+    info[9] = (double)nlss;
+    L.ret[f] = (stop != 4 && stop != 7) ? k : -1;
+    if (L.extra) { L.extra[2 * f] = n_jtj; L.extra[2 * f + 1] = n_broyden; }
+  }
+}
+
 }  // namespace cps

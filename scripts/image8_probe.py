@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Times dlevmar_der on a resident batch of per-contour m=8 fits in both execution shapes (a warp per fit / a thread
+"""Times dlevmar_der (or dlevmar_dif: third argument "dif") on a resident batch of per-contour m=8 fits in both execution shapes (a warp per fit / a thread
 per fit) with CUDA events and checks that they agree bit for bit."""
 import os
 import sys
@@ -12,6 +12,7 @@ from curvepointslam_b200 import lm, synth
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 paths = sys.argv[2].split(",") if len(sys.argv) > 2 else ["mono", "thread"]
+variant = lm.DIF if len(sys.argv) > 3 and sys.argv[3] == "dif" else lm.DER
 b = synth.make_image8_batch(B, K=64, seed=13)
 dev = torch.device("cuda", 0)
 d_meas, d_p0 = torch.from_numpy(b["meas"]).to(dev), torch.from_numpy(b["p0"]).to(dev)
@@ -29,7 +30,7 @@ for name in paths:
         d_p.copy_(d_p0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        ctx.fit_batched_dev(lm.IMAGE8, lm.DER, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(),
+        ctx.fit_batched_dev(lm.IMAGE8, variant, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(),
                             d_cnt.data_ptr(), 128, d_info.data_ptr(), d_ret.data_ptr(), None, stream=st.cuda_stream)
         e1.record(st)
         torch.cuda.synchronize()

@@ -180,6 +180,26 @@ def test_image8_thread_per_fit_bit_exact(sctx, K):
             assert_same_fit(gpu, cpu, check_mu=itmax > 0)
 
 
+@pytest.mark.parametrize("K", [64, 65, 63, 4, 5, 100])
+def test_image8_dif_thread_per_fit_bit_exact(sctx, K):
+    """m = 8 dif (secant Jacobian) through the thread-per-fit kernel: bit-exact against the oracle on the unblocked
+    loop (n*m <= 1024: up to K = 64), the blocked one, ragged tails; forward and central differences; explicit t."""
+    from oracle_lib import DIF, IMAGE8
+    b = synth.make_image8_batch(200, K=K, seed=72)
+    gpu = sctx.fit_batched(IMAGE8, DIF, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(IMAGE8, DIF, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    assert_same_fit(gpu, cpu)
+    assert (cpu["info"][:, 8] >= 1).all()
+    if K in (64, 100):
+        central = list(OPTS)
+        central[4] = -central[4]
+        t = np.tile(np.linspace(0.0, 1.0, K), 200)
+        for opts, itmax in [(central, 1000), (None, 1000), (OPTS, 1), (OPTS, 0), (OPTS, 12)]:
+            gpu = sctx.fit_batched(IMAGE8, DIF, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax, t=t)
+            cpu = oracle().fit_batch(IMAGE8, DIF, b["p0"], b["meas"], b["off"], b["counts"], opts, itmax=itmax, t=t)
+            assert_same_fit(gpu, cpu, check_mu=itmax > 0)
+
+
 def test_staged_ragged_with_explicit_t(sctx):
     """Caller-supplied t on a ragged batch: fits whose t stream starts on an odd double (the staging tiles then hold
     the row one element in) must give the same bits as t derived on the device and as the oracle."""
