@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from curvepointslam_b200 import synth  # noqa: E402
 from oracle_lib import DER, DIF, IMAGE8, MATH_DET, MATH_LIBM, STEREO19, build_oracle, oracle  # noqa: E402
 
-OPTS = [1e-10, 1e-10, 1e-10, 1e-20, 1e-5]  # curveFittingClass.cpp:661-662
+# curveFittingClass.cpp:659-660: opts[4] = LM_DIFF_DELTA*1E1, one ulp below the literal 1e-5; the vectors carry it
+OPTS = [1e-10, 1e-10, 1e-10, 1e-20, 1e-6 * 1e1]
 
 
 def main():
@@ -32,7 +33,7 @@ def main():
     counts[1] = (3, 2, 3, 2)
     b19 = synth.make_stereo19_batch(24, seed=101, counts=counts, round_pixels=True)
     b8 = synth.make_image8_batch(24, K=64, seed=102)
-    out = {}
+    out = {"opts": np.array(OPTS)}
     for tag, model, b in (("s19", STEREO19, b19), ("i8", IMAGE8, b8)):
         out[f"{tag}_meas"], out[f"{tag}_off"], out[f"{tag}_counts"], out[f"{tag}_p0"] = b["meas"], b["off"], b["counts"], b["p0"]
         for vname, variant in (("der", DER), ("dif", DIF)):

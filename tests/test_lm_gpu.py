@@ -240,3 +240,25 @@ def test_frame_pipeline_edges_to_fit(ctx):
     assert np.array_equal(_bits(p0), _bits(p0o))
     assert_same_fit(fit, cpu)
     assert (fit["ret"] >= 0).all()
+
+
+@pytest.mark.parametrize("path", ["monolithic", "staged"])
+@pytest.mark.parametrize("vname,variant", [("der", DER), ("dif", DIF)])
+@pytest.mark.parametrize("tag", ["s19", "i8"])
+def test_golden_vectors_from_reference_levmar_on_gpu(tag, vname, variant, path):
+    """The committed vectors the REFERENCE's levmar-2.5 produced (tests/golden/gen_lm_golden.py, deterministic math
+    mode) against the CUDA path, bit for bit, in both execution shapes: no oracle in between."""
+    import os
+    from oracle_lib import IMAGE8
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lm_reference_levmar.npz"))
+    c = lm.LmContext(0)
+    c.set_path(lm.PATH_MONOLITHIC if path == "monolithic" else lm.PATH_STAGED)
+    try:
+        r = c.fit_batched(STEREO19 if tag == "s19" else IMAGE8, variant, g[f"{tag}_p0"], g[f"{tag}_meas"],
+                          g[f"{tag}_off"], g[f"{tag}_counts"], [float(v) for v in g["opts"]])
+    finally:
+        c.close()
+    key = f"{tag}_{vname}_det"
+    assert np.array_equal(r["ret"], g[key + "_ret"])
+    assert np.array_equal(_bits(r["p"]), _bits(g[key + "_p"]))
+    assert np.array_equal(_bits(r["info"]), _bits(g[key + "_info"]))

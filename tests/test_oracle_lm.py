@@ -92,8 +92,8 @@ def test_batched_fits_bit_exact_vs_reference_levmar(model, variant, mode):
 @pytest.mark.parametrize("mname,mode", [("det", MATH_DET), ("libm", MATH_LIBM)])
 def test_golden_vectors_from_reference_levmar(tag, model, vname, variant, mname, mode):
     g = np.load(os.path.join(HERE, "golden", "lm_reference_levmar.npz"))
-    r = oracle().fit_batch(model, variant, g[f"{tag}_p0"], g[f"{tag}_meas"], g[f"{tag}_off"], g[f"{tag}_counts"], OPTS,
-                           math_mode=mode, nthreads=4)
+    r = oracle().fit_batch(model, variant, g[f"{tag}_p0"], g[f"{tag}_meas"], g[f"{tag}_off"], g[f"{tag}_counts"],
+                           [float(v) for v in g["opts"]], math_mode=mode, nthreads=4)
     key = f"{tag}_{vname}_{mname}"
     assert np.array_equal(r["ret"], g[key + "_ret"])
     if mode == MATH_DET:  # only +,-,*,/ : identical on any IEEE-754 host
