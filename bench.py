@@ -348,6 +348,7 @@ def main():
         "config": workload_config(args, B),
         "contours_per_sec": 4 * value,
         "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "bytes_scope": "per rank (every rank copies its own shard; the job moves n_gpus times as much)",
                 "api": f"cps_dlevmar_{args.variant}_batched (include/cps_lm.h), pinned host buffers, "
                        "the batch streams in while the fits that have arrived iterate"},
         "execution_shape": "staged (solve / eval / jac phase kernels, thread per fit)" if staged
