@@ -217,6 +217,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ctx.get_profile(reset=True)
+    ctx.get_profile_work(reset=True)
     launches_before = ctx.launch_stats()["launches"]
     e0.record(stream)
     for i in range(args.steps):
@@ -227,6 +228,7 @@ def main():
     kernel_ms = [a.elapsed_time(bb) for a, bb in kev]
     launches_value = ctx.launch_stats()["launches"] - launches_before  # kernels of libcps.so launched in the timed region
     prof = ctx.get_profile(reset=True)  # per-kernel CUDA-event time over the same timed region
+    jac_evals, tail_fits = ctx.get_profile_work(reset=True)  # work of staged_jac_kernel / fits the tail kernel took
     staged = prof["jac"][1] > 0
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside) -----------------------------
@@ -300,20 +302,27 @@ def main():
                 "unit": "GB/s", "note": "algorithmic bytes of a whole fit over the step; the path is FP64-bound, not HBM-bound"}
     if staged:
         # dominant kernel of the staged shape: staged_jac_kernel (Jacobian + J^T J + J^T e of every accepted step)
+        # Jacobian evaluations the kernel itself performed over all timed steps (counted on the device): the last few
+        # thousand fits of a step finish in the warp-per-fit tail kernel, whose evaluations are not credited here
         jac_ms, jac_n = prof["jac"]
+        per_eval = flops.f_jac(N_MEAS, M) + flops.f_jtj(N_MEAS, M) + flops.f_jte(N_MEAS, M)
+        flops_jac = jac_evals * per_eval / args.steps
+        njev_jac = jac_evals / args.steps
         jac_tf = flops_jac * args.steps / (jac_ms * 1e-3) / 1e12  # the profile covers all timed steps
         tot_prof = sum(v[0] for v in prof.values())
         roofline = {
             "bound": "fp64", "kernel": "staged_jac_kernel", "achieved": jac_tf, "peak": pk_fma.value, "unit": "TFLOP/s",
             "frac": jac_tf / pk_fma.value, "peak_source": peak_note, "peak_unfused": pk_ma.value,
             "frac_of_unfused": jac_tf / pk_ma.value,
-            "executed": {"achieved": njev * flops.staged_jac_executed_flops(N_MEAS) * args.steps / (jac_ms * 1e-3) / 1e12,
-                         "frac_of_unfused": njev * flops.staged_jac_executed_flops(N_MEAS) * args.steps
+            "executed": {"achieved": njev_jac * flops.staged_jac_executed_flops(N_MEAS) * args.steps / (jac_ms * 1e-3) / 1e12,
+                         "frac_of_unfused": njev_jac * flops.staged_jac_executed_flops(N_MEAS) * args.steps
                          / (jac_ms * 1e-3) / 1e12 / pk_ma.value,
                          "note": "operations the kernel really issues (structural zeros of the Jacobian skipped, "
                                  "no FMA): the algorithmic count above is the dense reference algorithm's"},
             "flops_per_launch": flops_jac * args.steps / max(jac_n, 1), "launches": int(jac_n),
             "avg_launch_ms": jac_ms / max(jac_n, 1),
+            "jacobian_evaluations_per_step": {"staged_jac_kernel": njev_jac, "all (sum of info[8])": float(njev)},
+            "tail_fits_per_step": tail_fits / args.steps,
             "kernel_share_of_step": {k: v[0] / tot_prof for k, v in prof.items()},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "launches_per_step": {k: v[1] / args.steps for k, v in prof.items()},
@@ -351,7 +360,7 @@ def main():
                 "bytes_scope": "per rank (every rank copies its own shard; the job moves n_gpus times as much)",
                 "api": f"cps_dlevmar_{args.variant}_batched (include/cps_lm.h), pinned host buffers, "
                        "the batch streams in while the fits that have arrived iterate"},
-        "execution_shape": "staged (solve / eval / jac phase kernels, thread per fit)" if staged
+        "execution_shape": "staged (solve / eval / jac phase kernels, thread per fit; the last fits finish in the warp-per-fit kernel)" if staged
                            else "monolithic (one persistent kernel, warp per fit)",
         "gpu_launches": launches_value,
         "clocks": clocks,

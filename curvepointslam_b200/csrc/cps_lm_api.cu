@@ -35,8 +35,9 @@ struct cps_lm_slot {
 
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
+constexpr int kStagedTailFits = 16384;  // staged der: the last fits (at most this many and B/2) go to the warp-per-fit kernel
 constexpr int kImage8ThreadMinFits = 16384;  // m = 8: a thread per fit from this many fits per call
-constexpr int kStagedMinFits = 16384;     // below this the monolithic kernel (a warp per fit) is faster (measured crossover: 12-16 k fits)
+constexpr int kStagedMinFits = 8192;   // der, m = 19: staged shape from this many fits per call (measured crossover ~6 k)
 
 struct cps_lm_ctx {
   int device = 0;
@@ -49,8 +50,9 @@ struct cps_lm_ctx {
   int last_rounds = 0;   // rounds of the last staged call
   // optional per-kernel timing of the staged rounds (CUDA events on the launching stream)
   int profiling = 0;
-  double prof_ms[3] = {0, 0, 0};        // solve, eval (incl. the initial pass), jac
-  long long prof_launches[3] = {0, 0, 0};
+  double prof_ms[4] = {0, 0, 0, 0};     // solve, eval (incl. the initial pass), jac, tail (warp-per-fit take-over)
+  long long prof_launches[4] = {0, 0, 0, 0};
+  long long prof_jac_evals = 0, prof_tail_fits = 0;  // Jacobian evaluations done by staged_jac_kernel; fits taken over
   std::vector<cudaEvent_t> ev_pool;
 };
 
@@ -122,13 +124,21 @@ extern "C" int cps_lm_set_profiling(cps_lm_ctx* c, int on) {
   return CPS_OK;
 }
 
-extern "C" int cps_lm_get_profile(cps_lm_ctx* c, double* ms3, long long* launches3, int reset) {
+extern "C" int cps_lm_get_profile(cps_lm_ctx* c, double* ms4, long long* launches4, int reset) {
   if (!c) return CPS_ERR_INVALID;
-  for (int i = 0; i < 3; ++i) {
-    if (ms3) ms3[i] = c->prof_ms[i];
-    if (launches3) launches3[i] = c->prof_launches[i];
+  for (int i = 0; i < 4; ++i) {
+    if (ms4) ms4[i] = c->prof_ms[i];
+    if (launches4) launches4[i] = c->prof_launches[i];
     if (reset) { c->prof_ms[i] = 0.0; c->prof_launches[i] = 0; }
   }
+  return CPS_OK;
+}
+
+extern "C" int cps_lm_get_profile_work(cps_lm_ctx* c, long long* jac_evals, long long* tail_fits, int reset) {
+  if (!c) return CPS_ERR_INVALID;
+  if (jac_evals) *jac_evals = c->prof_jac_evals;
+  if (tail_fits) *tail_fits = c->prof_tail_fits;
+  if (reset) { c->prof_jac_evals = 0; c->prof_tail_fits = 0; }
   return CPS_OK;
 }
 
@@ -318,6 +328,12 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   };
   size_t next_piece = 0, n_solve = 0;
   int cur = 1, rounds = 0;
+  long long jac_evals = 0, tail_taken = 0;
+  size_t tail_fits = std::min<size_t>(kStagedTailFits, B / 2);
+  if (const char* e = std::getenv("CPS_LM_STAGED_TAIL")) tail_fits = (size_t)std::max(0, std::atoi(e));  // 0: never
+  if (L.n_max > 40 * kTileRows ||
+      lm_warp_smem_doubles(19, Model<19>::SCRATCH, L.n_max, false) * (int)sizeof(double) > c->max_smem_optin)
+    tail_fits = 0;  // the warp-per-fit kernel cannot hold fits this long
   for (;;) {
     const int nxt = cur ^ 1;
     if (n_solve > 0) {
@@ -376,18 +392,42 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
       c->launches += 1;
     }
     CPS_CUDA(cudaGetLastError());
-    staged_publish_kernel<<<1, 1, 0, st>>>(A.cnt + 2 + nxt, sl.h_count);
+    staged_round_end_kernel<<<1, 1, 0, st>>>(A.cnt, nxt, sl.h_count);
     CPS_CUDA(cudaStreamSynchronize(st));
     spans_collect();
     n_solve = sl.h_count[0];
+    jac_evals = sl.h_count[2];
     cur = nxt;
     ++rounds;
     if (n_solve == 0 && next_piece == pieces.size()) break;
+    if (n_solve > 0 && n_solve <= tail_fits && next_piece == pieces.size()) {
+      // the late rounds run at the latency floor of three kernels for a few thousand fits: the persistent
+      // warp-per-fit kernel takes the stragglers over where they stand and carries each to its end
+      LmLaunch T = L;
+      T.B = (int)n_solve;
+      T.fit_list = A.solve_list[cur];
+      T.resume = A.scal;
+      T.resume_jtj = A.jtj;
+      T.resume_jte = A.jte;
+      tail_taken = (long long)n_solve;
+      span_begin(3);
+      const int rc = launch_fit<19, false>(c, sl, T, st);
+      span_end();
+      if (rc != CPS_OK) return rc;
+      CPS_CUDA(cudaStreamSynchronize(st));
+      spans_collect();
+      ++rounds;
+      break;
+    }
   }
   c->last_grid = jac_grid_max;
   c->last_block = kJacThreads;
   c->last_smem = jac_smem;
   c->last_rounds = rounds;
+  if (c->profiling) {
+    c->prof_jac_evals += jac_evals;
+    c->prof_tail_fits += tail_taken;
+  }
   return CPS_OK;
 }
 

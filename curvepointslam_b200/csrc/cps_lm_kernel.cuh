@@ -38,6 +38,14 @@ constexpr double kEpsilon = 1E-12;          // lm.c:35
 constexpr double kOneThird = 0.3333333334;  // lm.c:36 (sic)
 constexpr int kBlockSzSq = 32 * 32;         // lm_core.c:193,585 switch between the two J^T J loops
 
+// Per-fit scalars of a dlevmar_der iteration in flight (the staged shape's state, cps_lm_staged.cuh).  A fit parked
+// here is about to solve (J^T J + mu I) dp = J^T e: every check of the current outer iteration has passed and its
+// Jacobian evaluation has been counted.
+struct LmResume {
+  double e0, e_sq, g_inf, dp_sq, mu, p_sq, maxdiag, dL;
+  int nu, k, nfev, njev, nlss, pad0, pad1, pad2;
+};
+
 struct LmLaunch {
   int B;
   int n_max;  // capacity (doubles) of the per-warp measurement buffers; fits with n > n_max are refused
@@ -54,6 +62,10 @@ struct LmLaunch {
   int* extra;               // [B][2] (n_jtj, n_broyden) or nullptr
   double* jstore;           // per resident warp: dif [M][n_max] column-major Jacobian; der [n_max] residual + [n_max/2] t
   unsigned int* queue;      // next fit index
+  const int* fit_list;      // nullptr, or the B fit indices to work on (der: the staged shape's late fits)
+  const LmResume* resume;   // with fit_list: [fit] iteration state to continue from,
+  const double* resume_jtj; //   [fit][M(M+1)/2] lower triangle of J^T J at the fit's current p, row-major,
+  const double* resume_jte; //   [fit][M] J^T e
 };
 
 __host__ __device__ constexpr int lm_ldt(int M) { return M | 1; }  // tile stride of the unblocked (small-problem) path
@@ -775,28 +787,53 @@ __device__ __forceinline__ double nielsen(double mu, double dF, double dL) {
 // dlevmar_der, lm_core.c:60-423
 template <class MD>
 __device__ void lm_der(const WarpMem<MD::M>& w, const FitGeom& g, const LmLaunch& L, Accum<MD::M>& A,
-                       BlockAccum<MD::M, MD::M == 19>& BA, int n_items, LmResult& R, int lane) {
+                       BlockAccum<MD::M, MD::M == 19>& BA, int n_items, LmResult& R, int lane,
+                       const LmResume* rs = nullptr, const double* rs_jtj = nullptr,
+                       const double* rs_jte = nullptr) {
   constexpr int M = MD::M;
   const bool blocked = !(g.n * M < kBlockSzSq);  // strict "<" selects the unblocked loop, lm_core.c:193
   double mu = 0.0, g_inf = 0.0, p_sq = 0.0, dp_sq = DBL_MAX;
   int nu = 2, stop = 0, nfev = 0, njev = 0, nlss = 0, k;
+  double e_sq, e0;
+  // A fit taken over in mid-iteration (the staged shape's last fits) is about to solve: it brings J^T J, J^T e, the
+  // gradient statistics, mu, nu and its counters, and enters the damping loop directly.  Its residual vector is not
+  // needed before an accepted step replaces it.
+  bool resumed = rs != nullptr;
+  int k0 = 0;
+  if (resumed) {
+    e0 = rs->e0; e_sq = rs->e_sq; mu = rs->mu; nu = rs->nu; k0 = rs->k; nfev = rs->nfev; njev = rs->njev;
+    nlss = rs->nlss; dp_sq = rs->dp_sq; p_sq = rs->p_sq; g_inf = rs->g_inf;
+    for (int idx = lane; idx < M * M; idx += 32) {
+      const int i = idx / M, j = idx - i * M;
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      w.jtj[idx] = rs_jtj[hi * (hi + 1) / 2 + lo];
+    }
+    if (lane < M) {
+      w.jte[lane] = rs_jte[lane];
+      w.diag[lane] = rs_jtj[lane * (lane + 1) / 2 + lane];
+    }
+    __syncwarp();
+  } else {
+    eval_func<MD>(w, g, w.p, w.hx, lane);
+    nfev = 1;
+    e_sq = residual_sqnorm(w.hx, w.x, w.hx, g.n, lane);  // in shared memory, then published to e
+    for (int i = lane; i < g.n; i += 32) w.e[i] = w.hx[i];
+    __syncwarp();
+    e0 = e_sq;
+    if (!isfinite(e_sq)) stop = 7;
+  }
 
-  eval_func<MD>(w, g, w.p, w.hx, lane);
-  nfev = 1;
-  double e_sq = residual_sqnorm(w.hx, w.x, w.hx, g.n, lane);  // in shared memory, then published to e
-  for (int i = lane; i < g.n; i += 32) w.e[i] = w.hx[i];
-  __syncwarp();
-  const double e0 = e_sq;
-  if (!isfinite(e_sq)) stop = 7;
-
-  for (k = 0; k < L.itmax && !stop; ++k) {
-    if (e_sq <= L.eps3) { stop = 6; break; }
-    if (blocked) normal_eqs_blocked<MD, MD::M == 19, false>(w, g, BA, nullptr, 0, n_items, lane);
-    else normal_eqs_analytic<MD>(w, g, A, false, lane);
-    ++njev;
-    grad_stats<M>(w, p_sq, g_inf, lane);
-    if (g_inf <= L.eps1) { dp_sq = 0.0; stop = 1; break; }
-    if (k == 0) mu = L.tau * max_diag<M>(w);
+  for (k = k0; k < L.itmax && !stop; ++k) {
+    if (!resumed) {
+      if (e_sq <= L.eps3) { stop = 6; break; }
+      if (blocked) normal_eqs_blocked<MD, MD::M == 19, false>(w, g, BA, nullptr, 0, n_items, lane);
+      else normal_eqs_analytic<MD>(w, g, A, false, lane);
+      ++njev;
+      grad_stats<M>(w, p_sq, g_inf, lane);
+      if (g_inf <= L.eps1) { dp_sq = 0.0; stop = 1; break; }
+      if (k == 0) mu = L.tau * max_diag<M>(w);
+    }
+    resumed = false;
 
     for (;;) {
       const int solved = lu_solve<M>(w, mu, lane);
@@ -1133,6 +1170,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_k
     if (lane == 0) f = atomicAdd(L.queue, 1u);
     f = __shfl_sync(0xffffffffu, f, 0);
     if (f >= (unsigned)L.B) break;
+    if (L.fit_list) f = (unsigned int)L.fit_list[f];
 
     const long long o0 = L.off[f], o1 = L.off[f + 1];
     const long long nn = o1 - o0;
@@ -1203,7 +1241,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CPS_LM_MIN_BLOCKS) lm_fit_k
         n_items = build_items19(g, items, lane);
         __syncwarp();
       }
-      lm_der<MD>(w, g, L, A, BA, n_items, R, lane);
+      const bool takeover = L.fit_list && L.resume;
+      lm_der<MD>(w, g, L, A, BA, n_items, R, lane, takeover ? L.resume + f : nullptr,
+                 takeover ? L.resume_jtj + (size_t)f * (M * (M + 1) / 2) : nullptr,
+                 takeover ? L.resume_jte + (size_t)f * M : nullptr);
     }
 
     // info[] exactly as lm_core.c:396-409 / :800-813 (the diagonal of J^T J is the un-augmented one)

@@ -25,10 +25,7 @@
 
 namespace cps {
 
-struct StagedScal {  // per-fit scalars of the LM iteration, 96 bytes
-  double e0, e_sq, g_inf, dp_sq, mu, p_sq, maxdiag, dL;
-  int nu, k, nfev, njev, nlss, pad0, pad1, pad2;
-};
+using StagedScal = LmResume;  // per-fit scalars of the LM iteration, 96 bytes (cps_lm_kernel.cuh)
 
 constexpr int kLower19 = 19 * 20 / 2;  // J^T J is kept as its lower triangle, row-major: (i,j) -> i(i+1)/2 + j
 constexpr int kJacThreads = 128;       // jac kernel: threads per CTA (2 CTAs per SM: 256 fits resident per SM)
@@ -54,7 +51,7 @@ struct StagedArgs {
   int* jac_list;
   int* eval_list;
   int* solve_list[2];
-  unsigned int* cnt;   // [0] jac, [1] unused, [2], [3] solve lists
+  unsigned int* cnt;   // [0] jac, [1] Jacobian evaluations of the call so far, [2], [3] solve lists
   int init_first, init_count;  // range of the fit index an INIT launch covers
 };
 
@@ -659,6 +656,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
 // bytes would queue on a copy engine behind the megabytes of samples the host-buffer entry point is streaming in).
 __global__ void staged_publish_kernel(const unsigned int* __restrict__ src, volatile unsigned int* dst_host) {
   *dst_host = *src;
+  __threadfence_system();
+}
+
+// End of a round: the length of the next solve list for the host, and the running total of Jacobian evaluations the
+// jac kernel has performed in this call (cnt[1]; cnt[0] is the jac list length of the round that just ended).
+__global__ void staged_round_end_kernel(unsigned int* cnt, int nxt, volatile unsigned int* host) {
+  cnt[1] += cnt[0];
+  host[2] = cnt[1];
+  host[0] = cnt[2 + nxt];
   __threadfence_system();
 }
 

@@ -57,10 +57,17 @@ class LmContext:
 
     def get_profile(self, reset: bool = True):
         """Accumulated CUDA-event time and launch count of the staged shape's kernels: {kernel: (ms, launches)}."""
-        ms = (C.c_double * 3)()
-        n = (C.c_longlong * 3)()
+        ms = (C.c_double * 4)()
+        n = (C.c_longlong * 4)()
         _lib.check(_lib.lib().cps_lm_get_profile(self._h, ms, n, 1 if reset else 0), "cps_lm_get_profile")
-        return {k: (ms[i], n[i]) for i, k in enumerate(("solve", "eval", "jac"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("solve", "eval", "jac", "tail"))}
+
+    def get_profile_work(self, reset: bool = True):
+        """(Jacobian evaluations staged_jac_kernel performed, fits the tail kernel took over) while profiling was on."""
+        je, tf = C.c_longlong(0), C.c_longlong(0)
+        _lib.check(_lib.lib().cps_lm_get_profile_work(self._h, C.byref(je), C.byref(tf), 1 if reset else 0),
+                   "cps_lm_get_profile_work")
+        return int(je.value), int(tf.value)
 
     # -- host buffers ---------------------------------------------------------------------------------
     def fit_batched(self, model: int, variant: int, p0, meas, off, counts, opts=REFERENCE_OPTS,

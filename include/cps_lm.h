@@ -114,7 +114,7 @@ int cps_cleanup_and_group_edges_batched(cps_lm_ctx *ctx, int F, const int *pts, 
  *   MONOLITHIC  one persistent kernel, a warp per fit (best for a frame's worth of fits: one launch)
  *   STAGED      rounds of three phase kernels with a thread per fit in the Jacobian / J^T J phase (best for
  *               batches of tens of thousands of fits)
- *   AUTO        (default) STAGED from 16 384 fits per call upwards (the measured crossover on B200)
+ *   AUTO        (default) STAGED from 8 192 fits per call upwards (the measured crossover on B200 is ~6 k)
  */
 #define CPS_LM_PATH_AUTO 0
 #define CPS_LM_PATH_MONOLITHIC 1
@@ -123,10 +123,16 @@ int cps_lm_set_path(cps_lm_ctx *ctx, int path);
 /*
  * Per-kernel timing of the staged shape: with profiling on, every launch of its three kernels is bracketed by CUDA
  * events on the launching stream; cps_lm_get_profile returns the accumulated milliseconds and launch counts of
- * {solve, eval, jac} (and clears them when reset != 0).
+ * {solve, eval, jac, tail} (and clears them when reset != 0); tail is the warp-per-fit kernel that takes the last
+ * fits of a batch over from the rounds.
  */
 int cps_lm_set_profiling(cps_lm_ctx *ctx, int on);
-int cps_lm_get_profile(cps_lm_ctx *ctx, double *ms3, long long *launches3, int reset);
+int cps_lm_get_profile(cps_lm_ctx *ctx, double *ms4, long long *launches4, int reset);
+/*
+ * Work behind those times (accumulated while profiling is on): the Jacobian evaluations staged_jac_kernel performed
+ * (a fit counts once per accepted step it computed there) and the fits the tail kernel took over.
+ */
+int cps_lm_get_profile_work(cps_lm_ctx *ctx, long long *jac_evals, long long *tail_fits, int reset);
 /* geometry of the last launch and the number of kernel launches issued through this context */
 int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
 

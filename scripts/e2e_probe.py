@@ -21,6 +21,8 @@ h_info = torch.zeros((B, 10), dtype=torch.float64).pin_memory()
 h_ret = torch.zeros(B, dtype=torch.int32).pin_memory()
 opts = np.array(lm.REFERENCE_OPTS)
 ctx = lm.LmContext(0)
+if len(sys.argv) > 2:  # force an execution shape: mono | staged
+    ctx.set_path(lm.PATH_MONOLITHIC if sys.argv[2] == "mono" else lm.PATH_STAGED)
 ctx.set_profiling(True)
 fn = _lib.lib().cps_dlevmar_der_batched
 ts = []

@@ -243,3 +243,38 @@ def test_staged_device_entry_unaligned_samples(sctx):
     host = sctx.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
     assert np.array_equal(_bits(d_p.cpu().numpy()), _bits(host["p"]))
     assert np.array_equal(_bits(d_info.cpu().numpy()), _bits(host["info"]))
+
+
+def test_tail_takeover_is_bit_identical(monkeypatch):
+    """The last fits of a staged batch are handed to the warp-per-fit kernel in mid-iteration (their damping state
+    travels, the normal equations are rebuilt from p).  With the hand-over forced after the first round, late
+    (default) and off, the results must be the same bits, and the oracle's."""
+    rng = np.random.default_rng(3)
+    counts = rng.integers(5, 80, size=(512, 4)).astype(np.int32)
+    b = synth.make_stereo19_batch(512, seed=91, counts=counts, round_pixels=False)
+    p0 = b["p0"].copy()
+    p0[::7] += rng.normal(0, 0.4, size=p0[::7].shape)  # poor starts: rejected steps, long damping sequences
+    cpu = oracle().fit_batch(STEREO19, DER, p0, b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    outs = []
+    for tail in ("0", "100000", None):
+        if tail is None:
+            monkeypatch.delenv("CPS_LM_STAGED_TAIL", raising=False)
+        else:
+            monkeypatch.setenv("CPS_LM_STAGED_TAIL", tail)
+        c = lm.LmContext(0)
+        c.set_path(lm.PATH_STAGED)
+        c.set_profiling(True)
+        try:
+            for itmax in (1000, 3):
+                r = c.fit_batched(STEREO19, DER, p0, b["meas"], b["off"], b["counts"], OPTS, itmax=itmax)
+                if itmax == 1000:
+                    assert_same_fit(r, cpu)
+                outs.append((tail, itmax, r))
+            taken = c.get_profile_work()[1]
+            assert (taken == 0) == (tail == "0")
+        finally:
+            c.close()
+    for tail, itmax, r in outs[2:]:
+        ref = outs[0 if itmax == 1000 else 1][2]
+        assert np.array_equal(_bits(r["p"]), _bits(ref["p"])) and np.array_equal(_bits(r["info"]), _bits(ref["info"]))
+        assert np.array_equal(r["ret"], ref["ret"]) and np.array_equal(r["extra"], ref["extra"])
