@@ -20,8 +20,11 @@ done
 I8="python scripts/image8_probe.py 1048576 thread"
 $I8 > gpurun_out/plain_i8.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:image8_der_kernel -s 2 -c 1 -o gpurun_out/final_prof_image8 $I8 > gpurun_out/ncu_i8.log 2>&1
-# monolithic shape (a warp per fit): der at 8192 fits (below the switch-over), dif
-SMALL="python bench.py --fits 8192 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
+I8D="python scripts/image8_probe.py 1048576 thread dif"
+$I8D > gpurun_out/plain_i8d.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:image8_dif_kernel -s 2 -c 1 -o gpurun_out/final_prof_image8_dif $I8D > gpurun_out/ncu_i8d.log 2>&1
+# monolithic shape (a warp per fit): der at 4096 fits (below the switch-over), dif
+SMALL="python bench.py --fits 4096 --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 $SMALL > gpurun_out/plain1.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/final_launches_lm_der.csv $SMALL > gpurun_out/ncu_a.log 2>&1
 $SMALL > gpurun_out/plain2.log 2>&1 &&
@@ -33,4 +36,13 @@ python scripts/ekfprof.py > gpurun_out/plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ekf_cov_pipe_kernel -s 1 -c 1 -o gpurun_out/final_prof_ekf_cov python scripts/ekfprof.py > gpurun_out/ncu_d.log 2>&1
 python scripts/ekfprof.py > gpurun_out/plain5.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/final_launches_ekf.csv python scripts/ekfprof.py > gpurun_out/ncu_e.log 2>&1
-ls -la gpurun_out | tail -30
+# gpurun merges at most 64 MiB back: turn the reports into their text summaries here and keep only the jac report
+mkdir -p gpurun_out/export
+for K in staged_jac staged_solve staged_eval image8 image8_dif lm_der lm_dif ekf_cov; do
+  rep=gpurun_out/final_prof_$K.ncu-rep
+  [ -f $rep ] || continue
+  ncu -i $rep --page details --csv > gpurun_out/export/${K}_details.csv 2>/dev/null
+  [ $K != ekf_cov ] && python scripts/ncu_by_line.py $rep > gpurun_out/export/${K}_by_line.txt 2>/dev/null
+  [ $K != staged_jac ] && rm -f $rep
+done
+ls -la gpurun_out gpurun_out/export | tail -50
