@@ -187,6 +187,48 @@ def lm_sweep(device: int):
     return out
 
 
+def lm_sweep_resident(device: int):
+    """der throughput over B = 1k, 10k, 100k, 1M resident fits (m=19: four contours each).  The
+    batch is 16 384 distinct synthetic fits tiled on the device (the fits are independent: repeating them changes
+    nothing about the work per fit); CUDA events around the device-pointer entry."""
+    import torch
+
+    from curvepointslam_b200 import lm, synth
+    ctx = lm.LmContext(device)
+    dev = torch.device("cuda", device)
+    base = synth.make_stereo19_batch_fast(16384, K=64, seed=14)
+    b_meas, b_p0, b_cnt = (torch.from_numpy(base[k]).to(dev) for k in ("meas", "p0", "counts"))
+    out = []
+    st = torch.cuda.current_stream()
+    for B in (1000, 10000, 100000, 1000000):
+        reps = (B + 16383) // 16384
+        d_meas = b_meas.repeat(reps)[: B * 512].contiguous()
+        d_p0 = b_p0.repeat(reps, 1)[:B].contiguous()
+        d_cnt = b_cnt.repeat(reps, 1)[:B].contiguous()
+        d_off = torch.arange(B + 1, dtype=torch.int64, device=dev) * 512
+        d_p = torch.empty_like(d_p0)
+        d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+        d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+        ts = []
+        for it in range(4):
+            d_p.copy_(d_p0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            ctx.fit_batched_dev(lm.STEREO19, lm.DER, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(),
+                                d_cnt.data_ptr(), 512, d_info.data_ptr(), d_ret.data_ptr(), None, stream=st.cuda_stream)
+            e1.record(st)
+            torch.cuda.synchronize()
+            if it >= 1:
+                ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts))
+        out.append({"fits": B, "contours": 4 * B, "ms": ms, "fits_per_sec": B / (ms * 1e-3),
+                    "contours_per_sec": 4 * B / (ms * 1e-3), "stop_reason_2": int((d_info[:, 6] == 2).sum().item())})
+        del d_meas, d_p0, d_cnt, d_off, d_p, d_info, d_ret
+    ctx.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def image8_bench(device: int, B: int = 1 << 20):
     """Per-contour image-space fits (m=8, 64 points): the "8 x 8" problem of the north star; device-resident
     inputs, der and dif, with the reference levmar on all cores on a sample."""
@@ -255,6 +297,10 @@ def run(device: int = 0):
         res["lm_sweep_der_e2e"] = lm_sweep(device)
     except Exception as ex:
         res["lm_sweep_der_e2e"] = {"error": repr(ex)}
+    try:
+        res["lm_sweep_der_resident"] = lm_sweep_resident(device)
+    except Exception as ex:
+        res["lm_sweep_der_resident"] = {"error": repr(ex)}
     try:
         res["image8"] = image8_bench(device)
     except Exception as ex:

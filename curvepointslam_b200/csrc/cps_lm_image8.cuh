@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(kI8Threads, 2) image8_der_kernel(const LmLaunc
 // recomputed from the parameters on the fly: f(p) and f(p + dp) are four-term Bernstein sums, so the stored copies the
 // reference keeps (hx, wrk) are never needed -- a value recomputed from the same inputs by the same operations is the
 // same value.  The rank-one secant update (:745-755) is applied to a row on its way into the next J^T J build, like in
-// the warp-per-fit kernel; a finite-difference Jacobian (misc_core.c:135-209) in between simply overwrites the rows.
+// the warp-per-fit kernel; a finite-difference Jacobian (misc_core.c:135-209) is formed row by row inside the build that
+// follows it (one pass over the work area instead of two) and simply overwrites the rows.
 // A pending secant update: p at the time of the trial, the trial point and the step sit in the (then idle) LU work
 // matrix in shared memory, [element][thread]: elements 0-7, 8-15, 16-23.
 struct I8Pending {
@@ -395,17 +396,44 @@ __device__ __forceinline__ double i8_sum(const double (&w)[4], const double (&p)
   return a;
 }
 
-// one row of the normal-equation build: secant update if pending, residual, accumulation into acc (36 lower entries,
-// index i(i+1)/2 + j) and the J^T e chains
+// Finite-difference step sizes of a Jacobian evaluation (misc_core.c:135-209): d_j = max(|1e-4 p_j|, delta) and the
+// factor the difference is multiplied with, 1/d (forward) or 0.5/d (central).
+struct I8Fd {
+  double dlt[8], scale[8];
+  int forward;
+};
+
+// one row of the normal-equation build.  FROM_FD: the row is formed by finite differences -- forward
+// (f(p + d e_j) - f(p)) / d or central (f(p + d e_j) - f(p - d e_j)) / (2d) per column, where the perturbed evaluations
+// differ from the base one only in the sums that contain the perturbed parameter (the other columns reproduce the base
+// value exactly and give +0.0) -- and stored; otherwise it is loaded, and updated and written back if a secant update
+// is pending.  Then: residual, accumulation into acc (36 lower entries, index i(i+1)/2 + j) and the J^T e chains.
+template <bool FROM_FD>
 __device__ __forceinline__ void i8_dif_row(double2* q, const double (&w)[4], int uv, double xval, const double (&p)[8],
-                                           const I8Pending& P, double (&acc)[36], double (&jte)[8]) {
+                                           const I8Pending& P, const I8Fd& D, double (&acc)[36], double (&jte)[8]) {
   constexpr int T = kI8Threads;
   double jr[8];
-  {
+  const double base = i8_sum(w, p, uv);
+  if (FROM_FD) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) jr[j] = 0.0;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      const int j = 2 * kq + uv;
+      double hi = 0.0, lo = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double pk = p[2 * k + uv];
+        hi += w[k] * ((k == kq) ? pk + D.dlt[j] : pk);
+        lo += w[k] * ((k == kq) ? pk - D.dlt[j] : pk);
+      }
+      jr[j] = D.forward ? (hi - base) * D.scale[j] : (hi - lo) * D.scale[j];
+    }
+  } else {
     const double2 a0 = q[0], a1 = q[T], a2 = q[2 * T], a3 = q[3 * T];
     jr[0] = a0.x; jr[1] = a0.y; jr[2] = a1.x; jr[3] = a1.y; jr[4] = a2.x; jr[5] = a2.y; jr[6] = a3.x; jr[7] = a3.y;
   }
-  if (P.on) {
+  if (!FROM_FD && P.on) {
     double f0 = 0.0, f1 = 0.0, dp[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -422,12 +450,14 @@ __device__ __forceinline__ void i8_dif_row(double2* q, const double (&w)[4], int
     tmp = (d - tmp) / P.dp_sq;
 #pragma unroll
     for (int j = 0; j < 8; ++j) jr[j] += tmp * dp[j];
+  }
+  if (FROM_FD || P.on) {
     q[0] = make_double2(jr[0], jr[1]);
     q[T] = make_double2(jr[2], jr[3]);
     q[2 * T] = make_double2(jr[4], jr[5]);
     q[3 * T] = make_double2(jr[6], jr[7]);
   }
-  const double e = xval - i8_sum(w, p, uv);
+  const double e = xval - base;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -436,11 +466,12 @@ __device__ __forceinline__ void i8_dif_row(double2* q, const double (&w)[4], int
   }
 }
 
-// J^T J and J^T e from the stored Jacobian.  BLOCKED: per-32-row partial sums, ascending rows (misc_core.c:101-126,
-// lm_core.c:636-644); otherwise the unblocked loop over descending rows (lm_core.c:604-628, n*m <= 1024).
-template <bool BLOCKED>
+// J^T J and J^T e from the stored Jacobian, or (FROM_FD) from a finite-difference Jacobian formed and stored row by
+// row on the way.  BLOCKED: per-32-row partial sums, ascending rows (misc_core.c:101-126, lm_core.c:636-644); otherwise
+// the unblocked loop over descending rows (lm_core.c:604-628, n*m <= 1024).
+template <bool BLOCKED, bool FROM_FD>
 __device__ __forceinline__ void i8_dif_normal_eqs(const I8Fit& F, const double (&p)[8], double* J, EvalTiles* wt, int lane,
-                                                  const I8Pending& P, double (&jtj)[36], double (&jte)[8]) {
+                                                  const I8Pending& P, const I8Fd& D, double (&jtj)[36], double (&jte)[8]) {
   double* xrow = &wt->x[lane][0];
   double* trow = &wt->t[lane][0];
   const double* xt = xrow + F.xoff;
@@ -469,11 +500,11 @@ __device__ __forceinline__ void i8_dif_normal_eqs(const I8Fit& F, const double (
       double w[4];
       bernstein3(tt[l], w);
       if (BLOCKED) {
-        i8_dif_row(i8_jrow(J, 2 * s), w, 0, xt[2 * l], p, P, part, jte);
-        i8_dif_row(i8_jrow(J, 2 * s + 1), w, 1, xt[2 * l + 1], p, P, part, jte);
+        i8_dif_row<FROM_FD>(i8_jrow(J, 2 * s), w, 0, xt[2 * l], p, P, D, part, jte);
+        i8_dif_row<FROM_FD>(i8_jrow(J, 2 * s + 1), w, 1, xt[2 * l + 1], p, P, D, part, jte);
       } else {
-        i8_dif_row(i8_jrow(J, 2 * s + 1), w, 1, xt[2 * l + 1], p, P, jtj, jte);
-        i8_dif_row(i8_jrow(J, 2 * s), w, 0, xt[2 * l], p, P, jtj, jte);
+        i8_dif_row<FROM_FD>(i8_jrow(J, 2 * s + 1), w, 1, xt[2 * l + 1], p, P, D, jtj, jte);
+        i8_dif_row<FROM_FD>(i8_jrow(J, 2 * s), w, 0, xt[2 * l], p, P, D, jtj, jte);
       }
     }
     if (BLOCKED && ((b & 1) || b + 1 == nstage)) {
@@ -481,60 +512,6 @@ __device__ __forceinline__ void i8_dif_normal_eqs(const I8Fit& F, const double (
       for (int q = 0; q < 36; ++q) {
         jtj[q] += part[q];
         part[q] = 0.0;
-      }
-    }
-  }
-}
-
-// finite-difference Jacobian, row by row: forward (wrk - hx)/d or central (wrk2 - wrk)/(2d) per column, where the
-// perturbed evaluations differ from the base one only in the sums that contain the perturbed parameter (the others
-// reproduce the base value exactly and give +0.0)
-__device__ __forceinline__ void i8_dif_fd_jacobian(const I8Fit& F, const double (&p)[8], double* J, EvalTiles* wt, int lane,
-                                                   double delta, int forward) {
-  double* trow = &wt->t[lane][0];
-  const double* tt = trow + F.toff;
-  double dlt[8], scale[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    double d = 1E-04 * p[j];
-    d = fabs(d);
-    if (d < delta) d = delta;
-    dlt[j] = d;
-    scale[j] = forward ? 1.0 / d : 0.5 / d;
-  }
-  const int nstage = (F.n + 15) >> 4;
-#pragma unroll 1
-  for (int b = 0; b < nstage; ++b) {
-    row_fill(trow, F.toff, F.tp + 8 * b, min(8, F.nsamp - 8 * b));
-    cp_async_wait_all();
-    const int s_hi = min(8 * b + 8, F.nsamp);
-#pragma unroll 1
-    for (int s = 8 * b; s < s_hi; ++s) {
-      double w[4];
-      bernstein3(tt[s & 7], w);
-#pragma unroll
-      for (int uv = 0; uv < 2; ++uv) {
-        const double base = i8_sum(w, p, uv);
-        double jr[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) jr[j] = 0.0;
-#pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {
-          const int j = 2 * kq + uv;
-          double hi = 0.0, lo = 0.0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const double pk = p[2 * k + uv];
-            hi += w[k] * ((k == kq) ? pk + dlt[j] : pk);
-            lo += w[k] * ((k == kq) ? pk - dlt[j] : pk);
-          }
-          jr[j] = forward ? (hi - base) * scale[j] : (hi - lo) * scale[j];
-        }
-        double2* q = i8_jrow(J, 2 * s + uv);
-        q[0] = make_double2(jr[0], jr[1]);
-        q[kI8Threads] = make_double2(jr[2], jr[3]);
-        q[2 * kI8Threads] = make_double2(jr[4], jr[5]);
-        q[3 * kI8Threads] = make_double2(jr[6], jr[7]);
       }
     }
   }
@@ -595,11 +572,25 @@ __global__ void __launch_bounds__(kI8Threads, 2) image8_dif_kernel(const LmLaunc
     P.on = false;
     P.dp_sq = 1.0;
     P.sh = a;
+    I8Fd D;
+    D.forward = L.forward;
+#pragma unroll
+    for (int j = 0; j < M; ++j) { D.dlt[j] = 0.0; D.scale[j] = 0.0; }
+    bool fresh_fd = false;
 
     for (k = 0; k < L.itmax && !stop; ++k) {
       if (e_sq <= L.eps3) { stop = 6; break; }
       if ((updp && nu > 16) || updjac == K) {
-        i8_dif_fd_jacobian(F, p, J, wt, lane, L.delta, L.forward);
+        // finite-difference Jacobian at p: formed inside the normal-equation build that always follows
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          double d = 1E-04 * p[j];
+          d = fabs(d);
+          if (d < L.delta) d = L.delta;
+          D.dlt[j] = d;
+          D.scale[j] = L.forward ? 1.0 / d : 0.5 / d;
+        }
+        fresh_fd = true;
         ++njap;
         nfev += L.forward ? M : 2 * M;
         nu = 2; updjac = 0; updp = 0; newjac = 1;
@@ -607,8 +598,14 @@ __global__ void __launch_bounds__(kI8Threads, 2) image8_dif_kernel(const LmLaunc
       }
       if (newjac) {
         newjac = 0;
-        if (blocked) i8_dif_normal_eqs<true>(F, p, J, wt, lane, P, jtj, jte);
-        else i8_dif_normal_eqs<false>(F, p, J, wt, lane, P, jtj, jte);
+        if (fresh_fd) {
+          if (blocked) i8_dif_normal_eqs<true, true>(F, p, J, wt, lane, P, D, jtj, jte);
+          else i8_dif_normal_eqs<false, true>(F, p, J, wt, lane, P, D, jtj, jte);
+        } else {
+          if (blocked) i8_dif_normal_eqs<true, false>(F, p, J, wt, lane, P, D, jtj, jte);
+          else i8_dif_normal_eqs<false, false>(F, p, J, wt, lane, P, D, jtj, jte);
+        }
+        fresh_fd = false;
         P.on = false;
         ++n_jtj;
         p_sq = 0.0;

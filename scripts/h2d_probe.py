@@ -25,9 +25,10 @@ for pieces in (1, 16):
         ts.append(e0.elapsed_time(e1))
     ms = min(ts[1:])
     print(f"H2D {n * 8 / 1e9:.2f} GB in {pieces} piece(s): {ms:.2f} ms = {n * 8 / ms / 1e6:.1f} GB/s")
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-h_out.copy_(out, non_blocking=True)
-e1.record()
-torch.cuda.synchronize()
-print(f"D2H {B * 30 * 8 / 1e6:.1f} MB: {e0.elapsed_time(e1):.2f} ms")
+for it in range(4):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h_out.copy_(out, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"D2H {B * 30 * 8 / 1e6:.1f} MB: {e0.elapsed_time(e1):.2f} ms")
