@@ -36,7 +36,7 @@ struct cps_lm_slot {
 constexpr int kSlots = 2;
 constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffer entry points
 constexpr int kStagedTailFits = 16384;  // staged der: the last fits (at most this many and B/2) go to the warp-per-fit kernel
-constexpr int kImage8ThreadMinFits = 16384;  // m = 8: a thread per fit from this many fits per call
+constexpr int kImage8ThreadMinFits = 4096;  // m = 8: a thread per fit from this many fits per call (measured crossover)
 constexpr int kStagedMinFits = 8192;   // der, m = 19: staged shape from this many fits per call (measured crossover ~6 k)
 
 struct cps_lm_ctx {
