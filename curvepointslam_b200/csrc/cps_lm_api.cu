@@ -329,6 +329,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   size_t next_piece = 0, n_solve = 0;
   int cur = 1, rounds = 0;
   long long jac_evals = 0, tail_taken = 0;
+  size_t last_jac = 0;  // jac list length of the last round
   size_t tail_fits = std::min<size_t>(kStagedTailFits, B / 2);
   if (const char* e = std::getenv("CPS_LM_STAGED_TAIL")) tail_fits = (size_t)std::max(0, std::atoi(e));  // 0: never
   if (L.n_max > 40 * kTileRows ||
@@ -372,22 +373,22 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
       ++next_piece;
     }
     if (n_solve + added == 0) break;
-    // how many fits need a Jacobian: at most all that were solved plus the new arrivals; in the late rounds most
-    // fits are re-solving rejected steps and only a few accepted one, so the exact count is worth a read-back
-    size_t n_jac = n_solve + added;
+    // how many fits need a Jacobian: at most all that were solved plus the new arrivals.  In the late rounds most fits
+    // are re-solving rejected steps and only a few accepted one; the count falls from round to round, so last round's
+    // exact count (published with the round's end) plus a margin picks the two-threads-per-fit variant without a
+    // read-back in mid-round.  The kernel takes the real count from the device either way.
+    const size_t n_jac = n_solve + added;
     const size_t jac_cap = (size_t)jac_grid_max * kJacThreads;
-    if (n_jac * 2 > jac_cap && n_jac <= 4 * jac_cap) {
-      staged_publish_kernel<<<1, 1, 0, st>>>(A.cnt + 0, sl.h_count + 1);
-      CPS_CUDA(cudaStreamSynchronize(st));
-      n_jac = sl.h_count[1];
-      spans_collect();
-    }
+    const size_t jac_likely = rounds > 0 ? std::min(n_jac, last_jac + last_jac / 4 + added + 64) : n_jac;
+    // the grid follows the likely count (blocks without work leave at once, but a snug grid measures a little faster),
+    // with a floor that bounds the extra passes should many more fits than expected have accepted a step
+    const size_t jac_grid_items = std::max(jac_likely, std::min(n_jac, jac_cap / 4));
     if (n_jac > 0) {
       span_begin(2);
-      if (n_jac * 2 <= jac_cap)  // few fits: two threads per fit
-        staged_jac_kernel<true><<<grid_for(n_jac, kJacThreads / 2, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+      if (jac_likely * 2 <= jac_cap)  // few fits: two threads per fit
+        staged_jac_kernel<true><<<grid_for(jac_grid_items, kJacThreads / 2, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
       else
-        staged_jac_kernel<false><<<grid_for(n_jac, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+        staged_jac_kernel<false><<<grid_for(jac_grid_items, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
       span_end();
       c->launches += 1;
     }
@@ -396,6 +397,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     CPS_CUDA(cudaStreamSynchronize(st));
     spans_collect();
     n_solve = sl.h_count[0];
+    last_jac = sl.h_count[1];
     jac_evals = sl.h_count[2];
     cur = nxt;
     ++rounds;

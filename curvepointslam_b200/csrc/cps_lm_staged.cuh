@@ -654,16 +654,13 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
 
 // The host reads the list counters through pinned host memory the device writes directly (a cudaMemcpy of four
 // bytes would queue on a copy engine behind the megabytes of samples the host-buffer entry point is streaming in).
-__global__ void staged_publish_kernel(const unsigned int* __restrict__ src, volatile unsigned int* dst_host) {
-  *dst_host = *src;
-  __threadfence_system();
-}
-
-// End of a round: the length of the next solve list for the host, and the running total of Jacobian evaluations the
-// jac kernel has performed in this call (cnt[1]; cnt[0] is the jac list length of the round that just ended).
+// End of a round: the length of the next solve list for the host, the jac list length of the round that just ended
+// (cnt[0]: the host's estimate for the next round), and the running total of Jacobian evaluations the jac kernel has
+// performed in this call (cnt[1]).
 __global__ void staged_round_end_kernel(unsigned int* cnt, int nxt, volatile unsigned int* host) {
   cnt[1] += cnt[0];
   host[2] = cnt[1];
+  host[1] = cnt[0];
   host[0] = cnt[2 + nxt];
   __threadfence_system();
 }
