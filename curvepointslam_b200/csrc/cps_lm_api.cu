@@ -394,6 +394,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     }
     CPS_CUDA(cudaGetLastError());
     staged_round_end_kernel<<<1, 1, 0, st>>>(A.cnt, nxt, sl.h_count);
+    c->launches += 1;
     CPS_CUDA(cudaStreamSynchronize(st));
     spans_collect();
     n_solve = sl.h_count[0];
