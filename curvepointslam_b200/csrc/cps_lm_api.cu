@@ -714,7 +714,10 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
     int rc = fit_dev(c, sl, model, variant, nb, (double*)(d + D.o_p), (const double*)(d + D.o_meas),
                      t ? (const double*)(d + D.o_t) : nullptr, (const long long*)(d + D.o_off),
                      (const int*)(d + D.o_cnt), (int)n_max, itmax, opts, (double*)(d + D.o_info), (int*)(d + D.o_ret),
-                     extra ? (int*)(d + D.o_ext) : nullptr, st, CPS_LM_PATH_MONOLITHIC);
+                     extra ? (int*)(d + D.o_ext) : nullptr, st,
+                     // a chunk of m = 19 fits stays on the one-launch kernel (the staged rounds would block this
+                     // pipeline); the m = 8 thread-per-fit kernels are single launches and follow the context's choice
+                     model == CPS_MODEL_IMAGE8 ? CPS_LM_PATH_AUTO : CPS_LM_PATH_MONOLITHIC);
     if (rc != CPS_OK) return rc;
     CPS_CUDA(cudaMemcpyAsync(p + (size_t)f0 * m, d + D.o_p, sizeof(double) * (size_t)nb * m, cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaMemcpyAsync(info + (size_t)f0 * 10, d + D.o_info, sizeof(double) * (size_t)nb * 10,

@@ -170,6 +170,8 @@ def test_image8_thread_per_fit_bit_exact(sctx, K):
     from oracle_lib import IMAGE8
     b = synth.make_image8_batch(200, K=K, seed=71)
     gpu = sctx.fit_batched(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    st = sctx.launch_stats()
+    assert (st["grid"], st["block"]) == (2, 128), "the host entry did not reach the thread-per-fit kernel"
     cpu = oracle().fit_batch(IMAGE8, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
     assert_same_fit(gpu, cpu)
     if K == 64:
@@ -187,6 +189,8 @@ def test_image8_dif_thread_per_fit_bit_exact(sctx, K):
     from oracle_lib import DIF, IMAGE8
     b = synth.make_image8_batch(200, K=K, seed=72)
     gpu = sctx.fit_batched(IMAGE8, DIF, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    st = sctx.launch_stats()
+    assert (st["grid"], st["block"]) == (2, 128), "the host entry did not reach the thread-per-fit kernel"
     cpu = oracle().fit_batch(IMAGE8, DIF, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
     assert_same_fit(gpu, cpu)
     assert (cpu["info"][:, 8] >= 1).all()
