@@ -4,13 +4,16 @@
  * Line-by-line restatement (not a copy) of KalmanFilter::PredictKF (kalmanClass.cpp:161-272),
  * UpdateNCurvesAndPoints (:669-945), UpdatePoints (:948-1126), GetPredictedMeasurement (:1162-1199),
  * GetSplitMatrices (:1144-1159), get_Rbe_derivs (:1275-1298), generate_Rbe (common.h:174-186) on plain
- * row-major dense matrices.  The reference cannot be compiled here (OpenCV 1.x C API), and the OpenCV
- * routines it calls (cvGEMM, cvInvert(CV_SVD), cvTranspose, cvAddWeighted) are not vendored under
- * /root/reference, version unpinned; their arithmetic is restated as: dot products accumulated in
- * ascending k, a one-sided Jacobi SVD pseudo-inverse for cvInvert(CV_SVD).  PARITY PINNING: the
- * reference holds no test or golden vector for this path; the restatement is pinned against a cv2 4.13
- * transcription of the same lines run in this container (tests/golden/gen_ekf_golden.py ->
- * tests/golden/ekf_*.npz) and by numeric-Jacobian checks of H like the reference's own getHNumeric
+ * row-major dense matrices.  The OpenCV routines the reference calls (cvGEMM, cvInvert(CV_SVD), cvTranspose,
+ * cvAddWeighted) are not vendored under /root/reference (version unpinned); their arithmetic is restated as: dot
+ * products accumulated in ascending k, a one-sided Jacobi SVD pseudo-inverse for cvInvert(CV_SVD).
+ * PARITY PINNING: the reference's kalmanClass.cpp is compiled UNCHANGED by `make -C oracle ref` (against the
+ * OpenCV-1.x stand-ins of oracle/shim/) into oracle/_ref/libcps_ref.so; this restatement is checked against that
+ * build live and against the fixtures it wrote (tests/golden/ref_cps.npz, tests/test_ref_pinning.py): predict, H
+ * ingredients, predicted measurement, split matrices, rotation tables bit for bit; updates and augmentation within
+ * 1e-12 (two different SVD routines).  Also kept: the cv2 4.13 transcription of the same lines
+ * (tests/golden/gen_ekf_golden.py -> tests/golden/ekf_*.npz) and numeric-Jacobian checks of H like the reference's own
+ * getHNumeric
  * (:1327-1377).  Quirks kept on purpose: the sign of the (0,2) term of generate_Rbe/Reb
  * (common.h:178,193), the typo in get_Rbe_derivs (R_be_theta(1,1) written twice, (2,1) never set,
  * kalmanClass.cpp:1283-1284), PI = 3.1415926535.

@@ -16,16 +16,26 @@
 #include "orc_detmath.h"
 
 /* ---- Bernstein weights: binom[3][k] * pow(1-t, 3-k) * pow(t, k), curveFittingClass.cpp:1067-1068.
- * LIBM mode calls pow() like the reference.  DET mode uses pow(x,0)=1, pow(x,1)=x, pow(x,2)=x*x
- * (identical to a correctly rounded pow) and pow(x,3)=(x*x)*x (may differ from glibc by 1 ulp). */
+ * LIBM mode calls pow() like the reference does: inside a loop over k, i.e. with RUN-TIME exponents.  The
+ * exponent goes through a volatile so that the compiler cannot fold pow(x, 2.0) into x*x: glibc's pow is
+ * accurate to < 1 ulp but not correctly rounded, and pow(t, 2.0) != t*t for about one t in 10^4.  With the
+ * genuine calls this mode is bit-identical to the reference's own modelfunc compiled from
+ * /root/reference/curveFittingClass.cpp (tests/test_ref_pinning.py).  DET mode uses pow(x,0)=1, pow(x,1)=x,
+ * pow(x,2)=x*x and pow(x,3)=(x*x)*x (each may differ from glibc by 1 ulp). */
+static double orc_pow_rt(double x, int k)
+{
+  volatile double e = (double)k;
+  return pow(x, e);
+}
+
 void orc_bernstein3(double t, int math_mode, double w[4])
 {
   const double u = 1 - t;
   if (math_mode == ORC_MATH_LIBM) {
-    w[0] = 1.0 * pow(u, 3) * pow(t, 0);
-    w[1] = 3.0 * pow(u, 2) * pow(t, 1);
-    w[2] = 3.0 * pow(u, 1) * pow(t, 2);
-    w[3] = 1.0 * pow(u, 0) * pow(t, 3);
+    w[0] = 1.0 * orc_pow_rt(u, 3) * orc_pow_rt(t, 0);
+    w[1] = 3.0 * orc_pow_rt(u, 2) * orc_pow_rt(t, 1);
+    w[2] = 3.0 * orc_pow_rt(u, 1) * orc_pow_rt(t, 2);
+    w[3] = 1.0 * orc_pow_rt(u, 0) * orc_pow_rt(t, 3);
   } else {
     const double u2 = u * u, t2 = t * t;
     w[0] = (1.0 * (u2 * u)) * 1.0;

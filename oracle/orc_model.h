@@ -13,10 +13,13 @@
  * jacmodelfunc, :122-405, differentiates an older model); the one here is derived
  *  and pinned with the reference's own dlevmar_chkjac (tests/test_oracle_lm.py).
  *
- * The reference's model code needs OpenCV/GSL headers and cannot be compiled here, so this
- * restatement is pinned (a) structurally by compiling the reference's levmar against it and
- * (b) numerically by chkjac, by the round trip "generate from known parameters -> fit ->
- * recover them", and by the orc_ref_shim build (see oracle/Makefile) when available.
+ * PARITY PINNING: the reference's curveFittingClass.cpp is compiled UNCHANGED by `make -C oracle ref` (OpenCV-1.x /
+ * GSL stand-ins under oracle/shim/) into oracle/_ref/libcps_ref.so.  In ORC_MATH_LIBM mode this restatement is
+ * bit-identical to that build: modelfunc on random parameters, the m = 8 Bernstein evaluation, fit_curve end to end
+ * (packing, t, the live dlevmar_dif call, post-normalisation: parameters, info[0..9], return code), and
+ * cleanup_and_group_edges frame by frame (tests/test_ref_pinning.py, fixtures tests/golden/ref_cps.npz).  The
+ * initial guess agrees to 1e-13 (the reference's cvSVD is external to it).  ORC_MATH_DET is what the CUDA kernels
+ * compute (fixed sin/cos sequence, pow as multiplies): within 4 ulp of the reference per model value.
  */
 #ifndef ORC_MODEL_H
 #define ORC_MODEL_H

@@ -1,0 +1,2 @@
+/* oracle/shim/highgui.h -- see cxcore.h (test infrastructure: lets the reference sources compile unchanged). */
+#include "cxcore.h"

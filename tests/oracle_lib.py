@@ -230,3 +230,214 @@ def oracle() -> Oracle:
     if _ORACLE is None:
         _ORACLE = Oracle()
     return _ORACLE
+
+
+# ---- the reference's own C++ (kalmanClass.cpp, curveFittingClass.cpp) built unchanged into oracle/_ref/libcps_ref.so
+class RefCps:
+    """ctypes view of oracle/ref_harness.cpp.  Present only where `make -C oracle ref` ran (needs /root/reference at
+    BUILD time; the built library travels with the snapshot)."""
+
+    def __init__(self):
+        oracle()  # liborc.so and liblevmar_ref.so must be loaded (RTLD_GLOBAL) first
+        path = os.path.join(ORC_DIR, "_ref", "libcps_ref.so")
+        self.lib = C.CDLL(path)
+        L = self.lib
+        vp = C.c_void_p
+        L.refh_kf_create.restype = vp
+        L.refh_kf_destroy.argtypes = [vp]
+        L.refh_kf_set.argtypes = [vp, _dp, _dp, C.c_int, _ip, C.c_int, _ip, C.c_int]
+        L.refh_kf_dim.argtypes = [vp]
+        L.refh_kf_num_curves.argtypes = [vp]
+        L.refh_kf_num_points.argtypes = [vp]
+        L.refh_kf_get.argtypes = [vp, _dp, _dp, _ip, _ip]
+        L.refh_kf_predict.argtypes = [vp]
+        L.refh_kf_add_first_states.argtypes = [vp, _dp]
+        L.refh_kf_add_new_curve.argtypes = [vp, _dp, _dp]
+        L.refh_kf_add_new_points.argtypes = [vp, _dp, C.c_int]
+        L.refh_kf_update_curves_points.argtypes = [vp, _dp, C.c_int, _dp, _ip, _dp, _ip, C.c_int]
+        L.refh_kf_update_points.argtypes = [vp, _dp, _ip, C.c_int]
+        L.refh_kf_split_matrices.argtypes = [vp, C.c_double, _dp, _dp]
+        L.refh_kf_predicted_measurement.argtypes = [vp, _dp, C.c_int, _dp]
+        L.refh_kf_rbe_derivs.argtypes = [vp, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp]
+        L.refh_generate_rbe.argtypes = [C.c_double, C.c_double, C.c_double, _dp]
+        L.refh_modelfunc.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.refh_cp_earth2image.argtypes = [_dp, _dp, _dp, _dp, _dp]
+        L.refh_earth2body.argtypes = [_dp, _dp, _dp, _dp]
+        L.refh_bezier_eval.argtypes = [_dp, C.c_double, _dp, _dp]
+        L.refh_bezier_eval.restype = C.c_double
+        L.refh_closest_bezier_pt.argtypes = [_dp, _dp, _dp, _dp]
+        L.refh_control2coeffs.argtypes = [_dp, _dp]
+        L.refh_fit_curve.argtypes = [_dp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int]
+        L.refh_fit_curve.restype = C.c_double
+        L.refh_last_fit.argtypes = [_dp, _dp, _dp, _ip, _dp, _ip, _dp, _dp, _ip]
+        L.refh_cleanup_and_group_edges.argtypes = [_ip, _lp, C.c_int, _ip, _dp, _ip, _dp, C.c_longlong]
+
+    # -- KalmanFilter -----------------------------------------------------------------------------------------
+    class KF:
+        def __init__(self, ref):
+            self.r = ref
+            self.h = C.c_void_p(ref.lib.refh_kf_create())
+
+        def close(self):
+            if self.h:
+                self.r.lib.refh_kf_destroy(self.h)
+                self.h = None
+
+        def set(self, x, P, curve_inds, point_inds):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            P = np.ascontiguousarray(P, dtype=np.float64)
+            ci = np.ascontiguousarray(curve_inds, dtype=np.int32)
+            pi = np.ascontiguousarray(point_inds, dtype=np.int32)
+            assert x.size == 12 + 8 * ci.size + 3 * pi.size, "the reference derives N from num_curves / num_points"
+            self.r.lib.refh_kf_set(self.h, _ptr(x, _dp), _ptr(P, _dp), x.size, _ptr(ci, _ip), ci.size, _ptr(pi, _ip),
+                                   pi.size)
+
+        def get(self):
+            L = self.r.lib
+            N = L.refh_kf_dim(self.h)
+            nc, npt = L.refh_kf_num_curves(self.h), L.refh_kf_num_points(self.h)
+            x, P = np.zeros(N), np.zeros((N, N))
+            ci, pi = np.zeros(max(nc, 1), dtype=np.int32), np.zeros(max(npt, 1), dtype=np.int32)
+            L.refh_kf_get(self.h, _ptr(x, _dp), _ptr(P, _dp), _ptr(ci, _ip), _ptr(pi, _ip))
+            return x, P, ci[:nc], pi[:npt]
+
+        def predict(self):
+            self.r.lib.refh_kf_predict(self.h)
+
+        def add_first_states(self, z19):
+            z = np.ascontiguousarray(z19, dtype=np.float64)
+            self.r.lib.refh_kf_add_first_states(self.h, _ptr(z, _dp))
+
+        def add_new_curve(self, z8, A):
+            z = np.ascontiguousarray(z8, dtype=np.float64)
+            A = np.ascontiguousarray(A, dtype=np.float64)
+            self.r.lib.refh_kf_add_new_curve(self.h, _ptr(z, _dp), _ptr(A, _dp))
+
+        def add_new_points(self, xyz):
+            m = np.ascontiguousarray(xyz, dtype=np.float64)
+            self.r.lib.refh_kf_add_new_points(self.h, _ptr(m, _dp), m.size // 3)
+
+        def update_curves_points(self, z, A, curve_num, point_meas=None, point_nums=None):
+            z = np.ascontiguousarray(z, dtype=np.float64)
+            A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1, 16)
+            cn = np.ascontiguousarray(curve_num, dtype=np.int32)
+            pm = np.zeros(1) if point_meas is None or len(point_meas) == 0 else np.ascontiguousarray(point_meas, dtype=np.float64)
+            pn = np.zeros(1, dtype=np.int32) if point_nums is None or len(point_nums) == 0 else np.ascontiguousarray(point_nums, dtype=np.int32)
+            n_pts = 0 if point_nums is None else len(point_nums)
+            self.r.lib.refh_kf_update_curves_points(self.h, _ptr(z, _dp), cn.size, _ptr(A, _dp), _ptr(cn, _ip),
+                                                    _ptr(pm, _dp), _ptr(pn, _ip), n_pts)
+
+        def update_points(self, point_meas, point_nums):
+            pm = np.ascontiguousarray(point_meas, dtype=np.float64)
+            pn = np.ascontiguousarray(point_nums, dtype=np.int32)
+            self.r.lib.refh_kf_update_points(self.h, _ptr(pm, _dp), _ptr(pn, _ip), pn.size)
+
+        def split_matrices(self, t):
+            A1, A2 = np.zeros((4, 4)), np.zeros((4, 4))
+            self.r.lib.refh_kf_split_matrices(self.h, float(t), _ptr(A1, _dp), _ptr(A2, _dp))
+            return A1, A2
+
+        def predicted_measurement(self, A, num_curve):
+            A = np.ascontiguousarray(A, dtype=np.float64)
+            zh = np.zeros(8)
+            self.r.lib.refh_kf_predicted_measurement(self.h, _ptr(A, _dp), int(num_curve), _ptr(zh, _dp))
+            return zh
+
+    def kf(self):
+        return RefCps.KF(self)
+
+    # -- curve model / driver ---------------------------------------------------------------------------------
+    def modelfunc(self, p19, t, counts):
+        p = np.ascontiguousarray(p19, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        n = 2 * int(np.sum(counts))
+        assert t.size == n // 2
+        hx = np.zeros(n)
+        l1, l2, r1, r2 = (int(c) for c in counts)  # measurement order [L c1 | L c2 | R c1 | R c2]
+        self.lib.refh_modelfunc(_ptr(p, _dp), _ptr(hx, _dp), n, _ptr(t, _dp), l1, r1, l2, r2)
+        return hx
+
+    def generate_rbe(self, phi, theta, psi):
+        R = np.zeros((3, 3))
+        self.lib.refh_generate_rbe(float(phi), float(theta), float(psi), _ptr(R, _dp))
+        return R
+
+    def rbe_derivs(self, phi, theta, psi):
+        kf = self.kf()
+        a, b, c = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3))
+        self.lib.refh_kf_rbe_derivs(kf.h, float(phi), float(theta), float(psi), _ptr(a, _dp), _ptr(b, _dp), _ptr(c, _dp))
+        kf.close()
+        return a, b, c
+
+    def cp_earth2image(self, c_earth8, euler, translation):
+        c = np.ascontiguousarray(c_earth8, dtype=np.float64)
+        e = np.ascontiguousarray(euler, dtype=np.float64)
+        tr = np.ascontiguousarray(translation, dtype=np.float64)
+        l, r = np.zeros(8), np.zeros(8)
+        self.lib.refh_cp_earth2image(_ptr(c, _dp), _ptr(l, _dp), _ptr(r, _dp), _ptr(e, _dp), _ptr(tr, _dp))
+        return l, r
+
+    def bezier_eval(self, cp8, t):
+        cp = np.ascontiguousarray(cp8, dtype=np.float64)
+        pt, near = np.zeros(2), np.zeros(2)
+        self.lib.refh_bezier_eval(_ptr(cp, _dp), float(t), _ptr(pt, _dp), _ptr(near, _dp))
+        return near
+
+    def fit_curve(self, meas, counts):
+        """The reference's CurveFittingClass::fit_curve on one frame; meas packed [L c1 | L c2 | R c1 | R c2]."""
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        l1, l2, r1, r2 = (int(c) for c in counts)
+        o = np.cumsum([0, 2 * l1, 2 * l2, 2 * r1, 2 * r2])
+        seg = [np.ascontiguousarray(meas[o[i]:o[i + 1]]) for i in range(4)]
+        p = np.zeros(19)
+        err = self.lib.refh_fit_curve(_ptr(p, _dp), _ptr(seg[0], _dp), l1, _ptr(seg[1], _dp), l2, _ptr(seg[2], _dp), r1,
+                                      _ptr(seg[3], _dp), r2)
+        return p, err
+
+    def last_fit(self):
+        """What the last fit_curve handed to levmar (initial guess, packed measurements, t, counts, opts, itmax) and
+        what levmar returned before the post-normalisation (p_lm, info, ret)."""
+        n = self.lib.refh_last_fit(None, None, None, None, None, None, None, None, None)
+        p0, x, t, p_lm, info, opts = np.zeros(19), np.zeros(n), np.zeros(n // 2), np.zeros(19), np.zeros(10), np.zeros(5)
+        counts, itmax, ret = np.zeros(4, dtype=np.int32), C.c_int(0), C.c_int(0)
+        self.lib.refh_last_fit(_ptr(p0, _dp), _ptr(x, _dp), _ptr(t, _dp), _ptr(counts, _ip), _ptr(opts, _dp),
+                               C.byref(itmax), _ptr(p_lm, _dp), _ptr(info, _dp), C.byref(ret))
+        return dict(p0=p0, x=x, t=t, counts=counts, opts=opts, itmax=itmax.value, p_lm=p_lm, info=info, ret=ret.value)
+
+    def closest(self, p8, pt):
+        p = np.ascontiguousarray(p8, dtype=np.float64)
+        q = np.ascontiguousarray(pt, dtype=np.float64)
+        near, out = np.zeros(2), np.zeros(2)
+        self.lib.refh_closest_bezier_pt(_ptr(p, _dp), _ptr(q, _dp), _ptr(near, _dp), _ptr(out, _dp))
+        return near, out[0], out[1]
+
+    def control2coeffs(self, cp8):
+        c = np.ascontiguousarray(cp8, dtype=np.float64)
+        p = np.zeros(8)
+        self.lib.refh_control2coeffs(_ptr(c, _dp), _ptr(p, _dp))
+        return p
+
+    def cleanup_edges(self, pts, seg_off, tracked, reset=False):
+        pts = np.ascontiguousarray(pts, dtype=np.int32).reshape(-1, 2)
+        so = np.ascontiguousarray(seg_off, dtype=np.int64)
+        tr = np.ascontiguousarray(tracked, dtype=np.float64).copy()
+        cut = np.zeros(2, dtype=np.int32)
+        counts = np.zeros(4, dtype=np.int32)
+        cap = 2 * int(so[4] - so[0]) + 8
+        meas = np.zeros(cap)
+        ok = self.lib.refh_cleanup_and_group_edges(_ptr(pts, _ip), _ptr(so, _lp), 1 if reset else 0, _ptr(cut, _ip),
+                                                   _ptr(tr, _dp), _ptr(counts, _ip), _ptr(meas, _dp), cap)
+        return ok, counts, meas[:2 * int(counts.sum())], cut, tr
+
+
+_REFCPS = None
+
+
+def refcps():
+    """The reference build, or None where oracle/_ref/libcps_ref.so does not exist."""
+    global _REFCPS
+    if _REFCPS is None:
+        if not os.path.exists(os.path.join(ORC_DIR, "_ref", "libcps_ref.so")) or oracle().levmar is None:
+            return None
+        _REFCPS = RefCps()
+    return _REFCPS
