@@ -261,12 +261,20 @@ __global__ void __launch_bounds__(256) ekf_s_kernel(UpdateDesc d, const double* 
   }
   __syncthreads();
   // right-looking Cholesky on the lower triangle
+  // A pivot that is not positive (S singular, indefinite or not finite) fails the update: the flag is raised
+  // (reported by the next cps_ekf_sync as CPS_ERR_INVALID), S^-1 is written as zero so that the gain is zero and the
+  // kernels that follow leave x and P exactly as they were, and the factorisation carries on with a unit pivot so
+  // that no NaN / inf is ever produced.
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  __syncthreads();
   for (int k = 0; k < M; ++k) {
     __shared__ double piv;
     if (tid == 0) {
       const double v = L[k * M + k];
-      if (!(v > 0.0)) *flag = 1;
-      piv = sqrt(v);
+      const bool ok = (v > 0.0) && (v <= 1.79769313486231571e308);
+      if (!ok) { *flag = 1; bad = 1; }
+      piv = ok ? sqrt(v) : 1.0;
       L[k * M + k] = piv;
     }
     __syncthreads();
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(256) ekf_s_kernel(UpdateDesc d, const double* 
     const int r = e / M, s = e - r * M;
     double acc = 0.0;
     for (int k = (r > s ? r : s); k < M; ++k) acc += X[k * M + r] * X[k * M + s];
-    small[SM_SINV + r * MAXM + s] = acc;
+    small[SM_SINV + r * MAXM + s] = bad ? 0.0 : acc;
   }
 }
 
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(256) ekf_gain_kernel(UpdateDesc d, const doubl
     for (int o = 16; o > 0; o >>= 1) dx += __shfl_xor_sync(0xffffffffu, dx, o);
     if (lane == 0) {
       double v = x[row] + dx;
-      if (row >= 3 && row <= 5) {  // kalmanClass.cpp:902-913
+      if (row >= 3 && row <= 5 && fabs(v) < 1e6) {  // kalmanClass.cpp:902-913 (bounded: a wild angle cannot spin)
         while (v > kPI) v -= 2 * kPI;
         while (v < -kPI) v += 2 * kPI;
       }

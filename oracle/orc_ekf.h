@@ -66,6 +66,14 @@ int orc_gate_mahalanobis(const double *x, const double *P, int N, const int *poi
 /* per-landmark pack used by both sides: zhat (3) and the 6 unique entries of S^-1 */
 void orc_gate_pack(const double *x, const double *P, int N, const int *point_col, int n_land, double *pack9);
 
+/* the same from the pieces of P the gate reads (pose rows 6 x N, pose columns N x 6, one 3 x 3 diagonal block per
+ * landmark), for maps whose dense P does not fit a host buffer */
+void orc_gate_pack_pieces(const double *x, const double *pose_rows, const double *pose_cols, const double *diag3, int N,
+                          const int *point_col, int n_land, double *pack9);
+int orc_gate_mahalanobis_pieces(const double *x, const double *pose_rows, const double *pose_cols, const double *diag3,
+                                int N, const int *point_col, int n_land, const double *z, int nz, double gate,
+                                int *idx_out, double *d2_out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,10 @@ class Oracle:
                                            C.c_int]
         L.orc_gate_mahalanobis.restype = C.c_int
         L.orc_gate_pack.argtypes = [_dp, _dp, C.c_int, _ip, C.c_int, _dp]
+        L.orc_gate_pack_pieces.argtypes = [_dp, _dp, _dp, _dp, C.c_int, _ip, C.c_int, _dp]
+        L.orc_gate_mahalanobis_pieces.argtypes = [_dp, _dp, _dp, _dp, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_double,
+                                                  _ip, _dp, C.c_int]
+        L.orc_gate_mahalanobis_pieces.restype = C.c_int
         self.ref = None
         self.levmar = None
         rpath = os.path.join(ORC_DIR, "_ref", "liborc_refshim.so")
@@ -211,6 +215,28 @@ class Oracle:
         rc = self.lib.orc_gate_mahalanobis(_ptr(x, _dp), _ptr(P, _dp), x.size, _ptr(pc, _ip), pc.size, _ptr(z, _dp),
                                            z.shape[0], gate, _ptr(idx, _ip), _ptr(d2, _dp), nthreads)
         assert rc == 0
+        return idx, d2
+
+    def gate_pieces(self, x, pose_rows, pose_cols, diag3, point_col, z, gate, nthreads=1, want_pack=False):
+        """The gate from the pieces of P it reads: pose_rows [6, N], pose_cols [N, 6], diag3 [L, 3, 3]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        pr = np.ascontiguousarray(pose_rows, dtype=np.float64)
+        pcs = np.ascontiguousarray(pose_cols, dtype=np.float64)
+        d3 = np.ascontiguousarray(diag3, dtype=np.float64)
+        pc = np.ascontiguousarray(point_col, dtype=np.int32)
+        assert pr.shape == (6, x.size) and pcs.shape == (x.size, 6) and d3.shape == (pc.size, 3, 3)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 3)
+        idx = np.zeros(z.shape[0], dtype=np.int32)
+        d2 = np.zeros(z.shape[0])
+        rc = self.lib.orc_gate_mahalanobis_pieces(_ptr(x, _dp), _ptr(pr, _dp), _ptr(pcs, _dp), _ptr(d3, _dp), x.size,
+                                                  _ptr(pc, _ip), pc.size, _ptr(z, _dp), z.shape[0], gate, _ptr(idx, _ip),
+                                                  _ptr(d2, _dp), nthreads)
+        assert rc == 0
+        if want_pack:
+            pack = np.zeros((pc.size, 9))
+            self.lib.orc_gate_pack_pieces(_ptr(x, _dp), _ptr(pr, _dp), _ptr(pcs, _dp), _ptr(d3, _dp), x.size,
+                                          _ptr(pc, _ip), pc.size, _ptr(pack, _dp))
+            return idx, d2, pack
         return idx, d2
 
     def gate_pack(self, x, P, point_col):

@@ -11,7 +11,7 @@ Two layers:
 
 Tolerances.  Integer / index work and everything without a matrix inverse or SVD: bit-exact.  With an inverse
 (cvInvert(CV_SVD) is a Jacobi SVD pseudo-inverse in the stand-in, a Jacobi SVD of its own in the oracle): element-wise
-|a - b| <= 1e-9 * max(|b|, 1e-3 * max|b|) (the north star's 1e-9 relative, per element), observed ~1e-13 max-norm.
+|a - b| <= 1e-9 * max(|b|, 1e-2 * max|b|) (the north star's 1e-9 relative, per element; tests/parity.py says why 1e-2), observed ~1e-13 max-norm.
 """
 import ctypes as C
 import os
@@ -21,6 +21,7 @@ import pytest
 
 from curvepointslam_b200 import synth
 from oracle_lib import DIF, MATH_DET, MATH_LIBM, STEREO19, oracle, refcps
+from parity import elementwise_rel
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 G = np.load(os.path.join(HERE, "golden", "ref_cps.npz"))
@@ -30,10 +31,9 @@ need_ref = pytest.mark.skipif(refcps() is None, reason="oracle/_ref/libcps_ref.s
 EKF_CASES = ["c4", "c2p3", "p4", "c4p10"]
 
 
-def elementwise_ok(a, b, rtol=1e-9, floor=1e-3):
-    """|a - b| <= rtol * max(|b|, floor * max|b|): relative per element; entries below a thousandth of the largest one
-    (cross-covariances that cancel towards 0) are held to the absolute error 1e-12 * max|b| instead."""
-    return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), floor * np.abs(b).max())))
+def elementwise_ok(a, b, rtol=1e-9):
+    """tests/parity.py: |a - b| <= rtol * max(|b|, 1e-2 * max|b|), relative per element"""
+    return elementwise_rel(a, b) <= rtol
 
 
 def maxrel(a, b):
