@@ -10,6 +10,7 @@
 #include "cps_common.h"
 #include "cps_lm_kernel.cuh"
 #include "cps_lm_staged.cuh"
+#include "cps_lm_dif_staged.cuh"
 #include "cps_lm_image8.cuh"
 
 namespace cps {
@@ -38,6 +39,9 @@ constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffe
 constexpr int kStagedTailFits = 16384;  // staged der: the last fits (at most this many and B/2) go to the warp-per-fit kernel
 constexpr int kImage8ThreadMinFits = 4096;  // m = 8: a thread per fit from this many fits per call (measured crossover)
 constexpr int kStagedMinFits = 8192;   // der, m = 19: staged shape from this many fits per call (measured crossover ~6 k)
+constexpr int kDifStagedMinFits = 4096;  // dif, m = 19 (forward differences): staged shape from this many fits per call
+constexpr int kDifChunkFits = 131072;    // host-buffer entry, staged dif: fits per pipelined chunk (amortises the late rounds)
+constexpr size_t kDifMaxJBytes = (size_t)48 << 30;  // stored secant Jacobians of one staged dif pass (larger batches: several passes)
 
 struct cps_lm_ctx {
   int device = 0;
@@ -434,6 +438,207 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   return CPS_OK;
 }
 
+
+// dlevmar_dif for a large batch of Stereo19 fits as rounds of phase kernels (cps_lm_dif_staged.cuh): solve -> eval ->
+// build (finite-difference Jacobian | pending secant update, each with the J^T J rebuild).  The host only sizes
+// grids: it reads three integers per round.  A batch whose stored Jacobians (n_max x 20 doubles per fit) would not
+// fit kDifMaxJBytes is run as several passes over ranges of the fit index.
+int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, cudaStream_t st) {
+  using namespace cps;
+  const size_t B = (size_t)L.B;
+  auto a256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const int eval_smem = kEvalTableDoubles * kEvalThreads * (int)sizeof(double) + (kEvalThreads / 32) * (int)sizeof(WarpTiles);
+  const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
+  const int fd_smem = dif_build_smem_doubles<true>() * (int)sizeof(double);
+  const int upd_smem = dif_build_smem_doubles<false>() * (int)sizeof(double);
+  CPS_CUDA(cudaFuncSetAttribute(dif_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
+  CPS_CUDA(cudaFuncSetAttribute(dif_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
+  CPS_CUDA(cudaFuncSetAttribute(dif_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
+  CPS_CUDA(cudaFuncSetAttribute(dif_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fd_smem));
+  CPS_CUDA(cudaFuncSetAttribute(dif_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+  int eval_occ = 0, solve_occ = 0, fd_occ = 0, upd_occ = 0;
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_occ, dif_eval_kernel<false>, kEvalThreads, eval_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, dif_solve_kernel, kSolveThreads, solve_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fd_occ, dif_build_kernel<true>, kDifThreads, fd_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&upd_occ, dif_build_kernel<false>, kDifThreads, upd_smem));
+  if (eval_occ < 1 || solve_occ < 1 || fd_occ < 1 || upd_occ < 1) {
+    cps::set_last_error("staged dif kernels do not fit on this device");
+    return CPS_ERR_CUDA;
+  }
+  const int build_grid_max = c->sm_count * std::max(fd_occ, upd_occ);
+  const int ws_stride = build_grid_max * kDifFits;
+  const size_t j_stride = (size_t)L.n_max * kDifRow;
+  size_t o = 0;
+  const size_t o_scal = o; o = a256(o + sizeof(DifScal) * B);
+  const size_t o_jtj = o;  o = a256(o + sizeof(double) * kLower19 * B);
+  const size_t o_jte = o;  o = a256(o + sizeof(double) * 19 * B);
+  const size_t o_pdp = o;  o = a256(o + sizeof(double) * 19 * B);
+  const size_t o_dp = o;   o = a256(o + sizeof(double) * 19 * B);
+  const size_t o_pold = o; o = a256(o + sizeof(double) * 19 * B);
+  const size_t o_tws = o;  o = a256(o + (L.t ? 0 : sizeof(double) * (size_t)(L.n_max / 2) * B));
+  const size_t o_ws = o;   o = a256(o + sizeof(double) * kDifSums * (size_t)ws_stride);
+  const size_t o_fd = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_up = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_el = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_s0 = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_s1 = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_cnt = o;  o = a256(o + sizeof(unsigned int) * 4);
+  const size_t o_J = o;    o = a256(o + sizeof(double) * j_stride * B);
+  if (o > sl.staged_bytes) {
+    CPS_CUDA(cudaStreamSynchronize(st));
+    CPS_CUDA(cudaStreamSynchronize(sl.stream));
+    cudaFree(sl.d_staged);
+    sl.d_staged = nullptr;
+    sl.staged_bytes = 0;
+    CPS_CUDA(cudaMalloc(&sl.d_staged, o));
+    sl.staged_bytes = o;
+  }
+  if (!sl.h_count) CPS_CUDA(cudaMallocHost(&sl.h_count, sizeof(unsigned int) * 4));
+  char* d = sl.d_staged;
+  DifArgs A;
+  A.L = L;
+  A.scal = (DifScal*)(d + o_scal);
+  A.jtj = (double*)(d + o_jtj);
+  A.jte = (double*)(d + o_jte);
+  A.pdp = (double*)(d + o_pdp);
+  A.dp = (double*)(d + o_dp);
+  A.pold = (double*)(d + o_pold);
+  A.tws = L.t ? nullptr : (double*)(d + o_tws);
+  A.J = (double*)(d + o_J);
+  A.j_stride = j_stride;
+  A.ws = (double*)(d + o_ws);
+  A.ws_stride = ws_stride;
+  A.fd_list = (int*)(d + o_fd);
+  A.upd_list = (int*)(d + o_up);
+  A.eval_list = (int*)(d + o_el);
+  A.solve_list[0] = (int*)(d + o_s0);
+  A.solve_list[1] = (int*)(d + o_s1);
+  A.cnt = (unsigned int*)(d + o_cnt);
+  A.init_first = 0;
+  A.init_count = (int)B;
+  auto grid_for = [&](size_t items, int per_block, int cap) {
+    size_t gneed = (items + per_block - 1) / per_block;
+    if (gneed < 1) gneed = 1;
+    return (int)std::min<size_t>(gneed, (size_t)cap);
+  };
+  struct Span { int kind; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+  auto ev_get = [&]() -> cudaEvent_t {
+    if (ev_used == c->ev_pool.size()) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+      c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[ev_used++];
+  };
+  auto span_begin = [&](int kind) {
+    if (!c->profiling) return;
+    Span sp{kind, ev_get(), ev_get()};
+    if (sp.a && sp.b) { cudaEventRecord(sp.a, st); spans.push_back(sp); }
+  };
+  auto span_end = [&]() {
+    if (!c->profiling || spans.empty()) return;
+    cudaEventRecord(spans.back().b, st);
+  };
+  auto spans_collect = [&]() {
+    for (const Span& sp : spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+        c->prof_ms[sp.kind] += ms;
+        c->prof_launches[sp.kind] += 1;
+      }
+    }
+    spans.clear();
+    ev_used = 0;
+  };
+  auto builds = [&](size_t n_fd, size_t n_upd, int nxt) {
+    if (n_fd > 0) {
+      span_begin(2);
+      dif_build_kernel<true><<<grid_for(n_fd, kDifFits, c->sm_count * fd_occ), kDifThreads, fd_smem, st>>>(A, nxt);
+      span_end();
+      c->launches += 1;
+    }
+    if (n_upd > 0) {
+      span_begin(2);
+      dif_build_kernel<false><<<grid_for(n_upd, kDifFits, c->sm_count * upd_occ), kDifThreads, upd_smem, st>>>(A, nxt);
+      span_end();
+      c->launches += 1;
+    }
+  };
+  CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 4, st));
+  // iteration 0: validation, t, e0, loop top; every surviving fit needs its first finite-difference Jacobian
+  int cur = 0, rounds = 0;
+  span_begin(1);
+  dif_eval_kernel<true><<<grid_for(B, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, cur);
+  span_end();
+  c->launches += 1;
+  builds(B, 0, cur);
+  dif_round_end_kernel<<<1, 1, 0, st>>>(A.cnt, cur, sl.h_count);
+  c->launches += 1;
+  CPS_CUDA(cudaGetLastError());
+  CPS_CUDA(cudaStreamSynchronize(st));
+  spans_collect();
+  size_t n_solve = sl.h_count[0];
+  size_t last_fd = sl.h_count[1], last_upd = sl.h_count[2];
+  long long n_builds = (long long)last_fd;
+  while (n_solve > 0) {
+    const int nxt = cur ^ 1;
+    CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int) * 2, st));
+    CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
+    span_begin(0);
+    dif_solve_kernel<<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
+    span_end();
+    span_begin(1);
+    dif_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+    span_end();
+    c->launches += 2;
+    // the kernels read the real list lengths on the device; the grids follow an upper bound (a block without work
+    // leaves at once): at most every solved fit needs a build
+    (void)last_fd;
+    (void)last_upd;
+    builds(n_solve, n_solve, nxt);
+    dif_round_end_kernel<<<1, 1, 0, st>>>(A.cnt, nxt, sl.h_count);
+    c->launches += 1;
+    CPS_CUDA(cudaGetLastError());
+    CPS_CUDA(cudaStreamSynchronize(st));
+    spans_collect();
+    n_solve = sl.h_count[0];
+    last_fd = sl.h_count[1];
+    last_upd = sl.h_count[2];
+    n_builds += (long long)(last_fd + last_upd);
+    cur = nxt;
+    ++rounds;
+  }
+  c->last_grid = build_grid_max;
+  c->last_block = kDifThreads;
+  c->last_smem = upd_smem;
+  c->last_rounds = rounds;
+  if (c->profiling) c->prof_jac_evals += n_builds;
+  return CPS_OK;
+}
+
+int launch_staged_dif19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaStream_t st) {
+  const size_t per_fit = sizeof(double) * (size_t)L.n_max * cps::kDifRow;
+  const size_t max_fits = std::max<size_t>(1024, kDifMaxJBytes / std::max<size_t>(per_fit, 1));
+  int rounds = 0;
+  for (size_t first = 0; first < (size_t)L.B; first += max_fits) {
+    cps::LmLaunch R = L;
+    R.B = (int)std::min(max_fits, (size_t)L.B - first);
+    R.p = L.p + first * 19;
+    R.off = L.off + first;
+    R.counts = L.counts + first * 4;
+    R.info = L.info + first * 10;
+    R.ret = L.ret + first;
+    R.extra = L.extra ? L.extra + first * 2 : nullptr;
+    const int rc = launch_staged_dif19_range(c, sl, R, st);
+    if (rc != CPS_OK) return rc;
+    rounds += c->last_rounds;
+  }
+  c->last_rounds = rounds;
+  return CPS_OK;
+}
+
 // dlevmar_der / dlevmar_dif for a large batch of per-contour m = 8 fits: one kernel, a thread per fit
 // (cps_lm_image8.cuh).  Work area: [dif: the secant Jacobians, n_max x 8 per resident thread][t of every fit unless
 // the caller supplies it]
@@ -507,6 +712,10 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
   if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && path != CPS_LM_PATH_MONOLITHIC &&
       (path == CPS_LM_PATH_STAGED || B >= kStagedMinFits))
     return launch_staged_der19(c, sl, L, st, {StagedPiece{0, B, nullptr}});
+  // central differences (opts[4] < 0) and fits longer than the staged kernels' row index stay on the warp-per-fit kernel
+  if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DIF && L.forward && path != CPS_LM_PATH_MONOLITHIC &&
+      (path == CPS_LM_PATH_STAGED || B >= kDifStagedMinFits))
+    return launch_staged_dif19(c, sl, L, st);
   if (model == CPS_MODEL_IMAGE8 && path != CPS_LM_PATH_MONOLITHIC &&
       (path == CPS_LM_PATH_STAGED || B >= kImage8ThreadMinFits))
     return launch_image8(c, sl, L, st, variant == CPS_LM_DIF);
@@ -658,7 +867,10 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   const bool staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
                       (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits);
   if (staged) return fit_batched_host_staged(c, B, p, meas, t, off, counts, n_max, itmax, opts, info, ret, extra);
-  const int chunk = kChunkFits;
+  // staged dif: larger chunks (the late rounds of a chunk run at the latency floor of the kernels)
+  const bool dif_staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DIF && (!opts || opts[4] >= 0.0) &&
+                          c->path != CPS_LM_PATH_MONOLITHIC && (c->path == CPS_LM_PATH_STAGED || B >= kDifStagedMinFits);
+  const int chunk = dif_staged ? kDifChunkFits : kChunkFits;
   const int n_chunks = (B + chunk - 1) / chunk;
   struct Staged {
     int f0, nb;
@@ -717,7 +929,7 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
                      extra ? (int*)(d + D.o_ext) : nullptr, st,
                      // a chunk of m = 19 fits stays on the one-launch kernel (the staged rounds would block this
                      // pipeline); the m = 8 thread-per-fit kernels are single launches and follow the context's choice
-                     model == CPS_MODEL_IMAGE8 ? CPS_LM_PATH_AUTO : CPS_LM_PATH_MONOLITHIC);
+                     (model == CPS_MODEL_IMAGE8 || dif_staged) ? CPS_LM_PATH_AUTO : CPS_LM_PATH_MONOLITHIC);
     if (rc != CPS_OK) return rc;
     CPS_CUDA(cudaMemcpyAsync(p + (size_t)f0 * m, d + D.o_p, sizeof(double) * (size_t)nb * m, cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaMemcpyAsync(info + (size_t)f0 * 10, d + D.o_info, sizeof(double) * (size_t)nb * 10,

@@ -1,0 +1,837 @@
+// cps_lm_dif_staged.cuh -- dlevmar_dif (lm_core.c:429-828, the reference's one live call, curveFittingClass.cpp:681)
+// for large batches of Stereo19 fits as rounds of phase kernels, like cps_lm_staged.cuh does for dlevmar_der.
+//
+// The secant algorithm keeps an n x 19 Jacobian per fit (78 KB at n = 512) that every iteration reads, updates by a
+// rank-one correction (Broyden, :745-755) and contracts into J^T J / J^T e (:581-655).  The warp-per-fit kernel
+// (cps_lm_kernel.cuh lm_dif) spreads one fit's tiles over 32 lanes and runs every phase at the occupancy of the
+// hungriest; here every phase is its own kernel with the fits themselves as the parallelism (lane = fit):
+//
+//   solve  (J^T J + mu I) dp = J^T e by the reference's LU, step checks, dL                       lm_core.c:683-722
+//   eval   ||x - f(p+dp)||^2 in the reference's four chains (f is never stored: it is recomputed from the
+//          parameters wherever the reference reads hx / wrk -- same operations, same bits), accept / reject,
+//          damping, the loop-top checks and the Jacobian policy of the next iteration         :724-792, 557-579
+//   build  the J^T J / J^T e rebuild with the Jacobian produced on the way in: either the forward-difference
+//          Jacobian (misc_core.c:135-170) evaluated row by row, or the stored rows with the pending rank-one
+//          update applied; the rows are written back once                                      :569-655, 745-755
+//
+// build kernel shape: a CTA of four warps owns 32 fits (lane = fit).  Rows are walked four at a time: warp w
+// produces row 4b + w of each of its 32 fits (model values, the 19-term dot product of the update, the corrected
+// row) into a shared-memory stage, then every warp accumulates ITS QUARTER OF THE 190 + 19 SUMS over the four rows
+// (quarters: the triangle of columns 0..9, the triangle of columns 10..18, and the two halves of the 9 x 10
+// rectangle between them), statically unrolled into registers.  The reference's summation orders are loop orders
+// here: per-entry partial sums over 32-row blocks joined in ascending block order (misc_core.c:101-126; joined by
+// red.global.add.f64 at the L2 like the der path), J^T e one chain per column over ascending rows, the unblocked
+// descending loop when n*m <= 1024 (lm_core.c:585, "<=" in dif).  Bit-identical to the warp-per-fit kernel and to the
+// oracle / the reference levmar (tests/test_lm_dif_staged_gpu.py).
+#pragma once
+#include "cps_lm_staged.cuh"
+
+namespace cps {
+
+struct DifScal {  // per-fit scalars of a dlevmar_dif iteration in flight
+  double e0, e_sq, g_inf, dp_sq, mu, p_sq, maxdiag, dL, pend_dp_sq;
+  int nu, k, nfev, njap, nlss, n_jtj, n_broyden, updjac, updp, pend, accepted, pad;
+};
+
+constexpr int kDifK = 19;            // K = max(m, 10), lm_core.c:497
+constexpr int kDifRow = 20;          // doubles per stored Jacobian row (19 + 1: rows stay 16-byte aligned)
+constexpr int kDifStageRow = 22;     // shared-memory pitch of a staged row: 11 x 16 B (odd: LDS.128 of a quarter-warp
+                                     // hit distinct 16-byte slots); [0..18] J, [20] residual
+constexpr int kDifFits = 32;         // fits per CTA of the build kernels
+constexpr int kDifThreads = 128;     // four warps
+constexpr int kDifSums = kLower19 + 19;  // running sums of a fit in the L2 work area: 190 J^T J entries, 19 J^T e
+
+struct DifArgs {
+  LmLaunch L;
+  DifScal* scal;        // [B]
+  double* jtj;          // [B][190] lower triangle, row-major
+  double* jte;          // [B][19]
+  double* pdp;          // [B][19] trial point p + dp
+  double* dp;           // [B][19]
+  double* pold;         // [B][19] p at the time of the pending secant update
+  double* tws;          // [B][n_max/2] t when the caller passes none
+  double* J;            // [B][j_rows][20] stored secant Jacobians
+  size_t j_stride;      // doubles per fit in J
+  double* ws;           // [kDifSums][ws_stride] running sums of the resident fits
+  int ws_stride;
+  int* fd_list;         // fits whose next build evaluates a finite-difference Jacobian
+  int* upd_list;        // fits whose next build applies a pending secant update
+  int* eval_list;
+  int* solve_list[2];
+  unsigned int* cnt;    // [0] fd list, [1] upd list, [2], [3] solve lists
+  int init_first, init_count;
+};
+
+__device__ __forceinline__ void dif_finish(const DifArgs& A, int f, const DifScal& s, int stop) {
+  if (s.k >= A.L.itmax) stop = 3;  // lm_core.c:796
+  double* info = A.L.info + (size_t)f * 10;
+  info[0] = s.e0;
+  info[1] = s.e_sq;
+  info[2] = s.g_inf;
+  info[3] = s.dp_sq;
+  info[4] = s.mu / s.maxdiag;
+  info[5] = (double)s.k;
+  info[6] = (double)stop;
+  info[7] = (double)s.nfev;
+  info[8] = (double)s.njap;
+  info[9] = (double)s.nlss;
+  A.L.ret[f] = (stop != 4 && stop != 7) ? s.k : -1;
+  if (A.L.extra) { A.L.extra[2 * f] = s.n_jtj; A.L.extra[2 * f + 1] = s.n_broyden; }
+}
+
+__device__ __forceinline__ void dif_geom(const DifArgs& A, int f, FitGeom& g, long long& o0) {
+  o0 = A.L.off[f];
+  g.n = (int)(A.L.off[f + 1] - o0);
+  g.nsamp = g.n >> 1;
+  const int c0 = A.L.counts[4 * (size_t)f], c1 = A.L.counts[4 * (size_t)f + 1], c2 = A.L.counts[4 * (size_t)f + 2];
+  g.b1 = c0;
+  g.b2 = c0 + c1;
+  g.b3 = c0 + c1 + c2;
+}
+
+__device__ __forceinline__ const double* dif_t(const DifArgs& A, int f, long long o0) {
+  return A.L.t ? A.L.t + (o0 >> 1) : A.tws + (size_t)f * (A.L.n_max >> 1);
+}
+
+// Top of an outer iteration (lm_core.c:557-579) for a fit whose k has just been advanced: the loop bound, the
+// ||e||^2 <= eps3 stop, then the Jacobian policy.  Returns 0: stopped (info written), 1: needs a finite-difference
+// Jacobian, 2: needs a rebuild with the pending secant update, 3: straight to the solve with the J^T J it has.
+__device__ __forceinline__ int dif_loop_top(const DifArgs& A, int f, DifScal& s) {
+  if (s.k >= A.L.itmax) { dif_finish(A, f, s, 0); return 0; }
+  if (s.e_sq <= A.L.eps3) { dif_finish(A, f, s, 6); return 0; }
+  if ((s.updp && s.nu > 16) || s.updjac == kDifK) {
+    s.njap += 1;
+    s.nfev += A.L.forward ? 19 : 38;
+    s.nu = 2; s.updjac = 0; s.updp = 0;
+    s.pend = 0;  // the fresh Jacobian overwrites every entry a deferred secant update would have touched
+    return 1;
+  }
+  return s.pend ? 2 : 3;
+}
+
+// ---- eval: thread per fit ---------------------------------------------------------------------------------------
+// Same sample staging and the same four-chain ||e||^2 as staged_eval_kernel (cps_lm_staged.cuh); the iteration logic
+// is dlevmar_dif's.
+template <bool INIT>
+__global__ void __launch_bounds__(kEvalThreads, 3) dif_eval_kernel(const DifArgs A, int nxt) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double* Csm = smem + tid;
+  WarpTiles* wt = reinterpret_cast<WarpTiles*>(smem + kEvalTableDoubles * kEvalThreads) + wid;
+  const unsigned int total = INIT ? (unsigned int)A.init_count : A.cnt[2 + (nxt ^ 1)];
+  for (unsigned int base = (blockIdx.x * (kEvalThreads / 32) + wid) * 32; base < total;
+       base += gridDim.x * kEvalThreads) {
+    const unsigned int item = base + lane;
+    bool have = item < total;
+    int f = have ? (INIT ? A.init_first + (int)item : A.eval_list[item]) : 0;
+    if (f < 0) { have = false; f = 0; }
+    FitGeom g;
+    g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;
+    long long o0 = 0;
+    if (have) dif_geom(A, f, g, o0);
+    if (INIT && have) {
+      const long long nn = A.L.off[f + 1] - o0;
+      int ret_code = 0;
+      if (nn < 19) ret_code = -1;  // lm_core.c:493
+      else if (nn > A.L.n_max || (nn & 1)) ret_code = -2;
+      const int c3 = A.L.counts[4 * (size_t)f + 3];
+      if (ret_code == 0 && (g.b1 < 0 || g.b2 < g.b1 || g.b3 < g.b2 || c3 < 0 || g.b3 + c3 != g.nsamp)) ret_code = -3;
+      if (ret_code != 0) {
+        for (int q = 0; q < 10; ++q) A.L.info[(size_t)f * 10 + q] = 0.0;
+        A.L.ret[f] = ret_code;
+        if (A.L.extra) { A.L.extra[2 * f] = 0; A.L.extra[2 * f + 1] = 0; }
+        have = false;
+      }
+    }
+    if (!have) { g.n = 0; g.nsamp = 0; }
+    const double* x = A.L.meas + o0;
+    const bool derive_t = INIT && !A.L.t;
+    const double* tp = have ? dif_t(A, f, o0) : nullptr;
+    const double* pp = INIT ? A.L.p + (size_t)f * 19 : A.pdp + (size_t)f * 19;
+    const int xoff = ptr_parity(x), toff = tp ? ptr_parity(tp) : 0;
+    double firsty[4] = {0, 0, 0, 0}, spany[4] = {1, 1, 1, 1};
+    if (have) {
+      Trig tg;
+      make_trig(pp[16], pp[17], tg);
+      const double z = pp[18];
+#pragma unroll 1
+      for (int cp = 0; cp < 8; ++cp) {
+        double xb[3];
+        body_point(tg, pp[2 * cp], pp[2 * cp + 1], z, xb);
+        Csm[(3 * cp + 0) * kEvalThreads] = CPS_FX * (xb[1] + 0.5 * CPS_BASELINE) / xb[0] + CPS_CX;
+        Csm[(3 * cp + 1) * kEvalThreads] = CPS_FX * (xb[1] - 0.5 * CPS_BASELINE) / xb[0] + CPS_CX;
+        Csm[(3 * cp + 2) * kEvalThreads] = CPS_FY * (xb[2] / xb[0]) + CPS_CY;
+      }
+      if (derive_t) {
+        const int bnd[5] = {0, g.b1, g.b2, g.b3, g.nsamp};
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi)
+          if (bnd[sgi + 1] > bnd[sgi]) {
+            firsty[sgi] = x[2 * bnd[sgi] + 1];
+            spany[sgi] = x[2 * bnd[sgi + 1] - 1] - firsty[sgi];
+          }
+      }
+    }
+    const int nblk = (g.n + 31) >> 5;
+    const int full = (g.n >> 3) << 3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const double* xt = &wt->x[lane][xoff];
+    double* tt = &wt->t[lane][toff];
+    auto resid = [&](int s, double tval, double xu, double xv, double& eu, double& ev) {
+      const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
+      const int cb = 12 * (seg & 1), side = seg >> 1;
+      double w[4];
+      bernstein3(tval, w);
+      double au = 0.0, av = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        au += w[k] * Csm[(cb + 3 * k + side) * kEvalThreads];
+        av += w[k] * Csm[(cb + 3 * k + 2) * kEvalThreads];
+      }
+      eu = xu - au;
+      ev = xv - av;
+    };
+#pragma unroll 1
+    for (int b = nblk - 1; b >= 0; --b) {
+      row_fill(&wt->x[lane][0], xoff, x + 32 * b, min(32, g.n - 32 * b));
+      if (!derive_t) row_fill(&wt->t[lane][0], toff, tp + 16 * b, min(16, g.nsamp - 16 * b));
+      if (b > 0) {
+        prefetch_l2(x + 32 * (b - 1));
+        prefetch_l2(x + 32 * (b - 1) + 16);
+        if (!derive_t) prefetch_l2(tp + 16 * (b - 1));
+      }
+      cp_async_wait_all();
+      {
+        if (derive_t) {  // fit_curve:451-511
+          const int s_hi = min(16 * b + 16, g.nsamp);
+          for (int s = 16 * b; s < s_hi; ++s) {
+            const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
+            const double fy = seg == 0 ? firsty[0] : (seg == 1 ? firsty[1] : (seg == 2 ? firsty[2] : firsty[3]));
+            const double sy = seg == 0 ? spany[0] : (seg == 1 ? spany[1] : (seg == 2 ? spany[2] : spany[3]));
+            double v = (xt[2 * (s & 15) + 1] - fy) / sy;
+            v = (v < 0.0) ? 0.0 : v;
+            v = (v > 1.0) ? 1.0 : v;
+            tt[s & 15] = v;
+          }
+        }
+        const int g_hi = min(4 * b + 3, (full >> 3) - 1);
+#pragma unroll 1
+        for (int gq = g_hi; gq >= 4 * b; --gq) {
+          const int sa = 4 * gq, l = sa & 15;
+          double eu0, ev0, eu1, ev1, eu2, ev2, eu3, ev3;
+          resid(sa + 3, tt[l + 3], xt[2 * l + 6], xt[2 * l + 7], eu3, ev3);
+          resid(sa + 2, tt[l + 2], xt[2 * l + 4], xt[2 * l + 5], eu2, ev2);
+          resid(sa + 1, tt[l + 1], xt[2 * l + 2], xt[2 * l + 3], eu1, ev1);
+          resid(sa, tt[l], xt[2 * l], xt[2 * l + 1], eu0, ev0);
+          s0 += ev3 * ev3;
+          s1 += eu3 * eu3;
+          s2 += ev2 * ev2;
+          s3 += eu2 * eu2;
+          s0 += ev1 * ev1;
+          s1 += eu1 * eu1;
+          s2 += ev0 * ev0;
+          s3 += eu0 * eu0;
+        }
+      }
+      if (derive_t) {
+        double* tw = const_cast<double*>(tp) + 16 * b;
+        const int cnt = min(16, g.nsamp - 16 * b);
+        int i = 0;
+        for (; i + 2 <= cnt; i += 2) *reinterpret_cast<double2*>(tw + i) = make_double2(tt[i], tt[i + 1]);
+        if (i < cnt) tw[i] = tt[i];
+      }
+    }
+    int route = 0;  // 1: fd list, 2: upd list, 3: solve list
+    if (have) {
+      const int rem = g.n - full;
+      for (int k = 0; k < rem; k += 2) {
+        const int s = (full + k) >> 1;
+        double eu, ev;
+        resid(s, tp[s], x[2 * s], x[2 * s + 1], eu, ev);
+        const int cu = (7 - (rem - k)) & 3, cv = (7 - (rem - k - 1)) & 3;
+        const double du = eu * eu, dv = ev * ev;
+        if (cu == 0) s0 += du; else if (cu == 1) s1 += du; else if (cu == 2) s2 += du; else s3 += du;
+        if (cv == 0) s0 += dv; else if (cv == 1) s1 += dv; else if (cv == 2) s2 += dv; else s3 += dv;
+      }
+      const double e_new = ((s0 + s1) + s2) + s3;
+      DifScal* sp = A.scal + f;
+      if (INIT) {
+        DifScal s;
+        s.e0 = e_new; s.e_sq = e_new; s.g_inf = 0.0; s.dp_sq = DBL_MAX; s.mu = 0.0; s.p_sq = 0.0; s.maxdiag = 0.0;
+        s.dL = 0.0; s.pend_dp_sq = 1.0;
+        s.nu = 20;  // forces a Jacobian on the first pass, lm_core.c:555
+        s.k = 0; s.nfev = 1; s.njap = 0; s.nlss = 0; s.n_jtj = 0; s.n_broyden = 0;
+        s.updjac = 0; s.updp = 1; s.pend = 0; s.accepted = 0; s.pad = 0;
+        if (!isfinite(e_new)) { dif_finish(A, f, s, 7); }
+        else route = dif_loop_top(A, f, s);
+        *sp = s;
+      } else {
+        DifScal s = *sp;
+        s.nfev += 1;
+        if (!isfinite(e_new)) {  // lm_core.c:739-742
+          *sp = s;
+          dif_finish(A, f, s, 7);
+        } else {
+          const double dF = s.e_sq - e_new;
+          if (s.updp || dF > 0.0) {
+            // rank-one secant update (lm_core.c:745-755), deferred to the rebuild that always precedes the next solve:
+            // it needs p (f(p) = hx), p + dp (f = wrk), dp and ||dp||^2 of this iteration
+            double* po = A.pold + (size_t)f * 19;
+            const double* pc = A.L.p + (size_t)f * 19;
+#pragma unroll
+            for (int q = 0; q < 19; ++q) po[q] = pc[q];
+            s.pend = 1;
+            s.pend_dp_sq = s.dp_sq;
+            s.updjac += 1;
+            s.n_broyden += 1;
+          }
+          bool go_on = true;
+          if (s.dL > 0.0 && dF > 0.0) {
+            s.mu = nielsen(s.mu, dF, s.dL);
+            s.nu = 2;
+            double* pout = A.L.p + (size_t)f * 19;
+#pragma unroll
+            for (int q = 0; q < 19; ++q) pout[q] = pp[q];
+            s.e_sq = e_new;
+            s.updp = 1;
+            s.accepted = 1;
+          } else {
+            s.accepted = 0;
+            s.mu *= s.nu;
+            const int nu2 = (int)((unsigned)s.nu << 1);
+            if (nu2 <= s.nu) {
+              *sp = s;
+              dif_finish(A, f, s, 5);
+              go_on = false;
+            } else {
+              s.nu = nu2;
+            }
+          }
+          if (go_on) {
+            s.k += 1;
+            route = dif_loop_top(A, f, s);
+            *sp = s;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    staged_append(A.fd_list, A.cnt + 0, f, route == 1);
+    staged_append(A.upd_list, A.cnt + 1, f, route == 2);
+    staged_append(A.solve_list[nxt], A.cnt + 2 + nxt, f, route == 3);
+  }
+}
+
+// ---- solve: thread per fit ---------------------------------------------------------------------------------------
+// dlevmar_dif has no inner loop: a solve that fails (singular matrix) is a rejected step -- mu grows, k advances,
+// the loop top runs -- and unless that asks for a fresh Jacobian the same J^T J is solved again, here in place.
+__global__ void __launch_bounds__(kSolveThreads, 1) dif_solve_kernel(const DifArgs A, int cur) {
+  constexpr int M = 19, T = kSolveThreads;
+  extern __shared__ double smem[];
+  double* a = smem + threadIdx.x;
+  double* sc = smem + M * M * T + threadIdx.x;
+  double* bx = smem + (M * M + M) * T + threadIdx.x;
+  const unsigned int total = A.cnt[2 + cur];
+  for (unsigned int i = blockIdx.x * T + threadIdx.x; i < total; i += gridDim.x * T) {
+    const int f = A.solve_list[cur][i];
+    const double* lower = A.jtj + (size_t)f * kLower19;
+    const double* jte = A.jte + (size_t)f * M;
+    const double* pp = A.L.p + (size_t)f * M;
+    DifScal s = A.scal[f];
+    int out = -1;  // eval list entry
+    bool to_fd = false;
+    double dp[M];
+    for (;;) {
+      lu_fill_global19(a, bx, lower, jte, s.mu);
+      const int solved = lu_factor_solve<M, T>(a, sc, bx, dp);
+      s.nlss += 1;
+      if (solved) {
+        double dp_sq = 0.0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) dp_sq += dp[q] * dp[q];
+        s.dp_sq = dp_sq;
+        if (dp_sq <= A.L.eps2_sq * s.p_sq) { dif_finish(A, f, s, 2); break; }
+        if (dp_sq >= (s.p_sq + A.L.eps2) / (kEpsilon * kEpsilon)) { dif_finish(A, f, s, 4); break; }
+        double pv[M], gv[M];
+#pragma unroll
+        for (int q = 0; q < M; ++q) { pv[q] = pp[q]; gv[q] = jte[q]; }
+        double dL = 0.0;
+        double* pdp = A.pdp + (size_t)f * M;
+        double* dpo = A.dp + (size_t)f * M;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          pdp[q] = pv[q] + dp[q];
+          dpo[q] = dp[q];
+          dL += dp[q] * (s.mu * dp[q] + gv[q]);
+        }
+        s.dL = dL;
+        out = f;
+        break;
+      }
+      // rejected without a step, lm_core.c:783-792
+      s.mu *= s.nu;
+      const int nu2 = (int)((unsigned)s.nu << 1);
+      if (nu2 <= s.nu) { dif_finish(A, f, s, 5); break; }
+      s.nu = nu2;
+      s.k += 1;
+      const int route = dif_loop_top(A, f, s);
+      if (route == 0) break;
+      if (route == 1) { to_fd = true; break; }
+      // route 3 (nothing pending can exist here): solve the same matrix with the larger mu
+    }
+    A.scal[f] = s;
+    A.eval_list[i] = out;
+    if (to_fd) A.fd_list[atomicAdd(A.cnt + 0, 1u)] = f;
+  }
+}
+
+__global__ void dif_round_end_kernel(unsigned int* cnt, int nxt, volatile unsigned int* host) {
+  host[0] = cnt[2 + nxt];
+  host[1] = cnt[0];
+  host[2] = cnt[1];
+  __threadfence_system();
+}
+
+// ---- build: four warps x 32 fits -----------------------------------------------------------------------------------
+// Entry quarters (lower triangle, (i, j) with j <= i; QA..QD are compile-time so that every sum is a register):
+//   warp 0: i, j in 0..9                       55 entries
+//   warp 1: i, j in 10..18                     45 entries + the J^T e chains of columns 10..18
+//   warp 2: i in 10..18, j in 0..4             45 entries + the J^T e chains of columns 0..4
+//   warp 3: i in 10..18, j in 5..9             45 entries + the J^T e chains of columns 5..9
+struct DifQuarter {
+  double part[55];
+  double jte[9];
+};
+
+template <int Q>
+__device__ __forceinline__ void dif_accumulate(const double* row, DifQuarter& S) {
+  // row: this fit's staged row, [0..18] Jacobian, [20] residual; reads are 16-byte (two entries at a time)
+  if (Q == 0) {
+    double v[10];
+#pragma unroll
+    for (int c = 0; c < 10; c += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(row + c);
+      v[c] = t.x; v[c + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) S.part[i * (i + 1) / 2 + j] += v[i] * v[j];
+  } else if (Q == 1) {
+    double v[10];  // columns 10..19 (19 is padding)
+#pragma unroll
+    for (int c = 0; c < 10; c += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(row + 10 + c);
+      v[c] = t.x; v[c + 1] = t.y;
+    }
+    const double e = row[20];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) S.part[i * (i + 1) / 2 + j] += v[i] * v[j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S.jte[i] += v[i] * e;
+  } else {
+    constexpr int c0 = (Q == 2) ? 0 : 5;
+    double hi[10], lo[6];
+#pragma unroll
+    for (int c = 0; c < 10; c += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(row + 10 + c);
+      hi[c] = t.x; hi[c + 1] = t.y;
+    }
+    // columns c0..c0+4 out of three aligned pairs
+    constexpr int a0 = c0 & ~1;
+#pragma unroll
+    for (int c = 0; c < 6; c += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(row + a0 + c);
+      lo[c] = t.x; lo[c + 1] = t.y;
+    }
+    const double e = row[20];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) S.part[5 * i + j] += hi[i] * lo[c0 - a0 + j];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) S.jte[j] += lo[c0 - a0 + j] * e;
+  }
+}
+
+// slot of entry q of quarter Q in the running-sum work area (= index in the row-major lower triangle)
+template <int Q>
+__device__ __forceinline__ constexpr int dif_slot(int q) {
+  if (Q == 0) return q;  // tri(i, j) for i, j < 10 is the first 55 of the row-major lower triangle
+  return -1;
+}
+
+template <int Q>
+__device__ __forceinline__ void dif_fold(double* ws, size_t wsn, DifQuarter& S) {
+  if (Q == 0) {
+#pragma unroll
+    for (int q = 0; q < 55; ++q) { red_add_f64(ws + (size_t)q * wsn, S.part[q]); S.part[q] = 0.0; }
+  } else if (Q == 1) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        red_add_f64(ws + (size_t)tri(10 + i, 10 + j) * wsn, S.part[i * (i + 1) / 2 + j]);
+        S.part[i * (i + 1) / 2 + j] = 0.0;
+      }
+  } else {
+    constexpr int c0 = (Q == 2) ? 0 : 5;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        red_add_f64(ws + (size_t)tri(10 + i, c0 + j) * wsn, S.part[5 * i + j]);
+        S.part[5 * i + j] = 0.0;
+      }
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void dif_store_jte(double* ws, size_t wsn, const DifQuarter& S) {
+  if (Q == 1) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) __stcg(ws + (size_t)(kLower19 + 10 + i) * wsn, S.jte[i]);
+  } else if (Q >= 2) {
+    constexpr int c0 = (Q == 2) ? 0 : 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) __stcg(ws + (size_t)(kLower19 + c0 + j) * wsn, S.jte[j]);
+  }
+}
+
+// projected control points of a parameter vector: tab[(3*cp + {uL, uR, v}) * 32] (this fit's column of a [.][32] table)
+__device__ __forceinline__ void dif_project_all(const double* pp, double* tab) {
+  Trig tg;
+  make_trig(pp[16], pp[17], tg);
+  const double z = pp[18];
+#pragma unroll 1
+  for (int cp = 0; cp < 8; ++cp) {
+    double xb[3];
+    body_point(tg, pp[2 * cp], pp[2 * cp + 1], z, xb);
+    tab[(3 * cp + 0) * kDifFits] = CPS_FX * (xb[1] + 0.5 * CPS_BASELINE) / xb[0] + CPS_CX;
+    tab[(3 * cp + 1) * kDifFits] = CPS_FX * (xb[1] - 0.5 * CPS_BASELINE) / xb[0] + CPS_CX;
+    tab[(3 * cp + 2) * kDifFits] = CPS_FY * (xb[2] / xb[0]) + CPS_CY;
+  }
+}
+
+__device__ __forceinline__ void dif_project_one(const Trig& tg, double xe, double ye, double z, double* out3) {
+  double xb[3];
+  body_point(tg, xe, ye, z, xb);
+  out3[0 * kDifFits] = CPS_FX * (xb[1] + 0.5 * CPS_BASELINE) / xb[0] + CPS_CX;
+  out3[1 * kDifFits] = CPS_FX * (xb[1] - 0.5 * CPS_BASELINE) / xb[0] + CPS_CX;
+  out3[2 * kDifFits] = CPS_FY * (xb[2] / xb[0]) + CPS_CY;
+}
+
+// Shared-memory tables per fit, [entry][32 fits]:
+//   update build: 0..23 control points of p_old (f = hx), 24..47 of p + dp (f = wrk), 48..66 dp
+//   FD build:     0..23 control points of p, 24..71 the perturbed control point of columns 0..15 (3 values each),
+//                 72..143 all control points for theta+d, phi+d, z+d, 144..162 1/d
+constexpr int kDifTabUpd = 67;
+constexpr int kDifTabFd = 163;
+
+template <bool FD>
+constexpr int dif_build_smem_doubles() {
+  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * 4 * kDifFits * kDifStageRow + 2 * kDifFits;
+}
+
+// one model value: sum_k w_k * tab[(12*curve + 3k + sel) * 32], ascending k from 0.0 like closest_bezier_pt(cp, t, ..)
+__device__ __forceinline__ double dif_bez(const double (&w)[4], const double* tab, int cb_sel) {
+  double a = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a += w[k] * tab[(cb_sel + 3 * k) * kDifFits];
+  return a;
+}
+
+template <bool FD>
+__global__ void __launch_bounds__(kDifThreads, FD ? 2 : 2) dif_build_kernel(const DifArgs A, int nxt) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NTAB = FD ? kDifTabFd : kDifTabUpd;
+  constexpr int NBUF = FD ? 1 : 2;
+  double* tab = smem + lane;                                   // tab[entry * 32]
+  double* stage = smem + NTAB * kDifFits;                       // [NBUF][4][32][22]
+  long long* jbase = reinterpret_cast<long long*>(stage + NBUF * 4 * kDifFits * kDifStageRow);  // [32] row-0 offsets
+  int* nrows = reinterpret_cast<int*>(jbase + kDifFits);        // [32] n of each fit (0: no fit)
+  const size_t wsn = (size_t)A.ws_stride;
+  const unsigned int total = A.cnt[FD ? 0 : 1];
+  const int* list = FD ? A.fd_list : A.upd_list;
+  for (unsigned int base = blockIdx.x * kDifFits; base < total; base += gridDim.x * kDifFits) {
+    const unsigned int item = base + lane;
+    const bool have = item < total;
+    const int f = have ? list[item] : 0;
+    FitGeom g;
+    g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;
+    long long o0 = 0;
+    if (have) dif_geom(A, f, g, o0);
+    const double* x = A.L.meas + o0;
+    const double* tp = have ? dif_t(A, f, o0) : nullptr;
+    const double* pc = A.L.p + (size_t)f * 19;
+    double* Jf = A.J + (size_t)f * A.j_stride;
+    double* ws = A.ws + (size_t)blockIdx.x * kDifFits + lane;
+    const bool blocked = !(g.n * 19 <= kBlockSzSq);  // "<=" here, lm_core.c:585
+    DifScal sc;
+    if (have && wid == 0) sc = A.scal[f];
+    const bool accepted = have ? (A.scal[f].accepted != 0) : false;
+    const double pend_dp_sq = have ? A.scal[f].pend_dp_sq : 1.0;
+    __syncthreads();  // the previous group's tables and stage are no longer read
+    if (wid == 0) {
+      jbase[lane] = (long long)((size_t)f * A.j_stride);
+      nrows[lane] = g.n;
+    }
+    // ---- per-fit tables, spread over the four warps
+    if (have) {
+      if (!FD) {
+        if (wid == 0) dif_project_all(A.pold + (size_t)f * 19, tab);
+        if (wid == 1) dif_project_all(A.pdp + (size_t)f * 19, tab + 24 * kDifFits);
+        if (wid == 2) {
+          const double* dpp = A.dp + (size_t)f * 19;
+#pragma unroll 1
+          for (int q = 0; q < 19; ++q) tab[(48 + q) * kDifFits] = dpp[q];
+        }
+      } else {
+        // forward differences, misc_core.c:135-170: d = max(1e-4 |p_j|, delta); column j evaluated at p + d e_j
+        auto delta_of = [&](int j) {
+          double d = 1E-04 * pc[j];
+          d = fabs(d);
+          if (d < A.L.delta) d = A.L.delta;
+          return d;
+        };
+        if (wid == 0) {
+          dif_project_all(pc, tab);
+#pragma unroll 1
+          for (int j = 0; j < 19; ++j) tab[(144 + j) * kDifFits] = 1.0 / delta_of(j);
+        } else if (wid == 1) {  // control-point columns: only that control point moves; theta, phi (the trig) do not
+          Trig tg;
+          make_trig(pc[16], pc[17], tg);
+          const double z = pc[18];
+#pragma unroll 1
+          for (int j = 0; j < 16; ++j) {
+            const int cp = j >> 1;
+            double xe = pc[2 * cp], ye = pc[2 * cp + 1];
+            const double d = delta_of(j);
+            if (j & 1) ye = ye + d; else xe = xe + d;
+            dif_project_one(tg, xe, ye, z, tab + (24 + 3 * j) * kDifFits);
+          }
+        } else {  // theta + d | phi + d (warp 2), z + d (warp 3)
+          for (int q = (wid == 2 ? 0 : 2); q < (wid == 2 ? 2 : 3); ++q) {
+            double pw[19];
+#pragma unroll
+            for (int i = 0; i < 19; ++i) pw[i] = pc[i];
+            pw[16 + q] = pw[16 + q] + delta_of(16 + q);
+            dif_project_all(pw, tab + (72 + 24 * q) * kDifFits);
+          }
+        }
+      }
+    }
+    // running sums start at zero (every warp its own entries)
+    DifQuarter S;
+#pragma unroll
+    for (int q = 0; q < 55; ++q) S.part[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) S.jte[q] = 0.0;
+    if (wid == 0) {
+#pragma unroll 1
+      for (int q = 0; q < 55; ++q) __stcg(ws + (size_t)q * wsn, 0.0);
+    } else if (wid == 1) {
+#pragma unroll 1
+      for (int i = 0; i < 9; ++i)
+        for (int j = 0; j <= i; ++j) __stcg(ws + (size_t)tri(10 + i, 10 + j) * wsn, 0.0);
+    } else {
+      const int c0 = (wid == 2) ? 0 : 5;
+#pragma unroll 1
+      for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 5; ++j) __stcg(ws + (size_t)tri(10 + i, c0 + j) * wsn, 0.0);
+    }
+    __syncthreads();
+    int nmax = 0;
+    for (int q = 0; q < kDifFits; ++q) nmax = max(nmax, nrows[q]);
+    const int nsteps = (nmax + 3) >> 2;
+
+    // cooperative, coalesced copy of the four stored rows of step `st` of all 32 fits into stage buffer `buf`
+    auto issue_rows = [&](int st, int buf) {
+      if (FD) return;
+      double* sb = stage + (size_t)buf * 4 * kDifFits * kDifStageRow;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int q = i * kDifThreads + tid;           // 0..1279: (row-in-step, fit, 16-byte piece)
+        const int rr = q / 320, rem = q - rr * 320;
+        const int fi = rem / 10, piece = rem - fi * 10;
+        const int r = 4 * st + rr;
+        const bool ok = r < nrows[fi];
+        const double* src = A.J + jbase[fi] + (size_t)(ok ? r : 0) * kDifRow + 2 * piece;
+        const unsigned int d = (unsigned int)__cvta_generic_to_shared(sb + (rr * kDifFits + fi) * kDifStageRow + 2 * piece);
+        const int nbytes = ok ? 16 : 0;  // zero-fill rows past the end of a fit
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // the unblocked small-problem loop walks the rows downwards (lm_core.c:604-628); a CTA whose fits are all
+    // blocked walks upwards.  Mixed CTAs (rare: fits with fewer than 27 samples) run both directions, each fit
+    // taking part in its own.
+    bool any_blocked = false, any_small = false;
+    for (int q = 0; q < kDifFits; ++q) {
+      if (nrows[q] > 0) {
+        if (nrows[q] * 19 <= kBlockSzSq) any_small = true; else any_blocked = true;
+      }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool down = pass == 1;
+      if (down ? !any_small : !any_blocked) continue;
+      const bool mine = have && (blocked != down);
+      const int n_eff = mine ? g.n : 0;  // rows of this fit that take part in this pass
+      if (!FD) issue_rows(down ? nsteps - 1 : 0, 0);
+      for (int it = 0; it < nsteps; ++it) {
+        const int st = down ? nsteps - 1 - it : it;
+        const int buf = FD ? 0 : (it & 1);
+        double* sb = stage + (size_t)buf * 4 * kDifFits * kDifStageRow;
+        if (!FD) {
+          if (it + 1 < nsteps) {
+            issue_rows(down ? st - 1 : st + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+          } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+          }
+          __syncthreads();
+        }
+        // ---- produce row r = 4 st + wid of this lane's fit
+        {
+          const int r = 4 * st + wid;
+          double* row = sb + (wid * kDifFits + lane) * kDifStageRow;
+          if (r < n_eff) {
+            const int s = r >> 1, uv = r & 1;
+            const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
+            const int curve = seg & 1, side = seg >> 1;
+            const int cb_sel = 12 * curve + (uv ? 2 : side);
+            double w[4];
+            bernstein3(tp[s], w);
+            const double xr = x[r];
+            double jr[kDifRow];
+            if (FD) {
+              const double hx = dif_bez(w, tab, cb_sel);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int cp = j >> 1;
+                double hxx = hx;
+                if ((cp >> 2) == curve) {  // the perturbed control point belongs to this row's curve
+                  const int kk = cp & 3;
+                  double a = 0.0;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const double c = (k == kk) ? tab[(24 + 3 * j + (uv ? 2 : side)) * kDifFits]
+                                               : tab[(cb_sel + 3 * k) * kDifFits];
+                    a += w[k] * c;
+                  }
+                  hxx = a;
+                }
+                jr[j] = (hxx - hx) * tab[(144 + j) * kDifFits];
+              }
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const double hxx = dif_bez(w, tab + (72 + 24 * q) * kDifFits, cb_sel);
+                jr[16 + q] = (hxx - hx) * tab[(160 + q) * kDifFits];
+              }
+              jr[19] = 0.0;
+              row[20] = xr - hx;
+            } else {
+#pragma unroll
+              for (int c = 0; c < kDifRow; c += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(row + c);
+                jr[c] = t2.x; jr[c + 1] = t2.y;
+              }
+              const double hx = dif_bez(w, tab, cb_sel);
+              const double wrk = dif_bez(w, tab + 24 * kDifFits, cb_sel);
+              double tmp = 0.0;
+#pragma unroll
+              for (int l = 0; l < 19; ++l) tmp += jr[l] * tab[(48 + l) * kDifFits];
+              tmp = ((wrk - hx) - tmp) / pend_dp_sq;
+#pragma unroll
+              for (int j = 0; j < 19; ++j) jr[j] += tmp * tab[(48 + j) * kDifFits];
+              jr[19] = 0.0;
+              row[20] = xr - (accepted ? wrk : hx);
+            }
+#pragma unroll
+            for (int c = 0; c < kDifRow; c += 2) {
+              *reinterpret_cast<double2*>(row + c) = make_double2(jr[c], jr[c + 1]);
+              __stcg(reinterpret_cast<double2*>(Jf + (size_t)r * kDifRow + c), make_double2(jr[c], jr[c + 1]));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < kDifStageRow; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(0.0, 0.0);
+          }
+        }
+        __syncthreads();
+        // ---- every warp: its quarter of the sums over the four rows, in the pass's row order
+#pragma unroll 1
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int rr = down ? 3 - q4 : q4;
+          const double* row = sb + (rr * kDifFits + lane) * kDifStageRow;
+          if (wid == 0) dif_accumulate<0>(row, S);
+          else if (wid == 1) dif_accumulate<1>(row, S);
+          else if (wid == 2) dif_accumulate<2>(row, S);
+          else dif_accumulate<3>(row, S);
+        }
+        // end of a 32-row block (blocked pass) or of the fit: the partial sums join the running entries
+        const bool fold = down ? (it == nsteps - 1) : ((st & 7) == 7 || it == nsteps - 1);
+        if (fold) {
+          if (wid == 0) dif_fold<0>(ws, wsn, S);
+          else if (wid == 1) dif_fold<1>(ws, wsn, S);
+          else if (wid == 2) dif_fold<2>(ws, wsn, S);
+          else dif_fold<3>(ws, wsn, S);
+        }
+        __syncthreads();  // the stage buffer may be refilled (FD: rewritten) from here on
+      }
+    }
+    if (wid == 1) dif_store_jte<1>(ws, wsn, S);
+    else if (wid == 2) dif_store_jte<2>(ws, wsn, S);
+    else if (wid == 3) dif_store_jte<3>(ws, wsn, S);
+    __threadfence();
+    __syncthreads();
+    // ---- publish J^T J / J^T e, gradient statistics, stop 1, initial mu (lm_core.c:657-678)
+    bool to_solve = false;
+    if (have) {
+      double* Jout = A.jtj + (size_t)f * kLower19;
+      double* Jte = A.jte + (size_t)f * 19;
+      // the lower triangle in four slices of rows, one per warp
+      const int i_lo = wid == 0 ? 0 : (wid == 1 ? 10 : (wid == 2 ? 14 : 17));
+      const int i_hi = wid == 0 ? 10 : (wid == 1 ? 14 : (wid == 2 ? 17 : 19));
+#pragma unroll 1
+      for (int q = tri(i_lo, 0); q < tri(i_hi, 0); ++q) Jout[q] = __ldcg(ws + (size_t)q * wsn);
+      if (wid == 0) {
+        // columns 0..9 of J^T e belong to warps 2 / 3, 10..18 to warp 1: all in the work area by now
+        double p_sq = 0.0, g_inf = 0.0, big = -DBL_MAX;
+#pragma unroll 1
+        for (int q = 0; q < 19; ++q) {
+          const double v = __ldcg(ws + (size_t)(kLower19 + q) * wsn);
+          Jte[q] = v;
+          const double tmp = fabs(v);
+          if (g_inf < tmp) g_inf = tmp;
+          p_sq += pc[q] * pc[q];
+          const double d = __ldcg(ws + (size_t)tri(q, q) * wsn);
+          if (d > big) big = d;
+        }
+        sc.n_jtj += 1;
+        sc.pend = 0;
+        sc.g_inf = g_inf;
+        sc.p_sq = p_sq;
+        sc.maxdiag = big;
+        if (g_inf <= A.L.eps1) {
+          sc.dp_sq = 0.0;
+          A.scal[f] = sc;
+          dif_finish(A, f, sc, 1);
+        } else {
+          if (sc.k == 0) sc.mu = A.L.tau * big;
+          A.scal[f] = sc;
+          to_solve = true;
+        }
+      }
+    }
+    if (wid == 0) {
+      __syncwarp();
+      staged_append(A.solve_list[nxt], A.cnt + 2 + nxt, f, to_solve);
+    }
+  }
+}
+
+}  // namespace cps
