@@ -9,6 +9,7 @@
 #include "../../include/cps_lm.h"
 #include "cps_common.h"
 #include "cps_lm_kernel.cuh"
+#include <cstdio>
 #include "cps_lm_staged.cuh"
 #include "cps_lm_dif_staged.cuh"
 #include "cps_lm_image8.cuh"
@@ -32,6 +33,8 @@ struct cps_lm_slot {
   char* d_staged = nullptr;
   size_t staged_bytes = 0;
   unsigned int* h_count = nullptr;  // pinned: the number of fits that go into the next round
+  cudaStream_t side = nullptr;      // staged dif: the finite-difference builds run beside the update builds
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 constexpr int kSlots = 2;
@@ -104,6 +107,9 @@ extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
     cudaFree(s.d_stage);
     cudaFree(s.d_staged);
     if (s.h_count) cudaFreeHost(s.h_count);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.side) cudaStreamDestroy(s.side);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -466,7 +472,7 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
     return CPS_ERR_CUDA;
   }
   const int build_grid_max = c->sm_count * std::max(fd_occ, upd_occ);
-  const int ws_stride = build_grid_max * kDifFits;
+  const int ws_stride = 2 * build_grid_max * kDifFits;  // update kernel's CTAs | finite-difference kernel's CTAs
   const size_t j_stride = (size_t)L.n_max * kDifRow;
   size_t o = 0;
   const size_t o_scal = o; o = a256(o + sizeof(DifScal) * B);
@@ -552,19 +558,32 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
     spans.clear();
     ev_used = 0;
   };
+  if (!sl.side) {
+    CPS_CUDA(cudaStreamCreateWithFlags(&sl.side, cudaStreamNonBlocking));
+    CPS_CUDA(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+    CPS_CUDA(cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming));
+  }
+  // The two build kernels work on disjoint fits (and disjoint halves of the work area): the finite-difference one,
+  // usually a few thousand fits -- one partial wave -- runs on a side stream beside the update kernel.
   auto builds = [&](size_t n_fd, size_t n_upd, int nxt) {
+    const bool fork = n_fd > 0 && n_upd > 0;
+    span_begin(2);
     if (n_fd > 0) {
-      span_begin(2);
-      dif_build_kernel<true><<<grid_for(n_fd, kDifFits, c->sm_count * fd_occ), kDifThreads, fd_smem, st>>>(A, nxt);
-      span_end();
+      cudaStream_t s2 = fork ? sl.side : st;
+      if (fork) {
+        cudaEventRecord(sl.ev_fork, st);
+        cudaStreamWaitEvent(sl.side, sl.ev_fork, 0);
+      }
+      dif_build_kernel<true><<<grid_for(n_fd, kDifFits, c->sm_count * fd_occ), kDifThreads, fd_smem, s2>>>(A, nxt);
+      if (fork) cudaEventRecord(sl.ev_join, sl.side);
       c->launches += 1;
     }
     if (n_upd > 0) {
-      span_begin(2);
       dif_build_kernel<false><<<grid_for(n_upd, kDifFits, c->sm_count * upd_occ), kDifThreads, upd_smem, st>>>(A, nxt);
-      span_end();
       c->launches += 1;
     }
+    if (fork) cudaStreamWaitEvent(st, sl.ev_join, 0);
+    span_end();
   };
   CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 4, st));
   // iteration 0: validation, t, e0, loop top; every surviving fit needs its first finite-difference Jacobian
@@ -582,6 +601,8 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
   size_t n_solve = sl.h_count[0];
   size_t last_fd = sl.h_count[1], last_upd = sl.h_count[2];
   long long n_builds = (long long)last_fd;
+  const bool trace = std::getenv("CPS_DIF_TRACE") != nullptr;
+  double tr[3] = {c->prof_ms[0], c->prof_ms[1], c->prof_ms[2]};
   while (n_solve > 0) {
     const int nxt = cur ^ 1;
     CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int) * 2, st));
@@ -595,9 +616,8 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
     c->launches += 2;
     // the kernels read the real list lengths on the device; the grids follow an upper bound (a block without work
     // leaves at once): at most every solved fit needs a build
-    (void)last_fd;
     (void)last_upd;
-    builds(n_solve, n_solve, nxt);
+    builds(std::min(n_solve, std::max<size_t>(2 * last_fd + 4096, n_solve / 8)), n_solve, nxt);
     dif_round_end_kernel<<<1, 1, 0, st>>>(A.cnt, nxt, sl.h_count);
     c->launches += 1;
     CPS_CUDA(cudaGetLastError());
@@ -609,6 +629,10 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
     n_builds += (long long)(last_fd + last_upd);
     cur = nxt;
     ++rounds;
+    if (trace)
+      std::fprintf(stderr, "dif round %d: fd %zu upd %zu -> solve %zu; ms solve %.3f eval %.3f build %.3f\n", rounds, last_fd,
+                   last_upd, n_solve, c->prof_ms[0] - tr[0], c->prof_ms[1] - tr[1], c->prof_ms[2] - tr[2]);
+    for (int q = 0; q < 3; ++q) tr[q] = c->prof_ms[q];
   }
   c->last_grid = build_grid_max;
   c->last_block = kDifThreads;

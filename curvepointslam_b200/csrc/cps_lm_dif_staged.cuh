@@ -14,11 +14,11 @@
 //          Jacobian (misc_core.c:135-170) evaluated row by row, or the stored rows with the pending rank-one
 //          update applied; the rows are written back once                                      :569-655, 745-755
 //
-// build kernel shape: a CTA of four warps owns 32 fits (lane = fit).  Rows are walked four at a time: warp w
-// produces row 4b + w of each of its 32 fits (model values, the 19-term dot product of the update, the corrected
-// row) into a shared-memory stage, then every warp accumulates ITS QUARTER OF THE 190 + 19 SUMS over the four rows
-// (quarters: the triangle of columns 0..9, the triangle of columns 10..18, and the two halves of the 9 x 10
-// rectangle between them), statically unrolled into registers.  The reference's summation orders are loop orders
+// build kernel shape: a CTA of eight warps owns 32 fits (lane = fit).  Rows are walked eight at a time: warp w
+// produces row 8b + w of each of its 32 fits (model values, the 19-term dot product of the update, the corrected
+// row) into a shared-memory stage, then every warp accumulates ITS EIGHTH OF THE 190 + 19 SUMS over the eight rows
+// (the lower triangle cut into 5 triangles and 10 rectangles along column groups of four, two per warp), statically
+// unrolled into registers.  The reference's summation orders are loop orders
 // here: per-entry partial sums over 32-row blocks joined in ascending block order (misc_core.c:101-126; joined by
 // red.global.add.f64 at the L2 like the der path), J^T e one chain per column over ascending rows, the unblocked
 // descending loop when n*m <= 1024 (lm_core.c:585, "<=" in dif).  Bit-identical to the warp-per-fit kernel and to the
@@ -38,7 +38,7 @@ constexpr int kDifRow = 20;          // doubles per stored Jacobian row (19 + 1:
 constexpr int kDifStageRow = 22;     // shared-memory pitch of a staged row: 11 x 16 B (odd: LDS.128 of a quarter-warp
                                      // hit distinct 16-byte slots); [0..18] J, [20] residual
 constexpr int kDifFits = 32;         // fits per CTA of the build kernels
-constexpr int kDifThreads = 128;     // four warps
+constexpr int kDifThreads = 256;     // eight warps
 constexpr int kDifSums = kLower19 + 19;  // running sums of a fit in the L2 work area: 190 J^T J entries, 19 J^T e
 
 struct DifArgs {
@@ -52,7 +52,8 @@ struct DifArgs {
   double* tws;          // [B][n_max/2] t when the caller passes none
   double* J;            // [B][j_rows][20] stored secant Jacobians
   size_t j_stride;      // doubles per fit in J
-  double* ws;           // [kDifSums][ws_stride] running sums of the resident fits
+  double* ws;           // [kDifSums][ws_stride] running sums of the resident fits: first half of a row the update
+                        // kernel's CTAs, second half the finite-difference kernel's (they may run concurrently)
   int ws_stride;
   int* fd_list;         // fits whose next build evaluates a finite-difference Jacobian
   int* upd_list;        // fits whose next build applies a pending secant update
@@ -392,112 +393,92 @@ __global__ void dif_round_end_kernel(unsigned int* cnt, int nxt, volatile unsign
   __threadfence_system();
 }
 
-// ---- build: four warps x 32 fits -----------------------------------------------------------------------------------
-// Entry quarters (lower triangle, (i, j) with j <= i; QA..QD are compile-time so that every sum is a register):
-//   warp 0: i, j in 0..9                       55 entries
-//   warp 1: i, j in 10..18                     45 entries + the J^T e chains of columns 10..18
-//   warp 2: i in 10..18, j in 0..4             45 entries + the J^T e chains of columns 0..4
-//   warp 3: i in 10..18, j in 5..9             45 entries + the J^T e chains of columns 5..9
-struct DifQuarter {
-  double part[55];
-  double jte[9];
+// ---- build: eight warps x 32 fits ----------------------------------------------------------------------------------
+// The (zero-padded) 20 x 20 matrix is cut into 4 x 4 blocks; the 15 blocks of its lower triangle are dealt two to a
+// warp, the five 4-column groups of J^T e one to each of warps 0..4.  Every warp runs THE SAME instruction stream on
+// its own blocks (block coordinates are warp-uniform run-time values, the 36 sums of a thread compile-time
+// registers): one copy of the code for eight roles -- role-specialised copies of the sweep overflowed the
+// instruction cache (measured: "no instruction" was the top stall reason).  A diagonal block is computed in full
+// (its upper half is never stored); products with the padding column 19 are exact zeros.
+constexpr int kDifWarps = 8;
+constexpr int kDifSumsPerWarp = 36;  // 16 + 16 + 4
+
+struct DifRole {
+  int r0, c0, r1, c1;  // first column of the row / column group of block 0 and block 1
+  int jc;              // first column of the J^T e group
+  bool has1, hasj;     // block 1 / the J^T e group are real (otherwise computed and dropped)
+};
+__device__ __forceinline__ DifRole dif_role(int w) {
+  // pairs (R, C) in units of four columns: (1,0)(1,1) (2,0)(2,1) (3,0)(3,1) (3,2)(3,3) (4,0)(4,1) (4,2)(4,3) (0,0)(2,2) (4,4)-
+  const int R0 = w == 0 ? 1 : (w == 1 ? 2 : (w <= 3 ? 3 : (w <= 5 ? 4 : (w == 6 ? 0 : 4))));
+  const int C0 = (w == 3 || w == 5) ? 2 : (w == 7 ? 4 : 0);
+  const int R1 = w == 6 ? 2 : R0;
+  const int C1 = w == 6 ? 2 : (w == 7 ? 4 : C0 + 1);
+  DifRole r;
+  r.r0 = 4 * R0; r.c0 = 4 * C0; r.r1 = 4 * R1; r.c1 = 4 * C1;
+  r.has1 = w != 7;
+  r.hasj = w < 5;
+  r.jc = r.hasj ? 4 * w : 0;
+  return r;
+}
+
+struct DifSums {
+  double sum[kDifSumsPerWarp];  // [block 0: 4 x 4 | block 1: 4 x 4 | J^T e: 4]
 };
 
-template <int Q>
-__device__ __forceinline__ void dif_accumulate(const double* row, DifQuarter& S) {
-  // row: this fit's staged row, [0..18] Jacobian, [20] residual; reads are 16-byte (two entries at a time)
-  if (Q == 0) {
-    double v[10];
-#pragma unroll
-    for (int c = 0; c < 10; c += 2) {
-      const double2 t = *reinterpret_cast<const double2*>(row + c);
-      v[c] = t.x; v[c + 1] = t.y;
-    }
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) S.part[i * (i + 1) / 2 + j] += v[i] * v[j];
-  } else if (Q == 1) {
-    double v[10];  // columns 10..19 (19 is padding)
-#pragma unroll
-    for (int c = 0; c < 10; c += 2) {
-      const double2 t = *reinterpret_cast<const double2*>(row + 10 + c);
-      v[c] = t.x; v[c + 1] = t.y;
-    }
-    const double e = row[20];
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) S.part[i * (i + 1) / 2 + j] += v[i] * v[j];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) S.jte[i] += v[i] * e;
-  } else {
-    constexpr int c0 = (Q == 2) ? 0 : 5;
-    double hi[10], lo[6];
-#pragma unroll
-    for (int c = 0; c < 10; c += 2) {
-      const double2 t = *reinterpret_cast<const double2*>(row + 10 + c);
-      hi[c] = t.x; hi[c + 1] = t.y;
-    }
-    // columns c0..c0+4 out of three aligned pairs
-    constexpr int a0 = c0 & ~1;
-#pragma unroll
-    for (int c = 0; c < 6; c += 2) {
-      const double2 t = *reinterpret_cast<const double2*>(row + a0 + c);
-      lo[c] = t.x; lo[c + 1] = t.y;
-    }
-    const double e = row[20];
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-#pragma unroll
-      for (int j = 0; j < 5; ++j) S.part[5 * i + j] += hi[i] * lo[c0 - a0 + j];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) S.jte[j] += lo[c0 - a0 + j] * e;
-  }
+__device__ __forceinline__ void dif_load4(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-// slot of entry q of quarter Q in the running-sum work area (= index in the row-major lower triangle)
-template <int Q>
-__device__ __forceinline__ constexpr int dif_slot(int q) {
-  if (Q == 0) return q;  // tri(i, j) for i, j < 10 is the first 55 of the row-major lower triangle
-  return -1;
+__device__ __forceinline__ void dif_accumulate(const double* row, const DifRole& R, DifSums& S) {
+  // row: this fit's staged row, [0..18] Jacobian, [19] zero, [20] residual
+  double vr[4], vc[4];
+  dif_load4(row + R.r0, vr);
+  dif_load4(row + R.c0, vc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S.sum[4 * i + j] += vr[i] * vc[j];
+  if (R.r1 != R.r0) dif_load4(row + R.r1, vr);  // warp-uniform: six of the eight pairs share their row group
+  dif_load4(row + R.c1, vc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S.sum[16 + 4 * i + j] += vr[i] * vc[j];
+  dif_load4(row + R.jc, vc);
+  const double e = row[20];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) S.sum[32 + j] += vc[j] * e;
 }
 
-template <int Q>
-__device__ __forceinline__ void dif_fold(double* ws, size_t wsn, DifQuarter& S) {
-  if (Q == 0) {
+// the partial sums of a 32-row block join the running entries (ZERO: the running entries are cleared instead)
+template <bool ZERO>
+__device__ __forceinline__ void dif_fold(double* ws, size_t wsn, const DifRole& R, DifSums& S) {
 #pragma unroll
-    for (int q = 0; q < 55; ++q) { red_add_f64(ws + (size_t)q * wsn, S.part[q]); S.part[q] = 0.0; }
-  } else if (Q == 1) {
+  for (int b = 0; b < 2; ++b) {
+    const int r0 = b ? R.r1 : R.r0, c0 = b ? R.c1 : R.c0;
+    const bool real = b ? R.has1 : true;
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        red_add_f64(ws + (size_t)tri(10 + i, 10 + j) * wsn, S.part[i * (i + 1) / 2 + j]);
-        S.part[i * (i + 1) / 2 + j] = 0.0;
-      }
-  } else {
-    constexpr int c0 = (Q == 2) ? 0 : 5;
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        red_add_f64(ws + (size_t)tri(10 + i, c0 + j) * wsn, S.part[5 * i + j]);
-        S.part[5 * i + j] = 0.0;
+      for (int j = 0; j < 4; ++j) {
+        const int gi = r0 + i, gj = c0 + j;
+        if (real && gi < 19 && gj <= gi) {
+          double* slot = ws + (size_t)tri(gi, gj) * wsn;
+          if (ZERO) __stcg(slot, 0.0);
+          else red_add_f64(slot, S.sum[16 * b + 4 * i + j]);
+        }
+        if (!ZERO) S.sum[16 * b + 4 * i + j] = 0.0;
       }
   }
 }
 
-template <int Q>
-__device__ __forceinline__ void dif_store_jte(double* ws, size_t wsn, const DifQuarter& S) {
-  if (Q == 1) {
+__device__ __forceinline__ void dif_store_jte(double* ws, size_t wsn, const DifRole& R, const DifSums& S) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) __stcg(ws + (size_t)(kLower19 + 10 + i) * wsn, S.jte[i]);
-  } else if (Q >= 2) {
-    constexpr int c0 = (Q == 2) ? 0 : 5;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) __stcg(ws + (size_t)(kLower19 + c0 + j) * wsn, S.jte[j]);
-  }
+  for (int j = 0; j < 4; ++j)
+    if (R.hasj && R.jc + j < 19) __stcg(ws + (size_t)(kLower19 + R.jc + j) * wsn, S.sum[32 + j]);
 }
 
 // projected control points of a parameter vector: tab[(3*cp + {uL, uR, v}) * 32] (this fit's column of a [.][32] table)
@@ -532,7 +513,7 @@ constexpr int kDifTabFd = 163;
 
 template <bool FD>
 constexpr int dif_build_smem_doubles() {
-  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * 4 * kDifFits * kDifStageRow + 2 * kDifFits;
+  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * kDifWarps * kDifFits * kDifStageRow + kDifFits;
 }
 
 // one model value: sum_k w_k * tab[(12*curve + 3k + sel) * 32], ascending k from 0.0 like closest_bezier_pt(cp, t, ..)
@@ -543,19 +524,222 @@ __device__ __forceinline__ double dif_bez(const double (&w)[4], const double* ta
   return a;
 }
 
+// per-thread view of the group of 32 fits a CTA is working on
+struct DifCtx {
+  const DifArgs* A;
+  double* tab;     // this lane's column of the [entry][32] tables
+  double* stage;   // [NBUF][8][32][22]
+  const int* nrows;
+  const double* x;
+  const double* tp;
+  double* ws;
+  size_t wsn;
+  FitGeom g;
+  int lane, cfi, csub;
+  bool have, blocked, accepted;
+  double pend_dp_sq;
+};
+
+// The row sweep of one group: the same code for every warp, its blocks selected by the role.
 template <bool FD>
-__global__ void __launch_bounds__(kDifThreads, FD ? 2 : 2) dif_build_kernel(const DifArgs A, int nxt) {
+__device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) {
+  const DifRole R = dif_role(wid);
+  constexpr int NBUF = FD ? 1 : 2;
+  constexpr int STEP_DOUBLES = kDifWarps * kDifFits * kDifStageRow;
+  const DifArgs& A = *C.A;
+  double* const tab = C.tab;
+  double* const stage = C.stage;
+  const int* const nrows = C.nrows;
+  const double* const x = C.x;
+  const double* const tp = C.tp;
+  double* const ws = C.ws;
+  const size_t wsn = C.wsn;
+  const FitGeom g = C.g;
+  const int lane = C.lane, cfi = C.cfi, csub = C.csub;
+  const bool have = C.have, blocked = C.blocked, accepted = C.accepted;
+  const double pend_dp_sq = C.pend_dp_sq;
+    // running sums start at zero (every warp its own entries)
+    DifSums S;
+#pragma unroll
+    for (int q = 0; q < kDifSumsPerWarp; ++q) S.sum[q] = 0.0;
+    dif_fold<true>(ws, wsn, R, S);
+    __syncthreads();
+    int nmax = 0;
+    bool any_blocked = false, any_small = false;
+    for (int q = 0; q < kDifFits; ++q) {
+      const int nq = nrows[q];
+      nmax = max(nmax, nq);
+      if (nq > 0) {
+        if (nq * 19 <= kBlockSzSq) any_small = true; else any_blocked = true;
+      }
+    }
+    const int nsteps = (nmax + kDifWarps - 1) / kDifWarps;
+    // this thread's share of the cooperative copies: fit cfi of the group
+    const int cn = nrows[cfi];
+    double* cJ = A.J + (size_t)nrows[kDifFits + cfi] * A.j_stride;
+
+    auto issue_rows = [&](int st, int buf) {
+      double* sb = stage + (size_t)buf * STEP_DOUBLES;
+#pragma unroll 1
+      for (int i = 0; i < 10; ++i) {
+        const int pi = 8 * i + csub;               // piece 0..79 of the fit's eight rows
+        const int rr = pi / 10, piece = pi - 10 * rr;
+        const int r = kDifWarps * st + rr;
+        const bool ok = r < cn;
+        const double* src = cJ + (size_t)(ok ? r : 0) * kDifRow + 2 * piece;
+        const unsigned int d = (unsigned int)__cvta_generic_to_shared(sb + (rr * kDifFits + cfi) * kDifStageRow + 2 * piece);
+        const int nbytes = ok ? 16 : 0;  // zero-fill rows past the end of a fit
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto write_back = [&](int st, const double* sb, int n_lim) {
+#pragma unroll 2
+      for (int i = 0; i < 10; ++i) {
+        const int pi = 8 * i + csub;
+        const int rr = pi / 10, piece = pi - 10 * rr;
+        const int r = kDifWarps * st + rr;
+        if (r < n_lim) {
+          const double2 v = *reinterpret_cast<const double2*>(sb + (rr * kDifFits + cfi) * kDifStageRow + 2 * piece);
+          __stcg(reinterpret_cast<double2*>(cJ + (size_t)r * kDifRow + 2 * piece), v);
+        }
+      }
+    };
+
+    // The unblocked small-problem loop walks the rows downwards (lm_core.c:604-628), the blocked one upwards.  A
+    // group that holds fits of both kinds (rare: fits with fewer than 27 samples) runs both passes, each fit taking
+    // part in its own.
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool down = pass == 1;
+      if (down ? !any_small : !any_blocked) continue;
+      const bool mine = have && (blocked != down);
+      const int n_eff = mine ? g.n : 0;                     // rows of this lane's fit that take part in this pass
+      const bool cmine = cn > 0 && ((cn * 19 <= kBlockSzSq) == down);
+      const int cn_eff = cmine ? cn : 0;                    // the same for the fit this thread copies
+      if (!FD) issue_rows(down ? nsteps - 1 : 0, 0);
+      // sample and t of this lane's row of the first step
+      double x_next = 0.0, t_next = 0.0;
+      {
+        const int r = kDifWarps * (down ? nsteps - 1 : 0) + wid;
+        if (r < n_eff) { x_next = x[r]; t_next = tp[r >> 1]; }
+      }
+      for (int it = 0; it < nsteps; ++it) {
+        const int st = down ? nsteps - 1 - it : it;
+        const int buf = FD ? 0 : (it & 1);
+        double* sb = stage + (size_t)buf * STEP_DOUBLES;
+        if (!FD) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // [A] this step's rows have landed; everybody is done with the other buffer
+        if (!FD && it + 1 < nsteps) issue_rows(down ? st - 1 : st + 1, buf ^ 1);
+        // ---- produce row r = 8 st + wid of this lane's fit
+        {
+          const int r = kDifWarps * st + wid;
+          double* row = sb + (wid * kDifFits + lane) * kDifStageRow;
+          const double xr = x_next, tval = t_next;
+          {
+            const int rn = kDifWarps * (down ? st - 1 : st + 1) + wid;
+            if (it + 1 < nsteps && rn < n_eff) { x_next = x[rn]; t_next = tp[rn >> 1]; }
+          }
+          if (r < n_eff) {
+            const int sidx = r >> 1, uv = r & 1;
+            const int seg = (sidx >= g.b1) + (sidx >= g.b2) + (sidx >= g.b3);
+            const int curve = seg & 1, side = seg >> 1;
+            const int cb_sel = 12 * curve + (uv ? 2 : side);
+            double w[4];
+            bernstein3(tval, w);
+            if (FD) {
+              const double hx = dif_bez(w, tab, cb_sel);
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const int cp = j >> 1;
+                double v0 = 0.0, v1 = 0.0;  // (hx - hx) * (1/d) = +0.0 for the other curve's control points
+                if ((cp >> 2) == curve) {
+                  const int kk = cp & 3;
+                  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const double cbase = tab[(cb_sel + 3 * k) * kDifFits];
+                    const double c0 = (k == kk) ? tab[(24 + 3 * j + (uv ? 2 : side)) * kDifFits] : cbase;
+                    const double c1 = (k == kk) ? tab[(24 + 3 * (j + 1) + (uv ? 2 : side)) * kDifFits] : cbase;
+                    a0 += w[k] * c0;
+                    a1 += w[k] * c1;
+                  }
+                  v0 = (a0 - hx) * tab[(144 + j) * kDifFits];
+                  v1 = (a1 - hx) * tab[(144 + j + 1) * kDifFits];
+                }
+                *reinterpret_cast<double2*>(row + j) = make_double2(v0, v1);
+              }
+              double vq[3];
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const double hxx = dif_bez(w, tab + (72 + 24 * q) * kDifFits, cb_sel);
+                vq[q] = (hxx - hx) * tab[(160 + q) * kDifFits];
+              }
+              *reinterpret_cast<double2*>(row + 16) = make_double2(vq[0], vq[1]);
+              *reinterpret_cast<double2*>(row + 18) = make_double2(vq[2], 0.0);
+              *reinterpret_cast<double2*>(row + 20) = make_double2(xr - hx, 0.0);
+            } else {
+              const double hx = dif_bez(w, tab, cb_sel);
+              const double wrk = dif_bez(w, tab + 24 * kDifFits, cb_sel);
+              // rank-one secant update of the row, lm_core.c:745-755: tmp = (wrk_r - hx_r - J_r . dp) / ||dp||^2
+              double tmp = 0.0;
+#pragma unroll 3
+              for (int c = 0; c < 18; c += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(row + c);
+                tmp += t2.x * tab[(48 + c) * kDifFits];
+                tmp += t2.y * tab[(48 + c + 1) * kDifFits];
+              }
+              tmp += row[18] * tab[(48 + 18) * kDifFits];
+              tmp = ((wrk - hx) - tmp) / pend_dp_sq;
+#pragma unroll 3
+              for (int c = 0; c < 18; c += 2) {
+                double2 t2 = *reinterpret_cast<const double2*>(row + c);
+                t2.x += tmp * tab[(48 + c) * kDifFits];
+                t2.y += tmp * tab[(48 + c + 1) * kDifFits];
+                *reinterpret_cast<double2*>(row + c) = t2;
+              }
+              const double last = row[18] + tmp * tab[(48 + 18) * kDifFits];
+              *reinterpret_cast<double2*>(row + 18) = make_double2(last, 0.0);
+              *reinterpret_cast<double2*>(row + 20) = make_double2(xr - (accepted ? wrk : hx), 0.0);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < kDifStageRow; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(0.0, 0.0);
+          }
+        }
+        __syncthreads();  // [B] the four rows of every fit are complete
+        write_back(st, sb, cn_eff);
+        // ---- every warp: its share of the sums over the eight rows, in the pass's row order
+#pragma unroll 1
+        for (int q8 = 0; q8 < kDifWarps; ++q8) {
+          const int rr = down ? kDifWarps - 1 - q8 : q8;
+          const double* row = sb + (rr * kDifFits + lane) * kDifStageRow;
+          dif_accumulate(row, R, S);
+        }
+        // end of a 32-row block (blocked pass) or of the fit: the partial sums join the running entries
+        const bool fold = down ? (it == nsteps - 1) : ((st & 3) == 3 || it == nsteps - 1);
+        if (fold) dif_fold<false>(ws, wsn, R, S);
+      }
+      __syncthreads();  // the last step's stage is no longer read (the next pass refills it)
+    }
+    dif_store_jte(ws, wsn, R, S);
+}
+
+template <bool FD>
+__global__ void __launch_bounds__(kDifThreads, 2) dif_build_kernel(const DifArgs A, int nxt) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NTAB = FD ? kDifTabFd : kDifTabUpd;
   constexpr int NBUF = FD ? 1 : 2;
+  constexpr int STEP_DOUBLES = kDifWarps * kDifFits * kDifStageRow;  // one row per warp and fit
   double* tab = smem + lane;                                   // tab[entry * 32]
-  double* stage = smem + NTAB * kDifFits;                       // [NBUF][4][32][22]
-  long long* jbase = reinterpret_cast<long long*>(stage + NBUF * 4 * kDifFits * kDifStageRow);  // [32] row-0 offsets
-  int* nrows = reinterpret_cast<int*>(jbase + kDifFits);        // [32] n of each fit (0: no fit)
+  double* stage = smem + NTAB * kDifFits;                       // [NBUF][8][32][22]
+  int* nrows = reinterpret_cast<int*>(stage + NBUF * STEP_DOUBLES);  // [32] n of each fit (0: no fit), [32] fit index
   const size_t wsn = (size_t)A.ws_stride;
   const unsigned int total = A.cnt[FD ? 0 : 1];
   const int* list = FD ? A.fd_list : A.upd_list;
+  // cooperative copies between the stored Jacobians and the stage: the eight rows of a step are 1280 contiguous bytes
+  // of a fit; eight threads move a fit's 80 16-byte pieces, ten each (128 contiguous bytes per octet and instruction)
+  const int cfi = tid >> 3, csub = tid & 7;
   for (unsigned int base = blockIdx.x * kDifFits; base < total; base += gridDim.x * kDifFits) {
     const unsigned int item = base + lane;
     const bool have = item < total;
@@ -565,19 +749,16 @@ __global__ void __launch_bounds__(kDifThreads, FD ? 2 : 2) dif_build_kernel(cons
     long long o0 = 0;
     if (have) dif_geom(A, f, g, o0);
     const double* x = A.L.meas + o0;
-    const double* tp = have ? dif_t(A, f, o0) : nullptr;
+    const double* tp = have ? dif_t(A, f, o0) : A.L.meas;
     const double* pc = A.L.p + (size_t)f * 19;
-    double* Jf = A.J + (size_t)f * A.j_stride;
-    double* ws = A.ws + (size_t)blockIdx.x * kDifFits + lane;
+    double* ws = A.ws + (FD ? (size_t)(A.ws_stride / 2) : 0) + (size_t)blockIdx.x * kDifFits + lane;
     const bool blocked = !(g.n * 19 <= kBlockSzSq);  // "<=" here, lm_core.c:585
-    DifScal sc;
-    if (have && wid == 0) sc = A.scal[f];
     const bool accepted = have ? (A.scal[f].accepted != 0) : false;
     const double pend_dp_sq = have ? A.scal[f].pend_dp_sq : 1.0;
     __syncthreads();  // the previous group's tables and stage are no longer read
     if (wid == 0) {
-      jbase[lane] = (long long)((size_t)f * A.j_stride);
       nrows[lane] = g.n;
+      nrows[kDifFits + lane] = f;
     }
     // ---- per-fit tables, spread over the four warps
     if (have) {
@@ -613,179 +794,23 @@ __global__ void __launch_bounds__(kDifThreads, FD ? 2 : 2) dif_build_kernel(cons
             if (j & 1) ye = ye + d; else xe = xe + d;
             dif_project_one(tg, xe, ye, z, tab + (24 + 3 * j) * kDifFits);
           }
-        } else {  // theta + d | phi + d (warp 2), z + d (warp 3)
-          for (int q = (wid == 2 ? 0 : 2); q < (wid == 2 ? 2 : 3); ++q) {
+        } else if (wid <= 4) {  // theta + d (warp 2), phi + d (warp 3), z + d (warp 4)
+          {
+            const int q = wid - 2;
             double pw[19];
+            const double dq = delta_of(16 + q);
 #pragma unroll
-            for (int i = 0; i < 19; ++i) pw[i] = pc[i];
-            pw[16 + q] = pw[16 + q] + delta_of(16 + q);
+            for (int i = 0; i < 19; ++i) pw[i] = (i == 16 + q) ? pc[i] + dq : pc[i];
             dif_project_all(pw, tab + (72 + 24 * q) * kDifFits);
           }
         }
       }
     }
-    // running sums start at zero (every warp its own entries)
-    DifQuarter S;
-#pragma unroll
-    for (int q = 0; q < 55; ++q) S.part[q] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 9; ++q) S.jte[q] = 0.0;
-    if (wid == 0) {
-#pragma unroll 1
-      for (int q = 0; q < 55; ++q) __stcg(ws + (size_t)q * wsn, 0.0);
-    } else if (wid == 1) {
-#pragma unroll 1
-      for (int i = 0; i < 9; ++i)
-        for (int j = 0; j <= i; ++j) __stcg(ws + (size_t)tri(10 + i, 10 + j) * wsn, 0.0);
-    } else {
-      const int c0 = (wid == 2) ? 0 : 5;
-#pragma unroll 1
-      for (int i = 0; i < 9; ++i)
-        for (int j = 0; j < 5; ++j) __stcg(ws + (size_t)tri(10 + i, c0 + j) * wsn, 0.0);
-    }
-    __syncthreads();
-    int nmax = 0;
-    for (int q = 0; q < kDifFits; ++q) nmax = max(nmax, nrows[q]);
-    const int nsteps = (nmax + 3) >> 2;
-
-    // cooperative, coalesced copy of the four stored rows of step `st` of all 32 fits into stage buffer `buf`
-    auto issue_rows = [&](int st, int buf) {
-      if (FD) return;
-      double* sb = stage + (size_t)buf * 4 * kDifFits * kDifStageRow;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int q = i * kDifThreads + tid;           // 0..1279: (row-in-step, fit, 16-byte piece)
-        const int rr = q / 320, rem = q - rr * 320;
-        const int fi = rem / 10, piece = rem - fi * 10;
-        const int r = 4 * st + rr;
-        const bool ok = r < nrows[fi];
-        const double* src = A.J + jbase[fi] + (size_t)(ok ? r : 0) * kDifRow + 2 * piece;
-        const unsigned int d = (unsigned int)__cvta_generic_to_shared(sb + (rr * kDifFits + fi) * kDifStageRow + 2 * piece);
-        const int nbytes = ok ? 16 : 0;  // zero-fill rows past the end of a fit
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    // the unblocked small-problem loop walks the rows downwards (lm_core.c:604-628); a CTA whose fits are all
-    // blocked walks upwards.  Mixed CTAs (rare: fits with fewer than 27 samples) run both directions, each fit
-    // taking part in its own.
-    bool any_blocked = false, any_small = false;
-    for (int q = 0; q < kDifFits; ++q) {
-      if (nrows[q] > 0) {
-        if (nrows[q] * 19 <= kBlockSzSq) any_small = true; else any_blocked = true;
-      }
-    }
-    for (int pass = 0; pass < 2; ++pass) {
-      const bool down = pass == 1;
-      if (down ? !any_small : !any_blocked) continue;
-      const bool mine = have && (blocked != down);
-      const int n_eff = mine ? g.n : 0;  // rows of this fit that take part in this pass
-      if (!FD) issue_rows(down ? nsteps - 1 : 0, 0);
-      for (int it = 0; it < nsteps; ++it) {
-        const int st = down ? nsteps - 1 - it : it;
-        const int buf = FD ? 0 : (it & 1);
-        double* sb = stage + (size_t)buf * 4 * kDifFits * kDifStageRow;
-        if (!FD) {
-          if (it + 1 < nsteps) {
-            issue_rows(down ? st - 1 : st + 1, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-          } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-          }
-          __syncthreads();
-        }
-        // ---- produce row r = 4 st + wid of this lane's fit
-        {
-          const int r = 4 * st + wid;
-          double* row = sb + (wid * kDifFits + lane) * kDifStageRow;
-          if (r < n_eff) {
-            const int s = r >> 1, uv = r & 1;
-            const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
-            const int curve = seg & 1, side = seg >> 1;
-            const int cb_sel = 12 * curve + (uv ? 2 : side);
-            double w[4];
-            bernstein3(tp[s], w);
-            const double xr = x[r];
-            double jr[kDifRow];
-            if (FD) {
-              const double hx = dif_bez(w, tab, cb_sel);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int cp = j >> 1;
-                double hxx = hx;
-                if ((cp >> 2) == curve) {  // the perturbed control point belongs to this row's curve
-                  const int kk = cp & 3;
-                  double a = 0.0;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const double c = (k == kk) ? tab[(24 + 3 * j + (uv ? 2 : side)) * kDifFits]
-                                               : tab[(cb_sel + 3 * k) * kDifFits];
-                    a += w[k] * c;
-                  }
-                  hxx = a;
-                }
-                jr[j] = (hxx - hx) * tab[(144 + j) * kDifFits];
-              }
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                const double hxx = dif_bez(w, tab + (72 + 24 * q) * kDifFits, cb_sel);
-                jr[16 + q] = (hxx - hx) * tab[(160 + q) * kDifFits];
-              }
-              jr[19] = 0.0;
-              row[20] = xr - hx;
-            } else {
-#pragma unroll
-              for (int c = 0; c < kDifRow; c += 2) {
-                const double2 t2 = *reinterpret_cast<const double2*>(row + c);
-                jr[c] = t2.x; jr[c + 1] = t2.y;
-              }
-              const double hx = dif_bez(w, tab, cb_sel);
-              const double wrk = dif_bez(w, tab + 24 * kDifFits, cb_sel);
-              double tmp = 0.0;
-#pragma unroll
-              for (int l = 0; l < 19; ++l) tmp += jr[l] * tab[(48 + l) * kDifFits];
-              tmp = ((wrk - hx) - tmp) / pend_dp_sq;
-#pragma unroll
-              for (int j = 0; j < 19; ++j) jr[j] += tmp * tab[(48 + j) * kDifFits];
-              jr[19] = 0.0;
-              row[20] = xr - (accepted ? wrk : hx);
-            }
-#pragma unroll
-            for (int c = 0; c < kDifRow; c += 2) {
-              *reinterpret_cast<double2*>(row + c) = make_double2(jr[c], jr[c + 1]);
-              __stcg(reinterpret_cast<double2*>(Jf + (size_t)r * kDifRow + c), make_double2(jr[c], jr[c + 1]));
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < kDifStageRow; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(0.0, 0.0);
-          }
-        }
-        __syncthreads();
-        // ---- every warp: its quarter of the sums over the four rows, in the pass's row order
-#pragma unroll 1
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int rr = down ? 3 - q4 : q4;
-          const double* row = sb + (rr * kDifFits + lane) * kDifStageRow;
-          if (wid == 0) dif_accumulate<0>(row, S);
-          else if (wid == 1) dif_accumulate<1>(row, S);
-          else if (wid == 2) dif_accumulate<2>(row, S);
-          else dif_accumulate<3>(row, S);
-        }
-        // end of a 32-row block (blocked pass) or of the fit: the partial sums join the running entries
-        const bool fold = down ? (it == nsteps - 1) : ((st & 7) == 7 || it == nsteps - 1);
-        if (fold) {
-          if (wid == 0) dif_fold<0>(ws, wsn, S);
-          else if (wid == 1) dif_fold<1>(ws, wsn, S);
-          else if (wid == 2) dif_fold<2>(ws, wsn, S);
-          else dif_fold<3>(ws, wsn, S);
-        }
-        __syncthreads();  // the stage buffer may be refilled (FD: rewritten) from here on
-      }
-    }
-    if (wid == 1) dif_store_jte<1>(ws, wsn, S);
-    else if (wid == 2) dif_store_jte<2>(ws, wsn, S);
-    else if (wid == 3) dif_store_jte<3>(ws, wsn, S);
+    DifCtx C;
+    C.A = &A; C.tab = tab; C.stage = stage; C.nrows = nrows; C.x = x; C.tp = tp; C.ws = ws; C.wsn = wsn; C.g = g;
+    C.lane = lane; C.cfi = cfi; C.csub = csub; C.have = have; C.blocked = blocked; C.accepted = accepted;
+    C.pend_dp_sq = pend_dp_sq;
+    dif_group_sweep<FD>(C, wid);
     __threadfence();
     __syncthreads();
     // ---- publish J^T J / J^T e, gradient statistics, stop 1, initial mu (lm_core.c:657-678)
@@ -793,13 +818,11 @@ __global__ void __launch_bounds__(kDifThreads, FD ? 2 : 2) dif_build_kernel(cons
     if (have) {
       double* Jout = A.jtj + (size_t)f * kLower19;
       double* Jte = A.jte + (size_t)f * 19;
-      // the lower triangle in four slices of rows, one per warp
-      const int i_lo = wid == 0 ? 0 : (wid == 1 ? 10 : (wid == 2 ? 14 : 17));
-      const int i_hi = wid == 0 ? 10 : (wid == 1 ? 14 : (wid == 2 ? 17 : 19));
+      // the lower triangle in eight slices of about 24 entries, one per warp
 #pragma unroll 1
-      for (int q = tri(i_lo, 0); q < tri(i_hi, 0); ++q) Jout[q] = __ldcg(ws + (size_t)q * wsn);
+      for (int q = wid * 24; q < (wid == kDifWarps - 1 ? kLower19 : wid * 24 + 24); ++q) Jout[q] = __ldcg(ws + (size_t)q * wsn);
       if (wid == 0) {
-        // columns 0..9 of J^T e belong to warps 2 / 3, 10..18 to warp 1: all in the work area by now
+        // every warp's J^T e chains are in the work area by now
         double p_sq = 0.0, g_inf = 0.0, big = -DBL_MAX;
 #pragma unroll 1
         for (int q = 0; q < 19; ++q) {
@@ -811,6 +834,7 @@ __global__ void __launch_bounds__(kDifThreads, FD ? 2 : 2) dif_build_kernel(cons
           const double d = __ldcg(ws + (size_t)tri(q, q) * wsn);
           if (d > big) big = d;
         }
+        DifScal sc = A.scal[f];
         sc.n_jtj += 1;
         sc.pend = 0;
         sc.g_inf = g_inf;

@@ -25,8 +25,7 @@ for name, path in (("staged", lm.PATH_STAGED), ("warp", lm.PATH_MONOLITHIC)):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx.fit_batched_dev(STEREO19, DIF, B, p.data_ptr(), d["meas"].data_ptr(), None, d["off"].data_ptr(),
-                            d["counts"].data_ptr(), 512, 1000, list(lm.REFERENCE_OPTS), info.data_ptr(), ret.data_ptr(),
-                            extra.data_ptr())
+                            d["counts"].data_ptr(), 512, info.data_ptr(), ret.data_ptr(), extra.data_ptr())
         ctx.sync(); torch.cuda.synchronize()
         best = min(best, time.perf_counter() - t0)
         if rep == 0:
