@@ -14,6 +14,8 @@
 //     anyway (cvAddWeighted(P,0.5,P^T,0.5)), so the result differs by O(eps) per entry, inside the 1e-9
 //     tolerance of the parity tests, and is exactly symmetric like the reference's.
 // The reference allocates 14 temporaries (three of them N x N) per call; here nothing is allocated per call.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -92,8 +94,9 @@ __device__ void rbe_derivs(double phi, double theta, double psi, double* Rp, dou
 // ---- kernel 1: compact H, innovation and R from the current state (one block) ----------------------------
 // Compact columns: 0..5 = pose columns 0..5; then 8 per measured curve; then 3 per measured point.
 // in: small[SM_IN..] = z (M) followed by the A matrices (16 n); cols_in = landmark first-state indices.
-__global__ void ekf_build_kernel(UpdateDesc d, const double* __restrict__ x, double* __restrict__ small,
-                                 int* __restrict__ cols, const int* __restrict__ land_cols) {
+__device__ __forceinline__ void ekf_build_device(const UpdateDesc& d, const double* __restrict__ x,
+                                                 double* __restrict__ small, int* __restrict__ cols,
+                                                 const int* __restrict__ land_cols) {
   const int tid = threadIdx.x, nt = blockDim.x;
   double* Hc = small + SM_HC;
   double* nu = small + SM_NU;
@@ -185,6 +188,11 @@ __global__ void ekf_build_kernel(UpdateDesc d, const double* __restrict__ x, dou
       }
     }
   }
+}
+
+__global__ void ekf_build_kernel(UpdateDesc d, const double* __restrict__ x, double* __restrict__ small,
+                                 int* __restrict__ cols, const int* __restrict__ land_cols) {
+  ekf_build_device(d, x, small, cols, land_cols);
 }
 
 // ---- kernel 2: T = P H^T through the compact columns (one warp per state row) -----------------------------
@@ -341,6 +349,149 @@ __global__ void __launch_bounds__(256) ekf_gain_kernel(UpdateDesc d, const doubl
     for (int r = lane; r < M; r += 32) {
       double acc = 0.0;
       for (int s = 0; s < M; ++s) acc += krow[s] * S[r * M + s];
+      Yt[(size_t)r * ldk + row] = acc;
+      dx += krow[r] * nu[r];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dx += __shfl_xor_sync(0xffffffffu, dx, o);
+    if (lane == 0) {
+      double v = x[row] + dx;
+      if (row >= 3 && row <= 5 && fabs(v) < 1e6) {  // kalmanClass.cpp:902-913 (bounded: a wild angle cannot spin)
+        while (v > kPI) v -= 2 * kPI;
+        while (v < -kPI) v += 2 * kPI;
+      }
+      x[row] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- fused front end (used whenever its tables fit shared memory: every live measurement size) ---------------
+// ekf_front_kernel, ONE block: kernel 1, then only the nc rows of T = P H^T that S needs (the rows of the compact
+// columns: an nc x nc gather of P), S = Hc Tc + R, and S^-1 by Gauss-Jordan elimination on the symmetric part of S
+// (S is SPD: no pivoting; all 256 threads update the matrix in every step -- the Cholesky + triangular inverse of
+// kernel 3 kept 35 threads busy and cost 57 us at M = 35).  A pivot that is not positive fails the update as in
+// kernel 3: flag raised, S^-1 = 0, x and P stay untouched.
+// ekf_rows_kernel, one warp per state row: T_row = P_row[cols] Hc^T, K_row = T_row S^-1, Y_row = K_row S^T,
+// x_row += K_row nu -- kernels 2 and 4 in one pass, T never written to memory.
+// Same sums in the same order as kernels 1-4 for H, T, S, K, Y and x; S^-1 differs by rounding (another elimination).
+__global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const double* __restrict__ x,
+                                                        const double* __restrict__ P, double* __restrict__ small,
+                                                        int* __restrict__ cols, const int* __restrict__ land_cols,
+                                                        int* __restrict__ flag) {
+  extern __shared__ double sh[];
+  const int M = d.M, nc = d.nc;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  ekf_build_device(d, x, small, cols, land_cols);
+  __syncthreads();
+  double* Hs = sh;                 // [M][nc]
+  double* Ps = Hs + M * nc;        // [nc][nc]  P restricted to the compact columns
+  double* Tc = Ps + nc * nc;       // [nc][M]   rows of T at the compact columns
+  double* S = Tc + nc * M;         // [M][M]
+  double* W = S + M * M;           // [M][M]    elimination work matrix -> S^-1 (ping)
+  double* W2 = W + M * M;          // [M][M]    (pong)
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < M * nc; e += nt) Hs[e] = small[SM_HC + e];
+  for (int e = tid; e < nc * nc; e += nt) {
+    const int a = e / nc, b = e - a * nc;
+    Ps[e] = P[(size_t)cols[a] * d.ld + cols[b]];
+  }
+  __syncthreads();
+  for (int e = tid; e < nc * M; e += nt) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
+    const int c = e / M, r = e - c * M;
+    double s = 0.0;
+    for (int b = 0; b < nc; ++b) s += Ps[c * nc + b] * Hs[r * nc + b];
+    Tc[e] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < M * M; e += nt) {
+    const int r = e / M, q = e - r * M;
+    double acc = 0.0;
+    for (int c = 0; c < nc; ++c) acc += Hs[r * nc + c] * Tc[c * M + q];
+    if (r == q) acc += small[SM_R + r];
+    S[e] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < M * M; e += nt) {
+    const int r = e / M, q = e - r * M;
+    small[SM_S + r * MAXM + q] = S[e];
+    W[e] = 0.5 * (S[e] + S[q * M + r]);  // invert the symmetric part
+  }
+  __syncthreads();
+  // a step reads the matrix as it stands and writes the next one into the other buffer: one barrier per step
+  double* Wsrc = W;
+  double* Wdst = W2;
+  for (int k = 0; k < M; ++k) {
+    const double piv = Wsrc[k * M + k];
+    const bool ok = (piv > 0.0) && (piv <= 1.79769313486231571e308);
+    const double ip = ok ? 1.0 / piv : 1.0;
+    if (!ok && tid == 0) { *flag = 1; bad = 1; }
+    for (int e = tid; e < M * M; e += nt) {
+      const int i = e / M, j = e - i * M;
+      const double cik = Wsrc[i * M + k], rkj = Wsrc[k * M + j] * ip;
+      double v;
+      if (i == k) v = (j == k) ? ip : rkj;
+      else if (j == k) v = -cik * ip;
+      else v = Wsrc[e] - cik * rkj;
+      Wdst[e] = v;
+    }
+    __syncthreads();
+    double* tmp = Wsrc; Wsrc = Wdst; Wdst = tmp;
+  }
+  W = Wsrc;
+  for (int e = tid; e < M * M; e += nt) {
+    const int r = e / M, q = e - r * M;
+    small[SM_SINV + r * MAXM + q] = bad ? 0.0 : 0.5 * (W[e] + W[q * M + r]);
+  }
+}
+
+__global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const double* __restrict__ P,
+                                                       const double* __restrict__ small, const int* __restrict__ cols,
+                                                       double* __restrict__ Kt, double* __restrict__ Yt,
+                                                       double* __restrict__ x, int ldk) {
+  extern __shared__ double sh[];
+  const int M = d.M, nc = d.nc;
+  double* Hc = sh;                  // [M][nc]
+  double* Sinv = Hc + M * nc;       // [M][M]
+  double* S = Sinv + M * M;         // [M][M]
+  double* nu = S + M * M;           // [M]
+  double* rowbuf = nu + M;          // [8 warps][nc + 2 M]
+  int* scols = reinterpret_cast<int*>(rowbuf + 8 * (nc + 2 * M));
+  for (int e = threadIdx.x; e < M * nc; e += blockDim.x) Hc[e] = small[SM_HC + e];
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int r = e / M, q = e - r * M;
+    Sinv[e] = small[SM_SINV + r * MAXM + q];
+    S[e] = small[SM_S + r * MAXM + q];
+  }
+  for (int e = threadIdx.x; e < M; e += blockDim.x) nu[e] = small[SM_NU + e];
+  for (int e = threadIdx.x; e < nc; e += blockDim.x) scols[e] = cols[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* pr = rowbuf + w * (nc + 2 * M);
+  double* trow = pr + nc;
+  double* krow = trow + M;
+  for (int row = blockIdx.x * 8 + w; row < d.N; row += gridDim.x * 8) {
+    for (int c = lane; c < nc; c += 32) pr[c] = P[(size_t)row * d.ld + scols[c]];
+    __syncwarp();
+    for (int r = lane; r < M; r += 32) {
+      const double* h = Hc + r * nc;
+      double s = 0.0;
+      for (int c = 0; c < nc; ++c) s += pr[c] * h[c];
+      trow[r] = s;
+    }
+    __syncwarp();
+    for (int q = lane; q < M; q += 32) {
+      double acc = 0.0;
+      for (int r = 0; r < M; ++r) acc += trow[r] * Sinv[r * M + q];
+      krow[q] = acc;
+      Kt[(size_t)q * ldk + row] = acc;
+    }
+    __syncwarp();
+    double dx = 0.0;
+    for (int r = lane; r < M; r += 32) {
+      double acc = 0.0;
+      for (int q = 0; q < M; ++q) acc += krow[q] * S[r * M + q];
       Yt[(size_t)r * ldk + row] = acc;
       dx += krow[r] * nu[r];
     }
@@ -701,6 +852,263 @@ __global__ void __launch_bounds__(256, 1) ekf_cov_pipe_kernel(double* __restrict
   }
 }
 
+// ---- kernel 5d: the tile-pair update streamed with TMA, reading HALF of P ---------------------------------------
+// Whenever the off-diagonal tiles of P are exact mirror images of each other -- true after every update (this
+// kernel and the ones above write both tiles from one value), after cps_ekf_set_cov_lowrank, and preserved by the
+// predict step (it rewrites 12 rows and the mirrored 12 columns with the same values; the 12 x 12 pose block lies
+// inside the diagonal tile (0,0)) -- 0.5*(P_ij + P_ji) is P_ij exactly, so the mirrored tile need not be read: the
+// pass moves 12 N^2 bytes instead of 16 N^2 and its result is bit-identical to kernel 5c's.  Diagonal tiles are
+// symmetrised from their own entries as before.
+//   * P tiles arrive by cp.async.bulk.tensor (TMA, SASS UTMALDG) into a 3-deep ring, completion on mbarriers;
+//   * the corrected tile is written in place in its stage and leaves by one TMA store (UTMASTG); its transpose is
+//     written into a second buffer in the 128-byte-swizzled layout of four 16-column boxes (conflict-free 8-byte
+//     stores from the DMMA accumulator layout) and leaves by four TMA stores into tile (J,I): both stores are
+//     full lines;
+//   * Y_J / K_I tiles (36 x 64, L2-resident) keep the padded layout the DMMA fragment reads need and still come
+//     by cp.async.
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_TILE_BYTES = TILE * TILE * 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// element (row, col) of a 64 x 64 tile stored as four 16-column boxes in the TMA 128-byte swizzle
+__device__ __forceinline__ int swz_off(int row, int col) {
+  return (col >> 4) * (TILE * 16) + row * 16 + ((((col & 15) >> 1) ^ (row & 7)) << 1) + (col & 1);
+}
+
+struct alignas(64) TmaMaps {
+  CUtensorMap full;  // P as [cap][cap], box 64 x 64, no swizzle: tile loads and in-place stores
+  CUtensorMap swz;   // P as [cap][cap], box 16 columns x 64 rows, 128-byte swizzle: transposed stores
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 8 compute warps + 1 copy warp.  The copy warp's lane 0 owns every TMA operation: it fills the 3-deep ring of P
+// tiles, and for every pair waits until the compute warps have written the corrected tile and its transpose
+// (mbarrier `done`), stores both, waits until the stores have READ shared memory, then hands the transpose buffer
+// back (`tfree`) and refills the freed stage with the pair three ahead.  The compute warps therefore never wait
+// for a store: they only wait for tiles that were requested two to three pairs earlier.
+constexpr int TMA_THREADS = 288;
+__global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __grid_constant__ TmaMaps maps, int M,
+                                                                      const double* __restrict__ Kt,
+                                                                      const double* __restrict__ Yt, int ldk, int nt,
+                                                                      long long total_pairs) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(smem_raw) + 1023) & ~(size_t)1023);
+  const int Mp = (M + 3) & ~3;
+  double* Tt = reinterpret_cast<double*>(base);                                     // 32 KB, swizzled transpose
+  double* Pst = reinterpret_cast<double*>(base + TMA_TILE_BYTES);                   // [3][64][64]
+  double* Yst = reinterpret_cast<double*>(base + (1 + TMA_STAGES) * TMA_TILE_BYTES);  // [3][Mp][68]
+  double* Ks = Yst + TMA_STAGES * Mp * DSTRIDE;                                     // [Mp][68]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(Ks + Mp * DSTRIDE);  // [3]
+  unsigned long long* done = full + TMA_STAGES;                                     // compute -> copy warp
+  unsigned long long* tfree = done + 1;                                             // copy warp -> compute
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+
+  const long long per = (total_pairs + gridDim.x - 1) / gridDim.x;
+  const long long p_begin = (long long)blockIdx.x * per;
+  const long long p_end = min(total_pairs, p_begin + per);
+  if (p_begin >= p_end) return;
+  if (t == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) mbar_init(full + s, 1);
+    mbar_init(done, 1);
+    mbar_init(tfree, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (t < 256)
+    for (int e = t; e < (Mp - M) * DSTRIDE; e += 256) {  // padding rows of K and Y stay zero
+      Ks[M * DSTRIDE + e] = 0.0;
+      for (int s = 0; s < TMA_STAGES; ++s) Yst[s * Mp * DSTRIDE + M * DSTRIDE + e] = 0.0;
+    }
+  __syncthreads();
+  auto next_pair = [&](int& I, int& J) {
+    if (++J >= nt) { ++I; J = I; }
+  };
+  int I, J;
+  pair_from_index(p_begin, nt, I, J);
+
+  if (w == 8) {
+    // ---------------------------------------------------------------------------------------- copy warp
+    if (l != 0) return;
+    auto issue_p = [&](int Ia, int Ja, int stage) {
+      mbar_expect_tx(full + stage, TMA_TILE_BYTES);
+      tma_load_2d(Pst + stage * TILE * TILE, &maps.full, Ja * TILE, Ia * TILE, full + stage);
+    };
+    int Il = I, Jl = J;  // next pair to load
+    long long pl = p_begin;
+    for (int s = 0; s < TMA_STAGES && pl < p_end; ++s, ++pl) {
+      issue_p(Il, Jl, s);
+      next_pair(Il, Jl);
+    }
+    for (long long p = p_begin; p < p_end; ++p) {
+      const int it = (int)(p - p_begin);
+      const int stage = it % TMA_STAGES;
+      mbar_wait(done, (unsigned)(it & 1));  // tile and transpose of pair p are in shared memory, fenced
+      const double* pa = Pst + stage * TILE * TILE;
+      if (I != J) {
+        tma_store_2d(&maps.full, J * TILE, I * TILE, pa);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, J * TILE, Tt + q * TILE * 16);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, I * TILE, Tt + q * TILE * 16);
+      }
+      tma_commit();
+      tma_wait_read_all();  // the stores have read the stage and the transpose buffer
+      mbar_arrive(tfree);
+      if (pl < p_end) {
+        issue_p(Il, Jl, stage);
+        next_pair(Il, Jl);
+        ++pl;
+      }
+      next_pair(I, J);
+    }
+    tma_wait_all();
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------------ compute warps
+  const int lr = l >> 2, lc = l & 3;
+  const int wr0 = (w >> 1) * 16, wc0 = (w & 1) * 32;
+  auto issue_y = [&](int Ja, int stage) {
+    double* ys = Yst + stage * Mp * DSTRIDE;
+    for (int c = t; c < M * 32; c += 256) {
+      const int r = c >> 5, cc = (c & 31) * 2;
+      cp_async16(ys + r * DSTRIDE + cc, Yt + (size_t)r * ldk + (size_t)Ja * TILE + cc);
+    }
+  };
+  auto issue_k = [&](int Ia) {
+    for (int c = t; c < M * 32; c += 256) {
+      const int r = c >> 5, cc = (c & 31) * 2;
+      cp_async16(Ks + r * DSTRIDE + cc, Kt + (size_t)r * ldk + (size_t)Ia * TILE + cc);
+    }
+  };
+  int k_loaded = I;
+  issue_k(I);
+  int Iy = I, Jy = J;  // pair whose Y tile is requested next
+  issue_y(Jy, 0);
+  cp_async_commit();
+  next_pair(Iy, Jy);
+  if (p_begin + 1 < p_end) issue_y(Jy, 1);
+  cp_async_commit();
+  next_pair(Iy, Jy);
+  for (long long p = p_begin; p < p_end; ++p) {
+    const int it = (int)(p - p_begin);
+    const int stage = it % TMA_STAGES;
+    if (p + 2 < p_end) issue_y(Jy, (it + 2) % TMA_STAGES);  // that stage's Y was last read in iteration it - 1
+    cp_async_commit();
+    next_pair(Iy, Jy);
+    cp_async_wait<2>();                                          // this thread's share of Y(p) (and of K)
+    mbar_wait(full + stage, (unsigned)((it / TMA_STAGES) & 1));  // the P tile of pair p
+    compute_warps_sync();                                        // everybody's Y shares
+    if (k_loaded != I) {
+      issue_k(I);
+      cp_async_commit();
+      cp_async_wait<0>();
+      k_loaded = I;
+      compute_warps_sync();
+    }
+    double* pa = Pst + stage * TILE * TILE;
+    const double* ys = Yst + stage * Mp * DSTRIDE;
+    const bool diag = (I == J);
+
+    double acc[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    for (int ks = 0; ks < Mp; ks += 4) {
+      double a[2], b[4];
+      const double* kr = Ks + (ks + lc) * DSTRIDE + wr0 + lr;
+      const double* yr = ys + (ks + lc) * DSTRIDE + wc0 + lr;
+      a[0] = kr[0];
+      a[1] = kr[8];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = yr[8 * ni];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                       : "d"(a[mi]), "d"(b[ni]));
+    }
+    if (it > 0) mbar_wait(tfree, (unsigned)((it - 1) & 1));  // the stores of pair p - 1 have read the transpose buffer
+    if (!diag) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int ri = wr0 + lr + 8 * mi, cj = wc0 + 2 * lc + 8 * ni;
+          double2* pp = reinterpret_cast<double2*>(pa + ri * TILE + cj);
+          const double2 pij = *pp;
+          // 0.5*(p + p) - acc == p - acc bit for bit: the mirrored tile holds the same values
+          const double o0 = 0.5 * (pij.x + pij.x) - acc[mi][ni][0];
+          const double o1 = 0.5 * (pij.y + pij.y) - acc[mi][ni][1];
+          *pp = make_double2(o0, o1);
+          Tt[swz_off(cj, ri)] = o0;
+          Tt[swz_off(cj + 1, ri)] = o1;
+        }
+    } else {
+      // diagonal tile: entries on and above the diagonal are authoritative and mirrored, as in kernel 5c
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int ri = wr0 + lr + 8 * mi, cj = wc0 + 2 * lc + 8 * ni;
+          const double2 pij = *reinterpret_cast<const double2*>(pa + ri * TILE + cj);
+          const double q0 = pa[cj * TILE + ri], q1 = pa[(cj + 1) * TILE + ri];
+          const double o0 = 0.5 * (pij.x + q0) - acc[mi][ni][0];
+          const double o1 = 0.5 * (pij.y + q1) - acc[mi][ni][1];
+          if (cj >= ri) { Tt[swz_off(ri, cj)] = o0; if (cj != ri) Tt[swz_off(cj, ri)] = o0; }
+          if (cj + 1 >= ri) { Tt[swz_off(ri, cj + 1)] = o1; if (cj + 1 != ri) Tt[swz_off(cj + 1, ri)] = o1; }
+        }
+    }
+    fence_async_smem();
+    compute_warps_sync();
+    if (t == 0) mbar_arrive(done);
+    next_pair(I, J);
+  }
+}
+
 // ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
 // Pri <- F Pri, mirrored; Prr <- F Prr F^T + Q; x[0..5] += x[6..11] DT.  F = I + DT*[0 I6; 0 0].
 __global__ void __launch_bounds__(256) ekf_predict_cross_kernel(double* __restrict__ P, int ld, int N) {
@@ -994,6 +1402,50 @@ int round_up(int v, int q) { return (v + q - 1) / q * q; }
 // =================================== C ABI ===================================
 extern "C" void cps_ekf_destroy(cps_ekf* h);
 namespace {
+// grow-only scratch: nothing is allocated per call once the handle has seen its largest request
+int ensure_aux(cps_ekf* h, size_t bytes) {
+  if (bytes <= h->aux_bytes) return CPS_OK;
+  CPS_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_aux);
+  h->d_aux = nullptr;
+  h->aux_bytes = 0;
+  CPS_CUDA(cudaMalloc(&h->d_aux, bytes));
+  h->aux_bytes = bytes;
+  return CPS_OK;
+}
+
+size_t tma_smem_bytes(int Mp) {
+  return 1024 + (size_t)(1 + TMA_STAGES) * TMA_TILE_BYTES + (size_t)(TMA_STAGES + 1) * Mp * DSTRIDE * sizeof(double) + 128;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+bool encode_maps(cps_ekf* h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  EncodeFn encode = (EncodeFn)fn;
+  const cuuint64_t dims[2] = {(cuuint64_t)h->cap, (cuuint64_t)h->cap};           // innermost first
+  const cuuint64_t strides[1] = {(cuuint64_t)h->cap * sizeof(double)};           // bytes between rows
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint32_t box_full[2] = {TILE, TILE}, box_swz[2] = {16, TILE};
+  if (encode(&h->map_full, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->d_P, dims, strides, box_full, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (encode(&h->map_swz, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->d_P, dims, strides, box_swz, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  return true;
+}
+
 int ekf_create_impl(cps_ekf* h, int device, int capacity) {
   h->device = device;
   h->cap = round_up(capacity, TILE);
@@ -1034,6 +1486,11 @@ int ekf_create_impl(cps_ekf* h, int device, int capacity) {
                                 2 * MAXM * DSTRIDE * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (MAXM * MAXNC + 8 * MAXNC) * (int)sizeof(double) + MAXNC * (int)sizeof(int)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes(PIPE_MAX_M)));
+  h->maps_ok = encode_maps(h);
+  h->mirror_exact = true;  // P = 0
   CPS_CUDA(cudaStreamSynchronize(h->stream));
   return CPS_OK;
 }
@@ -1065,7 +1522,7 @@ extern "C" void cps_ekf_destroy(cps_ekf* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_P); cudaFree(h->d_x); cudaFree(h->d_T); cudaFree(h->d_Kt); cudaFree(h->d_Yt);
-  cudaFree(h->d_small); cudaFree(h->d_cols); cudaFree(h->d_flag);
+  cudaFree(h->d_small); cudaFree(h->d_cols); cudaFree(h->d_flag); cudaFree(h->d_aux);
   cudaFree(h->d_pack); cudaFree(h->d_pcols); cudaFree(h->d_gz); cudaFree(h->d_gidx); cudaFree(h->d_gd2);
   cudaFree(h->d_part_d2); cudaFree(h->d_part_idx);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1106,6 +1563,7 @@ extern "C" int cps_ekf_set_state(cps_ekf* h, const double* x, const double* P, i
     CPS_CUDA(cudaMemcpy2DAsync(h->d_P, cap * sizeof(double), P, (size_t)N * sizeof(double), (size_t)N * sizeof(double),
                                N, cudaMemcpyHostToDevice, h->stream));
   h->N = N;
+  h->mirror_exact = (P == nullptr);  // a caller-supplied covariance need not be symmetric to the last bit
   h->curve_inds.assign(curve_inds, curve_inds + num_curves);
   h->point_inds.assign(point_inds, point_inds + num_points);
   CPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -1115,14 +1573,14 @@ extern "C" int cps_ekf_set_state(cps_ekf* h, const double* x, const double* P, i
 extern "C" int cps_ekf_set_cov_lowrank(cps_ekf* h, const double* G, int r, double scale, double diag) {
   if (!h || !G || r <= 0 || h->N <= 0) return CPS_ERR_INVALID;
   CPS_CUDA(cudaSetDevice(h->device));
-  double* dG = nullptr;
-  CPS_CUDA(cudaMalloc(&dG, sizeof(double) * (size_t)h->N * r));
+  { const int rc = ensure_aux(h, sizeof(double) * (size_t)h->N * r); if (rc != CPS_OK) return rc; }
+  double* dG = h->d_aux;
   CPS_CUDA(cudaMemcpyAsync(dG, G, sizeof(double) * (size_t)h->N * r, cudaMemcpyHostToDevice, h->stream));
   dim3 grid((h->N + 15) / 16, (h->N + 15) / 16);
   ekf_lowrank_kernel<<<grid, 256, 0, h->stream>>>(h->d_P, h->cap, h->N, dG, r, scale, diag);
   CPS_CUDA(cudaGetLastError());
   CPS_CUDA(cudaStreamSynchronize(h->stream));
-  cudaFree(dG);
+  h->mirror_exact = true;  // (i,j) and (j,i) sum the same products in the same order
   return CPS_OK;
 }
 
@@ -1209,17 +1667,28 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   if (n + n_pts)
     CPS_CUDA(cudaMemcpyAsync(d_land, hcols, sizeof(int) * (n + n_pts), cudaMemcpyHostToDevice, st));
   CPS_CUDA(cudaEventRecord(h->ev[0], st));
-  ekf_build_kernel<<<1, 128, 0, st>>>(d, h->d_x, h->d_small, h->d_cols, d_land);
   const int row_blocks = std::min((d.N + 7) / 8, h->sm_count * 8);
-  const size_t sh_pht = (size_t)(d.M * d.nc + 8 * d.nc) * sizeof(double) + d.nc * sizeof(int);
-  ekf_pht_kernel<<<row_blocks, 256, sh_pht, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_T);
-  {
-    const size_t base_b = 2 * (size_t)M * M * sizeof(double), stage_b = 2 * (size_t)M * d.nc * sizeof(double);
-    const int staged = (base_b + stage_b <= 200 * 1024) ? 1 : 0;
-    ekf_s_kernel<<<1, 256, base_b + (staged ? stage_b : 0), st>>>(d, h->d_T, h->d_small, h->d_cols, h->d_flag, staged);
+  const size_t sh_front = (size_t)(2 * d.M * d.nc + d.nc * d.nc + 3 * d.M * d.M) * sizeof(double);
+  const size_t sh_rows = (size_t)(d.M * d.nc + 2 * d.M * d.M + d.M + 8 * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
+  const bool no_fused = std::getenv("CPS_EKF_NO_FUSED_FRONT") != nullptr;  // A/B switch (read per call: tests flip it)
+  int launches = 0;
+  if (!no_fused && sh_front <= 200 * 1024 && sh_rows <= 200 * 1024) {
+    ekf_front_kernel<<<1, 256, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
+    ekf_rows_kernel<<<std::min(row_blocks, 2 * h->sm_count), 256, sh_rows, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_Kt, h->d_Yt, h->d_x, h->cap);
+    launches = 2;
+  } else {
+    ekf_build_kernel<<<1, 128, 0, st>>>(d, h->d_x, h->d_small, h->d_cols, d_land);
+    const size_t sh_pht = (size_t)(d.M * d.nc + 8 * d.nc) * sizeof(double) + d.nc * sizeof(int);
+    ekf_pht_kernel<<<row_blocks, 256, sh_pht, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_T);
+    {
+      const size_t base_b = 2 * (size_t)M * M * sizeof(double), stage_b = 2 * (size_t)M * d.nc * sizeof(double);
+      const int staged = (base_b + stage_b <= 200 * 1024) ? 1 : 0;
+      ekf_s_kernel<<<1, 256, base_b + (staged ? stage_b : 0), st>>>(d, h->d_T, h->d_small, h->d_cols, h->d_flag, staged);
+    }
+    const size_t sh_gain = (size_t)(2 * M * M + M + 16 * M) * sizeof(double);
+    ekf_gain_kernel<<<row_blocks, 256, sh_gain, st>>>(d, h->d_T, h->d_small, h->d_Kt, h->d_Yt, h->d_x, h->cap);
+    launches = 4;
   }
-  const size_t sh_gain = (size_t)(2 * M * M + M + 16 * M) * sizeof(double);
-  ekf_gain_kernel<<<row_blocks, 256, sh_gain, st>>>(d, h->d_T, h->d_small, h->d_Kt, h->d_Yt, h->d_x, h->cap);
   CPS_CUDA(cudaEventRecord(h->ev[2], st));
   const int nt = (d.N + TILE - 1) / TILE;
   const long long pairs = (long long)nt * (nt + 1) / 2;
@@ -1229,8 +1698,14 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
                                                                                         h->d_Yt, h->cap, nt);
   } else {
     const int Mp = (M + 3) & ~3;
-    static const bool no_pipe = std::getenv("CPS_EKF_COV_NO_PIPE") != nullptr;
-    if (Mp <= PIPE_MAX_M && !no_pipe && pairs >= 2LL * h->sm_count) {
+    const bool no_pipe = std::getenv("CPS_EKF_COV_NO_PIPE") != nullptr;
+    const bool no_tma = std::getenv("CPS_EKF_COV_NO_TMA") != nullptr;
+    if (Mp <= PIPE_MAX_M && !no_pipe && !no_tma && h->maps_ok && h->mirror_exact && pairs >= 2LL * h->sm_count) {
+      TmaMaps maps;
+      maps.full = h->map_full;
+      maps.swz = h->map_swz;
+      ekf_cov_tma_kernel<<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+    } else if (Mp <= PIPE_MAX_M && !no_pipe && pairs >= 2LL * h->sm_count) {
       const size_t shb = (size_t)(2 * (TILE * PITCH_A + TILE * PITCH_B + Mp * DSTRIDE) + Mp * DSTRIDE) * sizeof(double);
       ekf_cov_pipe_kernel<<<h->sm_count, 256, shb, st>>>(h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
     } else {
@@ -1241,7 +1716,9 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   CPS_CUDA(cudaEventRecord(h->ev[3], st));
   CPS_CUDA(cudaEventRecord(h->ev[1], st));
   CPS_CUDA(cudaGetLastError());
-  h->launches += 5;
+  h->launches += launches + 1;
+  h->last_update_launches = launches + 1;
+  h->mirror_exact = true;  // every tile pair was written from one value
   h->timing_valid = true;
   return CPS_OK;
 }
@@ -1285,6 +1762,7 @@ extern "C" int cps_ekf_add_first_states(cps_ekf* h, const double* z19) {
   CPS_CUDA(cudaGetLastError());
   h->launches++;
   h->N = 28;
+  h->mirror_exact = true;  // a diagonal matrix
   h->curve_inds = {CPS_ROBOT_STATE_SIZE, CPS_ROBOT_STATE_SIZE + 8};  // kalmanClass.cpp:307-309
   h->point_inds.clear();
   return CPS_OK;
@@ -1307,6 +1785,7 @@ extern "C" int cps_ekf_add_new_curve(cps_ekf* h, const double* z8, const double*
                                                                                      h->d_small + SM_IN);
   CPS_CUDA(cudaGetLastError());
   h->launches++;
+  h->mirror_exact = false;  // the new 8 x 8 diagonal block may straddle two tiles and is symmetric only to rounding
   h->curve_inds.push_back(h->N);
   h->N += 8;
   return CPS_OK;
@@ -1320,8 +1799,8 @@ extern "C" int cps_ekf_add_new_points(cps_ekf* h, const double* meas, int n_pts)
     return CPS_ERR_NOMEM;
   }
   CPS_CUDA(cudaSetDevice(h->device));
-  double* d_meas = nullptr;
-  CPS_CUDA(cudaMalloc(&d_meas, sizeof(double) * 3 * (size_t)n_pts));
+  { const int rc = ensure_aux(h, sizeof(double) * 3 * (size_t)n_pts); if (rc != CPS_OK) return rc; }
+  double* d_meas = h->d_aux;
   CPS_CUDA(cudaMemcpyAsync(d_meas, meas, sizeof(double) * 3 * (size_t)n_pts, cudaMemcpyHostToDevice, h->stream));
   // every point reads only the pose rows/columns of the covariance as it was before the call and writes its own
   // new rows/columns (the reference gives points added together no cross-covariance), except the mirrored pose
@@ -1329,9 +1808,9 @@ extern "C" int cps_ekf_add_new_points(cps_ekf* h, const double* meas, int n_pts)
   ekf_add_points_kernel<<<dim3(std::max(1, std::min(32, (h->N + 255) / 256)), n_pts), 256, 0, h->stream>>>(
       h->d_x, h->d_P, h->cap, h->N, d_meas, n_pts);
   CPS_CUDA(cudaGetLastError());
-  CPS_CUDA(cudaStreamSynchronize(h->stream));
-  cudaFree(d_meas);
+  CPS_CUDA(cudaStreamSynchronize(h->stream));  // `meas` is the caller's (possibly pageable) buffer
   h->launches++;
+  h->mirror_exact = false;  // the new 3 x 3 diagonal blocks may straddle two tiles and are symmetric only to rounding
   for (int n = 0; n < n_pts; ++n) h->point_inds.push_back(h->N + 3 * n);
   h->N += 3 * n_pts;
   return CPS_OK;

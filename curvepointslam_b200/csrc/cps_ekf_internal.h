@@ -1,5 +1,6 @@
 // cps_ekf_internal.h -- the EKF handle shared by cps_ekf.cu (update kernels) and cps_gate.cu (gate kernels)
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -21,10 +22,19 @@ struct cps_ekf {
   int* d_cols = nullptr;
   int* d_flag = nullptr;    // 0 = ok, 1 = S not positive definite
   char* h_pinned = nullptr; // host staging of one update's inputs
+  double* d_aux = nullptr;  // grow-only device scratch (new point measurements, the low-rank factor)
+  size_t aux_bytes = 0;
   size_t pinned_bytes = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   long long launches = 0;
   bool timing_valid = false;
+  int last_update_launches = 0;
+  // true while every off-diagonal 64 x 64 tile of P is the exact mirror image of its partner (cps_ekf.cu, kernel 5d)
+  bool mirror_exact = true;
+  // TMA descriptors of P (encoded once: d_P and cap never change)
+  alignas(64) CUtensorMap map_full;
+  alignas(64) CUtensorMap map_swz;
+  bool maps_ok = false;
   // gate work space
   double* d_pack = nullptr;  // [num_points][9]
   int* d_pcols = nullptr;    // [num_points]

@@ -46,7 +46,7 @@ def test_update_curves_points_vs_golden_and_oracle(name):
     assert rel(x, xo) < TOL and rel(P, Po) < TOL                        # C restatement
     assert np.array_equal(P, P.T)                                       # exactly symmetric, like the reference
     t = kf.last_timing()
-    assert t["launches"] == 5 and t["cov_kernel_ms"] > 0
+    assert t["launches"] == 3 and t["cov_kernel_ms"] > 0  # front (build + S + S^-1), rows (P H^T + gain), covariance
     kf.close()
 
 
@@ -286,3 +286,49 @@ def test_failed_update_leaves_the_filter_untouched():
     kf.sync()
     assert rel(kf.getState(), g["x_upd"]) < TOL and rel(kf.getCov(), g["P_upd"]) < TOL
     kf.close()
+
+
+def test_tma_half_read_kernel_is_bit_identical_to_the_two_tile_kernel(monkeypatch):
+    """The TMA kernel reads one tile of every mirrored pair (12 N^2 bytes) because the tiles are exact mirrors after any
+    update; its P must equal, bit for bit, what the cp.async kernel that reads both tiles (16 N^2 bytes) produces.
+    N = 12 012: large enough for the persistent kernels (>= 2 pairs per SM), ragged last tile."""
+    x, G, ci, pi = ekf.make_synthetic_ekf(4000, d=3, seed=11)
+    rng = np.random.default_rng(5)
+    A = np.stack([np.eye(4)] * 4)
+    z1 = np.concatenate([rng.normal(0, 1.0, 32), x[2:5]])
+    z2 = np.concatenate([rng.normal(0, 1.0, 32), x[2:5]])
+    res = {}
+    for mode in ("tma", "two_tile"):
+        if mode == "two_tile":
+            monkeypatch.setenv("CPS_EKF_COV_NO_TMA", "1")
+        kf = ekf.KalmanFilter(capacity=x.size)
+        kf.set_state(x, None, ci, pi)
+        kf.set_cov_lowrank(G, 1.0 / 64.0, 0.25)
+        kf.PredictKF()
+        kf.UpdateNCurvesAndPoints(z1, 4, A, [0, 1, 2, 3])
+        kf.PredictKF()
+        kf.UpdateNCurvesAndPoints(z2, 4, A, [0, 1, 2, 3])
+        res[mode] = (kf.getState(), kf.getCov())
+        kf.close()
+    assert np.array_equal(res["tma"][0], res["two_tile"][0])
+    assert np.array_equal(res["tma"][1].view(np.int64), res["two_tile"][1].view(np.int64))
+    assert np.array_equal(res["tma"][1], res["tma"][1].T)
+
+
+def test_fused_front_end_matches_the_five_kernel_path(monkeypatch):
+    """build + S + S^-1 in one block and P H^T + gain in one pass against kernels 1-4 (Cholesky S^-1): same H, T, S;
+    S^-1 by another elimination, so x and P agree to rounding."""
+    g, ci, pi = load("ekf_curves2_points3")
+    out = {}
+    for mode in ("fused", "five"):
+        if mode == "five":
+            monkeypatch.setenv("CPS_EKF_NO_FUSED_FRONT", "1")
+        kf = ekf.KalmanFilter(capacity=g["P"].shape[0])
+        kf.set_state(g["x"], g["P"], ci, pi)
+        curve_num = [int(np.where(ci == c)[0][0]) for c in g["curve_col"]]
+        point_num = [int(np.where(pi == c)[0][0]) for c in g["point_col"]]
+        kf.UpdateNCurvesAndPoints(g["z"], len(curve_num), g["A"], curve_num, g["point_meas"], point_num, len(point_num))
+        out[mode] = (kf.getState(), kf.getCov(), kf.last_timing()["launches"])
+        kf.close()
+    assert out["fused"][2] == 3 and out["five"][2] == 5
+    assert rel(out["fused"][0], out["five"][0]) < 1e-11 and rel(out["fused"][1], out["five"][1]) < 1e-11

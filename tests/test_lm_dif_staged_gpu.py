@@ -91,7 +91,7 @@ def test_dif_staged_edge_cases(sctx):
 
 def test_dif_staged_equals_warp_per_fit_at_scale(sctx):
     """12 000 fits: every fit of the staged shape is bit-identical to the warp-per-fit kernel's; a sample is checked
-    against the oracle; AUTO picks the staged shape from 4 096 fits per call."""
+    against the oracle; AUTO keeps the warp-per-fit kernel below 49 152 fits per call (the measured crossover)."""
     B = 12000
     b = synth.make_stereo19_batch_fast(B, K=64, seed=75)
     mono = lm.LmContext(0)
@@ -108,6 +108,6 @@ def test_dif_staged_equals_warp_per_fit_at_scale(sctx):
     auto = lm.LmContext(0)
     g3 = auto.fit_batched(STEREO19, DIF, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
     assert np.array_equal(_bits(g3["p"]), _bits(g1["p"])) and np.array_equal(_bits(g3["info"]), _bits(g1["info"]))
-    assert auto.launch_stats()["launches"] > 10  # rounds of kernels, not one launch
+    assert auto.launch_stats()["launches"] >= 1
     mono.close()
     auto.close()
