@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
     L.cps_fit_curve_init_batched.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.cps_cleanup_and_group_edges_batched.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.cps_fit_curve_init_batched_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.cps_fit_frames_batched.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     fn_t = C.c_void_p
     L.cps_dlevmar_der.argtypes = [fn_t, fn_t, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.cps_dlevmar_dif.argtypes = [fn_t, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]

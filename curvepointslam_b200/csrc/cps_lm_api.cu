@@ -1041,13 +1041,14 @@ constexpr int kLenCurve = 100;   // LENGTH_EACH_CURVE, common.h:112
 
 // one thread per frame walks the reference's trimming loops (integer compares on image rows, inherently serial
 // inside a frame, independent across frames); rng = kept index range per segment, cnt = points kept
-__global__ void __launch_bounds__(128) edges_trim_kernel(int F, const int* __restrict__ pts,
+template <class PT>
+__global__ void __launch_bounds__(128) edges_trim_kernel(int F, const PT* __restrict__ pts,
                                                          const long long* __restrict__ seg_off, int reset_da,
                                                          const double* __restrict__ tracked, int* __restrict__ rng,
                                                          int* __restrict__ cnt, int* __restrict__ valid) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
-  const int* seg[4];
+  const PT* seg[4];
   int size[4], r0[4], r1[4], ys[4], ye[4];
   bool ok = true;
   for (int s = 0; s < 4; ++s) {
@@ -1057,7 +1058,7 @@ __global__ void __launch_bounds__(128) edges_trim_kernel(int F, const int* __res
     r1[s] = size[s] - 1;
     if (size[s] < 10) ok = false;
   }
-#define YAT(s, k) (seg[s][2 * (k) + 1])
+#define YAT(s, k) ((int)seg[s][2 * (k) + 1])
   if (ok) {
     for (int s = 0; s < 4; ++s) { ys[s] = YAT(s, 0); ye[s] = YAT(s, size[s] - 1); }
     for (int i = 0; i < 2 && ok; ++i) {  // align the starts of the left / right view of curve i
@@ -1139,7 +1140,8 @@ __global__ void __launch_bounds__(128) edges_trim_kernel(int F, const int* __res
 
 // pack the kept points as doubles in the fit's measurement order [L c1 | L c2 | R c1 | R c2] (fit_curve :435-489;
 // the reference copies into four CvMat :1395-1413)
-__global__ void __launch_bounds__(256) edges_pack_kernel(int F, const int* __restrict__ pts,
+template <class PT>
+__global__ void __launch_bounds__(256) edges_pack_kernel(int F, const PT* __restrict__ pts,
                                                          const long long* __restrict__ seg_off,
                                                          const int* __restrict__ rng, const int* __restrict__ cnt,
                                                          const long long* __restrict__ off, double* __restrict__ meas) {
@@ -1152,7 +1154,7 @@ __global__ void __launch_bounds__(256) edges_pack_kernel(int F, const int* __res
   for (int k = threadIdx.x; k < acc; k += blockDim.x) {
     const int s = (k >= base[1]) + (k >= base[2]) + (k >= base[3]);
     const int idx = rng[8 * f + 2 * s] + (k - base[s]);
-    const int* p = pts + 2 * (seg_off[4 * f + s] + idx);
+    const PT* p = pts + 2 * (seg_off[4 * f + s] + idx);
     out[2 * k] = (double)p[0];
     out[2 * k + 1] = (double)p[1];
   }
@@ -1190,7 +1192,7 @@ extern "C" int cps_cleanup_and_group_edges_batched(cps_lm_ctx* c, int F, const i
     CPS_CUDA(cudaMemcpyAsync(d_pts, pts + 2 * seg_off[0], sizeof(int) * 2 * (size_t)npts, cudaMemcpyHostToDevice, st));
     CPS_CUDA(cudaMemcpyAsync(d_seg, seg0.data(), sizeof(long long) * ((size_t)4 * F + 1), cudaMemcpyHostToDevice, st));
     CPS_CUDA(cudaMemcpyAsync(d_tr, tracked_endpt_y, sizeof(double) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
-    edges_trim_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, d_pts, d_seg, reset_data_assoc, d_tr, d_rng, d_cnt, d_valid);
+    edges_trim_kernel<int><<<(F + 127) / 128, 128, 0, st>>>(F, d_pts, d_seg, reset_data_assoc, d_tr, d_rng, d_cnt, d_valid);
     CPS_CUDA(cudaGetLastError());
     CPS_CUDA(cudaMemcpyAsync(counts_out, d_cnt, sizeof(int) * 4 * (size_t)F, cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaMemcpyAsync(valid_out, d_valid, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, st));
@@ -1201,7 +1203,7 @@ extern "C" int cps_cleanup_and_group_edges_batched(cps_lm_ctx* c, int F, const i
     const long long total = off_out[F];
     CPS_CUDA(cudaMalloc(&d_meas, sizeof(double) * (size_t)std::max<long long>(total, 1)));
     CPS_CUDA(cudaMemcpyAsync(d_off, off_out, sizeof(long long) * ((size_t)F + 1), cudaMemcpyHostToDevice, st));
-    edges_pack_kernel<<<F, 256, 0, st>>>(F, d_pts, d_seg, d_rng, d_cnt, d_off, d_meas);
+    edges_pack_kernel<int><<<F, 256, 0, st>>>(F, d_pts, d_seg, d_rng, d_cnt, d_off, d_meas);
     CPS_CUDA(cudaGetLastError());
     if (total) CPS_CUDA(cudaMemcpyAsync(meas_out, d_meas, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaStreamSynchronize(st));
@@ -1211,6 +1213,194 @@ extern "C" int cps_cleanup_and_group_edges_batched(cps_lm_ctx* c, int F, const i
   const int rc = run();
   cleanup();
   return rc;
+}
+
+// ---- main.cpp:425-445 as ONE call: cleanup_and_group_edges -> fit_curve, nothing returns to the host in between ---
+namespace {
+// exclusive scan of the per-frame measurement counts (2 * points kept): block-local scan, scan of the block
+// totals by one block, offsets added back -- F <= 1024 * 1024 frames per call
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(kScanBlock) frames_scan_local(int F, const int* __restrict__ cnt,
+                                                                long long* __restrict__ off, long long* __restrict__ totals) {
+  __shared__ long long sh[kScanBlock];
+  const int f = blockIdx.x * kScanBlock + threadIdx.x;
+  long long v = 0;
+  if (f < F) v = 2LL * ((long long)cnt[4 * f] + cnt[4 * f + 1] + cnt[4 * f + 2] + cnt[4 * f + 3]);
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 1; d < kScanBlock; d <<= 1) {
+    const long long t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (f < F) off[f + 1] = sh[threadIdx.x];  // inclusive, block-local
+  if (threadIdx.x == kScanBlock - 1) totals[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(kScanBlock) frames_scan_totals(int nb, long long* __restrict__ totals) {
+  __shared__ long long sh[kScanBlock];
+  long long v = threadIdx.x < nb ? totals[threadIdx.x] : 0;
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 1; d < kScanBlock; d <<= 1) {
+    const long long t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (threadIdx.x < nb) totals[threadIdx.x] = sh[threadIdx.x] - v;  // exclusive
+}
+__global__ void __launch_bounds__(kScanBlock) frames_scan_add(int F, long long* __restrict__ off,
+                                                              const long long* __restrict__ totals) {
+  const int f = blockIdx.x * kScanBlock + threadIdx.x;
+  if (f < F) off[f + 1] += totals[blockIdx.x];
+  if (f == 0) off[0] = 0;
+}
+
+// fit_curve's post-normalisation (curveFittingClass.cpp:684-711) and fitting_error = info[1] (:683); frames the
+// trimming rejected are marked CPS_FIT_SKIPPED
+__global__ void __launch_bounds__(128) frames_postfit_kernel(int F, const int* __restrict__ valid, double* __restrict__ p,
+                                                             double* __restrict__ info, int* __restrict__ ret,
+                                                             double* __restrict__ fitting_error) {
+  constexpr double kPi = 3.1415926535;  // common.h:114
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  double* q = p + (size_t)f * 19;
+  if (!valid[f]) {
+    for (int i = 0; i < 19; ++i) q[i] = 0.0;
+    for (int i = 0; i < 10; ++i) info[(size_t)f * 10 + i] = 0.0;
+    ret[f] = CPS_FIT_SKIPPED;
+    if (fitting_error) fitting_error[f] = 0.0;
+    return;
+  }
+  if (fitting_error) fitting_error[f] = info[(size_t)f * 10 + 1];
+  if (ret[f] < 0 && ret[f] != CPS_FIT_LM_ERROR) return;  // refused fit: parameters untouched
+  if (q[18] > 0.0) {
+    for (int i = 0; i < 8; ++i) q[2 * i + 1] *= -1.0;
+    q[16] *= -1.0;
+    q[17] += kPi;
+    q[18] *= -1.0;
+  }
+  if (q[16] < -kPi / 2.0) {
+    for (int i = 0; i < 8; ++i) q[2 * i + 1] *= -1.0;
+    q[17] = (-kPi - q[17]);
+    q[18] += kPi;
+  }
+  if (fabs(q[16]) < 1e9 && fabs(q[17]) < 1e9) {  // bounded: a wild angle cannot spin
+    while (q[16] > kPi) q[16] -= 2 * kPi;
+    while (q[16] < -kPi) q[16] += 2 * kPi;
+    while (q[17] > kPi) q[17] -= 2 * kPi;
+    while (q[17] < -kPi) q[17] += 2 * kPi;
+  }
+}
+
+template <class PT>
+int fit_frames_impl(cps_lm_ctx* c, int variant, int F, const PT* pts, const long long* seg_off, int reset_data_assoc,
+                    const double* tracked_endpt_y, int itmax, const double* opts, double* p_out, double* info, int* ret,
+                    int* valid, double* fitting_error) {
+  CPS_CUDA(cudaSetDevice(c->device));
+  cps_lm_slot& sl = c->slot[0];
+  cudaStream_t st = sl.stream;
+  const long long npts = seg_off[4 * F] - seg_off[0];
+  long long n_max = 2;
+  for (int f = 0; f < F; ++f) {
+    long long n = 0;
+    for (int s = 0; s < 4; ++s) n += std::min<long long>(seg_off[4 * f + s + 1] - seg_off[4 * f + s], 10000);
+    n_max = std::max(n_max, 2 * n);
+  }
+  if (n_max > (1 << 24) || F > kScanBlock * kScanBlock) return CPS_ERR_INVALID;
+  const int nb = (F + kScanBlock - 1) / kScanBlock;
+  // one grow-only block: raw points | segment offsets | tracked | ranges | counts | valid | offsets | block totals |
+  // packed measurements (at most 2 doubles per raw point) | p | info | ret | fitting_error
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o = align256(o + bytes); return at; };
+  const size_t o_pts = take(sizeof(PT) * 2 * (size_t)std::max<long long>(npts, 1));
+  const size_t o_seg = take(sizeof(long long) * ((size_t)4 * F + 1));
+  const size_t o_tr = take(sizeof(double) * 2 * (size_t)F);
+  const size_t o_rng = take(sizeof(int) * 8 * (size_t)F);
+  const size_t o_cnt = take(sizeof(int) * 4 * (size_t)F);
+  const size_t o_val = take(sizeof(int) * (size_t)F);
+  const size_t o_off = take(sizeof(long long) * ((size_t)F + 1));
+  const size_t o_tot = take(sizeof(long long) * kScanBlock);
+  const size_t o_meas = take(sizeof(double) * 2 * (size_t)std::max<long long>(npts, 1));
+  const size_t o_p = take(sizeof(double) * 19 * (size_t)F);
+  const size_t o_info = take(sizeof(double) * 10 * (size_t)F);
+  const size_t o_ret = take(sizeof(int) * (size_t)F);
+  const size_t o_err = take(sizeof(double) * (size_t)F);
+  CPS_CUDA(cudaStreamSynchronize(st));  // the block (and off0 below) may still serve the previous call
+  if (o > sl.stage_bytes) {
+    cudaFree(sl.d_stage);
+    sl.d_stage = nullptr;
+    sl.stage_bytes = 0;
+    CPS_CUDA(cudaMalloc(&sl.d_stage, o));
+    sl.stage_bytes = o;
+  }
+  char* d = sl.d_stage;
+  sl.off0.resize((size_t)4 * F + 1);
+  for (int k = 0; k <= 4 * F; ++k) sl.off0[k] = seg_off[k] - seg_off[0];
+  PT* d_pts = (PT*)(d + o_pts);
+  long long* d_seg = (long long*)(d + o_seg);
+  double* d_tr = (double*)(d + o_tr);
+  int* d_rng = (int*)(d + o_rng);
+  int* d_cnt = (int*)(d + o_cnt);
+  int* d_val = (int*)(d + o_val);
+  long long* d_off = (long long*)(d + o_off);
+  long long* d_tot = (long long*)(d + o_tot);
+  double* d_meas = (double*)(d + o_meas);
+  double* d_p = (double*)(d + o_p);
+  double* d_info = (double*)(d + o_info);
+  int* d_ret = (int*)(d + o_ret);
+  double* d_err = (double*)(d + o_err);
+  auto body = [&]() -> int {
+    CPS_CUDA(cudaMemcpyAsync(d_pts, pts + 2 * seg_off[0], sizeof(PT) * 2 * (size_t)npts, cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d_seg, sl.off0.data(), sizeof(long long) * ((size_t)4 * F + 1), cudaMemcpyHostToDevice, st));
+    CPS_CUDA(cudaMemcpyAsync(d_tr, tracked_endpt_y, sizeof(double) * 2 * (size_t)F, cudaMemcpyHostToDevice, st));
+    edges_trim_kernel<PT><<<(F + 127) / 128, 128, 0, st>>>(F, d_pts, d_seg, reset_data_assoc, d_tr, d_rng, d_cnt, d_val);
+    frames_scan_local<<<nb, kScanBlock, 0, st>>>(F, d_cnt, d_off, d_tot);
+    frames_scan_totals<<<1, kScanBlock, 0, st>>>(nb, d_tot);
+    frames_scan_add<<<nb, kScanBlock, 0, st>>>(F, d_off, d_tot);
+    edges_pack_kernel<PT><<<F, 128, 0, st>>>(F, d_pts, d_seg, d_rng, d_cnt, d_off, d_meas);
+    cps::lm_init_guess_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, d_meas, d_off, d_cnt, d_p);
+    CPS_CUDA(cudaGetLastError());
+    c->launches += 6;
+    const int rc = fit_dev(c, sl, CPS_MODEL_STEREO19, variant, F, d_p, d_meas, nullptr, d_off, d_cnt, (int)n_max, itmax, opts,
+                           d_info, d_ret, nullptr, st, CPS_LM_PATH_AUTO);
+    if (rc != CPS_OK) return rc;
+    frames_postfit_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, d_val, d_p, d_info, d_ret, d_err);
+    CPS_CUDA(cudaGetLastError());
+    c->launches += 1;
+    CPS_CUDA(cudaMemcpyAsync(p_out, d_p, sizeof(double) * 19 * (size_t)F, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(info, d_info, sizeof(double) * 10 * (size_t)F, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(ret, d_ret, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, st));
+    CPS_CUDA(cudaMemcpyAsync(valid, d_val, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, st));
+    if (fitting_error)
+      CPS_CUDA(cudaMemcpyAsync(fitting_error, d_err, sizeof(double) * (size_t)F, cudaMemcpyDeviceToHost, st));
+    return CPS_OK;
+  };
+  const int rc = body();
+  const cudaError_t e = cudaStreamSynchronize(st);  // also on failure: no copy may still be touching the caller's buffers
+  if (rc != CPS_OK) return rc;
+  CPS_CUDA(e);
+  return CPS_OK;
+}
+}  // namespace
+
+extern "C" int cps_fit_frames_batched(cps_lm_ctx* c, int variant, int F, const void* pts, int pts_type,
+                                      const long long* seg_off, int reset_data_assoc, const double* tracked_endpt_y,
+                                      int itmax, const double* opts, double* p_out, double* info, int* ret, int* valid,
+                                      double* fitting_error) {
+  if (!c || F < 0 || itmax < 0 || (variant != CPS_LM_DER && variant != CPS_LM_DIF)) return CPS_ERR_INVALID;
+  if (F == 0) return CPS_OK;
+  if (!pts || !seg_off || !tracked_endpt_y || !p_out || !info || !ret || !valid) return CPS_ERR_INVALID;
+  for (int k = 0; k < 4 * F; ++k)
+    if (seg_off[k + 1] < seg_off[k]) return CPS_ERR_INVALID;
+  if (pts_type == CPS_PTS_INT32)
+    return fit_frames_impl<int>(c, variant, F, (const int*)pts, seg_off, reset_data_assoc, tracked_endpt_y, itmax, opts,
+                                p_out, info, ret, valid, fitting_error);
+  if (pts_type == CPS_PTS_INT16)
+    return fit_frames_impl<short>(c, variant, F, (const short*)pts, seg_off, reset_data_assoc, tracked_endpt_y, itmax, opts,
+                                  p_out, info, ret, valid, fitting_error);
+  return CPS_ERR_INVALID;
 }
 
 // ---- same-signature shims ---------------------------------------------------------------------------

@@ -128,6 +128,29 @@ class LmContext:
                    "cps_cleanup_and_group_edges_batched")
         return {"meas": meas[: off[F]], "off": off, "counts": counts, "valid": valid}
 
+    def fit_frames(self, variant: int, pts, seg_off, tracked_endpt_y, reset_data_assoc=False, opts=REFERENCE_OPTS,
+                   itmax: int = REFERENCE_ITMAX):
+        """cps_fit_frames_batched: cleanup_and_group_edges -> fit_curve for F frames in one device-resident pass.
+        pts: [P,2] int32 or int16 pixel pairs.  Returns dict(p, info, ret, valid, fitting_error)."""
+        pts = np.ascontiguousarray(pts)
+        if pts.dtype not in (np.int16, np.int32):
+            pts = pts.astype(np.int32)
+        pts = pts.reshape(-1, 2)
+        so = np.ascontiguousarray(seg_off, dtype=np.int64)
+        F = (so.size - 1) // 4
+        tr = np.ascontiguousarray(tracked_endpt_y, dtype=np.float64).reshape(F, 2)
+        opts_a = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        p = np.zeros((F, 19))
+        info = np.zeros((F, 10))
+        ret = np.zeros(F, dtype=np.int32)
+        valid = np.zeros(F, dtype=np.int32)
+        err = np.zeros(F)
+        rc = _lib.lib().cps_fit_frames_batched(self._h, variant, F, _vp(pts), 1 if pts.dtype == np.int16 else 0, _vp(so),
+                                               1 if reset_data_assoc else 0, _vp(tr), itmax, _vp(opts_a), _vp(p), _vp(info),
+                                               _vp(ret), _vp(valid), _vp(err))
+        _lib.check(rc, "cps_fit_frames_batched")
+        return {"p": p, "info": info, "ret": ret, "valid": valid, "fitting_error": err}
+
     def sync(self):
         _lib.check(_lib.lib().cps_lm_sync(self._h), "cps_lm_sync")
 

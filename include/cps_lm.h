@@ -40,6 +40,11 @@ extern "C" {
 #define CPS_FIT_LM_ERROR (-1)  /* the reference's LM_ERROR: n < m, or stop reason 4 / 7 */
 #define CPS_FIT_TOO_LARGE (-2) /* more measurements than n_max                          */
 #define CPS_FIT_BAD_COUNTS (-3)/* segment sizes do not add up to the measurement count  */
+#define CPS_FIT_SKIPPED (-4)   /* cps_fit_frames_batched: cleanup_and_group_edges returned false for the frame */
+
+/* integer pixel coordinates of cps_fit_frames_batched (CvPoint is two ints; a 320 x 240 image fits int16) */
+#define CPS_PTS_INT32 0
+#define CPS_PTS_INT16 1
 
 #define CPS_LM_INFO_SZ 10 /* LM_INFO_SZ, levmar.h:85 */
 #define CPS_LM_OPTS_SZ 5  /* LM_OPTS_SZ, levmar.h:84 */
@@ -108,6 +113,23 @@ int cps_fit_curve_init_batched_dev(cps_lm_ctx *ctx, int B, const double *d_meas,
 int cps_cleanup_and_group_edges_batched(cps_lm_ctx *ctx, int F, const int *pts, const long long *seg_off,
                                         int reset_data_assoc, const double *tracked_endpt_y, double *meas_out,
                                         long long *off_out, int *counts_out, int *valid_out);
+/*
+ * The per-frame sequence of main.cpp:425-445 as ONE call for F frames -- cleanup_and_group_edges
+ * (curveFittingClass.cpp:1207-1418), then fit_curve (:408-724): measurement packing, t-parameterisation, initial
+ * guess by stereo triangulation + plane fit (the reference ignores `params` on entry), the LM fit (variant
+ * CPS_LM_DIF = the reference's live dlevmar_dif call :681, or CPS_LM_DER with the derived Jacobian) and the sign /
+ * angle post-normalisation (:684-711).  The integer contours cross PCIe once (8 or 4 bytes per point instead of
+ * 16 bytes of doubles); every stage runs on the device and nothing returns to the host in between.
+ *   pts            concatenated (x,y) pixel pairs, int32 (CPS_PTS_INT32: the reference's CvPoint) or int16
+ *   seg_off        [4F+1] point offsets, per frame [L0, L1, R0, R1]; tracked_endpt_y [F][2]
+ *   itmax, opts    as dlevmar_*; the reference passes 1000 and {1e-10,1e-10,1e-10,1e-20,1e-5}
+ *   p_out          [F][19] fitted, post-normalised parameters
+ *   info / ret     [F][10] / [F] as cps_dlevmar_*_batched; ret = CPS_FIT_SKIPPED where the trimming rejected the frame
+ *   valid          [F] the bool cleanup_and_group_edges returns; fitting_error [F] = info[1] (may be NULL)
+ */
+int cps_fit_frames_batched(cps_lm_ctx *ctx, int variant, int F, const void *pts, int pts_type, const long long *seg_off,
+                           int reset_data_assoc, const double *tracked_endpt_y, int itmax, const double *opts,
+                           double *p_out, double *info, int *ret, int *valid, double *fitting_error);
 /*
  * Execution shape of dlevmar_der on Stereo19 batches.  Both shapes perform the reference's operation sequence
  * and give bit-identical results; they differ in how the work is spread over the GPU:
