@@ -384,8 +384,106 @@ def lm_dif_bench(device: int, B: int = 65536, reps: int = 2):
     return out
 
 
+def frames_bench(device: int, F: int = 131072, distinct: int = 1024, reps: int = 2):
+    """main.cpp:425-445 end to end through cps_fit_frames_batched: integer contours (int16 pixel pairs, 4 bytes per point)
+    from pinned host memory -> cleanup_and_group_edges -> t -> initial guess -> LM -> post-normalisation -> parameters
+    back on the host; every stage on the device, copies inside the timed region.  F frames tiled from `distinct`
+    synthetic stereo frames (frames are independent: repeating them changes nothing about the work per frame)."""
+    import torch
+
+    from curvepointslam_b200 import _lib, lm, synth
+    pts, so, tr = synth.make_edge_frames(distinct, seed=31, consistent=True)
+    reps_t = (F + distinct - 1) // distinct
+    seg_len = np.diff(so)
+    pts_all = np.tile(pts.astype(np.int16), (reps_t, 1))[: int(seg_len.sum()) * reps_t]
+    so_all = np.concatenate([[0], np.cumsum(np.tile(seg_len, reps_t))]).astype(np.int64)[: 4 * F + 1]
+    tr_all = np.tile(tr, (reps_t, 1))[:F]
+    npts = int(so_all[-1])
+    h_pts = torch.from_numpy(np.ascontiguousarray(pts_all[:npts])).pin_memory()
+    h_so = torch.from_numpy(so_all).pin_memory()
+    h_tr = torch.from_numpy(np.ascontiguousarray(tr_all)).pin_memory()
+    h_p = torch.zeros((F, 19), dtype=torch.float64).pin_memory()
+    h_info = torch.zeros((F, 10), dtype=torch.float64).pin_memory()
+    h_ret = torch.zeros(F, dtype=torch.int32).pin_memory()
+    h_val = torch.zeros(F, dtype=torch.int32).pin_memory()
+    opts = np.array(lm.REFERENCE_OPTS)
+    ctx = lm.LmContext(device)
+    out = {"frames": F, "contours": 4 * F, "points": npts, "points_per_contour_mean": npts / (4.0 * F),
+           "h2d_bytes_per_step": int(h_pts.numel() * 2 + h_so.numel() * 8 + h_tr.numel() * 8),
+           "d2h_bytes_per_step": int(h_p.numel() * 8 + h_info.numel() * 8 + h_ret.numel() * 4 + h_val.numel() * 4),
+           "api": "cps_fit_frames_batched (include/cps_lm.h), int16 pixel pairs, pinned host buffers"}
+    for name, var, Fv in (("der", lm.DER, F), ("dif", lm.DIF, min(F, 65536))):
+        ts = []
+        for it in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = _lib.lib().cps_fit_frames_batched(ctx._h, var, Fv, h_pts.data_ptr(), 1, h_so.data_ptr(), 1, h_tr.data_ptr(),
+                                                   lm.REFERENCE_ITMAX, opts.ctypes.data, h_p.data_ptr(), h_info.data_ptr(),
+                                                   h_ret.data_ptr(), h_val.data_ptr(), None)
+            _lib.check(rc, "cps_fit_frames_batched")
+            if it >= 1:
+                ts.append(time.perf_counter() - t0)
+        dt = float(np.mean(ts))
+        info = h_info.numpy()[:Fv]
+        out[name] = {"frames": Fv, "e2e_ms": dt * 1e3, "frames_per_sec": Fv / dt, "contours_per_sec": 4 * Fv / dt,
+                     "valid_frames": int(h_val.numpy()[:Fv].sum()), "iters_mean": float(info[:, 5].mean()),
+                     "stop_reason_2": int((info[:, 6] == 2).sum())}
+    ctx.close()
+    return out
+
+
+def gate_sharded_bench(device: int, rank: int, world: int, L: int = 20000, nz: int = 10000, reps: int = 3, seed: int = 3):
+    """SURVEY 8(e) row 2 on hardware: the Mahalanobis gate sharded by measurement over the ranks of the job (landmark
+    state replicated: every rank forms the same covariance from the same seed), one all-gather of the int32
+    indices (curvepointslam_b200/shard.py gather_gate over NCCL).  Rank 0 also gates all measurements alone and the
+    gathered indices must equal that bit for bit.  Returns the line on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    from curvepointslam_b200 import shard
+    x, G, ci, pi = ekf.make_synthetic_ekf(L, d=3, seed=seed)
+    kf = ekf.KalmanFilter(capacity=x.size, device=device)
+    kf.set_state(x, None, ci, pi)
+    kf.set_cov_lowrank(G, 0.05 / 64.0, 0.25)
+    rng = np.random.default_rng(seed)
+    lm_xyz = x[pi[0]: pi[0] + 3 * len(pi)].reshape(-1, 3)
+    z = lm_xyz[rng.integers(0, len(pi), nz)] - x[:3] + rng.normal(0, 5.0, (nz, 3))
+    lo, hi = shard.shard_range(nz, rank, world)
+    dev = torch.device("cuda", device)
+    ts = []
+    full = None
+    for it in range(reps + 1):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx = kf.gate(z[lo:hi], ekf.CHI2_3DOF_99, want_d2=False)
+        full = shard.gather_gate(torch.from_numpy(idx).to(dev), nz, rank, world)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 1:
+            ts.append(e0.elapsed_time(e1))
+    tt = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        alone = kf.gate(z, ekf.CHI2_3DOF_99, want_d2=False)
+        t_alone = kf.gate_timing()
+        out = {"landmarks": len(pi), "measurements": nz, "ranks": world, "ms_sharded_incl_gather_max_over_ranks": float(tt.item()),
+               "single_gpu_sweep_ms": t_alone["sweep_ms"] + t_alone["pack_ms"],
+               "indices_equal_single_gpu": bool(np.array_equal(full.cpu().numpy(), alone)),
+               "note": "host-buffer entry (copies and the landmark pack inside): at 1.9 MB of packed landmarks and 40 KB of "
+                       "indices the gate is latency-, not bandwidth-bound; sharding pays only for far larger sweeps"}
+    kf.close()
+    return out
+
+
 def run(device: int = 0):
     res = {"ekf_update": [], "gate": None}
+    try:
+        res["frames_e2e"] = frames_bench(device)
+    except Exception as ex:
+        res["frames_e2e"] = {"error": repr(ex)}
     try:
         res["lm_dif"] = lm_dif_bench(device)
     except Exception as ex:

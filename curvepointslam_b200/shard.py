@@ -30,6 +30,26 @@ def gather_rows(local, total: int, rank: int, world: int):
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
 
 
+def gather_rows_to_root(local, total: int, rank: int, world: int, dst: int = 0):
+    """The same exchange with one consumer: rank `dst` receives the global [total, ...] tensor, the others None.  This is
+    what a caller that continues on one host (the reference's single process) needs, and moves world-times less data
+    than the all-gather."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, out, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
 def gather_fits(local_p, total: int, rank: int, world: int):
     """The fits' only exchange: the fitted parameter blocks [b_r, m] of all ranks -> [total, m]."""
     return gather_rows(local_p, total, rank, world)

@@ -102,9 +102,20 @@ class Oracle:
             lv.dlevmar_L2nrmxmy.restype = C.c_double
             lv.dlevmar_trans_mat_mat_mult.argtypes = [_dp, _dp, C.c_int, C.c_int]
 
+        # timing build (-O3 -march=native) of the same reference levmar + restated model: bench.py's CPU arm only
+        self.ref_fast = None
+        fpath = os.path.join(ORC_DIR, "_ref", "liborc_refshim_o3.so")
+        if os.path.exists(fpath):
+            try:
+                self.ref_fast = C.CDLL(fpath, mode=os.RTLD_NOW | os.RTLD_LOCAL | getattr(os, "RTLD_DEEPBIND", 0))
+                self.ref_fast.ref_fit_batch.argtypes = _FIT_ARGS
+                self.ref_fast.ref_fit_batch.restype = C.c_int
+            except OSError:  # built for another CPU (-march=native travels with the snapshot): fall back to the -O2 build
+                self.ref_fast = None
+
     # ---- batched fits ---------------------------------------------------------------------------
     def fit_batch(self, model, variant, p0, meas, off, counts, opts, itmax=1000, t=None, math_mode=MATH_DET,
-                  nthreads=1, use_ref=False):
+                  nthreads=1, use_ref=False, fast=False):
         """Runs B fits; returns dict(p, info, ret, extra).  use_ref=True routes the LM core through the
         reference's own dlevmar_der/dlevmar_dif (oracle/_ref)."""
         B = len(off) - 1
@@ -119,6 +130,8 @@ class Oracle:
         ret = np.zeros(B, dtype=np.int32)
         extra = np.zeros((B, 2), dtype=np.int32)
         fn = self.ref.ref_fit_batch if use_ref else self.lib.orc_fit_batch
+        if use_ref and fast and self.ref_fast is not None:
+            fn = self.ref_fast.ref_fit_batch  # timing build: not bit-identical to the checker
         rc = fn(model, variant, math_mode, B, _ptr(p, _dp), _ptr(meas, _dp), _ptr(t_a, _dp), _ptr(off, _lp),
                 _ptr(counts, _ip), itmax, _ptr(opts_a, _dp), _ptr(info, _dp), _ptr(ret, _ip), _ptr(extra, _ip),
                 nthreads)

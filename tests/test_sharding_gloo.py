@@ -39,6 +39,10 @@ def _worker(rank, world, port, out_dir):
     r = oracle().fit_batch(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
     full = shard.gather_fits(torch.from_numpy(r["p"]), TOTAL, rank, world)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full.numpy())
+    root = shard.gather_rows_to_root(torch.from_numpy(r["p"]), TOTAL, rank, world, dst=0)
+    assert (root is None) == (rank != 0)
+    if rank == 0:
+        assert torch.equal(root, full)
     dist.barrier()
     dist.destroy_process_group()
 
