@@ -17,6 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcps.so")
+OUT_LEVMAR = os.path.join(HERE, "libcps_levmar.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -66,6 +67,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     if force or _stale(OUT, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-cudart", "static"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    # libcps_levmar.so: dlevmar_der / dlevmar_dif under levmar's own names, forwarding to libcps.so
+    shim_src = os.path.join(CSRC, "cps_levmar_shim.c")
+    if force or _stale(OUT_LEVMAR, [shim_src, OUT] + headers):
+        gcc = shutil.which("gcc") or "gcc"
+        cmd = [gcc, "-O2", "-fPIC", "-shared", "-o", OUT_LEVMAR, shim_src, "-L" + HERE, "-lcps", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -1418,6 +1418,36 @@ extern "C" void cps_jacmodelfunc_image8(double*, double*, int, int, void*) {
   cps::set_last_error("cps_jacmodelfunc_image8 is a device-model token and is never executed on the host");
 }
 
+// registered host callbacks: pointers the same-signature entry points accept as names of a device model
+namespace {
+std::mutex g_reg_mutex;
+std::vector<std::pair<void*, int>> g_reg_func, g_reg_jac;
+int registered_model(const std::vector<std::pair<void*, int>>& tab, void* fn) {
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  for (const auto& e : tab)
+    if (e.first == fn) return e.second;
+  return 0;
+}
+}  // namespace
+
+extern "C" int cps_register_model(void (*func)(double*, double*, int, int, void*), int model_id) {
+  if (!func || (model_id != CPS_MODEL_STEREO19 && model_id != CPS_MODEL_IMAGE8)) return CPS_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  for (auto& e : g_reg_func)
+    if (e.first == (void*)func) { e.second = model_id; return CPS_OK; }
+  g_reg_func.emplace_back((void*)func, model_id);
+  return CPS_OK;
+}
+
+extern "C" int cps_register_jacobian(void (*jacf)(double*, double*, int, int, void*), int model_id) {
+  if (!jacf || (model_id != CPS_MODEL_STEREO19 && model_id != CPS_MODEL_IMAGE8)) return CPS_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(g_reg_mutex);
+  for (auto& e : g_reg_jac)
+    if (e.first == (void*)jacf) { e.second = model_id; return CPS_OK; }
+  g_reg_jac.emplace_back((void*)jacf, model_id);
+  return CPS_OK;
+}
+
 namespace {
 cps_lm_ctx* shim_ctx() {
   static thread_local cps_lm_ctx* ctx = nullptr;
@@ -1433,15 +1463,17 @@ int shim_fit(int variant, void (*func)(double*, double*, int, int, void*),
              void (*jacf)(double*, double*, int, int, void*), double* p, double* x, int m, int n, int itmax,
              double* opts, double* info, double* work, double* covar, void* adata) {
   int model;
-  if (func == cps_modelfunc && m == 19) model = CPS_MODEL_STEREO19;
-  else if (func == cps_modelfunc_image8 && m == 8) model = CPS_MODEL_IMAGE8;
+  const int reg = registered_model(g_reg_func, (void*)func);
+  if ((func == cps_modelfunc || reg == CPS_MODEL_STEREO19) && m == 19) model = CPS_MODEL_STEREO19;
+  else if ((func == cps_modelfunc_image8 || reg == CPS_MODEL_IMAGE8) && m == 8) model = CPS_MODEL_IMAGE8;
   else {
     cps::set_last_error("unknown model callback: the device path has no CPU fallback for host callbacks");
     return CPS_ERR_UNSUPPORTED;
   }
   if (variant == CPS_LM_DER) {
-    if ((model == CPS_MODEL_STEREO19 && jacf != cps_jacmodelfunc) ||
-        (model == CPS_MODEL_IMAGE8 && jacf != cps_jacmodelfunc_image8)) {
+    const int jreg = registered_model(g_reg_jac, (void*)jacf);
+    if ((model == CPS_MODEL_STEREO19 && jacf != cps_jacmodelfunc && jreg != CPS_MODEL_STEREO19) ||
+        (model == CPS_MODEL_IMAGE8 && jacf != cps_jacmodelfunc_image8 && jreg != CPS_MODEL_IMAGE8)) {
       cps::set_last_error("unknown Jacobian callback");
       return CPS_ERR_UNSUPPORTED;
     }

@@ -11,6 +11,7 @@
 // Everything numeric happens in the CUDA kernels behind cps_*; nothing here computes on the CPU except the
 // reference's post-fit sign/angle normalisation of 19 numbers (curveFittingClass.cpp:684-711).
 #pragma once
+#include <cstddef>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -39,9 +40,33 @@ inline void check(int rc, const char* what) {
   if (rc != CPS_OK) throw std::runtime_error(std::string(what) + ": " + cps_last_error());
 }
 
+// struct mydata (curveFittingClass.h:22-31) and its restatement in cps_lm.h must agree field by field: the
+// same-signature levmar entry points read the reference's own funcdata through it
+struct reference_mydata_layout {  // the reference's declaration, with DisplayClass* as an opaque pointer
+  double* orig_meas;
+  double* t;
+  int* curve_num;
+  int num_left1;
+  int num_right1;
+  int num_left2;
+  int num_right2;
+  void* disp;
+};
+static_assert(sizeof(cps_mydata) == sizeof(reference_mydata_layout), "cps_mydata must mirror struct mydata");
+static_assert(offsetof(cps_mydata, t) == offsetof(reference_mydata_layout, t) &&
+                  offsetof(cps_mydata, num_left1) == offsetof(reference_mydata_layout, num_left1) &&
+                  offsetof(cps_mydata, num_right1) == offsetof(reference_mydata_layout, num_right1) &&
+                  offsetof(cps_mydata, num_left2) == offsetof(reference_mydata_layout, num_left2) &&
+                  offsetof(cps_mydata, num_right2) == offsetof(reference_mydata_layout, num_right2) &&
+                  offsetof(cps_mydata, disp) == offsetof(reference_mydata_layout, disp),
+              "cps_mydata must mirror struct mydata (curveFittingClass.h:22-31)");
+
 class KalmanFilter {
  public:
-  explicit KalmanFilter(int capacity, int device = 0) : x(nullptr), num_curves(0), num_points(0) {
+  // The reference's KalmanFilter() takes no argument and re-allocates P on every augmentation
+  // (kalmanClass.cpp:362-389); here P lives on the device inside a fixed capacity: the default holds the pose, 64
+  // curves and 500 points (2 024 states, 33 MB) -- pass a capacity for larger maps.
+  explicit KalmanFilter(int capacity = 12 + 8 * 64 + 3 * 500, int device = 0) : x(nullptr), num_curves(0), num_points(0) {
     check(cps_ekf_create(&dev_, device, capacity), "cps_ekf_create");
   }
   ~KalmanFilter() {
@@ -61,6 +86,19 @@ class KalmanFilter {
     num_points = (int)points.size();
     delete x;
     x = new CvMat(N, 1);
+  }
+  // state augmentation, kalmanClass.h:43-47, same argument lists (kalmanClass.cpp:275-311, 314-499, 502-666)
+  void AddFirstStates(CvMat* measurement) {
+    check(cps_ekf_add_first_states(dev_, measurement->data.db), "cps_ekf_add_first_states");
+    refresh_tables();
+  }
+  void AddNewCurve(CvMat* measurement, CvMat* A) {
+    check(cps_ekf_add_new_curve(dev_, measurement->data.db, A->data.db), "cps_ekf_add_new_curve");
+    refresh_tables();
+  }
+  void AddNewPoints(double* measurements, int n_pts) {
+    check(cps_ekf_add_new_points(dev_, measurements, n_pts), "cps_ekf_add_new_points");
+    refresh_tables();
   }
   void PredictKF() { check(cps_ekf_predict(dev_), "cps_ekf_predict"); }  // kalmanClass.cpp:161-272
   // kalmanClass.cpp:669-945, same argument list
@@ -87,11 +125,38 @@ class KalmanFilter {
     return cps_gate_mahalanobis(dev_, z, nz, gate, idx, d2);
   }
 
+  // the reference's public member P (kalmanClass.h:153) read through a block view: the covariance stays on the
+  // device; P_block(r0, c0, nr, nc) returns the nr x nc block as a CvMat (displayClass.cpp reads the pose block)
+  CvMat P_block(int r0, int c0, int nr, int nc) {
+    CvMat m(nr, nc);
+    GetCovBlock(r0, c0, nr, nc, m.data.db);
+    return m;
+  }
+  int dim() {
+    int N = 0;
+    check(cps_ekf_dims(dev_, &N, nullptr, nullptr), "cps_ekf_dims");
+    return N;
+  }
+
   CvMat* x;  // host view refreshed by getState(); the covariance stays on the device
   int num_curves, num_points;
   std::vector<int> curve_inds, point_inds;
 
  private:
+  void refresh_tables() {
+    int N = 0, nc = 0, np = 0;
+    check(cps_ekf_dims(dev_, &N, &nc, &np), "cps_ekf_dims");
+    curve_inds.assign((size_t)nc, 0);
+    point_inds.assign((size_t)np, 0);
+    std::vector<int> ci((size_t)nc + 1), pi((size_t)np + 1);
+    check(cps_ekf_get_index_tables(dev_, ci.data(), pi.data()), "cps_ekf_get_index_tables");
+    for (int k = 0; k < nc; ++k) curve_inds[(size_t)k] = ci[(size_t)k];
+    for (int k = 0; k < np; ++k) point_inds[(size_t)k] = pi[(size_t)k];
+    num_curves = nc;
+    num_points = np;
+    delete x;
+    x = new CvMat(N, 1);
+  }
   cps_ekf* dev_ = nullptr;
 };
 
@@ -102,10 +167,11 @@ class CurveFittingClass {
   CurveFittingClass(const CurveFittingClass&) = delete;
   CurveFittingClass& operator=(const CurveFittingClass&) = delete;
 
-  // fit_curve (curveFittingClass.cpp:408-724) from the point where the initial guess is known: params holds the
-  // 19 initial parameters on entry and the fitted, normalised parameters on exit; L/R are the 2k x 1 interleaved
-  // (x,y) contour matrices of the left / right image.
-  void fit_curve(double* params, CvMat** featuresLeftImage, CvMat** featuresRightImage) {
+  // fit_curve (curveFittingClass.cpp:408-724): like the reference it IGNORES params on entry -- the initial guess is
+  // the stereo triangulation + plane fit of :516-651 (cps_fit_curve_init_batched) -- and returns the fitted,
+  // normalised parameters; L/R are the 2k x 1 interleaved (x,y) contour matrices of the left / right image.  The
+  // fourth argument of the reference (DisplayClass*, only stored) is accepted and ignored.
+  void fit_curve(double* params, CvMat** featuresLeftImage, CvMat** featuresRightImage, void* /*display*/ = nullptr) {
     CvMat* seg[4] = {featuresLeftImage[0], featuresLeftImage[1], featuresRightImage[0], featuresRightImage[1]};
     std::vector<double> meas;
     int counts[4];
@@ -114,6 +180,7 @@ class CurveFittingClass {
       meas.insert(meas.end(), seg[s]->data.db, seg[s]->data.db + 2 * counts[s]);
     }
     long long off[2] = {0, (long long)meas.size()};
+    check(cps_fit_curve_init_batched(ctx_, 1, meas.data(), off, counts, params), "cps_fit_curve_init_batched");
     double opts[5] = {1E-10, 1E-10, 1E-10, 1E-20, 1E-06 * 1E1};  // :661-662
     double info[CPS_LM_INFO_SZ];
     int ret = 0;

@@ -176,6 +176,18 @@ struct cps_mydata {
   int num_right2;
   void *disp;
 };
+/*
+ * Registers a host function pointer as a NAME for a device model, so that existing code which passes its own model
+ * function -- the reference's `modelfunc` (curveFittingClass.cpp:82, declared curveFittingClass.h:37) -- keeps
+ * compiling and linking unchanged: cps_register_model(modelfunc, CPS_MODEL_STEREO19) once at start-up, after which
+ * dlevmar_dif(modelfunc, ...) / cps_dlevmar_dif(modelfunc, ...) run the Stereo19 device model.  The pointer is only
+ * compared, never called.  The derived analytic Jacobian has no counterpart in the reference (its jacmodelfunc is
+ * stale); cps_register_jacobian names it for dlevmar_der callers.
+ * libcps_levmar.so (csrc/cps_levmar_shim.c) exports dlevmar_der / dlevmar_dif under levmar's own names
+ * (levmar.h:98-107) on top of these entry points: relink against it instead of liblevmar.a.
+ */
+int cps_register_model(void (*func)(double *p, double *hx, int m, int n, void *adata), int model_id);
+int cps_register_jacobian(void (*jacf)(double *p, double *j, int m, int n, void *adata), int model_id);
 void cps_modelfunc(double *p, double *hx, int m, int n, void *adata);
 void cps_jacmodelfunc(double *p, double *jac, int m, int n, void *adata);
 void cps_modelfunc_image8(double *p, double *hx, int m, int n, void *adata);

@@ -245,6 +245,7 @@ void refh_control2coeffs(const double *cp8, double *p8)
  * records what fit_curve hands to levmar -- the initial guess, the packed measurements, t, the segment sizes, opts,
  * itmax -- forwards to the reference's real dlevmar_dif, and records what came back before fit_curve's
  * post-normalisation touches it. */
+#ifndef REFH_GPU
 static struct {
   std::vector<double> p0, x, t, p_lm;
   int m, n, itmax, counts[4], ret, calls;
@@ -290,6 +291,14 @@ int refh_last_fit(double *p0, double *x, double *t, int *counts4, double *opts5,
   if (ret) *ret = g_hook.ret;
   return n;
 }
+
+#else  /* REFH_GPU */
+/* The relinked build (oracle/Makefile, libcps_ref_gpu.so): curveFittingClass.cpp is compiled without any macro, its
+ * dlevmar_dif call (:681) binds to libcps_levmar.so, i.e. to the CUDA path.  The one line a maintainer adds to main():
+ * tell the library that the pointer `modelfunc` names the Stereo19 device model. */
+extern "C" int cps_register_model(void (*func)(double *, double *, int, int, void *), int model_id);
+int refh_register_gpu_model(void) { return cps_register_model(modelfunc, 19); }
+#endif
 
 /* fit_curve(params, L, R, display): the four contour segments as 2k x 1 CvMat of interleaved (x, y), exactly what
  * cleanup_and_group_edges hands over (curveFittingClass.cpp:1397-1414).  Returns fitting_error (= info[1]). */
