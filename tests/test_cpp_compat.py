@@ -51,8 +51,15 @@ def test_cpp_caller_matches_oracle(tmp_path):
     rel = lambda a, bb: np.abs(a - bb).max() / np.abs(bb).max()
     assert rel(x, xo) < 1e-9 and rel(P, Po) < 1e-9
     # the reference writes opts[4] = LM_DIFF_DELTA*1E1 (curveFittingClass.cpp:662), which is NOT the double 1e-5
-    fit = oracle().fit_batch(STEREO19, DIF, b["p0"], b["meas"], b["off"], b["counts"], [1e-10, 1e-10, 1e-10, 1e-20, 1e-6 * 1e1])
-    exp = fit["p"][0].copy()
+    # like the reference, the mirror's fit_curve ignores params on entry: the initial guess is the stereo triangulation
+    # + plane fit of curveFittingClass.cpp:516-651
     import ctypes as C
+    dp = C.POINTER(C.c_double)
+    p0 = np.zeros((1, 19))
+    cnt = np.ascontiguousarray(b["counts"][0], dtype=np.int32)
+    m0 = np.ascontiguousarray(b["meas"])
+    oracle().lib.orc_stereo19_init_guess(m0.ctypes.data_as(dp), cnt.ctypes.data_as(C.POINTER(C.c_int)), p0[0].ctypes.data_as(dp), 0, 1)
+    fit = oracle().fit_batch(STEREO19, DIF, p0, b["meas"], b["off"], b["counts"], [1e-10, 1e-10, 1e-10, 1e-20, 1e-6 * 1e1])
+    exp = fit["p"][0].copy()
     oracle().lib.orc_stereo19_postfit(exp.ctypes.data_as(C.POINTER(C.c_double)))
     assert np.array_equal(p.view(np.int64), exp.view(np.int64)) and err == fit["info"][0, 1]
