@@ -417,8 +417,11 @@ __device__ __forceinline__ DifRole dif_role(int w) {
   DifRole r;
   r.r0 = 4 * R0; r.c0 = 4 * C0; r.r1 = 4 * R1; r.c1 = 4 * C1;
   r.has1 = w != 7;
-  r.hasj = w < 5;
-  r.jc = r.hasj ? 4 * w : 0;
+  // the J^T e chains of a 4-column group go to a warp whose block 0 has that group as its ROW group, so the chain's
+  // operands are the ones the block loads anyway: groups 1, 2, 3, 0, 4 on warps 0, 1, 3, 6, 7 (warps 3 and 7 share a
+  // scheduler with the lightest arithmetic load: block (4,4) stands alone)
+  r.hasj = w == 0 || w == 1 || w == 3 || w == 6 || w == 7;
+  r.jc = r.r0;
   return r;
 }
 
@@ -437,20 +440,21 @@ __device__ __forceinline__ void dif_accumulate(const double* row, const DifRole&
   double vr[4], vc[4];
   dif_load4(row + R.r0, vr);
   dif_load4(row + R.c0, vc);
+  const double e = row[20];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) S.sum[4 * i + j] += vr[i] * vc[j];
+  if (R.hasj) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S.sum[32 + j] += vr[j] * e;
+  }
   if (R.r1 != R.r0) dif_load4(row + R.r1, vr);  // warp-uniform: six of the eight pairs share their row group
   dif_load4(row + R.c1, vc);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) S.sum[16 + 4 * i + j] += vr[i] * vc[j];
-  dif_load4(row + R.jc, vc);
-  const double e = row[20];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) S.sum[32 + j] += vc[j] * e;
 }
 
 // the partial sums of a 32-row block join the running entries (ZERO: the running entries are cleared instead)
