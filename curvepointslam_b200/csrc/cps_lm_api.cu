@@ -733,8 +733,10 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
   L.p = d_p; L.meas = d_meas; L.t = d_t; L.off = d_off; L.counts = d_counts;
   L.info = d_info; L.ret = d_ret; L.extra = d_extra;
   if (path == CPS_LM_PATH_AUTO) path = c->path;
+  // fits longer than the warp-per-fit kernel's compact item list (40 row blocks = 1 280 measurements) always take the
+  // staged kernels, which walk the rows of a fit without any such list (the reference accepts 4 x 10 000 points)
   if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && path != CPS_LM_PATH_MONOLITHIC &&
-      (path == CPS_LM_PATH_STAGED || B >= kStagedMinFits))
+      (path == CPS_LM_PATH_STAGED || B >= kStagedMinFits || L.n_max > 40 * cps::kTileRows))
     return launch_staged_der19(c, sl, L, st, {StagedPiece{0, B, nullptr}});
   // central differences (opts[4] < 0) and fits longer than the staged kernels' row index stay on the warp-per-fit kernel
   if (model == CPS_MODEL_STEREO19 && variant == CPS_LM_DIF && L.forward && path != CPS_LM_PATH_MONOLITHIC &&
@@ -889,7 +891,7 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   if (n_max > (1 << 24)) return CPS_ERR_INVALID;
   CPS_CUDA(cudaSetDevice(c->device));
   const bool staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
-                      (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits);
+                      (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits || n_max > 40 * cps::kTileRows);
   if (staged) return fit_batched_host_staged(c, B, p, meas, t, off, counts, n_max, itmax, opts, info, ret, extra);
   // staged dif: larger chunks (the late rounds of a chunk run at the latency floor of the kernels)
   const bool dif_staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DIF && (!opts || opts[4] >= 0.0) &&

@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
       int ret_code = 0;
       if (nn < 19) ret_code = -1;  // lm_core.c:117
       else if (nn > A.L.n_max || (nn & 1)) ret_code = -2;
-      else if (nn > 40 * kTileRows) ret_code = -2;  // same limit as the monolithic kernel's compact path
       const int c3 = A.L.counts[4 * (size_t)f + 3];
       if (ret_code == 0 && (g.b1 < 0 || g.b2 < g.b1 || g.b3 < g.b2 || c3 < 0 || g.b3 + c3 != g.nsamp)) ret_code = -3;
       if (ret_code != 0) {

@@ -38,7 +38,9 @@ extern "C" {
 
 /* per-fit codes written to ret[] besides the reference's own values */
 #define CPS_FIT_LM_ERROR (-1)  /* the reference's LM_ERROR: n < m, or stop reason 4 / 7 */
-#define CPS_FIT_TOO_LARGE (-2) /* more measurements than n_max                          */
+#define CPS_FIT_TOO_LARGE (-2) /* more measurements than n_max; Stereo19 dlevmar_der with the path FORCED to the
+                                * warp-per-fit kernel (cps_lm_set_path MONOLITHIC): more than 1 280 measurements
+                                * (the default path sends such batches to the staged kernels, which have no limit) */
 #define CPS_FIT_BAD_COUNTS (-3)/* segment sizes do not add up to the measurement count  */
 #define CPS_FIT_SKIPPED (-4)   /* cps_fit_frames_batched: cleanup_and_group_edges returned false for the frame */
 

@@ -58,6 +58,19 @@ def test_stereo19_ragged_bit_exact(ctx, variant):
 
 
 @pytest.mark.parametrize("variant", [DER, DIF])
+def test_stereo19_long_contours_bit_exact(ctx, variant):
+    """Contours as long as a frame is tall (the reference takes up to 10 000 points per segment,
+    curveFittingClass.cpp:1383-1396): n = 3 840 and a ragged neighbour, far beyond the 1 280 measurements the
+    warp-per-fit der kernel's compact item list holds -- such batches take the staged kernels whatever their size."""
+    counts = np.array([[480, 480, 480, 480], [161, 160, 161, 160], [300, 17, 222, 401], [64, 64, 64, 64]], dtype=np.int32)
+    b = synth.make_stereo19_batch(4, seed=27, counts=counts, round_pixels=True)
+    gpu = ctx.fit_batched(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=4)
+    assert (gpu["ret"] >= 0).all()
+    assert_same_fit(gpu, cpu)
+
+
+@pytest.mark.parametrize("variant", [DER, DIF])
 def test_stereo19_explicit_t(ctx, variant):
     b = synth.make_stereo19_batch(32, K=40, seed=13)
     t = np.tile(np.linspace(0.0, 1.0, 40), 32 * 4)
