@@ -46,6 +46,7 @@ def lib() -> C.CDLL:
     L.cps_lm_set_profiling.argtypes = [vp, C.c_int]
     L.cps_lm_get_profile.argtypes = [vp, dp, lp, C.c_int]
     L.cps_lm_get_profile_work.argtypes = [vp, vp, vp, C.c_int]
+    L.cps_lm_get_solve_handovers.argtypes = [vp, vp]
     L.cps_lm_launch_stats.argtypes = [vp, ip, ip, ip, lp]
     L.cps_fit_curve_init_batched.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.cps_cleanup_and_group_edges_batched.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp]

@@ -59,6 +59,7 @@ struct cps_lm_ctx {
   int profiling = 0;
   double prof_ms[4] = {0, 0, 0, 0};     // solve, eval (incl. the initial pass), jac, tail (warp-per-fit take-over)
   long long prof_launches[4] = {0, 0, 0, 0};
+  long long solve_handovers = 0;  // systems of the last staged der call that left the block-arrow solve for the dense one
   long long prof_jac_evals = 0, prof_tail_fits = 0;  // Jacobian evaluations done by staged_jac_kernel; fits taken over
   std::vector<cudaEvent_t> ev_pool;
 };
@@ -141,6 +142,12 @@ extern "C" int cps_lm_get_profile(cps_lm_ctx* c, double* ms4, long long* launche
     if (launches4) launches4[i] = c->prof_launches[i];
     if (reset) { c->prof_ms[i] = 0.0; c->prof_launches[i] = 0; }
   }
+  return CPS_OK;
+}
+
+extern "C" int cps_lm_get_solve_handovers(cps_lm_ctx* c, long long* systems) {
+  if (!c || !systems) return CPS_ERR_INVALID;
+  *systems = c->solve_handovers;
   return CPS_OK;
 }
 
@@ -242,16 +249,22 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   const int jac_smem = kJacTableDoubles * kJacThreads * (int)sizeof(double) + (kJacThreads / 32) * (int)sizeof(WarpTiles);
   const int eval_smem = kEvalTableDoubles * kEvalThreads * (int)sizeof(double) + (kEvalThreads / 32) * (int)sizeof(WarpTiles);
   const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
+  const int arrow_smem = kArrowDoubles * kArrowThreads * (int)sizeof(double);
+  // CPS_LM_DENSE_SOLVE=1: the dense work matrix for every system (A/B measurements, tests of the hand-over)
+  const bool dense_solve = std::getenv("CPS_LM_DENSE_SOLVE") != nullptr;
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
   CPS_CUDA(cudaFuncSetAttribute(staged_jac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_smem));
-  CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
-  int jac_occ = 0, solve_occ = 0, eval_occ = 0;
+  CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
+  CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
+  CPS_CUDA(cudaFuncSetAttribute(staged_solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, arrow_smem));
+  int jac_occ = 0, solve_occ = 0, eval_occ = 0, arrow_occ = 0;
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&arrow_occ, staged_solve_kernel<true, false>, kArrowThreads, arrow_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jac_occ, staged_jac_kernel<false>, kJacThreads, jac_smem));
-  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel, kSolveThreads, solve_smem));
+  CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel<false, false>, kSolveThreads, solve_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_occ, staged_eval_kernel<false>, kEvalThreads, eval_smem));
-  if (jac_occ < 1 || solve_occ < 1 || eval_occ < 1) {
+  if (jac_occ < 1 || solve_occ < 1 || eval_occ < 1 || arrow_occ < 1) {
     cps::set_last_error("staged LM kernels do not fit on this device");
     return CPS_ERR_CUDA;
   }
@@ -269,7 +282,8 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   const size_t o_el = o;   o = a256(o + sizeof(int) * B);
   const size_t o_s0 = o;   o = a256(o + sizeof(int) * B);
   const size_t o_s1 = o;   o = a256(o + sizeof(int) * B);
-  const size_t o_cnt = o;  o = a256(o + sizeof(unsigned int) * 4);
+  const size_t o_fb = o;   o = a256(o + sizeof(int) * B);
+  const size_t o_cnt = o;  o = a256(o + sizeof(unsigned int) * 8);
   if (o > sl.staged_bytes) {
     CPS_CUDA(cudaStreamSynchronize(st));
     CPS_CUDA(cudaStreamSynchronize(sl.stream));
@@ -295,6 +309,8 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   A.solve_list[0] = (int*)(d + o_s0);
   A.solve_list[1] = (int*)(d + o_s1);
   A.cnt = (unsigned int*)(d + o_cnt);
+  A.fb_list = (int*)(d + o_fb);
+  A.force_handover = std::getenv("CPS_LM_FORCE_HANDOVER") ? std::atoi(std::getenv("CPS_LM_FORCE_HANDOVER")) : 0;
   A.init_first = 0;
   A.init_count = 0;
 
@@ -303,7 +319,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     if (gneed < 1) gneed = 1;
     return (int)std::min<size_t>(gneed, (size_t)cap);
   };
-  CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 4, st));
+  CPS_CUDA(cudaMemsetAsync(A.cnt, 0, sizeof(unsigned int) * 8, st));
   // per-kernel timing (cps_lm_set_profiling): an event pair around every launch, read after the round's sync
   struct Span { int kind; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -349,9 +365,17 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     const int nxt = cur ^ 1;
     if (n_solve > 0) {
       span_begin(0);
-      staged_solve_kernel<<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
+      if (dense_solve) {
+        staged_solve_kernel<false, false><<<grid_for(n_solve, kSolveThreads, c->sm_count * solve_occ), kSolveThreads, solve_smem, st>>>(A, cur);
+        c->launches += 1;
+      } else {
+        // block-arrow work matrix (96 systems per SM); the systems it hands back (cnt[4]: none, on every batch measured)
+        // go through the dense one
+        staged_solve_kernel<true, false><<<grid_for(n_solve, kArrowThreads, c->sm_count * arrow_occ), kArrowThreads, arrow_smem, st>>>(A, cur);
+        staged_solve_kernel<false, true><<<4, kSolveThreads, solve_smem, st>>>(A, cur);
+        c->launches += 2;
+      }
       span_end();
-      c->launches += 1;
     }
     CPS_CUDA(cudaMemsetAsync(A.cnt + 0, 0, sizeof(unsigned int), st));
     CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
@@ -410,6 +434,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     n_solve = sl.h_count[0];
     last_jac = sl.h_count[1];
     jac_evals = sl.h_count[2];
+    c->solve_handovers = sl.h_count[3];
     cur = nxt;
     ++rounds;
     if (n_solve == 0 && next_piece == pieces.size()) break;

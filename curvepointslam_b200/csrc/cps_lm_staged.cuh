@@ -51,7 +51,10 @@ struct StagedArgs {
   int* jac_list;
   int* eval_list;
   int* solve_list[2];
-  unsigned int* cnt;   // [0] jac, [1] Jacobian evaluations of the call so far, [2], [3] solve lists
+  unsigned int* cnt;   // [0] jac, [1] Jacobian evaluations of the call so far, [2], [3] solve lists,
+                       // [4] entries of fb_list this round, [5] of the call so far
+  int* fb_list;        // positions in the solve list whose system the block-arrow solve handed to the dense one
+  int force_handover;  // test knob: > 0 hands every force_handover-th list position over regardless
   int init_first, init_count;  // range of the fit index an INIT launch covers
 };
 
@@ -587,16 +590,347 @@ __device__ __forceinline__ int lu_factor_solve(double* a, double* sc, double* bx
   return 1;
 }
 
+// ---- the same solve on the block-arrow form of the Stereo19 matrix --------------------------------------------
+// J^T J + mu I of the derived Jacobian has two 8 x 8 blocks of structural zeros (the control points of one curve
+// against those of the other, written as +0.0 by the jac kernel): in the dense work matrix 128 of 361 entries are
+// zeros that no elimination step touches while the pivot of a control-point column comes from that curve's own eight
+// rows.  Only what can become non-zero is stored:
+//   rows 0..15   11 entries each: the eight columns of the row's own curve, then columns 16..18 (theta, phi, z)
+//   rows 16..18  all 19 columns
+// 233 doubles instead of 361 (+ 19 scales + 19 right-hand side = 271 per thread): 96 threads per SM instead of 64,
+// and the sweep never visits the zero blocks.  Every arithmetic operation that is performed is the dense
+// algorithm's, in its order; the operations left out are subtractions of a product with a structural zero, which
+// change nothing as long as the other factor is finite.  The two assumptions are checked, not trusted: (i) the scaled
+// pivot search of a control-point column must pick one of that curve's rows (measured: always, on 1 800 matrices of
+// scripts/pivot_stats.py); (ii) every stored factor and every solution entry must be finite.  A thread that finds
+// either violated puts its list position on the fallback list and the dense kernel solves that system afterwards.
+constexpr int kArrowThreads = 96;
+constexpr int kArrowMat = 16 * 11 + 3 * 19;           // 233
+constexpr int kArrowDoubles = kArrowMat + 19 + 19;    // + scales + right-hand side
+
+// first entry of row i's own-block columns (block b = i / 8 for i < 16; for the bottom rows the columns 8 b ..) and
+// of its columns 16..18
+__device__ __forceinline__ int arrow_blk(int i, int b) { return i < 16 ? i * 11 : 176 + (i - 16) * 19 + 8 * b; }
+__device__ __forceinline__ int arrow_tail(int i) { return i < 16 ? i * 11 + 8 : 176 + (i - 16) * 19 + 16; }
+
+// a_ik -= l_i u_k for the rows in `rowmask` (bit = row index 0..18), W consecutive stored entries starting at local
+// column c0 of the window (`tail`: columns 16..18, otherwise the own-block columns of block b); four rows in flight
+template <int T, int W, int NR>
+__device__ __forceinline__ void arrow_update_rows(double* a, const int (&base)[NR], const int (&lpos)[NR], const double (&u)[W]) {
+  double l[NR], x[NR][W];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    l[r] = a[lpos[r] * T];
+#pragma unroll
+    for (int c = 0; c < W; ++c) x[r][c] = a[(base[r] + c) * T];
+  }
+  double p[NR][W];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < W; ++c) p[r][c] = l[r] * u[c];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < W; ++c) x[r][c] -= p[r][c];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < W; ++c) a[(base[r] + c) * T] = x[r][c];
+}
+
+template <int T, int W>
+__device__ __forceinline__ void arrow_update_cols(double* a, int j, int b, bool tail, int c0, unsigned int rowmask) {
+  // pivot row j (a row of block b, or a bottom row when b == 2)
+  const int jb = (tail ? arrow_tail(j) : arrow_blk(j, b)) + c0;
+  double u[W];
+#pragma unroll
+  for (int c = 0; c < W; ++c) u[c] = a[(jb + c) * T];
+  unsigned int m = rowmask;
+#pragma unroll 1
+  while (m) {
+    int base[4], lpos[4];
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = m ? (__ffs(m) - 1) : 0;
+      if (m) { m &= m - 1; ++n; }
+      base[r] = (tail ? arrow_tail(i) : arrow_blk(i, b)) + c0;
+      lpos[r] = (b == 2 ? arrow_tail(i) + (j - 16) : arrow_blk(i, b) + (j - 8 * b));  // the multiplier l_ij
+    }
+    if (n == 4) {
+      arrow_update_rows<T, W, 4>(a, base, lpos, u);
+    } else {
+      if (n >= 2) {
+        const int b2[2] = {base[0], base[1]}, l2[2] = {lpos[0], lpos[1]};
+        arrow_update_rows<T, W, 2>(a, b2, l2, u);
+      }
+      if (n & 1) {
+        const int b1[1] = {n == 1 ? base[0] : base[2]}, l1[1] = {n == 1 ? lpos[0] : lpos[2]};
+        arrow_update_rows<T, W, 1>(a, b1, l1, u);
+      }
+    }
+  }
+}
+
+// local columns lo..hi-1 of a window in chunks of at most six
+template <int T>
+__device__ __forceinline__ void arrow_update_window(double* a, int j, int b, bool tail, int lo, int hi, unsigned int rowmask) {
+  int c0 = lo;
+  for (; c0 + 6 <= hi; c0 += 6) arrow_update_cols<T, 6>(a, j, b, tail, c0, rowmask);
+  switch (hi - c0) {
+    case 5: arrow_update_cols<T, 5>(a, j, b, tail, c0, rowmask); break;
+    case 4: arrow_update_cols<T, 4>(a, j, b, tail, c0, rowmask); break;
+    case 3: arrow_update_cols<T, 3>(a, j, b, tail, c0, rowmask); break;
+    case 2: arrow_update_cols<T, 2>(a, j, b, tail, c0, rowmask); break;
+    case 1: arrow_update_cols<T, 1>(a, j, b, tail, c0, rowmask); break;
+    default: break;
+  }
+}
+
+// the work matrix from the lower triangle in global memory (cp.async, everything in flight at once), mu on the diagonal
+template <int T>
+__device__ __forceinline__ void arrow_fill19(double* a, double* bx, const double* lower, const double* jte, double mu) {
+#pragma unroll 1
+  for (int i = 0; i < 16; ++i) {
+    const int b = i >> 3, r0 = 8 * b;
+    for (int k = 0; k < 8; ++k) {
+      const int col = r0 + k;
+      cp_async8(a + (i * 11 + k) * T, lower + (col <= i ? tri(i, col) : tri(col, i)));
+    }
+    for (int q = 0; q < 3; ++q) cp_async8(a + (i * 11 + 8 + q) * T, lower + tri(16 + q, i));
+  }
+#pragma unroll 1
+  for (int q = 0; q < 3; ++q)
+    for (int k = 0; k < 19; ++k) cp_async8(a + (176 + q * 19 + k) * T, lower + (k <= 16 + q ? tri(16 + q, k) : tri(k, 16 + q)));
+#pragma unroll
+  for (int i = 0; i < 19; ++i) cp_async8(bx + i * T, jte + i);
+  cp_async_wait_all();
+  double d[19];
+#pragma unroll
+  for (int i = 0; i < 19; ++i) d[i] = a[(i < 16 ? i * 11 + (i & 7) : 176 + (i - 16) * 19 + i) * T];
+#pragma unroll
+  for (int i = 0; i < 19; ++i) a[(i < 16 ? i * 11 + (i & 7) : 176 + (i - 16) * 19 + i) * T] = d[i] + mu;
+}
+
+// 1: solved, 0: a row is entirely zero (the dense routine's return 0), -1: the structure does not hold for this
+// system -> dense kernel
+template <int T>
+__device__ __forceinline__ int arrow_factor_solve(double* a, double* sc, double* bx, double (&xout)[19]) {
+  constexpr int M = 19;
+  {  // row scales over the stored entries (the entries left out are zeros)
+    int singular = 0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < 16; i0 += 4) {
+      double v[4][11];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 11; ++c) v[r][c] = fabs(a[((i0 + r) * 11 + c) * T]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double big = 0.0;
+#pragma unroll
+        for (int c = 0; c < 11; ++c)
+          if (v[r][c] > big) big = v[r][c];
+        if (big == 0.0) singular = 1;
+        sc[(i0 + r) * T] = 1.0 / big;
+      }
+    }
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) {
+      double v[19];
+#pragma unroll
+      for (int c = 0; c < 19; ++c) v[c] = fabs(a[(176 + q * 19 + c) * T]);
+      double big = 0.0;
+#pragma unroll
+      for (int c = 0; c < 19; ++c)
+        if (v[c] > big) big = v[c];
+      if (big == 0.0) singular = 1;
+      sc[(16 + q) * T] = 1.0 / big;
+    }
+    if (singular) return 0;
+  }
+  // ---- columns of the two curves
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j) {
+    const int b = j >> 3, jl = j & 7, r0 = 8 * b;
+    int piv = -1;
+    {
+      double merit[8], mt[3];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) merit[r] = (r >= jl) ? sc[(r0 + r) * T] * fabs(a[((r0 + r) * 11 + jl) * T]) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) mt[q] = sc[(16 + q) * T] * fabs(a[(176 + q * 19 + j) * T]);
+      double big = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r >= jl && merit[r] >= big) { big = merit[r]; piv = r0 + r; }
+      // the dense search goes on over the other curve's rows (merit exactly 0: they win only against big == 0) and the
+      // bottom rows
+      if (piv < 0 || !(big > 0.0)) return -1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (mt[q] >= big) return -1;
+    }
+    if (piv != j) {
+      double rp[11], rj[11];
+#pragma unroll
+      for (int c = 0; c < 11; ++c) { rp[c] = a[(piv * 11 + c) * T]; rj[c] = a[(j * 11 + c) * T]; }
+#pragma unroll
+      for (int c = 0; c < 11; ++c) { a[(piv * 11 + c) * T] = rj[c]; a[(j * 11 + c) * T] = rp[c]; }
+      sc[piv * T] = sc[j * T];
+      const double tb = bx[piv * T], tj = bx[j * T];
+      bx[piv * T] = tj;
+      bx[j * T] = tb;
+    }
+    // (the pivot cannot be zero: its merit is positive)
+    const double inv = 1.0 / a[(j * 11 + jl) * T];
+    unsigned int rowmask = 0;
+    {
+      double l[8], lt[3];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) l[r] = (r > jl) ? a[((r0 + r) * 11 + jl) * T] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) lt[q] = a[(176 + q * 19 + j) * T];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r > jl) {
+          a[((r0 + r) * 11 + jl) * T] = l[r] * inv;
+          if (l[r] != 0.0) rowmask |= 1u << (r0 + r);
+        }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        a[(176 + q * 19 + j) * T] = lt[q] * inv;
+        if (lt[q] != 0.0) rowmask |= 1u << (16 + q);
+      }
+    }
+    arrow_update_window<T>(a, j, b, false, jl + 1, 8, rowmask);  // the rest of the curve's columns
+    arrow_update_window<T>(a, j, b, true, 0, 3, rowmask);        // theta, phi, z
+  }
+  // ---- theta, phi, z: a dense 3 x 3 on the bottom rows
+  int piv = 15;
+#pragma unroll 1
+  for (int j = 16; j < M; ++j) {
+    {
+      double big = 0.0;
+      for (int i = j; i < M; ++i) {
+        const double merit = sc[i * T] * fabs(a[(176 + (i - 16) * 19 + j) * T]);
+        if (merit >= big) { big = merit; piv = i; }
+      }
+      if (piv < j) return -1;  // no valid merit: the dense routine would keep a pivot row from the curves' part
+    }
+    if (piv != j) {
+      double rp[M], rj[M];
+#pragma unroll
+      for (int k = 0; k < M; ++k) { rp[k] = a[(176 + (piv - 16) * 19 + k) * T]; rj[k] = a[(176 + (j - 16) * 19 + k) * T]; }
+#pragma unroll
+      for (int k = 0; k < M; ++k) { a[(176 + (piv - 16) * 19 + k) * T] = rj[k]; a[(176 + (j - 16) * 19 + k) * T] = rp[k]; }
+      sc[piv * T] = sc[j * T];
+      const double tb = bx[piv * T], tj = bx[j * T];
+      bx[piv * T] = tj;
+      bx[j * T] = tb;
+    }
+    const int jj = 176 + (j - 16) * 19 + j;
+    if (a[jj * T] == 0.0) a[jj * T] = DBL_EPSILON;
+    if (j != M - 1) {
+      const double inv = 1.0 / a[jj * T];
+      unsigned int rowmask = 0;
+      for (int i = j + 1; i < M; ++i) {
+        const double l = a[(176 + (i - 16) * 19 + j) * T];
+        a[(176 + (i - 16) * 19 + j) * T] = l * inv;
+        if (l != 0.0) rowmask |= 1u << i;
+      }
+      arrow_update_window<T>(a, j, 2, true, j - 16 + 1, 3, rowmask);
+    }
+  }
+  // ---- every stored factor finite?  (then the products with structural zeros that were left out are exact zeros)
+  {
+    bool finite = true;
+#pragma unroll 1
+    for (int e0 = 0; e0 < kArrowMat - 1; e0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = a[(e0 + q) * T];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) finite = finite && (fabs(v[q]) <= DBL_MAX);
+    }
+    finite = finite && (fabs(a[(kArrowMat - 1) * T]) <= DBL_MAX);
+    if (!finite) return -1;
+  }
+  // ---- substitutions on the permuted right-hand side, in registers
+  double bv[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) bv[i] = bx[i * T];
+  bool started = false;
+#pragma unroll
+  for (int j = 0; j < M - 1; ++j) {
+    const double xj = bv[j];
+    if (!started && xj != 0.0) started = true;
+    if (started) {
+      if (j < 16) {
+        const int b = j >> 3, jl = j & 7;
+        double l[8], lt[3];
+#pragma unroll
+        for (int r = jl + 1; r < 8; ++r) l[r] = a[((8 * b + r) * 11 + jl) * T];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) lt[q] = a[(176 + q * 19 + j) * T];
+#pragma unroll
+        for (int r = jl + 1; r < 8; ++r) bv[8 * b + r] -= l[r] * xj;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) bv[16 + q] -= lt[q] * xj;
+      } else {
+#pragma unroll
+        for (int i = j + 1; i < M; ++i) bv[i] -= a[(176 + (i - 16) * 19 + j) * T] * xj;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = M - 1; i >= 0; --i) {
+    double sum = bv[i];
+    if (i >= 16) {
+      double u[M];
+#pragma unroll
+      for (int jj = i; jj < M; ++jj) u[jj] = a[(176 + (i - 16) * 19 + jj) * T];
+#pragma unroll
+      for (int jj = i + 1; jj < M; ++jj) sum -= u[jj] * bv[jj];
+      bv[i] = sum / u[i];
+    } else {
+      const int b = i >> 3, il = i & 7;
+      double u[11];
+#pragma unroll
+      for (int c = il; c < 11; ++c) u[c] = a[(i * 11 + c) * T];
+#pragma unroll
+      for (int c = il + 1; c < 8; ++c) sum -= u[c] * bv[8 * b + c];  // ascending columns, like the dense loop
+#pragma unroll
+      for (int q = 0; q < 3; ++q) sum -= u[8 + q] * bv[16 + q];
+      bv[i] = sum / u[il];
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    xout[i] = bv[i];
+    finite = finite && (fabs(bv[i]) <= DBL_MAX);
+  }
+  return finite ? 1 : -1;
+}
+
 // Every entry of the solve list yields an entry of the eval list at the same position (the fit, or -1 if it stopped
 // here), which keeps neighbouring fits -- neighbouring memory -- together from kernel to kernel.
-__global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const StagedArgs A, int cur) {
-  constexpr int M = 19, T = kSolveThreads;
+// ARROW: the block-arrow work matrix, 96 threads per CTA; a system that does not keep the structure goes to fb_list.
+// SUB: the dense solve over the positions listed in fb_list.
+template <bool ARROW, bool SUB>
+__global__ void __launch_bounds__(ARROW ? kArrowThreads : kSolveThreads, 1) staged_solve_kernel(const StagedArgs A, int cur) {
+  constexpr int M = 19, T = ARROW ? kArrowThreads : kSolveThreads;
+  constexpr int MAT = ARROW ? kArrowMat : M * M;
   extern __shared__ double smem[];
   double* a = smem + threadIdx.x;
-  double* sc = smem + M * M * T + threadIdx.x;
-  double* bx = smem + (M * M + M) * T + threadIdx.x;
-  const unsigned int total = A.cnt[2 + cur];
-  for (unsigned int i = blockIdx.x * T + threadIdx.x; i < total; i += gridDim.x * T) {
+  double* sc = smem + MAT * T + threadIdx.x;
+  double* bx = smem + (MAT + M) * T + threadIdx.x;
+  const unsigned int total = SUB ? A.cnt[4] : A.cnt[2 + cur];
+  for (unsigned int i0 = blockIdx.x * T + threadIdx.x; i0 < total; i0 += gridDim.x * T) {
+    const unsigned int i = SUB ? (unsigned int)A.fb_list[i0] : i0;
     const int f = A.solve_list[cur][i];
     const double* lower = A.jtj + (size_t)f * kLower19;
     const double* jte = A.jte + (size_t)f * M;
@@ -609,9 +943,18 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
     int stop = 0;
     bool to_eval = false;
     double dp[M];
+    bool handed_over = false;
     for (;;) {
-      lu_fill_global19(a, bx, lower, jte, mu);
-      const int solved = lu_factor_solve<M, T>(a, sc, bx, dp);
+      int solved;
+      if (ARROW) {
+        arrow_fill19<T>(a, bx, lower, jte, mu);
+        solved = arrow_factor_solve<T>(a, sc, bx, dp);
+        if (A.force_handover > 0 && i % (unsigned int)A.force_handover == 0u) solved = -1;
+        if (solved < 0) { handed_over = true; break; }  // nothing of the fit's state has been touched
+      } else {
+        lu_fill_global19(a, bx, lower, jte, mu);
+        solved = lu_factor_solve<M, T>(a, sc, bx, dp);
+      }
       ++nlss;
       if (solved) {
         dp_sq = 0.0;
@@ -626,6 +969,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
       const int nu2 = (int)((unsigned)nu << 1);
       if (nu2 <= nu) { stop = 5; break; }
       nu = nu2;
+    }
+    if (handed_over) {
+      A.fb_list[atomicAdd(A.cnt + 4, 1u)] = (int)i;
+      continue;
     }
     if (to_eval) {
       double pv[M], gv[M];
@@ -657,6 +1004,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) staged_solve_kernel(const St
 // (cnt[0]: the host's estimate for the next round), and the running total of Jacobian evaluations the jac kernel has
 // performed in this call (cnt[1]).
 __global__ void staged_round_end_kernel(unsigned int* cnt, int nxt, volatile unsigned int* host) {
+  cnt[5] += cnt[4];
+  cnt[4] = 0;
+  host[3] = cnt[5];
   cnt[1] += cnt[0];
   host[2] = cnt[1];
   host[1] = cnt[0];

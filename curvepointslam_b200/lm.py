@@ -69,6 +69,12 @@ class LmContext:
                    "cps_lm_get_profile_work")
         return int(je.value), int(tf.value)
 
+    def solve_handovers(self) -> int:
+        """Systems of the last staged dlevmar_der call that the block-arrow solve handed to the dense one."""
+        n = C.c_longlong(0)
+        _lib.check(_lib.lib().cps_lm_get_solve_handovers(self._h, C.byref(n)), "cps_lm_get_solve_handovers")
+        return int(n.value)
+
     # -- host buffers ---------------------------------------------------------------------------------
     def fit_batched(self, model: int, variant: int, p0, meas, off, counts, opts=REFERENCE_OPTS,
                     itmax: int = REFERENCE_ITMAX, t=None):

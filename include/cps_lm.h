@@ -157,6 +157,13 @@ int cps_lm_get_profile(cps_lm_ctx *ctx, double *ms4, long long *launches4, int r
  * (a fit counts once per accepted step it computed there) and the fits the tail kernel took over.
  */
 int cps_lm_get_profile_work(cps_lm_ctx *ctx, long long *jac_evals, long long *tail_fits, int reset);
+/*
+ * The staged dlevmar_der solves (J^T J + mu I) dp = J^T e on the block-arrow form of the Stereo19 matrix (the two
+ * 8 x 8 blocks of structural zeros are not stored) and hands a system to the dense solve when the reference's scaled
+ * pivot search would leave a curve's own rows or a factor is not finite (Axb_core.c:1044-1132 is followed either
+ * way).  Number of systems of the last staged call that took that detour (0 on every batch measured so far).
+ */
+int cps_lm_get_solve_handovers(cps_lm_ctx *ctx, long long *systems);
 /* geometry of the last launch and the number of kernel launches issued through this context */
 int cps_lm_launch_stats(cps_lm_ctx *ctx, int *grid, int *block, int *smem_bytes, long long *launches);
 

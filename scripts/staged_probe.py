@@ -25,6 +25,8 @@ for name in paths:
     ctx = lm.LmContext(0)
     ctx.set_path(lm.PATH_MONOLITHIC if name == "mono" else lm.PATH_STAGED)
     ts = []
+    if os.environ.get("PROBE_PROFILE"):
+        ctx.set_profiling(True)
     for it in range(6):
         d_p.copy_(d_p0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,6 +37,8 @@ for name in paths:
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = min(ts[2:])
+    if os.environ.get("PROBE_PROFILE"):
+        print("profile (6 calls):", ctx.get_profile(), "solve hand-overs of the last call:", ctx.solve_handovers())
     res[name] = (d_p.cpu().numpy().copy(), d_info.cpu().numpy().copy())
     print(f"{name}: {ms:.3f} ms for {B} fits = {B / ms * 1e3 / 1e6:.3f} M fits/s   all {['%.2f' % t for t in ts]}  "
           f"stats {ctx.launch_stats()}", flush=True)

@@ -282,3 +282,34 @@ def test_tail_takeover_is_bit_identical(monkeypatch):
         ref = outs[0 if itmax == 1000 else 1][2]
         assert np.array_equal(_bits(r["p"]), _bits(ref["p"])) and np.array_equal(_bits(r["info"]), _bits(ref["info"]))
         assert np.array_equal(r["ret"], ref["ret"]) and np.array_equal(r["extra"], ref["extra"])
+
+
+def test_block_arrow_solve_and_hand_over(monkeypatch):
+    """The staged solve works on the block-arrow form of J^T J + mu I (zero blocks not stored) and hands a system to
+    the dense solve when the reference's pivot search would leave the structure.  Default, every third system forced
+    through the hand-over, and the dense solve for everything: the same bits, and the oracle's (which is the
+    reference's dAx_eq_b_LU_noLapack bit for bit, tests/test_oracle_lm.py)."""
+    rng = np.random.default_rng(17)
+    counts = rng.integers(5, 90, size=(700, 4)).astype(np.int32)
+    b = synth.make_stereo19_batch(700, seed=93, counts=counts, round_pixels=True)
+    p0 = b["p0"].copy()
+    p0[::5] += rng.normal(0, 0.5, size=p0[::5].shape)  # poor starts: rejected steps, large mu, re-solves
+    cpu = oracle().fit_batch(STEREO19, DER, p0, b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    seen = {}
+    for env, val in ((None, None), ("CPS_LM_FORCE_HANDOVER", "3"), ("CPS_LM_DENSE_SOLVE", "1")):
+        monkeypatch.delenv("CPS_LM_FORCE_HANDOVER", raising=False)
+        monkeypatch.delenv("CPS_LM_DENSE_SOLVE", raising=False)
+        monkeypatch.setenv("CPS_LM_STAGED_TAIL", "0")  # every solve of the batch in the staged kernels
+        if env:
+            monkeypatch.setenv(env, val)
+        c = lm.LmContext(0)
+        c.set_path(lm.PATH_STAGED)
+        try:
+            r = c.fit_batched(STEREO19, DER, p0, b["meas"], b["off"], b["counts"], OPTS)
+            assert_same_fit(r, cpu)
+            seen[env] = c.solve_handovers()
+        finally:
+            c.close()
+    # these poor starts do produce systems whose pivot leaves a curve's own rows (about 8 % of the solves; none on the
+    # benchmark batches): the hand-over is exercised even without forcing it
+    assert seen["CPS_LM_DENSE_SOLVE"] == 0 and seen[None] > 0 and seen["CPS_LM_FORCE_HANDOVER"] > seen[None], seen
