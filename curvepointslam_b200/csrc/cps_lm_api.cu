@@ -249,7 +249,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   const int jac_smem = kJacTableDoubles * kJacThreads * (int)sizeof(double) + (kJacThreads / 32) * (int)sizeof(WarpTiles);
   const int eval_smem = kEvalTableDoubles * kEvalThreads * (int)sizeof(double) + (kEvalThreads / 32) * (int)sizeof(WarpTiles);
   const int solve_smem = kSolveDoubles * kSolveThreads * (int)sizeof(double);
-  const int arrow_smem = kArrowDoubles * kArrowThreads * (int)sizeof(double);
+  const int arrow_smem = kArrowSlots * kArrowPitch * (int)sizeof(double);
   // CPS_LM_DENSE_SOLVE=1: the dense work matrix for every system (A/B measurements, tests of the hand-over)
   const bool dense_solve = std::getenv("CPS_LM_DENSE_SOLVE") != nullptr;
   CPS_CUDA(cudaFuncSetAttribute(staged_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem));

@@ -607,6 +607,9 @@ __device__ __forceinline__ int lu_factor_solve(double* a, double* sc, double* bx
 constexpr int kArrowThreads = 96;
 constexpr int kArrowMat = 16 * 11 + 3 * 19;           // 233
 constexpr int kArrowDoubles = kArrowMat + 19 + 19;    // + scales + right-hand side
+constexpr int kArrowPitch = kArrowThreads + 1;        // doubles between two entries of a system ([entry][thread], padded:
+                                                      // the warp-cooperative fill writes one system's entries from 32 lanes)
+constexpr int kArrowSlots = kArrowDoubles + 1;        // + a flag: the jac kernel's structural zeros were not zeros
 
 // first entry of row i's own-block columns (block b = i / 8 for i < 16; for the bottom rows the columns 8 b ..) and
 // of its columns 16..18
@@ -918,20 +921,93 @@ __device__ __forceinline__ int arrow_factor_solve(double* a, double* sc, double*
 
 // Every entry of the solve list yields an entry of the eval list at the same position (the fit, or -1 if it stopped
 // here), which keeps neighbouring fits -- neighbouring memory -- together from kernel to kernel.
+// Where entry e of the row-major lower triangle goes in the block-arrow matrix: (first, second) position, -1: none.
+// Entries of the zero blocks (rows 8..15 x columns 0..7) have no position at all.
+__device__ __forceinline__ short2 arrow_map_entry(int e) {
+  int i = 0;
+  while ((i + 1) * (i + 2) / 2 <= e) ++i;
+  const int k = e - i * (i + 1) / 2;
+  short2 m;
+  if (i < 16) {
+    if ((i >> 3) != (k >> 3)) { m.x = -1; m.y = -1; return m; }
+    m.x = (short)(i * 11 + (k & 7));
+    m.y = (short)(i != k ? k * 11 + (i & 7) : -1);
+  } else {
+    const int q = i - 16;
+    m.x = (short)(176 + q * 19 + k);
+    m.y = (short)(k < 16 ? k * 11 + 8 + q : (i != k ? 176 + (k - 16) * 19 + i : -1));
+  }
+  return m;
+}
+
+// Warp-cooperative fill: the 190 + 19 doubles of a system are contiguous in global memory, so the 32 lanes read them
+// as full lines and scatter them into that system's column of the work area; one system after the other, four in
+// flight.  (A thread copying its own system touches 32 different lines per instruction, 8 bytes of each.)
+template <int TS>
+__device__ __forceinline__ void arrow_fill_coop(double* wcol, int lane, int f, const double* jtj, const double* jte, const short2* amap) {
+  wcol[lane + kArrowDoubles * TS] = 0.0;  // this thread's flag
+  __syncwarp();
+#pragma unroll 1
+  for (int s0 = 0; s0 < 32; s0 += 4) {
+    int fs[4];
+    double v[4][6], r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fs[q] = __shfl_sync(0xffffffffu, f, s0 + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double* lo = jtj + (size_t)(fs[q] < 0 ? 0 : fs[q]) * kLower19;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        const int e = lane + 32 * t;
+        v[q][t] = (fs[q] >= 0 && e < kLower19) ? __ldcg(lo + e) : 0.0;
+      }
+      r[q] = (fs[q] >= 0 && lane < 19) ? __ldcg(jte + (size_t)fs[q] * 19 + lane) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (fs[q] < 0) continue;
+      double* col = wcol + (s0 + q);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        const int e = lane + 32 * t;
+        if (e < kLower19) {
+          const short2 m = amap[e];
+          if (m.x >= 0) col[m.x * TS] = v[q][t];
+          else if (v[q][t] != 0.0) col[kArrowDoubles * TS] = 1.0;
+          if (m.y >= 0) col[m.y * TS] = v[q][t];
+        }
+      }
+      if (lane < 19) col[(kArrowMat + 19 + lane) * TS] = r[q];
+    }
+  }
+  __syncwarp();
+}
+
 // ARROW: the block-arrow work matrix, 96 threads per CTA; a system that does not keep the structure goes to fb_list.
 // SUB: the dense solve over the positions listed in fb_list.
 template <bool ARROW, bool SUB>
 __global__ void __launch_bounds__(ARROW ? kArrowThreads : kSolveThreads, 1) staged_solve_kernel(const StagedArgs A, int cur) {
   constexpr int M = 19, T = ARROW ? kArrowThreads : kSolveThreads;
+  constexpr int TS = ARROW ? kArrowPitch : T;  // doubles between two entries of a thread's system
   constexpr int MAT = ARROW ? kArrowMat : M * M;
   extern __shared__ double smem[];
+  __shared__ short2 amap[ARROW ? kLower19 : 1];
   double* a = smem + threadIdx.x;
-  double* sc = smem + MAT * T + threadIdx.x;
-  double* bx = smem + (MAT + M) * T + threadIdx.x;
+  double* sc = smem + MAT * TS + threadIdx.x;
+  double* bx = smem + (MAT + M) * TS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (ARROW) {
+    for (int e = threadIdx.x; e < kLower19; e += T) amap[e] = arrow_map_entry(e);
+    __syncthreads();
+  }
   const unsigned int total = SUB ? A.cnt[4] : A.cnt[2 + cur];
-  for (unsigned int i0 = blockIdx.x * T + threadIdx.x; i0 < total; i0 += gridDim.x * T) {
-    const unsigned int i = SUB ? (unsigned int)A.fb_list[i0] : i0;
-    const int f = A.solve_list[cur][i];
+  for (unsigned int base = blockIdx.x * T; base < total; base += gridDim.x * T) {
+    const unsigned int i0 = base + threadIdx.x;
+    const bool have = i0 < total;
+    const unsigned int i = have ? (SUB ? (unsigned int)A.fb_list[i0] : i0) : 0u;
+    const int f = have ? A.solve_list[cur][i] : -1;
+    if (ARROW) arrow_fill_coop<TS>(smem + (threadIdx.x - lane), lane, f, A.jtj, A.jte, amap);
+    if (!have) continue;
     const double* lower = A.jtj + (size_t)f * kLower19;
     const double* jte = A.jte + (size_t)f * M;
     const double* pp = A.L.p + (size_t)f * M;
@@ -944,11 +1020,22 @@ __global__ void __launch_bounds__(ARROW ? kArrowThreads : kSolveThreads, 1) stag
     bool to_eval = false;
     double dp[M];
     bool handed_over = false;
+    bool filled = ARROW;  // the first system is in place (without mu)
     for (;;) {
       int solved;
       if (ARROW) {
-        arrow_fill19<T>(a, bx, lower, jte, mu);
-        solved = arrow_factor_solve<T>(a, sc, bx, dp);
+        if (filled) {
+          filled = false;
+          if (a[kArrowDoubles * TS] != 0.0) { handed_over = true; break; }
+          double d[M];
+#pragma unroll
+          for (int q = 0; q < M; ++q) d[q] = a[(q < 16 ? q * 11 + (q & 7) : 176 + (q - 16) * 19 + q) * TS];
+#pragma unroll
+          for (int q = 0; q < M; ++q) a[(q < 16 ? q * 11 + (q & 7) : 176 + (q - 16) * 19 + q) * TS] = d[q] + mu;
+        } else {
+          arrow_fill19<TS>(a, bx, lower, jte, mu);  // a re-solve with a larger mu (the previous system was singular)
+        }
+        solved = arrow_factor_solve<TS>(a, sc, bx, dp);
         if (A.force_handover > 0 && i % (unsigned int)A.force_handover == 0u) solved = -1;
         if (solved < 0) { handed_over = true; break; }  // nothing of the fit's state has been touched
       } else {
