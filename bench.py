@@ -393,12 +393,13 @@ def main():
                                    "over the device time of the step"},
             "hbm": hbm_part,
             # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of staged_jac_kernel at
-            # 262144 fits (profiles/r1s_ncu_full_staged_jac_details.csv), per launch
-            "traffic": 3.44e9 * (B / 262144.0),
-            "traffic_source": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full` "
-                              "capture of staged_jac_kernel at 262144 fits (profiles/r1_final_ncu_full_staged_jac_details.csv; "
-                              "the kernel is unchanged since), scaled by the batch size",
-            "traffic_note": "ncu: 2.41 GB read + 1.03 GB written per full-batch launch of staged_jac_kernel at 262144 "
+            # 262144 fits (profiles/r2_final_ncu_full_staged_jac_details.csv: 2.423 GB + 1.015 GB), per launch
+            "traffic": 3.438e9 * (B / 262144.0),
+            "traffic_source": "ncu, not this run (a profiler cannot run inside a timed bench): dram__bytes_read.sum + "
+                              "dram__bytes_write.sum of the round-2 `ncu --set full` capture of staged_jac_kernel at 262144 fits "
+                              "(profiles/r2_final_ncu_full_staged_jac_details.csv, scripts/gpu_r2_profiles.sh), scaled by the "
+                              "batch size",
+            "traffic_note": "ncu: 2.42 GB read + 1.01 GB written per full-batch launch of staged_jac_kernel at 262144 "
                             "fits (samples 1.6 GB + J^T J / work-area traffic); algorithmic 0.4 GB of J^T J output + 1.6 "
                             "GB of samples",
         }

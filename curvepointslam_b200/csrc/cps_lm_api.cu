@@ -59,6 +59,7 @@ struct cps_lm_ctx {
   int profiling = 0;
   double prof_ms[4] = {0, 0, 0, 0};     // solve, eval (incl. the initial pass), jac, tail (warp-per-fit take-over)
   long long prof_launches[4] = {0, 0, 0, 0};
+  cudaEvent_t ev_last = nullptr;  // end of the last device-entry call (calls on different streams serialise on it)
   long long solve_handovers = 0;  // systems of the last staged der call that left the block-arrow solve for the dense one
   long long prof_jac_evals = 0, prof_tail_fits = 0;  // Jacobian evaluations done by staged_jac_kernel; fits taken over
   std::vector<cudaEvent_t> ev_pool;
@@ -114,6 +115,7 @@ extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->ev_last) cudaEventDestroy(c->ev_last);
   delete c;
 }
 
@@ -787,8 +789,14 @@ extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int
   if (B == 0) return CPS_OK;
   CPS_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
-  return fit_dev(c, c->slot[0], model, variant, B, d_p, d_meas, d_t, d_off, d_counts, n_max, itmax, opts, d_info,
-                 d_ret, d_extra, st, CPS_LM_PATH_AUTO);
+  // the context has ONE fit queue and work area: a call on another stream queues behind the previous call's kernels
+  // instead of resetting the queue they are still reading
+  if (!c->ev_last) CPS_CUDA(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
+  else CPS_CUDA(cudaStreamWaitEvent(st, c->ev_last, 0));
+  const int rc = fit_dev(c, c->slot[0], model, variant, B, d_p, d_meas, d_t, d_off, d_counts, n_max, itmax, opts, d_info,
+                         d_ret, d_extra, st, CPS_LM_PATH_AUTO);
+  cudaEventRecord(c->ev_last, st);
+  return rc;
 }
 
 namespace {

@@ -81,6 +81,8 @@ int cps_dlevmar_dif_batched(cps_lm_ctx *ctx, int model, int B, double *p, const 
  * default stream, as in any CUDA call).  n_max = an even upper bound on off[f+1]-off[f].  The monolithic shape (see
  * cps_lm_set_path) only enqueues work and returns; the staged shape returns when the fits are done (its host loop
  * reads the number of fits still iterating after every round).  Either way the outputs are ordered on `stream`.
+ * A context owns one fit queue and one work area: calls made on different streams are ordered one after the other (the
+ * later call's stream waits for the earlier call's kernels); use one context per stream for concurrent batches.
  */
 int cps_lm_fit_batched_dev(cps_lm_ctx *ctx, int model, int variant, int B, double *d_p, const double *d_meas,
                            const double *d_t, const long long *d_off, const int *d_counts, int n_max, int itmax,
