@@ -99,6 +99,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pixel_batch(B, seed, first):
+    """The bench's contours: synthetic samples rounded to integer pixel coordinates -- what the reference's detector
+    hands to fit_curve (CvPoint sequences, featureDetector.cpp:213-288).  Every arm (resident, end to end, CPU) fits the
+    same values; the end-to-end arm ships them as the int16 pairs they are."""
+    from curvepointslam_b200 import synth
+    b = synth.make_stereo19_batch_fast(B, K=K_PTS, seed=seed, first=first)
+    b["meas"] = np.rint(b["meas"])
+    assert np.abs(b["meas"]).max() < 32767
+    return b
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path: levmar-2.5 compiled unchanged (oracle/_ref) driven
     by the restated model, all host threads, on a bounded sample of the same workload."""
@@ -114,7 +125,7 @@ def reference_arm(args, rank, world):
     per_fit_core_s = 0.6e-3 if variant == DER else 5.5e-3
     sample = int(max(256, min(args.fits, 1.5 * cores / per_fit_core_s)))  # about 1.5 s per step
     sample = (sample // 64) * 64
-    b = synth.make_stereo19_batch_fast(sample, K=K_PTS, seed=args.seed, first=0)
+    b = pixel_batch(sample, args.seed, 0)
     opts = list(lm.REFERENCE_OPTS)
     fast = use_ref and o.ref_fast is not None  # the -O3 timing build of the same sources (oracle/Makefile)
     run = lambda: o.fit_batch(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], opts, nthreads=cores,
@@ -130,7 +141,7 @@ def reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "bezier_lm_fits_per_sec", "value": val, "unit": "fits/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (integer pixel coordinates, like the reference's CvPoint contours)",
         "config": dict(workload_config(args, args.fits), reference_arm_fits_per_step=sample,
                        reference_arm_note=f"a rate metric: the CPU arm runs {sample} fits of the same per-fit workload per "
                                           "step (bounded sample), not the GPU arm's batch"),
@@ -184,8 +195,9 @@ def main():
     ctx.set_profiling(True)  # CUDA-event pairs around the staged shape's kernels (about 130 events per step)
 
     # ---- synthetic shard of this rank (weak scaling: B fits per GPU) ---------------------------------
-    b = synth.make_stereo19_batch_fast(B, K=K_PTS, seed=args.seed, first=first_fit)
+    b = pixel_batch(B, args.seed, first_fit)
     h_meas = torch.from_numpy(b["meas"]).pin_memory()
+    h_pix = torch.from_numpy(b["meas"].astype(np.int16)).pin_memory()  # what the end-to-end arm ships
     h_p0 = torch.from_numpy(b["p0"]).pin_memory()
     h_off = torch.from_numpy(b["off"]).pin_memory()
     h_cnt = torch.from_numpy(b["counts"]).pin_memory()
@@ -284,13 +296,13 @@ def main():
     h_info = torch.zeros((B, 10), dtype=torch.float64).pin_memory()
     h_ret = torch.zeros(B, dtype=torch.int32).pin_memory()
     h_p = h_p.pin_memory()
-    fn = _lib.lib().cps_dlevmar_der_batched if variant == lm.DER else _lib.lib().cps_dlevmar_dif_batched
+    fn = _lib.lib().cps_dlevmar_batched_pix
     opts = np.array(lm.REFERENCE_OPTS)
 
     def step_e2e():
-        rc = fn(ctx._h, M, B, h_p.data_ptr(), h_meas.data_ptr(), None, h_off.data_ptr(), h_cnt.data_ptr(),
+        rc = fn(ctx._h, M, variant, B, h_p.data_ptr(), h_pix.data_ptr(), 1, h_off.data_ptr(), h_cnt.data_ptr(),
                 lm.REFERENCE_ITMAX, opts.ctypes.data, h_info.data_ptr(), h_ret.data_ptr(), None)
-        _lib.check(rc, "cps_dlevmar_*_batched")
+        _lib.check(rc, "cps_dlevmar_batched_pix")
         if world > 1:
             d_p.copy_(h_p, non_blocking=True)
             gather_async(d_p)
@@ -354,7 +366,7 @@ def main():
     achieved_tf = fl / (kernel_ms_avg * 1e-3) / 1e12
     value = fits_all * args.steps / (ms_total * 1e-3)
     e2e_val = fits_all * args.steps / (e2e_ms * 1e-3)
-    h2d = h_meas.numel() * 8 + h_p0.numel() * 8 + h_off.numel() * 8 + h_cnt.numel() * 4
+    h2d = h_pix.numel() * 2 + h_p0.numel() * 8 + h_off.numel() * 8 + h_cnt.numel() * 4
     d2h = h_p.numel() * 8 + h_info.numel() * 8 + h_ret.numel() * 4
     peak_note = ("measured live by cps_measure_fp64_peak (DFMA stream; MEASURED_PEAKS.json has no FP64 entry); a kernel "
                  f"that may not fuse multiply-adds (bit-exact parity) tops out at {pk_ma.value:.2f} TFLOP/s")
@@ -417,14 +429,15 @@ def main():
     line = {
         "metric": "bezier_lm_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic (integer pixel coordinates, like the reference's CvPoint contours)",
         "config": dict(workload_config(args, B), exchange="gather of the fitted control points to rank 0 (NCCL), "
                        "asynchronous on a side stream: step i's gather rides under step i+1's kernels; the timed region "
                        "ends when the last gather has landed", total_fits_per_step=fits_all),
         "contours_per_sec": 4 * value,
         "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "bytes_scope": "per rank (every rank copies its own shard; the job moves n_gpus times as much)",
-                "api": f"cps_dlevmar_{args.variant}_batched (include/cps_lm.h), pinned host buffers, "
+                "api": f"cps_dlevmar_batched_pix, variant {args.variant} (include/cps_lm.h): the contours' integer pixel "
+                       "coordinates as int16 pairs (the double entry cps_dlevmar_*_batched moves 4x the bytes), pinned host buffers, "
                        "the batch streams in while the fits that have arrived iterate"},
         "execution_shape": "staged (solve / eval / jac phase kernels, thread per fit; the last fits finish in the warp-per-fit kernel)" if staged
                            else "monolithic (one persistent kernel, warp per fit)",

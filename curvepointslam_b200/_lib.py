@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
     host_args = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.cps_dlevmar_der_batched.argtypes = host_args
     L.cps_dlevmar_dif_batched.argtypes = host_args
+    L.cps_dlevmar_batched_pix.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
     L.cps_lm_fit_batched_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp,
                                          vp, vp, vp, vp]
     L.cps_lm_set_path.argtypes = [vp, C.c_int]

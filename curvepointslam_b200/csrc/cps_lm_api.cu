@@ -803,13 +803,38 @@ namespace {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Samples that arrive as integer pixel coordinates (the reference's CvPoint contours; 4 or 2 bytes per coordinate on
+// the bus instead of 8) become the doubles the kernels read -- exactly, every pixel coordinate is a double.
+template <typename T>
+__global__ void pix_to_meas_kernel(const T* __restrict__ src, double* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (double)src[i];
+}
+inline size_t pix_size(int pix_type) { return pix_type == CPS_PTS_INT16 ? sizeof(short) : sizeof(int); }
+// host samples [first, first + count) -> device doubles at `dst`, through `stage` when they are integers (pix_type < 0: doubles)
+int copy_samples(const void* host, int pix_type, long long first, long long count, double* dst, void* stage,
+                 cudaStream_t st) {
+  if (count <= 0) return CPS_OK;
+  if (pix_type < 0) {
+    CPS_CUDA(cudaMemcpyAsync(dst, (const double*)host + first, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, st));
+    return CPS_OK;
+  }
+  const size_t es = pix_size(pix_type);
+  CPS_CUDA(cudaMemcpyAsync(stage, (const char*)host + es * (size_t)first, es * (size_t)count, cudaMemcpyHostToDevice, st));
+  const int grid = (int)std::min<long long>((count + 1023) / 1024, 4096);
+  if (pix_type == CPS_PTS_INT16) pix_to_meas_kernel<short><<<grid, 256, 0, st>>>((const short*)stage, dst, count);
+  else pix_to_meas_kernel<int><<<grid, 256, 0, st>>>((const int*)stage, dst, count);
+  CPS_CUDA(cudaGetLastError());
+  return CPS_OK;
+}
+
 // Host buffers, staged shape: the whole batch gets one staging block; p / offsets / counts go first, then the samples
 // in pieces on the copy stream (slot 1), each followed by an event.  The rounds (slot 0's stream) pick a piece up as
 // soon as its event has fired, so the fits of the first pieces are already iterating while the rest of the batch
 // is still crossing PCIe; results come back in one copy at the end.
-int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas, const double* t, const long long* off,
-                            const int* counts, long long n_max, int itmax, const double* opts, double* info, int* ret,
-                            int* extra) {
+int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const void* meas, int pix_type, const double* t,
+                            const long long* off, const int* counts, long long n_max, int itmax, const double* opts,
+                            double* info, int* ret, int* extra) {
   constexpr int m = 19, nseg = 4;
   cps_lm_slot& sl = c->slot[0];
   cudaStream_t st = sl.stream, cp = c->slot[1].stream;
@@ -821,7 +846,8 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas,
   size_t o_info = align256(o_cnt + sizeof(int) * (size_t)B * nseg);
   size_t o_ret = align256(o_info + sizeof(double) * (size_t)B * 10);
   size_t o_ext = align256(o_ret + sizeof(int) * (size_t)B);
-  const size_t bytes = align256(o_ext + sizeof(int) * (size_t)B * 2);
+  size_t o_pix = align256(o_ext + sizeof(int) * (size_t)B * 2);
+  const size_t bytes = align256(o_pix + (pix_type < 0 ? 0 : pix_size(pix_type) * (size_t)total));
   CPS_CUDA(cudaStreamSynchronize(st));
   CPS_CUDA(cudaStreamSynchronize(cp));
   if (bytes > sl.stage_bytes) {
@@ -863,8 +889,9 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas,
       CPS_CUDA(cudaMemcpyAsync(d + o_cnt + sizeof(int) * (size_t)f0 * nseg, counts + (size_t)f0 * nseg,
                                sizeof(int) * (size_t)(f1 - f0) * nseg, cudaMemcpyHostToDevice, cp));
       if (m1 > m0) {
-        CPS_CUDA(cudaMemcpyAsync(d + o_meas + sizeof(double) * (size_t)m0, meas + base + m0,
-                                 sizeof(double) * (size_t)(m1 - m0), cudaMemcpyHostToDevice, cp));
+        const int rc_s = copy_samples(meas, pix_type, base + m0, m1 - m0, (double*)(d + o_meas) + m0,
+                                      d + o_pix + (pix_type < 0 ? 0 : pix_size(pix_type) * (size_t)m0), cp);
+        if (rc_s != CPS_OK) return rc_s;
         if (t)
           CPS_CUDA(cudaMemcpyAsync(d + o_t + sizeof(double) * (size_t)(m0 / 2), t + (base + m0) / 2,
                                    sizeof(double) * (size_t)((m1 - m0) / 2), cudaMemcpyHostToDevice, cp));
@@ -906,8 +933,8 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const double* meas,
 // Host buffers: the batch is cut into chunks of kChunkFits fits; chunk i+1 is copied (and its results of
 // chunk i-1 copied back) on the other slot's stream while chunk i computes.  Pinned host memory makes the
 // copies truly asynchronous; pageable memory works but serialises.
-int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, const double* meas, const double* t,
-                     const long long* off, const int* counts, int itmax, const double* opts, double* info,
+int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, const void* meas, int pix_type,
+                     const double* t, const long long* off, const int* counts, int itmax, const double* opts, double* info,
                      int* ret, int* extra) {
   if (!c || B < 0 || !p || !meas || !off || !counts || !info || !ret || itmax < 0) return CPS_ERR_INVALID;
   if (model != CPS_MODEL_STEREO19 && model != CPS_MODEL_IMAGE8) return CPS_ERR_UNSUPPORTED;
@@ -925,7 +952,7 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   CPS_CUDA(cudaSetDevice(c->device));
   const bool staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
                       (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits || n_max > 40 * cps::kTileRows);
-  if (staged) return fit_batched_host_staged(c, B, p, meas, t, off, counts, n_max, itmax, opts, info, ret, extra);
+  if (staged) return fit_batched_host_staged(c, B, p, meas, pix_type, t, off, counts, n_max, itmax, opts, info, ret, extra);
   // staged dif: larger chunks (the late rounds of a chunk run at the latency floor of the kernels)
   const bool dif_staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DIF && (!opts || opts[4] >= 0.0) &&
                           c->path != CPS_LM_PATH_MONOLITHIC && (c->path == CPS_LM_PATH_STAGED || B >= kDifStagedMinFits);
@@ -933,7 +960,7 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   const int n_chunks = (B + chunk - 1) / chunk;
   struct Staged {
     int f0, nb;
-    size_t o_p, o_meas, o_t, o_off, o_cnt, o_info, o_ret, o_ext;
+    size_t o_p, o_meas, o_t, o_off, o_cnt, o_info, o_ret, o_ext, o_pix;
   } desc[kSlots];
   // copies of chunk ci into its slot's staging block: p | meas | t | off | counts | info | ret | extra
   auto stage_in = [&](int ci) -> int {
@@ -952,7 +979,8 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
     D.o_info = align256(D.o_cnt + sizeof(int) * (size_t)nb * nseg);
     D.o_ret = align256(D.o_info + sizeof(double) * (size_t)nb * 10);
     D.o_ext = align256(D.o_ret + sizeof(int) * (size_t)nb);
-    const size_t bytes = align256(D.o_ext + sizeof(int) * (size_t)nb * 2);
+    D.o_pix = align256(D.o_ext + sizeof(int) * (size_t)nb * 2);
+    const size_t bytes = align256(D.o_pix + (pix_type < 0 ? 0 : pix_size(pix_type) * (size_t)total));
     // the slot's previous chunk must have drained before its staging block / offsets are reused
     CPS_CUDA(cudaStreamSynchronize(st));
     if (bytes > sl.stage_bytes) {
@@ -966,7 +994,10 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
     sl.off0.resize((size_t)nb + 1);
     for (int f = 0; f <= nb; ++f) sl.off0[f] = off[f0 + f] - base;
     CPS_CUDA(cudaMemcpyAsync(d + D.o_p, p + (size_t)f0 * m, sizeof(double) * (size_t)nb * m, cudaMemcpyHostToDevice, st));
-    CPS_CUDA(cudaMemcpyAsync(d + D.o_meas, meas + base, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, st));
+    {
+      const int rc_s = copy_samples(meas, pix_type, base, total, (double*)(d + D.o_meas), d + D.o_pix, st);
+      if (rc_s != CPS_OK) return rc_s;
+    }
     if (t)
       CPS_CUDA(cudaMemcpyAsync(d + D.o_t, t + base / 2, sizeof(double) * (size_t)(total / 2), cudaMemcpyHostToDevice, st));
     CPS_CUDA(cudaMemcpyAsync(d + D.o_off, sl.off0.data(), sizeof(long long) * (size_t)(nb + 1), cudaMemcpyHostToDevice, st));
@@ -1003,7 +1034,11 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
     if (ci + 1 < n_chunks) rc = stage_in(ci + 1);
     if (rc == CPS_OK) rc = run(ci);
   }
-  if (rc != CPS_OK) return rc;
+  if (rc != CPS_OK) {
+    // copies into / out of the caller's buffers may still be queued: they must not outlive this call
+    for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(c->slot[i].stream);
+    return rc;
+  }
   for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
   return CPS_OK;
 }
@@ -1013,13 +1048,21 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
 extern "C" int cps_dlevmar_der_batched(cps_lm_ctx* c, int model, int B, double* p, const double* meas,
                                        const double* t, const long long* off, const int* counts, int itmax,
                                        const double* opts, double* info, int* ret, int* extra) {
-  return fit_batched_host(c, model, CPS_LM_DER, B, p, meas, t, off, counts, itmax, opts, info, ret, extra);
+  return fit_batched_host(c, model, CPS_LM_DER, B, p, meas, -1, t, off, counts, itmax, opts, info, ret, extra);
 }
 
 extern "C" int cps_dlevmar_dif_batched(cps_lm_ctx* c, int model, int B, double* p, const double* meas,
                                        const double* t, const long long* off, const int* counts, int itmax,
                                        const double* opts, double* info, int* ret, int* extra) {
-  return fit_batched_host(c, model, CPS_LM_DIF, B, p, meas, t, off, counts, itmax, opts, info, ret, extra);
+  return fit_batched_host(c, model, CPS_LM_DIF, B, p, meas, -1, t, off, counts, itmax, opts, info, ret, extra);
+}
+
+extern "C" int cps_dlevmar_batched_pix(cps_lm_ctx* c, int model, int variant, int B, double* p, const void* pix, int pix_type,
+                                       const long long* off, const int* counts, int itmax, const double* opts,
+                                       double* info, int* ret, int* extra) {
+  if (pix_type != CPS_PTS_INT32 && pix_type != CPS_PTS_INT16) return CPS_ERR_INVALID;
+  if (variant != CPS_LM_DER && variant != CPS_LM_DIF) return CPS_ERR_INVALID;
+  return fit_batched_host(c, model, variant, B, p, pix, pix_type, nullptr, off, counts, itmax, opts, info, ret, extra);
 }
 
 // ---- fit_curve's initial guess -------------------------------------------------------------------------------
@@ -1526,7 +1569,7 @@ int shim_fit(int variant, void (*func)(double*, double*, int, int, void*),
   long long off[2] = {0, n};
   int ret = 0;
   double linfo[CPS_LM_INFO_SZ];
-  int rc = fit_batched_host(c, model, variant, 1, p, x, d->t, off, counts, itmax, opts, linfo, &ret, nullptr);
+  int rc = fit_batched_host(c, model, variant, 1, p, x, -1, d->t, off, counts, itmax, opts, linfo, &ret, nullptr);
   if (rc != CPS_OK) return rc;
   if (info) std::memcpy(info, linfo, sizeof linfo);
   return ret;

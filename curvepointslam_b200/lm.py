@@ -96,6 +96,27 @@ class LmContext:
         _lib.check(rc, "cps_dlevmar_*_batched")
         return {"p": p, "info": info, "ret": ret, "extra": extra}
 
+    def fit_batched_pix(self, model: int, variant: int, p0, pix, off, counts, opts=REFERENCE_OPTS,
+                        itmax: int = REFERENCE_ITMAX):
+        """The same with the samples as integer pixel coordinates (int32 or int16 array, measurement order): 4 or 2
+        bytes per coordinate cross the bus instead of 8."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        B = len(off) - 1
+        m = 19 if model == STEREO19 else 8
+        p = np.ascontiguousarray(p0, dtype=np.float64).reshape(B, m).copy()
+        pix = np.ascontiguousarray(pix)
+        if pix.dtype not in (np.int32, np.int16):
+            raise TypeError("pix must be int32 or int16")
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        opts_a = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        info = np.zeros((B, 10))
+        ret = np.zeros(B, dtype=np.int32)
+        extra = np.zeros((B, 2), dtype=np.int32)
+        rc = _lib.lib().cps_dlevmar_batched_pix(self._h, model, variant, B, _vp(p), _vp(pix), 1 if pix.dtype == np.int16 else 0,
+                                               _vp(off), _vp(counts), itmax, _vp(opts_a), _vp(info), _vp(ret), _vp(extra))
+        _lib.check(rc, "cps_dlevmar_batched_pix")
+        return {"p": p, "info": info, "ret": ret, "extra": extra}
+
     # -- device buffers (raw pointers, e.g. torch tensors' data_ptr()) ---------------------------------
     def fit_batched_dev(self, model: int, variant: int, B: int, d_p: int, d_meas: int, d_t: int | None,
                         d_off: int, d_counts: int, n_max: int, d_info: int, d_ret: int, d_extra: int | None,

@@ -77,6 +77,17 @@ int cps_dlevmar_dif_batched(cps_lm_ctx *ctx, int model, int B, double *p, const 
                             double *info, int *ret, int *extra);
 
 /*
+ * The same fits with the samples as INTEGER pixel coordinates -- what the reference's detector produces (CvPoint
+ * contours, featureDetector.cpp:213-288, packed by fit_curve :435-489) -- in the measurement order and with the `off`
+ * (in measurements) and `counts` of the entries above.  The samples cross PCIe as 4 (CPS_PTS_INT32) or 2
+ * (CPS_PTS_INT16) bytes per coordinate instead of 8 and become doubles on the device (exactly: a pixel coordinate is a
+ * double); t is derived from the image rows as fit_curve does.  variant = CPS_LM_DER / CPS_LM_DIF.
+ */
+int cps_dlevmar_batched_pix(cps_lm_ctx *ctx, int model, int variant, int B, double *p, const void *pix, int pix_type,
+                            const long long *off, const int *counts, int itmax, const double *opts, double *info,
+                            int *ret, int *extra);
+
+/*
  * Same with DEVICE buffers already resident in HBM, on `stream` (a cudaStream_t passed as void*; NULL = the CUDA
  * default stream, as in any CUDA call).  n_max = an even upper bound on off[f+1]-off[f].  The monolithic shape (see
  * cps_lm_set_path) only enqueues work and returns; the staged shape returns when the fits are done (its host loop

@@ -71,6 +71,30 @@ def test_stereo19_long_contours_bit_exact(ctx, variant):
 
 
 @pytest.mark.parametrize("variant", [DER, DIF])
+@pytest.mark.parametrize("dtype", [np.int32, np.int16])
+def test_integer_pixel_samples_equal_the_double_entry(ctx, variant, dtype):
+    """cps_dlevmar_batched_pix: CvPoint-style integer samples cross the bus as 4 / 2 bytes per coordinate; results are
+    the bits of the double entry on the same values (and so the oracle's), on a ragged batch (warp-per-fit kernel) and
+    on one large enough for the staged kernels' pipelined host entry."""
+    rng = np.random.default_rng(9)
+    counts = rng.integers(5, 102, size=(64, 4)).astype(np.int32)
+    b = synth.make_stereo19_batch(64, seed=33, counts=counts, round_pixels=True)
+    pix = b["meas"].astype(dtype)
+    assert np.array_equal(pix.astype(np.float64), b["meas"])
+    a = ctx.fit_batched_pix(STEREO19, variant, b["p0"], pix, b["off"], b["counts"], OPTS)
+    c = ctx.fit_batched(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    cpu = oracle().fit_batch(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], OPTS, nthreads=8)
+    assert_same_fit(a, c)
+    assert_same_fit(a, cpu)
+    if variant == DER:
+        big = synth.make_stereo19_batch_fast(9000, K=64, seed=34)
+        big["meas"] = np.rint(big["meas"])
+        a = ctx.fit_batched_pix(STEREO19, DER, big["p0"], big["meas"].astype(dtype), big["off"], big["counts"], OPTS)
+        c = ctx.fit_batched(STEREO19, DER, big["p0"], big["meas"], big["off"], big["counts"], OPTS)
+        assert_same_fit(a, c)
+
+
+@pytest.mark.parametrize("variant", [DER, DIF])
 def test_stereo19_explicit_t(ctx, variant):
     b = synth.make_stereo19_batch(32, K=40, seed=13)
     t = np.tile(np.linspace(0.0, 1.0, 40), 32 * 4)
