@@ -392,29 +392,40 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   double* W2 = W + M * M;          // [M][M]    (pong)
   __shared__ int bad;
   if (tid == 0) bad = 0;
+  // (row, column) of entry e = tid + q * nt of a [.][W] matrix, advanced without a division per entry (the integer
+  // divisions by the run-time M and nc were a quarter of this kernel's issue slots and most of its latency)
+  struct Walk {
+    int i, j, di, dj, W;
+    __device__ Walk(int e0, int step, int W_) : i(e0 / W_), j(e0 - (e0 / W_) * W_), di(step / W_), dj(step - (step / W_) * W_), W(W_) {}
+    __device__ void next() { i += di; j += dj; if (j >= W) { j -= W; ++i; } }
+  };
   for (int e = tid; e < M * nc; e += nt) Hs[e] = small[SM_HC + e];
-  for (int e = tid; e < nc * nc; e += nt) {
-    const int a = e / nc, b = e - a * nc;
-    Ps[e] = P[(size_t)cols[a] * d.ld + cols[b]];
+  {
+    Walk w(tid, nt, nc);
+    for (int e = tid; e < nc * nc; e += nt, w.next()) Ps[e] = P[(size_t)cols[w.i] * d.ld + cols[w.j]];
   }
   __syncthreads();
-  for (int e = tid; e < nc * M; e += nt) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
-    const int c = e / M, r = e - c * M;
+  Walk wt(tid, nt, M);
+  for (int e = tid; e < nc * M; e += nt, wt.next()) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
+    const int c = wt.i, r = wt.j;
     double s = 0.0;
     for (int b = 0; b < nc; ++b) s += Ps[c * nc + b] * Hs[r * nc + b];
     Tc[e] = s;
   }
   __syncthreads();
-  for (int e = tid; e < M * M; e += nt) {
-    const int r = e / M, q = e - r * M;
+  const Walk w0(tid, nt, M);  // the start of every [M][M] walk below
+  Walk ws = w0;
+  for (int e = tid; e < M * M; e += nt, ws.next()) {
+    const int r = ws.i, q = ws.j;
     double acc = 0.0;
     for (int c = 0; c < nc; ++c) acc += Hs[r * nc + c] * Tc[c * M + q];
     if (r == q) acc += small[SM_R + r];
     S[e] = acc;
   }
   __syncthreads();
-  for (int e = tid; e < M * M; e += nt) {
-    const int r = e / M, q = e - r * M;
+  Walk wc = w0;
+  for (int e = tid; e < M * M; e += nt, wc.next()) {
+    const int r = wc.i, q = wc.j;
     small[SM_S + r * MAXM + q] = S[e];
     W[e] = 0.5 * (S[e] + S[q * M + r]);  // invert the symmetric part
   }
@@ -427,8 +438,9 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
     const bool ok = (piv > 0.0) && (piv <= 1.79769313486231571e308);
     const double ip = ok ? 1.0 / piv : 1.0;
     if (!ok && tid == 0) { *flag = 1; bad = 1; }
-    for (int e = tid; e < M * M; e += nt) {
-      const int i = e / M, j = e - i * M;
+    Walk wg = w0;
+    for (int e = tid; e < M * M; e += nt, wg.next()) {
+      const int i = wg.i, j = wg.j;
       const double cik = Wsrc[i * M + k], rkj = Wsrc[k * M + j] * ip;
       double v;
       if (i == k) v = (j == k) ? ip : rkj;
@@ -440,8 +452,9 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
     double* tmp = Wsrc; Wsrc = Wdst; Wdst = tmp;
   }
   W = Wsrc;
-  for (int e = tid; e < M * M; e += nt) {
-    const int r = e / M, q = e - r * M;
+  Walk wf = w0;
+  for (int e = tid; e < M * M; e += nt, wf.next()) {
+    const int r = wf.i, q = wf.j;
     small[SM_SINV + r * MAXM + q] = bad ? 0.0 : 0.5 * (W[e] + W[q * M + r]);
   }
 }
