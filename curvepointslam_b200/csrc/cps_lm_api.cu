@@ -3,8 +3,13 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <vector>
+
+#include <cuda.h>  // types of the one driver entry point the asynchronous device entry uses (resolved at run time)
 
 #include "../../include/cps_lm.h"
 #include "cps_common.h"
@@ -63,6 +68,29 @@ struct cps_lm_ctx {
   long long solve_handovers = 0;  // systems of the last staged der call that left the block-arrow solve for the dense one
   long long prof_jac_evals = 0, prof_tail_fits = 0;  // Jacobian evaluations done by staged_jac_kernel; fits taken over
   std::vector<cudaEvent_t> ev_pool;
+  // asynchronous device entry (cps_lm_set_async): a worker thread runs the staged shape's host loop on a private stream;
+  // the caller's stream waits on a sequence number in mapped host memory
+  struct AsyncJob {
+    int model, variant, B, n_max, itmax;
+    double* d_p; const double* d_meas; const double* d_t; const long long* d_off; const int* d_counts;
+    bool has_opts; double opts[5];
+    double* d_info; int* d_ret; int* d_extra;
+    cudaEvent_t ev_in;
+    unsigned int seq;
+  };
+  int async_on = 0;
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::deque<AsyncJob> jobs;
+  bool stop = false;
+  unsigned int seq_issued = 0, seq_done = 0;
+  volatile unsigned int* flag_host = nullptr;
+  CUdeviceptr flag_dev = 0;
+  cudaStream_t async_stream = nullptr;
+  int async_rc = 0;
+  std::string async_error;
+  void* wait_value32 = nullptr;  // cuStreamWaitValue32
 };
 
 extern "C" const char* cps_last_error(void) { return cps::g_last_error.c_str(); }
@@ -101,6 +129,16 @@ extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
 extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->worker.joinable()) {
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->stop = true;
+    }
+    c->cv_job.notify_all();
+    c->worker.join();
+  }
+  if (c->async_stream) cudaStreamDestroy(c->async_stream);
+  if (c->flag_host) cudaFreeHost((void*)c->flag_host);
   for (int i = 0; i < kSlots; ++i) {
     cps_lm_slot& s = c->slot[i];
     if (s.stream) cudaStreamSynchronize(s.stream);
@@ -121,8 +159,16 @@ extern "C" void cps_lm_destroy(cps_lm_ctx* c) {
 
 extern "C" int cps_lm_sync(cps_lm_ctx* c) {
   if (!c) return CPS_ERR_INVALID;
+  int rc = CPS_OK;
+  if (c->async_on) {  // every call handed to the worker has run; the first error among them is reported here
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->cv_done.wait(lk, [&] { return c->seq_done == c->seq_issued; });
+    rc = c->async_rc;
+    if (rc != CPS_OK) cps::set_last_error(c->async_error);
+    c->async_rc = CPS_OK;
+  }
   for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
-  return CPS_OK;
+  return rc;
 }
 
 extern "C" int cps_lm_set_path(cps_lm_ctx* c, int path) {
@@ -778,6 +824,75 @@ int fit_dev(cps_lm_ctx* c, cps_lm_slot& sl, int model, int variant, int B, doubl
 }
 }  // namespace
 
+namespace {
+// the worker of the asynchronous device entry: one call at a time, in the order they were made
+void async_worker(cps_lm_ctx* c) {
+  cudaSetDevice(c->device);
+  for (;;) {
+    cps_lm_ctx::AsyncJob j;
+    {
+      std::unique_lock<std::mutex> lk(c->mu);
+      c->cv_job.wait(lk, [&] { return c->stop || !c->jobs.empty(); });
+      if (c->jobs.empty()) return;  // stop requested and nothing left
+      j = c->jobs.front();
+      c->jobs.pop_front();
+    }
+    cudaStream_t st = c->async_stream;
+    int rc = CPS_OK;
+    if (cudaStreamWaitEvent(st, j.ev_in, 0) != cudaSuccess) rc = CPS_ERR_CUDA;  // the caller's earlier work on its stream
+    cudaEventDestroy(j.ev_in);
+    if (rc == CPS_OK)
+      rc = fit_dev(c, c->slot[0], j.model, j.variant, j.B, j.d_p, j.d_meas, j.d_t, j.d_off, j.d_counts, j.n_max, j.itmax,
+                   j.has_opts ? j.opts : nullptr, j.d_info, j.d_ret, j.d_extra, st, CPS_LM_PATH_AUTO);
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == CPS_OK) rc = CPS_ERR_CUDA;
+    __sync_synchronize();
+    *c->flag_host = j.seq;  // releases the caller's stream (also after an error: it must not wait for ever)
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->seq_done = j.seq;
+      if (rc != CPS_OK && c->async_rc == CPS_OK) {
+        c->async_rc = rc;
+        c->async_error = cps_last_error();
+      }
+    }
+    c->cv_done.notify_all();
+  }
+}
+}  // namespace
+
+extern "C" int cps_lm_set_async(cps_lm_ctx* c, int on) {
+  if (!c) return CPS_ERR_INVALID;
+  if (!on) {
+    const int rc = cps_lm_sync(c);
+    c->async_on = 0;
+    return rc;
+  }
+  if (c->async_on) return CPS_OK;
+  CPS_CUDA(cudaSetDevice(c->device));
+  if (!c->wait_value32) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &c->wait_value32, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !c->wait_value32) {
+      c->wait_value32 = nullptr;
+      cps::set_last_error("cuStreamWaitValue32 is not available from this driver");
+      return CPS_ERR_UNSUPPORTED;
+    }
+  }
+  if (!c->flag_host) {
+    unsigned int* h = nullptr;
+    CPS_CUDA(cudaHostAlloc((void**)&h, sizeof(unsigned int), cudaHostAllocMapped));
+    *h = 0;
+    c->flag_host = h;
+    void* dptr = nullptr;
+    CPS_CUDA(cudaHostGetDevicePointer(&dptr, h, 0));
+    c->flag_dev = (CUdeviceptr)dptr;
+  }
+  if (!c->async_stream) CPS_CUDA(cudaStreamCreateWithFlags(&c->async_stream, cudaStreamNonBlocking));
+  if (!c->worker.joinable()) c->worker = std::thread(async_worker, c);
+  c->async_on = 1;
+  return CPS_OK;
+}
+
 extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int B, double* d_p,
                                       const double* d_meas, const double* d_t, const long long* d_off,
                                       const int* d_counts, int n_max, int itmax, const double* opts,
@@ -789,6 +904,31 @@ extern "C" int cps_lm_fit_batched_dev(cps_lm_ctx* c, int model, int variant, int
   if (B == 0) return CPS_OK;
   CPS_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
+  if (c->async_on) {
+    // the call is queued for the worker and returns; `stream` is made to wait, on the device, until the worker has
+    // finished it, so whatever the caller enqueues next sees the results
+    cps_lm_ctx::AsyncJob j;
+    j.model = model; j.variant = variant; j.B = B; j.n_max = n_max; j.itmax = itmax;
+    j.d_p = d_p; j.d_meas = d_meas; j.d_t = d_t; j.d_off = d_off; j.d_counts = d_counts;
+    j.has_opts = opts != nullptr;
+    if (opts) std::memcpy(j.opts, opts, sizeof j.opts);
+    j.d_info = d_info; j.d_ret = d_ret; j.d_extra = d_extra;
+    CPS_CUDA(cudaEventCreateWithFlags(&j.ev_in, cudaEventDisableTiming));
+    CPS_CUDA(cudaEventRecord(j.ev_in, st));
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      j.seq = ++c->seq_issued;
+      c->jobs.push_back(j);
+    }
+    c->cv_job.notify_one();
+    typedef CUresult (*wait_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    if (((wait_fn)c->wait_value32)((CUstream)st, c->flag_dev, j.seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+      cps_lm_sync(c);  // could not make the stream wait: fall back to waiting here
+      cps::set_last_error("cuStreamWaitValue32 failed");
+      return CPS_ERR_CUDA;
+    }
+    return CPS_OK;
+  }
   // the context has ONE fit queue and work area: a call on another stream queues behind the previous call's kernels
   // instead of resetting the queue they are still reading
   if (!c->ev_last) CPS_CUDA(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));

@@ -69,6 +69,10 @@ class LmContext:
                    "cps_lm_get_profile_work")
         return int(je.value), int(tf.value)
 
+    def set_async(self, on: bool):
+        """Asynchronous device entry: fit_batched_dev queues the call for a worker thread and makes `stream` wait for it."""
+        _lib.check(_lib.lib().cps_lm_set_async(self._h, 1 if on else 0), "cps_lm_set_async")
+
     def solve_handovers(self) -> int:
         """Systems of the last staged dlevmar_der call that the block-arrow solve handed to the dense one."""
         n = C.c_longlong(0)

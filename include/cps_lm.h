@@ -99,6 +99,17 @@ int cps_lm_fit_batched_dev(cps_lm_ctx *ctx, int model, int variant, int B, doubl
                            const double *d_t, const long long *d_off, const int *d_counts, int n_max, int itmax,
                            const double *opts, double *d_info, int *d_ret, int *d_extra, void *stream);
 int cps_lm_sync(cps_lm_ctx *ctx);
+/*
+ * Asynchronous device entry.  With on != 0, cps_lm_fit_batched_dev only queues the call and returns, for EVERY
+ * execution shape: a worker thread owned by the context runs it (the staged shapes' round loop included) on a private
+ * stream that first waits for the work already enqueued on the caller's `stream`, and `stream` itself is made to wait
+ * on the device (cuStreamWaitValue32 on a sequence number the worker publishes) until the call has finished -- so the
+ * caller's next kernels, copies and events on `stream` are ordered after the fits without the host ever blocking.
+ * Calls run one at a time in the order they were made.  An error of a queued call is returned by the next
+ * cps_lm_sync (which also waits for the queue to drain).  Off by default (the call then returns when the staged rounds
+ * are done, see above).
+ */
+int cps_lm_set_async(cps_lm_ctx *ctx, int on);
 
 /*
  * fit_curve's initial guess for B Stereo19 fits (curveFittingClass.cpp:516-651): stereo triangulation of the start /

@@ -313,3 +313,51 @@ def test_block_arrow_solve_and_hand_over(monkeypatch):
     # these poor starts do produce systems whose pivot leaves a curve's own rows (about 8 % of the solves; none on the
     # benchmark batches): the hand-over is exercised even without forcing it
     assert seen["CPS_LM_DENSE_SOLVE"] == 0 and seen[None] > 0 and seen["CPS_LM_FORCE_HANDOVER"] > seen[None], seen
+
+
+@pytest.mark.parametrize("variant", ["der", "dif"])
+def test_asynchronous_device_entry_honours_its_stream(variant):
+    """cps_lm_set_async: cps_lm_fit_batched_dev returns at once for the staged shapes too (their round loop runs on the
+    context's worker thread) and the caller's stream is made to wait on the device, so work enqueued on that stream
+    before and after the call is ordered around the fits: the initial guesses are written by a copy enqueued BEFORE the
+    call, the results are read by a copy enqueued AFTER it, nothing synchronises in between, and the bits are those of
+    the synchronous call."""
+    import time
+    import torch
+    var = lm.DER if variant == "der" else lm.DIF
+    B = 40000 if variant == "der" else 6000
+    b = synth.make_stereo19_batch_fast(B, K=64, seed=68)
+    dev = torch.device("cuda", 0)
+    d_meas, d_off, d_cnt = (torch.from_numpy(b[k]).to(dev) for k in ("meas", "off", "counts"))
+    h_p0 = torch.from_numpy(b["p0"]).pin_memory()
+    outs = {}
+    for mode in ("sync", "async"):
+        c = lm.LmContext(0)
+        c.set_path(lm.PATH_STAGED)
+        c.set_async(mode == "async")
+        d_p = torch.zeros((B, 19), dtype=torch.float64, device=dev)
+        d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+        d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+        h_out = torch.zeros((B, 19), dtype=torch.float64).pin_memory()
+        h_info = torch.zeros((B, 10), dtype=torch.float64).pin_memory()
+        st = torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            d_p.copy_(h_p0, non_blocking=True)  # before the call, on the caller's stream
+            t0 = time.perf_counter()
+            c.fit_batched_dev(19, var, B, d_p.data_ptr(), d_meas.data_ptr(), None, d_off.data_ptr(), d_cnt.data_ptr(), 512,
+                              d_info.data_ptr(), d_ret.data_ptr(), None, opts=OPTS, stream=st.cuda_stream)
+            host_s = time.perf_counter() - t0
+            h_out.copy_(d_p, non_blocking=True)  # after the call, on the caller's stream
+            h_info.copy_(d_info, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(st)
+        done.synchronize()  # only the caller's own event is waited for
+        outs[mode] = (h_out.numpy().copy(), h_info.numpy().copy(), host_s)
+        c.sync()
+        c.close()
+    assert np.array_equal(_bits(outs["sync"][0]), _bits(outs["async"][0]))
+    assert np.array_equal(_bits(outs["sync"][1]), _bits(outs["async"][1]))
+    assert (outs["async"][1][:, 6] == 2).all()
+    # the synchronous call blocks for the whole fit; the asynchronous one only queues it
+    assert outs["async"][2] < 0.25 * outs["sync"][2], (outs["async"][2], outs["sync"][2])
