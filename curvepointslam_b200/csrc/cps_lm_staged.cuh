@@ -716,6 +716,89 @@ __device__ __forceinline__ void arrow_fill19(double* a, double* bx, const double
   for (int i = 0; i < 19; ++i) a[(i < 16 ? i * 11 + (i & 7) : 176 + (i - 16) * 19 + i) * T] = d[i] + mu;
 }
 
+// Elimination of column j = 8 b + JL (a control-point column of curve b).  Rows that take part: JL..7 of the curve's
+// block and the three bottom rows; columns: JL+1..7 of the block and 16..18.  Returns false when the reference's pivot
+// search would leave the curve's rows (-> dense solve).
+template <int T, int JL>
+__device__ __forceinline__ bool arrow_block_step(double* a, double* sc, double* bx, int b) {
+  const int r0 = 8 * b, j = r0 + JL;
+  double* blk = a + (r0 * 11) * T;        // block row r, stored column c (0..7 own, 8..10 = columns 16..18): blk[(r*11 + c)*T]
+  double* tlb = a + (176 + r0) * T;        // bottom row q, own-block column c: tlb[(q*19 + c)*T]
+  double* tlt = a + (176 + 16) * T;        // bottom row q, column 16 + c:      tlt[(q*19 + c)*T]
+  int piv = -1;
+  {
+    double merit[8], mt[3];
+#pragma unroll
+    for (int r = JL; r < 8; ++r) merit[r] = sc[(r0 + r) * T] * fabs(blk[(r * 11 + JL) * T]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) mt[q] = sc[(16 + q) * T] * fabs(tlb[(q * 19 + JL) * T]);
+    double big = 0.0;
+#pragma unroll
+    for (int r = JL; r < 8; ++r)
+      if (merit[r] >= big) { big = merit[r]; piv = r; }
+    // the dense search goes on over the other curve's rows (merit exactly 0: they win only against big == 0) and the
+    // bottom rows
+    if (piv < 0 || !(big > 0.0)) return false;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (mt[q] >= big) return false;
+  }
+  if (piv != JL) {
+    double rp[11], rj[11];
+#pragma unroll
+    for (int c = 0; c < 11; ++c) { rp[c] = blk[(piv * 11 + c) * T]; rj[c] = blk[(JL * 11 + c) * T]; }
+#pragma unroll
+    for (int c = 0; c < 11; ++c) { blk[(piv * 11 + c) * T] = rj[c]; blk[(JL * 11 + c) * T] = rp[c]; }
+    sc[(r0 + piv) * T] = sc[j * T];
+    const double tb = bx[(r0 + piv) * T], tj = bx[j * T];
+    bx[(r0 + piv) * T] = tj;
+    bx[j * T] = tb;
+  }
+  // (the pivot cannot be zero: its merit is positive)
+  const double inv = 1.0 / blk[(JL * 11 + JL) * T];
+  // multipliers, stored where the eliminated entries were
+  double lm[8], lt[3];
+#pragma unroll
+  for (int r = JL + 1; r < 8; ++r) lm[r] = blk[(r * 11 + JL) * T];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) lt[q] = tlb[(q * 19 + JL) * T];
+#pragma unroll
+  for (int r = JL + 1; r < 8; ++r) { lm[r] *= inv; blk[(r * 11 + JL) * T] = lm[r]; }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { lt[q] *= inv; tlb[(q * 19 + JL) * T] = lt[q]; }
+  // pivot row right of the diagonal: own columns JL+1..7, then 16..18
+  double u[11];
+#pragma unroll
+  for (int c = JL + 1; c < 11; ++c) u[c] = blk[(JL * 11 + c) * T];
+  // a_ik -= l_i u_k: the block's rows below the pivot ...
+#pragma unroll
+  for (int r = JL + 1; r < 8; ++r) {
+    double x[11];
+#pragma unroll
+    for (int c = JL + 1; c < 11; ++c) x[c] = blk[(r * 11 + c) * T];
+#pragma unroll
+    for (int c = JL + 1; c < 11; ++c) x[c] -= lm[r] * u[c];
+#pragma unroll
+    for (int c = JL + 1; c < 11; ++c) blk[(r * 11 + c) * T] = x[c];
+  }
+  // ... and the three bottom rows (their entries in the other curve's columns meet zeros of the pivot row)
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double x[11];
+#pragma unroll
+    for (int c = JL + 1; c < 8; ++c) x[c] = tlb[(q * 19 + c) * T];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[8 + c] = tlt[(q * 19 + c) * T];
+#pragma unroll
+    for (int c = JL + 1; c < 11; ++c) x[c] -= lt[q] * u[c];
+#pragma unroll
+    for (int c = JL + 1; c < 8; ++c) tlb[(q * 19 + c) * T] = x[c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tlt[(q * 19 + c) * T] = x[8 + c];
+  }
+  return true;
+}
+
 // 1: solved, 0: a row is entirely zero (the dense routine's return 0), -1: the structure does not hold for this
 // system -> dense kernel
 template <int T>
@@ -754,62 +837,20 @@ __device__ __forceinline__ int arrow_factor_solve(double* a, double* sc, double*
     }
     if (singular) return 0;
   }
-  // ---- columns of the two curves
+  // ---- columns of the two curves: one elimination step per column, the column's position inside its curve (JL) a
+  // compile-time value so that every row and column of the step has a fixed offset (no row masks, no index tables)
 #pragma unroll 1
-  for (int j = 0; j < 16; ++j) {
-    const int b = j >> 3, jl = j & 7, r0 = 8 * b;
-    int piv = -1;
-    {
-      double merit[8], mt[3];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) merit[r] = (r >= jl) ? sc[(r0 + r) * T] * fabs(a[((r0 + r) * 11 + jl) * T]) : 0.0;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) mt[q] = sc[(16 + q) * T] * fabs(a[(176 + q * 19 + j) * T]);
-      double big = 0.0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r >= jl && merit[r] >= big) { big = merit[r]; piv = r0 + r; }
-      // the dense search goes on over the other curve's rows (merit exactly 0: they win only against big == 0) and the
-      // bottom rows
-      if (piv < 0 || !(big > 0.0)) return -1;
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (mt[q] >= big) return -1;
-    }
-    if (piv != j) {
-      double rp[11], rj[11];
-#pragma unroll
-      for (int c = 0; c < 11; ++c) { rp[c] = a[(piv * 11 + c) * T]; rj[c] = a[(j * 11 + c) * T]; }
-#pragma unroll
-      for (int c = 0; c < 11; ++c) { a[(piv * 11 + c) * T] = rj[c]; a[(j * 11 + c) * T] = rp[c]; }
-      sc[piv * T] = sc[j * T];
-      const double tb = bx[piv * T], tj = bx[j * T];
-      bx[piv * T] = tj;
-      bx[j * T] = tb;
-    }
-    // (the pivot cannot be zero: its merit is positive)
-    const double inv = 1.0 / a[(j * 11 + jl) * T];
-    unsigned int rowmask = 0;
-    {
-      double l[8], lt[3];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) l[r] = (r > jl) ? a[((r0 + r) * 11 + jl) * T] : 0.0;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) lt[q] = a[(176 + q * 19 + j) * T];
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r > jl) {
-          a[((r0 + r) * 11 + jl) * T] = l[r] * inv;
-          if (l[r] != 0.0) rowmask |= 1u << (r0 + r);
-        }
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        a[(176 + q * 19 + j) * T] = lt[q] * inv;
-        if (lt[q] != 0.0) rowmask |= 1u << (16 + q);
-      }
-    }
-    arrow_update_window<T>(a, j, b, false, jl + 1, 8, rowmask);  // the rest of the curve's columns
-    arrow_update_window<T>(a, j, b, true, 0, 3, rowmask);        // theta, phi, z
+  for (int b = 0; b < 2; ++b) {
+    int ok = 1;
+    ok = ok && arrow_block_step<T, 0>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 1>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 2>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 3>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 4>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 5>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 6>(a, sc, bx, b);
+    ok = ok && arrow_block_step<T, 7>(a, sc, bx, b);
+    if (!ok) return -1;
   }
   // ---- theta, phi, z: a dense 3 x 3 on the bottom rows
   int piv = 15;
