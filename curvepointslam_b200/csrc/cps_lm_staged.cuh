@@ -218,16 +218,29 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const double* xt = &wt->x[lane][xoff];
     double* tt = &wt->t[lane][toff];
+    // the eight projected control-point coordinates of the current contour segment stay in registers: they change
+    // three times per fit, and reading them from the table for every sample was most of this kernel's shared-memory
+    // traffic (same values, same operations)
+    int cur_seg = -1;
+    double cu[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0};
     auto resid = [&](int s, double tval, double xu, double xv, double& eu, double& ev) {
       const int seg = (s >= g.b1) + (s >= g.b2) + (s >= g.b3);
-      const int cb = 12 * (seg & 1), side = seg >> 1;
+      if (seg != cur_seg) {
+        cur_seg = seg;
+        const int cb = 12 * (seg & 1), side = seg >> 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cu[k] = Csm[(cb + 3 * k + side) * kEvalThreads];
+          cv[k] = Csm[(cb + 3 * k + 2) * kEvalThreads];
+        }
+      }
       double w[4];
       bernstein3(tval, w);
       double au = 0.0, av = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        au += w[k] * Csm[(cb + 3 * k + side) * kEvalThreads];
-        av += w[k] * Csm[(cb + 3 * k + 2) * kEvalThreads];
+        au += w[k] * cu[k];
+        av += w[k] * cv[k];
       }
       eu = xu - au;
       ev = xv - av;
