@@ -528,9 +528,11 @@ __device__ __forceinline__ void dif_project_one(const Trig& tg, double xe, doubl
 constexpr int kDifTabUpd = 67;
 constexpr int kDifTabFd = 163;
 
+constexpr int kDifXtPitch = 13;  // per fit and step: 8 samples + 4 t (+1: an odd pitch spreads the banks)
 template <bool FD>
 constexpr int dif_build_smem_doubles() {
-  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * kDifWarps * kDifFits * kDifStageRow + kDifFits;
+  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * kDifWarps * kDifFits * kDifStageRow + kDifFits +
+         (FD ? 0 : 2 * kDifFits * kDifXtPitch);
 }
 
 // one model value: sum_k w_k * tab[(12*curve + 3k + sel) * 32], ascending k from 0.0 like closest_bezier_pt(cp, t, ..)
@@ -546,6 +548,7 @@ struct DifCtx {
   const DifArgs* A;
   double* tab;     // this lane's column of the [entry][32] tables
   double* stage;   // [NBUF][8][32][22]
+  double* xt;      // update build: [2][32][13] the step's 8 samples and 4 t of every fit
   const int* nrows;
   const double* x;
   const double* tp;
@@ -566,6 +569,7 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
   const DifArgs& A = *C.A;
   double* const tab = C.tab;
   double* const stage = C.stage;
+  double* const xt = C.xt;
   const int* const nrows = C.nrows;
   const double* const x = C.x;
   const double* const tp = C.tp;
@@ -594,6 +598,16 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
     // this thread's share of the cooperative copies: fit cfi of the group
     const int cn = nrows[cfi];
     double* cJ = A.J + (size_t)nrows[kDifFits + cfi] * A.j_stride;
+    // samples and t of the copied fit (update build): the eight samples of a step are 64 contiguous bytes, its four
+    // t values 32; read per lane they cost a 32-byte sector for every 8 bytes and a global latency in the producing phase
+    const double* cx = nullptr;
+    const double* ct = nullptr;
+    if (!FD && cn > 0) {
+      const int fc = nrows[kDifFits + cfi];
+      const long long oc = A.L.off[fc];
+      cx = A.L.meas + oc;
+      ct = dif_t(A, fc, oc);
+    }
 
     auto issue_rows = [&](int st, int buf) {
       double* sb = stage + (size_t)buf * STEP_DOUBLES;
@@ -607,6 +621,19 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
         const unsigned int d = (unsigned int)__cvta_generic_to_shared(sb + (rr * kDifFits + cfi) * kDifStageRow + 2 * piece);
         const int nbytes = ok ? 16 : 0;  // zero-fill rows past the end of a fit
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+      }
+      {
+        double* xb = xt + ((size_t)buf * kDifFits + cfi) * kDifXtPitch;
+        const int rx = kDifWarps * st + csub;
+        const bool okx = cx != nullptr && rx < cn;
+        const unsigned int dx = (unsigned int)__cvta_generic_to_shared(xb + csub);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dx), "l"(okx ? cx + rx : A.L.meas), "r"(okx ? 8 : 0) : "memory");
+        if (csub < 4) {
+          const int sx = 4 * st + csub;
+          const bool okt = cx != nullptr && 2 * sx < cn;
+          const unsigned int dt = (unsigned int)__cvta_generic_to_shared(xb + 8 + csub);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dt), "l"(okt ? ct + sx : A.L.meas), "r"(okt ? 8 : 0) : "memory");
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -636,7 +663,7 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
       if (!FD) issue_rows(down ? nsteps - 1 : 0, 0);
       // sample and t of this lane's row of the first step
       double x_next = 0.0, t_next = 0.0;
-      {
+      if (FD) {
         const int r = kDifWarps * (down ? nsteps - 1 : 0) + wid;
         if (r < n_eff) { x_next = x[r]; t_next = tp[r >> 1]; }
       }
@@ -651,8 +678,12 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
         {
           const int r = kDifWarps * st + wid;
           double* row = sb + (wid * kDifFits + lane) * kDifStageRow;
-          const double xr = x_next, tval = t_next;
-          {
+          double xr = x_next, tval = t_next;
+          if (!FD) {
+            const double* xb = xt + ((size_t)buf * kDifFits + lane) * kDifXtPitch;
+            xr = xb[wid];
+            tval = xb[8 + (wid >> 1)];
+          } else {
             const int rn = kDifWarps * (down ? st - 1 : st + 1) + wid;
             if (it + 1 < nsteps && rn < n_eff) { x_next = x[rn]; t_next = tp[rn >> 1]; }
           }
@@ -751,6 +782,7 @@ __global__ void __launch_bounds__(kDifThreads, 2) dif_build_kernel(const DifArgs
   double* tab = smem + lane;                                   // tab[entry * 32]
   double* stage = smem + NTAB * kDifFits;                       // [NBUF][8][32][22]
   int* nrows = reinterpret_cast<int*>(stage + NBUF * STEP_DOUBLES);  // [32] n of each fit (0: no fit), [32] fit index
+  double* xt = stage + NBUF * STEP_DOUBLES + kDifFits;                // update build: samples / t of the step
   const size_t wsn = (size_t)A.ws_stride;
   const unsigned int total = A.cnt[FD ? 0 : 1];
   const int* list = FD ? A.fd_list : A.upd_list;
@@ -824,7 +856,7 @@ __global__ void __launch_bounds__(kDifThreads, 2) dif_build_kernel(const DifArgs
       }
     }
     DifCtx C;
-    C.A = &A; C.tab = tab; C.stage = stage; C.nrows = nrows; C.x = x; C.tp = tp; C.ws = ws; C.wsn = wsn; C.g = g;
+    C.A = &A; C.tab = tab; C.stage = stage; C.xt = xt; C.nrows = nrows; C.x = x; C.tp = tp; C.ws = ws; C.wsn = wsn; C.g = g;
     C.lane = lane; C.cfi = cfi; C.csub = csub; C.have = have; C.blocked = blocked; C.accepted = accepted;
     C.pend_dp_sq = pend_dp_sq;
     dif_group_sweep<FD>(C, wid);
