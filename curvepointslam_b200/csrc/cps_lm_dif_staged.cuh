@@ -532,7 +532,7 @@ constexpr int kDifXtPitch = 13;  // per fit and step: 8 samples + 4 t (+1: an od
 template <bool FD>
 constexpr int dif_build_smem_doubles() {
   return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * kDifWarps * kDifFits * kDifStageRow + kDifFits +
-         (FD ? 0 : 2 * kDifFits * kDifXtPitch);
+         2 * kDifFits * kDifXtPitch;
 }
 
 // one model value: sum_k w_k * tab[(12*curve + 3k + sel) * 32], ascending k from 0.0 like closest_bezier_pt(cp, t, ..)
@@ -602,13 +602,26 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
     // t values 32; read per lane they cost a 32-byte sector for every 8 bytes and a global latency in the producing phase
     const double* cx = nullptr;
     const double* ct = nullptr;
-    if (!FD && cn > 0) {
+    if (cn > 0) {
       const int fc = nrows[kDifFits + cfi];
       const long long oc = A.L.off[fc];
       cx = A.L.meas + oc;
       ct = dif_t(A, fc, oc);
     }
 
+    auto issue_xt = [&](int st, int buf) {
+      double* xb = xt + ((size_t)buf * kDifFits + cfi) * kDifXtPitch;
+      const int rx = kDifWarps * st + csub;
+      const bool okx = cx != nullptr && rx < cn;
+      const unsigned int dx = (unsigned int)__cvta_generic_to_shared(xb + csub);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dx), "l"(okx ? cx + rx : A.L.meas), "r"(okx ? 8 : 0) : "memory");
+      if (csub < 4) {
+        const int sx = 4 * st + csub;
+        const bool okt = cx != nullptr && 2 * sx < cn;
+        const unsigned int dt = (unsigned int)__cvta_generic_to_shared(xb + 8 + csub);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dt), "l"(okt ? ct + sx : A.L.meas), "r"(okt ? 8 : 0) : "memory");
+      }
+    };
     auto issue_rows = [&](int st, int buf) {
       double* sb = stage + (size_t)buf * STEP_DOUBLES;
 #pragma unroll 1
@@ -622,19 +635,7 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
         const int nbytes = ok ? 16 : 0;  // zero-fill rows past the end of a fit
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
       }
-      {
-        double* xb = xt + ((size_t)buf * kDifFits + cfi) * kDifXtPitch;
-        const int rx = kDifWarps * st + csub;
-        const bool okx = cx != nullptr && rx < cn;
-        const unsigned int dx = (unsigned int)__cvta_generic_to_shared(xb + csub);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dx), "l"(okx ? cx + rx : A.L.meas), "r"(okx ? 8 : 0) : "memory");
-        if (csub < 4) {
-          const int sx = 4 * st + csub;
-          const bool okt = cx != nullptr && 2 * sx < cn;
-          const unsigned int dt = (unsigned int)__cvta_generic_to_shared(xb + 8 + csub);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dt), "l"(okt ? ct + sx : A.L.meas), "r"(okt ? 8 : 0) : "memory");
-        }
-      }
+      issue_xt(st, buf);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto write_back = [&](int st, const double* sb, int n_lim) {
@@ -661,32 +662,23 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
       const bool cmine = cn > 0 && ((cn * 19 <= kBlockSzSq) == down);
       const int cn_eff = cmine ? cn : 0;                    // the same for the fit this thread copies
       if (!FD) issue_rows(down ? nsteps - 1 : 0, 0);
+      else { issue_xt(down ? nsteps - 1 : 0, 0); asm volatile("cp.async.commit_group;" ::: "memory"); }
       // sample and t of this lane's row of the first step
-      double x_next = 0.0, t_next = 0.0;
-      if (FD) {
-        const int r = kDifWarps * (down ? nsteps - 1 : 0) + wid;
-        if (r < n_eff) { x_next = x[r]; t_next = tp[r >> 1]; }
-      }
+
       for (int it = 0; it < nsteps; ++it) {
         const int st = down ? nsteps - 1 - it : it;
         const int buf = FD ? 0 : (it & 1);
         double* sb = stage + (size_t)buf * STEP_DOUBLES;
-        if (!FD) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // [A] this step's rows have landed; everybody is done with the other buffer
         if (!FD && it + 1 < nsteps) issue_rows(down ? st - 1 : st + 1, buf ^ 1);
+        if (FD && it + 1 < nsteps) { issue_xt(down ? st - 1 : st + 1, (it & 1) ^ 1); asm volatile("cp.async.commit_group;" ::: "memory"); }
         // ---- produce row r = 8 st + wid of this lane's fit
         {
           const int r = kDifWarps * st + wid;
           double* row = sb + (wid * kDifFits + lane) * kDifStageRow;
-          double xr = x_next, tval = t_next;
-          if (!FD) {
-            const double* xb = xt + ((size_t)buf * kDifFits + lane) * kDifXtPitch;
-            xr = xb[wid];
-            tval = xb[8 + (wid >> 1)];
-          } else {
-            const int rn = kDifWarps * (down ? st - 1 : st + 1) + wid;
-            if (it + 1 < nsteps && rn < n_eff) { x_next = x[rn]; t_next = tp[rn >> 1]; }
-          }
+          const double* xb = xt + ((size_t)(it & 1) * kDifFits + lane) * kDifXtPitch;
+          const double xr = xb[wid], tval = xb[8 + (wid >> 1)];
           if (r < n_eff) {
             const int sidx = r >> 1, uv = r & 1;
             const int seg = (sidx >= g.b1) + (sidx >= g.b2) + (sidx >= g.b3);
@@ -782,7 +774,7 @@ __global__ void __launch_bounds__(kDifThreads, 2) dif_build_kernel(const DifArgs
   double* tab = smem + lane;                                   // tab[entry * 32]
   double* stage = smem + NTAB * kDifFits;                       // [NBUF][8][32][22]
   int* nrows = reinterpret_cast<int*>(stage + NBUF * STEP_DOUBLES);  // [32] n of each fit (0: no fit), [32] fit index
-  double* xt = stage + NBUF * STEP_DOUBLES + kDifFits;                // update build: samples / t of the step
+  double* xt = stage + NBUF * STEP_DOUBLES + kDifFits;                // samples / t of the step, two buffers
   const size_t wsn = (size_t)A.ws_stride;
   const unsigned int total = A.cnt[FD ? 0 : 1];
   const int* list = FD ? A.fd_list : A.upd_list;
