@@ -407,96 +407,119 @@ __global__ void dif_round_end_kernel(unsigned int* cnt, int nxt, volatile unsign
 }
 
 // ---- build: eight warps x 32 fits ----------------------------------------------------------------------------------
-// The (zero-padded) 20 x 20 matrix is cut into 4 x 4 blocks; the 15 blocks of its lower triangle are dealt two to a
-// warp, the five 4-column groups of J^T e one to each of warps 0..4.  Every warp runs THE SAME instruction stream on
-// its own blocks (block coordinates are warp-uniform run-time values, the 36 sums of a thread compile-time
-// registers): one copy of the code for eight roles -- role-specialised copies of the sweep overflowed the
-// instruction cache (measured: "no instruction" was the top stall reason).  A diagonal block is computed in full
-// (its upper half is never stored); products with the padding column 19 are exact zeros.
+// The lower triangle of the 19 x 19 matrix is cut along column groups of four (g0..g3: two control points each; g4:
+// theta, phi, z) and dealt to the eight warps together with the J^T e chains (table below).  The producing phase and
+// the copies are ONE instruction stream for all warps; only the accumulate / fold code is instantiated per role
+// (role-specialised copies of the whole sweep overflowed the instruction cache: "no instruction" was the top stall
+// reason).
 constexpr int kDifWarps = 8;
-constexpr int kDifSumsPerWarp = 36;  // 16 + 16 + 4
-
-struct DifRole {
-  int r0, c0, r1, c1;  // first column of the row / column group of block 0 and block 1
-  int jc;              // first column of the J^T e group
-  bool has1, hasj;     // block 1 / the J^T e group are real (otherwise computed and dropped)
-};
-__device__ __forceinline__ DifRole dif_role(int w) {
-  // pairs (R, C) in units of four columns: (1,0)(1,1) (2,0)(2,1) (3,0)(3,1) (3,2)(3,3) (4,0)(4,1) (4,2)(4,3) (0,0)(2,2) (4,4)-
-  const int R0 = w == 0 ? 1 : (w == 1 ? 2 : (w <= 3 ? 3 : (w <= 5 ? 4 : (w == 6 ? 0 : 4))));
-  const int C0 = (w == 3 || w == 5) ? 2 : (w == 7 ? 4 : 0);
-  const int R1 = w == 6 ? 2 : R0;
-  const int C1 = w == 6 ? 2 : (w == 7 ? 4 : C0 + 1);
-  DifRole r;
-  r.r0 = 4 * R0; r.c0 = 4 * C0; r.r1 = 4 * R1; r.c1 = 4 * C1;
-  r.has1 = w != 7;
-  // the J^T e chains of a 4-column group go to a warp whose block 0 has that group as its ROW group, so the chain's
-  // operands are the ones the block loads anyway: groups 1, 2, 3, 0, 4 on warps 0, 1, 3, 6, 7 (warps 3 and 7 share a
-  // scheduler with the lightest arithmetic load: block (4,4) stands alone)
-  r.hasj = w == 0 || w == 1 || w == 3 || w == 6 || w == 7;
-  r.jc = r.r0;
-  return r;
-}
-
-struct DifSums {
-  double sum[kDifSumsPerWarp];  // [block 0: 4 x 4 | block 1: 4 x 4 | J^T e: 4]
-};
-
 __device__ __forceinline__ void dif_load4(const double* p, double (&v)[4]) {
   const double2 a = *reinterpret_cast<const double2*>(p);
   const double2 b = *reinterpret_cast<const double2*>(p + 2);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-__device__ __forceinline__ void dif_accumulate(const double* row, const DifRole& R, DifSums& S) {
-  // row: this fit's staged row, [0..18] Jacobian, [19] zero, [20] residual
-  double vr[4], vc[4];
-  dif_load4(row + R.r0, vr);
-  dif_load4(row + R.c0, vc);
-  const double e = row[20];
+// ---- the 190 + 19 sums dealt to the eight warps in their exact shapes: no padding column, no upper halves of the
+// diagonal blocks.  Column groups g0..g3 = four control-point columns each, g4 = theta, phi, z (three columns).
+//   warp 0: (1,0) + diag 0        26 sums     warp 4: (3,1) + (3,2)              32
+//   warp 1: (2,0) + diag 1        26          warp 5: (4,0) + (4,1) + J^T e g4   27
+//   warp 2: (2,1) + diag 2        26          warp 6: (4,2) + (4,3) + diag 4     30
+//   warp 3: (3,0) + diag 3        26          warp 7: J^T e g0..g3               16
+// (a uniform two-4x4-blocks-per-warp scheme formed 276 products per row for these 209 sums: build 200 -> 170 ms per
+// 65 536-fit call).  The eight roles are eight instantiations of the accumulate / fold code only -- a few hundred
+// instructions, not eight copies of the sweep.
+constexpr int kDifExactSums = 32;
+__host__ __device__ constexpr int dif_gn(int G) { return G == 4 ? 3 : 4; }
+
+// visitors over the items of a role: FULL(R, C) = rows of group R x columns of group C, DIAG(G) = lower triangle of
+// group G's square, JTE(G) = J^T e of group G's columns; `off` = first sum of the item in the thread's array
+#define DIF_ROLE_ITEMS(ROLE, X)                                                      \
+  if constexpr (ROLE == 0) { X(FULL, 1, 0, 0) X(DIAG, 0, 0, 16) }                    \
+  if constexpr (ROLE == 1) { X(FULL, 2, 0, 0) X(DIAG, 1, 1, 16) }                    \
+  if constexpr (ROLE == 2) { X(FULL, 2, 1, 0) X(DIAG, 2, 2, 16) }                    \
+  if constexpr (ROLE == 3) { X(FULL, 3, 0, 0) X(DIAG, 3, 3, 16) }                    \
+  if constexpr (ROLE == 4) { X(FULL, 3, 1, 0) X(FULL, 3, 2, 16) }                    \
+  if constexpr (ROLE == 5) { X(FULL, 4, 0, 0) X(FULL, 4, 1, 12) X(JTE, 4, 4, 24) }   \
+  if constexpr (ROLE == 6) { X(FULL, 4, 2, 0) X(FULL, 4, 3, 12) X(DIAG, 4, 4, 24) }  \
+  if constexpr (ROLE == 7) { X(JTE, 0, 0, 0) X(JTE, 1, 1, 4) X(JTE, 2, 2, 8) X(JTE, 3, 3, 12) }
+
+enum { DIF_FULL = 0, DIF_DIAG = 1, DIF_JTE = 2 };
+
+template <int ROLE>
+__device__ __forceinline__ void dif_acc_exact(const double* row, double (&s)[kDifExactSums]) {
+  // the column groups this role reads (each loaded once), then its items
+  double g[5][4];
+  constexpr bool need[8][5] = {{1, 1, 0, 0, 0}, {1, 1, 1, 0, 0}, {0, 1, 1, 0, 0}, {1, 0, 0, 1, 0},
+                               {0, 1, 1, 1, 0}, {1, 1, 0, 0, 1}, {0, 0, 1, 1, 1}, {1, 1, 1, 1, 0}};
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) S.sum[4 * i + j] += vr[i] * vc[j];
-  if (R.hasj) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) S.sum[32 + j] += vr[j] * e;
+  for (int q = 0; q < 5; ++q)
+    if (need[ROLE][q]) dif_load4(row + 4 * q, g[q]);
+  double e = 0.0;
+  if (ROLE == 5 || ROLE == 7) e = row[20];
+#define DIF_ACC_ITEM(KIND, R, C, OFF)                                                         \
+  if (DIF_##KIND == DIF_FULL) {                                                               \
+    _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i)                                     \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) s[OFF + 4 * i + j] += g[R][i] * g[C][j];  \
+  } else if (DIF_##KIND == DIF_DIAG) {                                                        \
+    _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i)                                     \
+      _Pragma("unroll") for (int j = 0; j <= i; ++j) s[OFF + i * (i + 1) / 2 + j] += g[R][i] * g[R][j]; \
+  } else {                                                                                    \
+    _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i) s[OFF + i] += g[R][i] * e;          \
   }
-  if (R.r1 != R.r0) dif_load4(row + R.r1, vr);  // warp-uniform: six of the eight pairs share their row group
-  dif_load4(row + R.c1, vc);
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) S.sum[16 + 4 * i + j] += vr[i] * vc[j];
+  DIF_ROLE_ITEMS(ROLE, DIF_ACC_ITEM)
+#undef DIF_ACC_ITEM
 }
 
-// the partial sums of a 32-row block join the running entries (ZERO: the running entries are cleared instead)
-template <bool ZERO>
-__device__ __forceinline__ void dif_fold(double* ws, size_t wsn, const DifRole& R, DifSums& S) {
-#pragma unroll
-  for (int b = 0; b < 2; ++b) {
-    const int r0 = b ? R.r1 : R.r0, c0 = b ? R.c1 : R.c0;
-    const bool real = b ? R.has1 : true;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gi = r0 + i, gj = c0 + j;
-        if (real && gi < 19 && gj <= gi) {
-          double* slot = ws + (size_t)tri(gi, gj) * wsn;
-          if (ZERO) __stcg(slot, 0.0);
-          else red_add_f64(slot, S.sum[16 * b + 4 * i + j]);
-        }
-        if (!ZERO) S.sum[16 * b + 4 * i + j] = 0.0;
-      }
+// the partial sums of a 32-row block join the running entries (ZERO: the running entries are cleared instead);
+// the J^T e chains are not block sums and stay in the registers until the end
+template <int ROLE, bool ZERO>
+__device__ __forceinline__ void dif_fold_exact(double* ws, size_t wsn, double (&s)[kDifExactSums]) {
+  // (the slot addresses are formed here, at every fold: hoisted out of the step loop -- for all eight roles -- they
+  // would occupy a few hundred registers' worth of stack)
+  asm volatile("" : "+l"(ws), "+l"(wsn));
+#define DIF_FOLD_ITEM(KIND, R, C, OFF)                                                        \
+  if (DIF_##KIND == DIF_FULL) {                                                               \
+    _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i)                                     \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                         \
+        double* slot = ws + (size_t)tri(4 * R + i, 4 * C + j) * wsn;                          \
+        if (ZERO) __stcg(slot, 0.0);                                                          \
+        else { red_add_f64(slot, s[OFF + 4 * i + j]); s[OFF + 4 * i + j] = 0.0; }             \
+      }                                                                                       \
+  } else if (DIF_##KIND == DIF_DIAG) {                                                        \
+    _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i)                                     \
+      _Pragma("unroll") for (int j = 0; j <= i; ++j) {                                        \
+        double* slot = ws + (size_t)tri(4 * R + i, 4 * R + j) * wsn;                          \
+        if (ZERO) __stcg(slot, 0.0);                                                          \
+        else { red_add_f64(slot, s[OFF + i * (i + 1) / 2 + j]); s[OFF + i * (i + 1) / 2 + j] = 0.0; } \
+      }                                                                                       \
   }
+  DIF_ROLE_ITEMS(ROLE, DIF_FOLD_ITEM)
+#undef DIF_FOLD_ITEM
 }
 
-__device__ __forceinline__ void dif_store_jte(double* ws, size_t wsn, const DifRole& R, const DifSums& S) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (R.hasj && R.jc + j < 19) __stcg(ws + (size_t)(kLower19 + R.jc + j) * wsn, S.sum[32 + j]);
+template <int ROLE>
+__device__ __forceinline__ void dif_store_jte_exact(double* ws, size_t wsn, const double (&s)[kDifExactSums]) {
+  asm volatile("" : "+l"(ws), "+l"(wsn));
+#define DIF_JTE_ITEM(KIND, R, C, OFF)                                                         \
+  if (DIF_##KIND == DIF_JTE) {                                                                \
+    _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i) __stcg(ws + (size_t)(kLower19 + 4 * R + i) * wsn, s[OFF + i]); \
+  }
+  DIF_ROLE_ITEMS(ROLE, DIF_JTE_ITEM)
+#undef DIF_JTE_ITEM
 }
+
+// run-time warp index -> compile-time role
+#define DIF_DISPATCH(wid, CALL)        \
+  switch (wid) {                       \
+    case 0: { CALL(0) } break;         \
+    case 1: { CALL(1) } break;         \
+    case 2: { CALL(2) } break;         \
+    case 3: { CALL(3) } break;         \
+    case 4: { CALL(4) } break;         \
+    case 5: { CALL(5) } break;         \
+    case 6: { CALL(6) } break;         \
+    default: { CALL(7) } break;        \
+  }
 
 // projected control points of a parameter vector: tab[(3*cp + {uL, uR, v}) * 32] (this fit's column of a [.][32] table)
 __device__ __forceinline__ void dif_project_all(const double* pp, double* tab) {
@@ -563,7 +586,6 @@ struct DifCtx {
 // The row sweep of one group: the same code for every warp, its blocks selected by the role.
 template <bool FD>
 __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) {
-  const DifRole R = dif_role(wid);
   constexpr int NBUF = FD ? 1 : 2;
   constexpr int STEP_DOUBLES = kDifWarps * kDifFits * kDifStageRow;
   const DifArgs& A = *C.A;
@@ -580,10 +602,12 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
   const bool have = C.have, blocked = C.blocked, accepted = C.accepted;
   const double pend_dp_sq = C.pend_dp_sq;
     // running sums start at zero (every warp its own entries)
-    DifSums S;
+    double S[kDifExactSums];
 #pragma unroll
-    for (int q = 0; q < kDifSumsPerWarp; ++q) S.sum[q] = 0.0;
-    dif_fold<true>(ws, wsn, R, S);
+    for (int q = 0; q < kDifExactSums; ++q) S[q] = 0.0;
+#define DIF_CALL_ZERO(ROLE) dif_fold_exact<ROLE, true>(ws, wsn, S);
+    DIF_DISPATCH(wid, DIF_CALL_ZERO)
+#undef DIF_CALL_ZERO
     __syncthreads();
     int nmax = 0;
     bool any_blocked = false, any_small = false;
@@ -749,19 +773,23 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
         __syncthreads();  // [B] the four rows of every fit are complete
         write_back(st, sb, cn_eff);
         // ---- every warp: its share of the sums over the eight rows, in the pass's row order
-#pragma unroll 1
-        for (int q8 = 0; q8 < kDifWarps; ++q8) {
-          const int rr = down ? kDifWarps - 1 - q8 : q8;
-          const double* row = sb + (rr * kDifFits + lane) * kDifStageRow;
-          dif_accumulate(row, R, S);
-        }
         // end of a 32-row block (blocked pass) or of the fit: the partial sums join the running entries
         const bool fold = down ? (it == nsteps - 1) : ((st & 3) == 3 || it == nsteps - 1);
-        if (fold) dif_fold<false>(ws, wsn, R, S);
+        {
+          const double* row0 = sb + ((down ? kDifWarps - 1 : 0) * kDifFits + lane) * kDifStageRow;
+          const int rstep = (down ? -1 : 1) * kDifFits * kDifStageRow;
+#define DIF_CALL_ACC(ROLE)                                                                      \
+  _Pragma("unroll 2") for (int q8 = 0; q8 < kDifWarps; ++q8) dif_acc_exact<ROLE>(row0 + q8 * rstep, S); \
+  if (fold) dif_fold_exact<ROLE, false>(ws, wsn, S);
+          DIF_DISPATCH(wid, DIF_CALL_ACC)
+#undef DIF_CALL_ACC
+        }
       }
       __syncthreads();  // the last step's stage is no longer read (the next pass refills it)
     }
-    dif_store_jte(ws, wsn, R, S);
+#define DIF_CALL_JTE(ROLE) dif_store_jte_exact<ROLE>(ws, wsn, S);
+    DIF_DISPATCH(wid, DIF_CALL_JTE)
+#undef DIF_CALL_JTE
 }
 
 template <bool FD>
