@@ -446,7 +446,7 @@ __host__ __device__ constexpr int dif_gn(int G) { return G == 4 ? 3 : 4; }
 enum { DIF_FULL = 0, DIF_DIAG = 1, DIF_JTE = 2 };
 
 template <int ROLE>
-__device__ __forceinline__ void dif_acc_exact(const double* row, double (&s)[kDifExactSums]) {
+__device__ __forceinline__ void dif_acc_exact(const double* row, const double* eptr, double (&s)[kDifExactSums]) {
   // the column groups this role reads (each loaded once), then its items
   double g[5][4];
   constexpr bool need[8][5] = {{1, 1, 0, 0, 0}, {1, 1, 1, 0, 0}, {0, 1, 1, 0, 0}, {1, 0, 0, 1, 0},
@@ -455,7 +455,7 @@ __device__ __forceinline__ void dif_acc_exact(const double* row, double (&s)[kDi
   for (int q = 0; q < 5; ++q)
     if (need[ROLE][q]) dif_load4(row + 4 * q, g[q]);
   double e = 0.0;
-  if (ROLE == 5 || ROLE == 7) e = row[20];
+  if (ROLE == 5 || ROLE == 7) e = eptr[0];
 #define DIF_ACC_ITEM(KIND, R, C, OFF)                                                         \
   if (DIF_##KIND == DIF_FULL) {                                                               \
     _Pragma("unroll") for (int i = 0; i < dif_gn(R); ++i)                                     \
@@ -552,11 +552,51 @@ constexpr int kDifTabUpd = 67;
 constexpr int kDifTabFd = 163;
 
 constexpr int kDifXtPitch = 13;  // per fit and step: 8 samples + 4 t (+1: an odd pitch spreads the banks)
+// The stage of a step, [fit][8 rows][20] with a pitch of 162 doubles per fit: the eight rows of a fit are 1 280 contiguous
+// bytes in global memory AND in the stage, so they come and go as ONE bulk copy per fit (cp.async.bulk, the TMA unit)
+// instead of ten 16-byte cp.async and ten load + store pairs per thread; 162 = 8 * 20 + 2 makes a warp's 16-byte
+// accesses (lane = fit) fall into distinct banks.  The residuals of the step follow as [8][32].
+constexpr int kDifFitPitch = kDifWarps * kDifRow + 2;
+constexpr int kDifStepDoubles = kDifFits * kDifFitPitch + kDifWarps * kDifFits;
 template <bool FD>
 constexpr int dif_build_smem_doubles() {
-  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * kDifWarps * kDifFits * kDifStageRow + kDifFits +
-         2 * kDifFits * kDifXtPitch;
+  return (FD ? kDifTabFd : kDifTabUpd) * kDifFits + (FD ? 1 : 2) * kDifStepDoubles + kDifFits + 2 * kDifFits * kDifXtPitch + 2;
 }
+
+__device__ __forceinline__ unsigned int dif_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dif_mbar_init(unsigned long long* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dif_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void dif_mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dif_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dif_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dif_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dif_mbar_wait(unsigned long long* bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DIF_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DIF_WAIT_DONE;\n"
+      "bra DIF_WAIT_LOOP;\n"
+      "DIF_WAIT_DONE:\n"
+      "}\n" ::"r"(dif_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void dif_bulk_load(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dif_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(dif_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dif_bulk_store(void* dst, const void* src, unsigned int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(dif_smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void dif_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void dif_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // one model value: sum_k w_k * tab[(12*curve + 3k + sel) * 32], ascending k from 0.0 like closest_bezier_pt(cp, t, ..)
 __device__ __forceinline__ double dif_bez(const double (&w)[4], const double* tab, int cb_sel) {
@@ -571,7 +611,9 @@ struct DifCtx {
   const DifArgs* A;
   double* tab;     // this lane's column of the [entry][32] tables
   double* stage;   // [NBUF][8][32][22]
-  double* xt;      // update build: [2][32][13] the step's 8 samples and 4 t of every fit
+  double* xt;      // [2][32][13] the step's 8 samples and 4 t of every fit
+  unsigned long long* mbar;  // [2] arrival of a buffer's bulk loads
+  unsigned int phase0, phase1;
   const int* nrows;
   const double* x;
   const double* tp;
@@ -585,13 +627,14 @@ struct DifCtx {
 
 // The row sweep of one group: the same code for every warp, its blocks selected by the role.
 template <bool FD>
-__device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) {
+__device__ __forceinline__ void dif_group_sweep(DifCtx& C, const int wid) {
   constexpr int NBUF = FD ? 1 : 2;
-  constexpr int STEP_DOUBLES = kDifWarps * kDifFits * kDifStageRow;
+  constexpr int STEP_DOUBLES = kDifStepDoubles;
   const DifArgs& A = *C.A;
   double* const tab = C.tab;
   double* const stage = C.stage;
   double* const xt = C.xt;
+  unsigned long long* const mbar = C.mbar;
   const int* const nrows = C.nrows;
   const double* const x = C.x;
   const double* const tp = C.tp;
@@ -646,32 +689,31 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dt), "l"(okt ? ct + sx : A.L.meas), "r"(okt ? 8 : 0) : "memory");
       }
     };
-    auto issue_rows = [&](int st, int buf) {
-      double* sb = stage + (size_t)buf * STEP_DOUBLES;
-#pragma unroll 1
-      for (int i = 0; i < 10; ++i) {
-        const int pi = 8 * i + csub;               // piece 0..79 of the fit's eight rows
-        const int rr = pi / 10, piece = pi - 10 * rr;
-        const int r = kDifWarps * st + rr;
-        const bool ok = r < cn;
-        const double* src = cJ + (size_t)(ok ? r : 0) * kDifRow + 2 * piece;
-        const unsigned int d = (unsigned int)__cvta_generic_to_shared(sb + (rr * kDifFits + cfi) * kDifStageRow + 2 * piece);
-        const int nbytes = ok ? 16 : 0;  // zero-fill rows past the end of a fit
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+    // the first warp moves the rows: thread `tid` < 32 owns fit `tid` of the group
+    const int tid = threadIdx.x;
+    const int bn = tid < kDifFits ? nrows[tid] : 0;
+    double* const bJ = A.J + (size_t)(tid < kDifFits ? nrows[kDifFits + tid] : 0) * A.j_stride;
+    unsigned int ph0 = C.phase0, ph1 = C.phase1;  // parities of the two buffers' barriers (they persist across groups)
+    auto issue_rows = [&](int st, int buf, int bn_eff) {
+      if (tid < kDifFits) {
+        dif_bulk_wait_read();  // the store that last read this buffer has let go of it
+        const int rows = min(kDifWarps, bn_eff - kDifWarps * st);
+        if (rows > 0) {
+          dif_mbar_expect_tx(mbar + buf, (unsigned int)rows * kDifRow * 8);
+          dif_bulk_load(stage + (size_t)buf * STEP_DOUBLES + tid * kDifFitPitch, bJ + (size_t)kDifWarps * st * kDifRow,
+                        (unsigned int)rows * kDifRow * 8, mbar + buf);
+        } else {
+          dif_mbar_arrive(mbar + buf);
+        }
       }
       issue_xt(st, buf);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto write_back = [&](int st, const double* sb, int n_lim) {
-#pragma unroll 2
-      for (int i = 0; i < 10; ++i) {
-        const int pi = 8 * i + csub;
-        const int rr = pi / 10, piece = pi - 10 * rr;
-        const int r = kDifWarps * st + rr;
-        if (r < n_lim) {
-          const double2 v = *reinterpret_cast<const double2*>(sb + (rr * kDifFits + cfi) * kDifStageRow + 2 * piece);
-          __stcg(reinterpret_cast<double2*>(cJ + (size_t)r * kDifRow + 2 * piece), v);
-        }
+    auto write_back = [&](int st, const double* sb, int bn_eff) {
+      if (tid < kDifFits) {
+        const int rows = min(kDifWarps, bn_eff - kDifWarps * st);
+        if (rows > 0)
+          dif_bulk_store(bJ + (size_t)kDifWarps * st * kDifRow, sb + tid * kDifFitPitch, (unsigned int)rows * kDifRow * 8);
       }
     };
 
@@ -683,9 +725,9 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
       if (down ? !any_small : !any_blocked) continue;
       const bool mine = have && (blocked != down);
       const int n_eff = mine ? g.n : 0;                     // rows of this lane's fit that take part in this pass
-      const bool cmine = cn > 0 && ((cn * 19 <= kBlockSzSq) == down);
-      const int cn_eff = cmine ? cn : 0;                    // the same for the fit this thread copies
-      if (!FD) issue_rows(down ? nsteps - 1 : 0, 0);
+      const bool bmine = bn > 0 && ((bn * 19 <= kBlockSzSq) == down);
+      const int bn_eff = bmine ? bn : 0;                    // the same for the fit whose rows this thread moves
+      if (!FD) issue_rows(down ? nsteps - 1 : 0, 0, bn_eff);
       else { issue_xt(down ? nsteps - 1 : 0, 0); asm volatile("cp.async.commit_group;" ::: "memory"); }
       // sample and t of this lane's row of the first step
 
@@ -694,13 +736,18 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
         const int buf = FD ? 0 : (it & 1);
         double* sb = stage + (size_t)buf * STEP_DOUBLES;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // [A] this step's rows have landed; everybody is done with the other buffer
-        if (!FD && it + 1 < nsteps) issue_rows(down ? st - 1 : st + 1, buf ^ 1);
+        if (FD && tid < kDifFits) dif_bulk_wait_read();  // the one stage buffer: last step's store has read it
+        __syncthreads();  // [A] this step's samples have landed; everybody is done with the other buffer
+        if (!FD) {
+          if (buf == 0) { dif_mbar_wait(mbar + 0, ph0); ph0 ^= 1u; } else { dif_mbar_wait(mbar + 1, ph1); ph1 ^= 1u; }
+        }
+        if (!FD && it + 1 < nsteps) issue_rows(down ? st - 1 : st + 1, buf ^ 1, bn_eff);
         if (FD && it + 1 < nsteps) { issue_xt(down ? st - 1 : st + 1, (it & 1) ^ 1); asm volatile("cp.async.commit_group;" ::: "memory"); }
         // ---- produce row r = 8 st + wid of this lane's fit
         {
           const int r = kDifWarps * st + wid;
-          double* row = sb + (wid * kDifFits + lane) * kDifStageRow;
+          double* row = sb + lane * kDifFitPitch + wid * kDifRow;
+          double* erow = sb + kDifFits * kDifFitPitch + wid * kDifFits + lane;
           const double* xb = xt + ((size_t)(it & 1) * kDifFits + lane) * kDifXtPitch;
           const double xr = xb[wid], tval = xb[8 + (wid >> 1)];
           if (r < n_eff) {
@@ -740,7 +787,7 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
               }
               *reinterpret_cast<double2*>(row + 16) = make_double2(vq[0], vq[1]);
               *reinterpret_cast<double2*>(row + 18) = make_double2(vq[2], 0.0);
-              *reinterpret_cast<double2*>(row + 20) = make_double2(xr - hx, 0.0);
+              erow[0] = xr - hx;
             } else {
               const double hx = dif_bez(w, tab, cb_sel);
               const double wrk = dif_bez(w, tab + 24 * kDifFits, cb_sel);
@@ -763,23 +810,26 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
               }
               const double last = row[18] + tmp * tab[(48 + 18) * kDifFits];
               *reinterpret_cast<double2*>(row + 18) = make_double2(last, 0.0);
-              *reinterpret_cast<double2*>(row + 20) = make_double2(xr - (accepted ? wrk : hx), 0.0);
+              erow[0] = xr - (accepted ? wrk : hx);
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < kDifStageRow; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(0.0, 0.0);
+            for (int c = 0; c < kDifRow; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(0.0, 0.0);
+            erow[0] = 0.0;
           }
         }
-        __syncthreads();  // [B] the four rows of every fit are complete
-        write_back(st, sb, cn_eff);
+        dif_fence_async_smem();  // the corrected rows are about to be read by the bulk stores
+        __syncthreads();  // [B] the eight rows of every fit are complete
+        write_back(st, sb, bn_eff);
         // ---- every warp: its share of the sums over the eight rows, in the pass's row order
         // end of a 32-row block (blocked pass) or of the fit: the partial sums join the running entries
         const bool fold = down ? (it == nsteps - 1) : ((st & 3) == 3 || it == nsteps - 1);
         {
-          const double* row0 = sb + ((down ? kDifWarps - 1 : 0) * kDifFits + lane) * kDifStageRow;
-          const int rstep = (down ? -1 : 1) * kDifFits * kDifStageRow;
+          const double* row0 = sb + lane * kDifFitPitch + (down ? kDifWarps - 1 : 0) * kDifRow;
+          const double* e0 = sb + kDifFits * kDifFitPitch + (down ? kDifWarps - 1 : 0) * kDifFits + lane;
+          const int rstep = (down ? -1 : 1) * kDifRow, estep = (down ? -1 : 1) * kDifFits;
 #define DIF_CALL_ACC(ROLE)                                                                      \
-  _Pragma("unroll 2") for (int q8 = 0; q8 < kDifWarps; ++q8) dif_acc_exact<ROLE>(row0 + q8 * rstep, S); \
+  _Pragma("unroll 2") for (int q8 = 0; q8 < kDifWarps; ++q8) dif_acc_exact<ROLE>(row0 + q8 * rstep, e0 + q8 * estep, S); \
   if (fold) dif_fold_exact<ROLE, false>(ws, wsn, S);
           DIF_DISPATCH(wid, DIF_CALL_ACC)
 #undef DIF_CALL_ACC
@@ -790,6 +840,9 @@ __device__ __forceinline__ void dif_group_sweep(const DifCtx& C, const int wid) 
 #define DIF_CALL_JTE(ROLE) dif_store_jte_exact<ROLE>(ws, wsn, S);
     DIF_DISPATCH(wid, DIF_CALL_JTE)
 #undef DIF_CALL_JTE
+    if (tid < kDifFits) dif_bulk_wait_read();
+    C.phase0 = ph0;
+    C.phase1 = ph1;
 }
 
 template <bool FD>
@@ -798,11 +851,19 @@ __global__ void __launch_bounds__(kDifThreads, 2) dif_build_kernel(const DifArgs
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NTAB = FD ? kDifTabFd : kDifTabUpd;
   constexpr int NBUF = FD ? 1 : 2;
-  constexpr int STEP_DOUBLES = kDifWarps * kDifFits * kDifStageRow;  // one row per warp and fit
+  constexpr int STEP_DOUBLES = kDifStepDoubles;
   double* tab = smem + lane;                                   // tab[entry * 32]
   double* stage = smem + NTAB * kDifFits;                       // [NBUF][8][32][22]
   int* nrows = reinterpret_cast<int*>(stage + NBUF * STEP_DOUBLES);  // [32] n of each fit (0: no fit), [32] fit index
   double* xt = stage + NBUF * STEP_DOUBLES + kDifFits;                // samples / t of the step, two buffers
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(xt + 2 * kDifFits * kDifXtPitch);
+  if (tid == 0) {
+    dif_mbar_init(mbar + 0, kDifFits);
+    dif_mbar_init(mbar + 1, kDifFits);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned int phase0 = 0, phase1 = 0;
   const size_t wsn = (size_t)A.ws_stride;
   const unsigned int total = A.cnt[FD ? 0 : 1];
   const int* list = FD ? A.fd_list : A.upd_list;
@@ -876,10 +937,12 @@ __global__ void __launch_bounds__(kDifThreads, 2) dif_build_kernel(const DifArgs
       }
     }
     DifCtx C;
-    C.A = &A; C.tab = tab; C.stage = stage; C.xt = xt; C.nrows = nrows; C.x = x; C.tp = tp; C.ws = ws; C.wsn = wsn; C.g = g;
+    C.A = &A; C.tab = tab; C.stage = stage; C.xt = xt; C.mbar = mbar; C.phase0 = phase0; C.phase1 = phase1; C.nrows = nrows; C.x = x; C.tp = tp; C.ws = ws; C.wsn = wsn; C.g = g;
     C.lane = lane; C.cfi = cfi; C.csub = csub; C.have = have; C.blocked = blocked; C.accepted = accepted;
     C.pend_dp_sq = pend_dp_sq;
     dif_group_sweep<FD>(C, wid);
+    phase0 = C.phase0;
+    phase1 = C.phase1;
     __threadfence();
     __syncthreads();
     // ---- publish J^T J / J^T e, gradient statistics, stop 1, initial mu (lm_core.c:657-678)
