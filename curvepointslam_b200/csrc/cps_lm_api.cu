@@ -47,7 +47,7 @@ constexpr int kChunkFits = 32768;  // fits per pipelined chunk of the host-buffe
 constexpr int kStagedTailFits = 16384;  // staged der: the last fits (at most this many and B/2) go to the warp-per-fit kernel
 constexpr int kImage8ThreadMinFits = 4096;  // m = 8: a thread per fit from this many fits per call (measured crossover)
 constexpr int kStagedMinFits = 8192;   // der, m = 19: staged shape from this many fits per call (measured crossover ~6 k)
-constexpr int kDifStagedMinFits = 49152;  // dif, m = 19 (forward differences): staged shape from this many fits per call (measured crossover ~35 k)
+constexpr int kDifStagedMinFits = 14336;  // dif, m = 19 (forward differences): staged shape from this many fits per call (measured crossover ~12 k)
 constexpr int kDifChunkFits = 131072;    // host-buffer entry, staged dif: fits per pipelined chunk (amortises the late rounds)
 constexpr size_t kDifMaxJBytes = (size_t)48 << 30;  // stored secant Jacobians of one staged dif pass (larger batches: several passes)
 

@@ -91,7 +91,7 @@ def test_dif_staged_edge_cases(sctx):
 
 def test_dif_staged_equals_warp_per_fit_at_scale(sctx):
     """12 000 fits: every fit of the staged shape is bit-identical to the warp-per-fit kernel's; a sample is checked
-    against the oracle; AUTO keeps the warp-per-fit kernel below 49 152 fits per call (the measured crossover)."""
+    against the oracle; AUTO keeps the warp-per-fit kernel below 14 336 fits per call (the measured crossover is about 12 k)."""
     B = 12000
     b = synth.make_stereo19_batch_fast(B, K=64, seed=75)
     mono = lm.LmContext(0)
