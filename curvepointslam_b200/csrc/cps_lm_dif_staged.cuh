@@ -628,7 +628,6 @@ struct DifCtx {
 // The row sweep of one group: the same code for every warp, its blocks selected by the role.
 template <bool FD>
 __device__ __forceinline__ void dif_group_sweep(DifCtx& C, const int wid) {
-  constexpr int NBUF = FD ? 1 : 2;
   constexpr int STEP_DOUBLES = kDifStepDoubles;
   const DifArgs& A = *C.A;
   double* const tab = C.tab;
@@ -636,8 +635,6 @@ __device__ __forceinline__ void dif_group_sweep(DifCtx& C, const int wid) {
   double* const xt = C.xt;
   unsigned long long* const mbar = C.mbar;
   const int* const nrows = C.nrows;
-  const double* const x = C.x;
-  const double* const tp = C.tp;
   double* const ws = C.ws;
   const size_t wsn = C.wsn;
   const FitGeom g = C.g;
@@ -664,7 +661,6 @@ __device__ __forceinline__ void dif_group_sweep(DifCtx& C, const int wid) {
     const int nsteps = (nmax + kDifWarps - 1) / kDifWarps;
     // this thread's share of the cooperative copies: fit cfi of the group
     const int cn = nrows[cfi];
-    double* cJ = A.J + (size_t)nrows[kDifFits + cfi] * A.j_stride;
     // samples and t of the copied fit (update build): the eight samples of a step are 64 contiguous bytes, its four
     // t values 32; read per lane they cost a 32-byte sector for every 8 bytes and a global latency in the producing phase
     const double* cx = nullptr;
