@@ -478,6 +478,55 @@ def gate_sharded_bench(device: int, rank: int, world: int, L: int = 20000, nz: i
     return out
 
 
+def lm_der_fma_bench(device: int = 0, B: int = 262144, reps: int = 3):
+    """The OPTIONAL fused-arithmetic mode of the staged dlevmar_der kernels (cps_lm_set_arith(CPS_ARITH_FMA), off by
+    default): throughput on the bench's batch and how far its results are from the exact mode's (which are the reference
+    levmar's bit for bit)."""
+    import torch
+
+    from curvepointslam_b200 import lm, synth
+    dev = torch.device("cuda", device)
+    b = synth.make_stereo19_batch_fast(B, K=64, seed=2026)
+    b["meas"] = np.rint(b["meas"])
+    d = {k: torch.from_numpy(b[k]).to(dev) for k in ("meas", "p0", "off", "counts")}
+    st = torch.cuda.current_stream()
+    out = {}
+    ctx = lm.LmContext(device)
+    try:
+        for mode in ("exact", "fma"):
+            ctx.set_arith(mode == "fma")
+            d_p = torch.empty_like(d["p0"])
+            d_info = torch.zeros((B, 10), dtype=torch.float64, device=dev)
+            d_ret = torch.zeros(B, dtype=torch.int32, device=dev)
+            ts = []
+            for it in range(reps + 1):
+                d_p.copy_(d["p0"])
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                ctx.fit_batched_dev(lm.STEREO19, lm.DER, B, d_p.data_ptr(), d["meas"].data_ptr(), None, d["off"].data_ptr(),
+                                    d["counts"].data_ptr(), 512, d_info.data_ptr(), d_ret.data_ptr(), None, stream=st.cuda_stream)
+                e1.record(st)
+                torch.cuda.synchronize()
+                if it >= 1:
+                    ts.append(e0.elapsed_time(e1))
+            out[mode] = (float(np.mean(ts)), d_p.cpu().numpy(), d_info.cpu().numpy())
+    finally:
+        ctx.set_arith(False)
+        ctx.close()
+    ms_e, p_e, i_e = out["exact"]
+    ms_f, p_f, i_f = out["fma"]
+    rel = np.abs(p_f - p_e).max(axis=1) / np.abs(p_e).max(axis=1)
+    e_rel = np.abs(i_f[:, 1] - i_e[:, 1]) / i_e[:, 1]
+    return {"fits": B, "mode": "cps_lm_set_arith(CPS_ARITH_FMA): fused multiply-adds in the staged jac / eval kernels; NOT the default, NOT bit-exact",
+            "value": B / (ms_f * 1e-3), "unit": "fits/s", "ms_per_step": ms_f, "exact_mode_ms_per_step": ms_e,
+            "speedup_over_exact": ms_e / ms_f,
+            "distance_from_exact_mode": {"params_within_1e-9": float((rel < 1e-9).mean()), "params_within_1e-10": float((rel < 1e-10).mean()),
+                                         "params_rel_median": float(np.median(rel)), "params_rel_max": float(rel.max()),
+                                         "sumsq_rel_max": float(e_rel.max()), "same_stop_reason": float((i_f[:, 6] == i_e[:, 6]).mean()),
+                                         "same_iteration_count": float((i_f[:, 5] == i_e[:, 5]).mean()),
+                                         "note": "SURVEY D7: two CPU builds of the reference itself agree within 1e-9 on 93.5 % of der fits"}}
+
+
 def run(device: int = 0):
     res = {"ekf_update": [], "gate": None}
     try:
@@ -488,6 +537,10 @@ def run(device: int = 0):
         res["lm_dif"] = lm_dif_bench(device)
     except Exception as ex:
         res["lm_dif"] = {"error": repr(ex)}
+    try:
+        res["lm_der_fma"] = lm_der_fma_bench(device)
+    except Exception as ex:
+        res["lm_der_fma"] = {"error": repr(ex)}
     for L in (1000, 5000, 20000):
         try:
             res["ekf_update"].append(ekf_update_bench(device, L))

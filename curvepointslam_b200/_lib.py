@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
                                          vp, vp, vp, vp]
     L.cps_lm_set_path.argtypes = [vp, C.c_int]
     L.cps_lm_set_async.argtypes = [vp, C.c_int]
+    L.cps_lm_set_arith.argtypes = [vp, C.c_int]
     L.cps_lm_set_profiling.argtypes = [vp, C.c_int]
     L.cps_lm_get_profile.argtypes = [vp, dp, lp, C.c_int]
     L.cps_lm_get_profile_work.argtypes = [vp, vp, vp, C.c_int]

@@ -26,6 +26,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # translation unit -> extra flags
 UNITS = {
     "cps_lm_api.cu": ["-fmad=false"],
+    "cps_lm_fast.cu": [],  # the optional fused-arithmetic build of the staged der kernels (cps_lm_set_arith)
     "cps_gate.cu": ["-fmad=false"],
     "cps_closest.cu": ["-fmad=false"],
     "cps_ekf.cu": [],

@@ -59,6 +59,7 @@ struct cps_lm_ctx {
   int last_grid = 0, last_block = 0, last_smem = 0;
   long long launches = 0;
   int path = 0;          // CPS_LM_PATH_AUTO / _MONOLITHIC / _STAGED
+  int arith = 0;         // CPS_ARITH_EXACT / CPS_ARITH_FMA (staged der only)
   int last_rounds = 0;   // rounds of the last staged call
   // optional per-kernel timing of the staged rounds (CUDA events on the launching stream)
   int profiling = 0;
@@ -94,6 +95,11 @@ struct cps_lm_ctx {
 };
 
 extern "C" const char* cps_last_error(void) { return cps::g_last_error.c_str(); }
+
+// cps_lm_fast.cu: the staged der kernels once more, with fused multiply-adds (cps_lm_set_arith)
+extern "C" int cps_fast_prepare(int jac_smem, int eval_smem);
+extern "C" void cps_fast_launch_jac(int two_threads, int grid, int block, int smem, cudaStream_t st, const void* args, int nxt);
+extern "C" void cps_fast_launch_eval(int init, int grid, int block, int smem, cudaStream_t st, const void* args, int nxt);
 
 extern "C" void cps_lm_destroy(cps_lm_ctx* c);
 extern "C" int cps_lm_create(cps_lm_ctx** out, int device) {
@@ -169,6 +175,12 @@ extern "C" int cps_lm_sync(cps_lm_ctx* c) {
   }
   for (int i = 0; i < kSlots; ++i) CPS_CUDA(cudaStreamSynchronize(c->slot[i].stream));
   return rc;
+}
+
+extern "C" int cps_lm_set_arith(cps_lm_ctx* c, int arith) {
+  if (!c || (arith != CPS_ARITH_EXACT && arith != CPS_ARITH_FMA)) return CPS_ERR_INVALID;
+  c->arith = arith;
+  return CPS_OK;
 }
 
 extern "C" int cps_lm_set_path(cps_lm_ctx* c, int path) {
@@ -312,6 +324,11 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jac_occ, staged_jac_kernel<false>, kJacThreads, jac_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_occ, staged_solve_kernel<false, false>, kSolveThreads, solve_smem));
   CPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_occ, staged_eval_kernel<false>, kEvalThreads, eval_smem));
+  const bool fma = c->arith == CPS_ARITH_FMA;
+  if (fma && cps_fast_prepare(jac_smem, eval_smem) != 0) {
+    cps::set_last_error("the fused-arithmetic kernels do not fit on this device");
+    return CPS_ERR_CUDA;
+  }
   if (jac_occ < 1 || solve_occ < 1 || eval_occ < 1 || arrow_occ < 1) {
     cps::set_last_error("staged LM kernels do not fit on this device");
     return CPS_ERR_CUDA;
@@ -429,7 +446,8 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     CPS_CUDA(cudaMemsetAsync(A.cnt + 2 + nxt, 0, sizeof(unsigned int), st));
     if (n_solve > 0) {
       span_begin(1);
-      staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+      if (fma) cps_fast_launch_eval(0, grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st, &A, nxt);
+      else staged_eval_kernel<false><<<grid_for(n_solve, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
       span_end();
       c->launches += 1;
     }
@@ -447,7 +465,8 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
         A.init_first = P.first;
         A.init_count = P.count;
         span_begin(1);
-        staged_eval_kernel<true><<<grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
+        if (fma) cps_fast_launch_eval(1, grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st, &A, nxt);
+        else staged_eval_kernel<true><<<grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
         span_end();
         c->launches += 1;
         added += (size_t)P.count;
@@ -467,10 +486,13 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
     const size_t jac_grid_items = std::max(jac_likely, std::min(n_jac, jac_cap / 4));
     if (n_jac > 0) {
       span_begin(2);
-      if (jac_likely * 2 <= jac_cap)  // few fits: two threads per fit
-        staged_jac_kernel<true><<<grid_for(jac_grid_items, kJacThreads / 2, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
-      else
-        staged_jac_kernel<false><<<grid_for(jac_grid_items, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+      if (jac_likely * 2 <= jac_cap) {  // few fits: two threads per fit
+        if (fma) cps_fast_launch_jac(1, grid_for(jac_grid_items, kJacThreads / 2, jac_grid_max), kJacThreads, jac_smem, st, &A, nxt);
+        else staged_jac_kernel<true><<<grid_for(jac_grid_items, kJacThreads / 2, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+      } else {
+        if (fma) cps_fast_launch_jac(0, grid_for(jac_grid_items, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st, &A, nxt);
+        else staged_jac_kernel<false><<<grid_for(jac_grid_items, kJacThreads, jac_grid_max), kJacThreads, jac_smem, st>>>(A, nxt);
+      }
       span_end();
       c->launches += 1;
     }

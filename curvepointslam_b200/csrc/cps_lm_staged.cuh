@@ -1264,6 +1264,24 @@ __device__ __forceinline__ void jac_products_b(unsigned int Dsa, unsigned int Cs
 __device__ __forceinline__ void jac_pass_a(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt,
                                            int s0, int s1, double (&pa)[36], double (&jte_cp)[8]) {
   if (s0 >= s1) return;
+#ifdef CPS_FMA
+  // the optional fused arithmetic (cps_lm_fast.cu: this header compiled with multiply-add contraction): one fused
+  // multiply-add per sum and row, no products in flight; NOT the reference's operation sequence
+#pragma unroll 2
+  for (int r = 2 * s0; r < 2 * s1; ++r) {
+    RowIn in;
+    jac_row_in(Csa, xt, tt, r, in);
+    double v[8];
+    jac_row_cp(Dsa, r, in.w, v);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) pa[a * (a + 1) / 2 + b] = fma(v[a], v[b], pa[a * (a + 1) / 2 + b]);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) jte_cp[a] = fma(v[a], in.e, jte_cp[a]);
+  }
+  return;
+#endif
   double pr[36], pe[8];
   jac_products_a(Dsa, Csa, xt, tt, 2 * s0, pr, pe);
 #pragma unroll 2  // two rows per trip give the scheduler independent work to interleave (measured: -5 %; 4: worse)
@@ -1284,6 +1302,35 @@ __device__ __forceinline__ void jac_pass_a(unsigned int Dsa, unsigned int Csa, c
 __device__ __forceinline__ void jac_pass_b(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt,
                                            int s0, int s1, double (&pb)[30], double (&jte_q)[3]) {
   if (s0 >= s1) return;
+#ifdef CPS_FMA
+#pragma unroll 2
+  for (int r = 2 * s0; r < 2 * s1; ++r) {
+    RowIn in;
+    jac_row_in(Csa, xt, tt, r, in);
+    double v[8];
+    jac_row_cp(Dsa, r, in.w, v);
+    const unsigned int d = Dsa + (r & 1) * (20 * kJacPitch);
+    double vq[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a = fma(in.w[k], lds_pinned(d + (5 * k + 2 + q) * kJacPitch), a);
+      vq[q] = a;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) pb[8 * q + b] = fma(vq[q], v[b], pb[8 * q + b]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int r2 = 0; r2 <= q; ++r2) pb[24 + q * (q + 1) / 2 + r2] = fma(vq[q], vq[r2], pb[24 + q * (q + 1) / 2 + r2]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) jte_q[q] = fma(vq[q], in.e, jte_q[q]);
+  }
+  return;
+#endif
   double pr[30], pe[3];
   jac_products_b(Dsa, Csa, xt, tt, 2 * s0, pr, pe);
 #pragma unroll 2  // two rows per trip give the scheduler independent work to interleave (measured: -5 %; 4: worse)
@@ -1299,6 +1346,47 @@ __device__ __forceinline__ void jac_pass_b(unsigned int Dsa, unsigned int Csa, c
 #pragma unroll
   for (int q = 0; q < 3; ++q) jte_q[q] += pe[q];
 }
+
+#ifdef CPS_FMA
+// fused arithmetic, one thread per fit: both halves of the entries in ONE walk over the rows (no products in flight, so
+// all 66 sums fit in registers and the row inputs are formed once)
+__device__ __forceinline__ void jac_pass_ab(unsigned int Dsa, unsigned int Csa, const double* xt, const double* tt, int s0,
+                                            int s1, double (&pa)[36], double (&pb)[30], double (&jte_cp)[8],
+                                            double (&jte_q)[3]) {
+#pragma unroll 2
+  for (int r = 2 * s0; r < 2 * s1; ++r) {
+    RowIn in;
+    jac_row_in(Csa, xt, tt, r, in);
+    double v[8];
+    jac_row_cp(Dsa, r, in.w, v);
+    const unsigned int d = Dsa + (r & 1) * (20 * kJacPitch);
+    double vq[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a = fma(in.w[k], lds_pinned(d + (5 * k + 2 + q) * kJacPitch), a);
+      vq[q] = a;
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) pa[a * (a + 1) / 2 + b] = fma(v[a], v[b], pa[a * (a + 1) / 2 + b]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) pb[8 * q + b] = fma(vq[q], v[b], pb[8 * q + b]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int r2 = 0; r2 <= q; ++r2) pb[24 + q * (q + 1) / 2 + r2] = fma(vq[q], vq[r2], pb[24 + q * (q + 1) / 2 + r2]);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) jte_cp[a] = fma(v[a], in.e, jte_cp[a]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) jte_q[q] = fma(vq[q], in.e, jte_q[q]);
+  }
+}
+#endif
 
 // derivative table and projected control points of one contour segment (curve, side): the four control points of
 // prep_jac / prep_func of the monolithic kernel, same expressions
@@ -1457,6 +1545,24 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
           // address, program order per address): no load latency is exposed.
           if (seg_lo != cur_seg) enter_segment(seg_lo);
           double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
+#ifdef CPS_FMA
+          if (doA && doB) {
+            double pa[36], pb[30];
+#pragma unroll
+            for (int q = 0; q < 36; ++q) pa[q] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 30; ++q) pb[q] = 0.0;
+            jac_pass_ab(Dsa, Csa, xt, tt, s_lo, blk_end, pa, pb, jte_cp, jte_q);
+#pragma unroll
+            for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
+#pragma unroll
+            for (int q = 0; q < 24; ++q) red_add_f64(acc + (36 + q) * wsn, pb[q]);
+            double* accq = ws + (size_t)(kWsAcc + 120) * wsn;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) red_add_f64(accq + q * wsn, pb[24 + q]);
+          } else
+#endif
+          {
           if (doA) {
             double pa[36];
 #pragma unroll
@@ -1475,6 +1581,7 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
             double* accq = ws + (size_t)(kWsAcc + 120) * wsn;
 #pragma unroll
             for (int q = 0; q < 6; ++q) red_add_f64(accq + q * wsn, pb[24 + q]);
+          }
           }
         } else {
           // the block straddles segments: its partial sums are kept per curve in the work area while the pieces are

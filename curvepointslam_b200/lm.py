@@ -73,6 +73,10 @@ class LmContext:
         """Asynchronous device entry: fit_batched_dev queues the call for a worker thread and makes `stream` wait for it."""
         _lib.check(_lib.lib().cps_lm_set_async(self._h, 1 if on else 0), "cps_lm_set_async")
 
+    def set_arith(self, fma: bool):
+        """Fused multiply-adds in the staged dlevmar_der kernels (not bit-identical to the reference; default exact)."""
+        _lib.check(_lib.lib().cps_lm_set_arith(self._h, 1 if fma else 0), "cps_lm_set_arith")
+
     def solve_handovers(self) -> int:
         """Systems of the last staged dlevmar_der call that the block-arrow solve handed to the dense one."""
         n = C.c_longlong(0)

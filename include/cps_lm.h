@@ -169,6 +169,18 @@ int cps_fit_frames_batched(cps_lm_ctx *ctx, int variant, int F, const void *pts,
 #define CPS_LM_PATH_STAGED 2
 int cps_lm_set_path(cps_lm_ctx *ctx, int path);
 /*
+ * Arithmetic of the staged dlevmar_der kernels (Stereo19 batches that take the staged shape; everything else is always
+ * exact).  CPS_ARITH_EXACT (default): the reference's floating-point operation sequence, every multiply and add issued
+ * separately -- results equal the reference levmar's bit for bit.  CPS_ARITH_FMA: the Jacobian / J^T J and evaluation
+ * kernels use fused multiply-adds (half the FP64 instructions in the sums); results then differ from the reference's
+ * in the last bits of every sum, i.e. the way two CPU builds of the reference differ from each other (same stop reason
+ * and ||e||^2 within 1e-10 on every fit, parameters within 1e-9 on about 95 % of the fits: bench.py extras.lm_der_fma,
+ * tests/test_lm_staged_gpu.py).  The last fits of a batch (the warp-per-fit tail kernel) and the solve stay exact.
+ */
+#define CPS_ARITH_EXACT 0
+#define CPS_ARITH_FMA 1
+int cps_lm_set_arith(cps_lm_ctx *ctx, int arith);
+/*
  * Per-kernel timing of the staged shape: with profiling on, every launch of its three kernels is bracketed by CUDA
  * events on the launching stream; cps_lm_get_profile returns the accumulated milliseconds and launch counts of
  * {solve, eval, jac, tail} (and clears them when reset != 0); tail is the warp-per-fit kernel that takes the last

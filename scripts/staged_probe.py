@@ -27,6 +27,8 @@ for name in paths:
     ts = []
     if os.environ.get("PROBE_PROFILE"):
         ctx.set_profiling(True)
+    if os.environ.get("PROBE_FMA") and name == "staged":
+        ctx.set_arith(True)
     for it in range(6):
         d_p.copy_(d_p0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -361,3 +361,29 @@ def test_asynchronous_device_entry_honours_its_stream(variant):
     assert (outs["async"][1][:, 6] == 2).all()
     # the synchronous call blocks for the whole fit; the asynchronous one only queues it
     assert outs["async"][2] < 0.25 * outs["sync"][2], (outs["async"][2], outs["sync"][2])
+
+
+def test_fused_arithmetic_mode_distribution():
+    """cps_lm_set_arith(CPS_ARITH_FMA): the staged der kernels with fused multiply-adds.  Not the reference's operation
+    sequence, so not bit-identical -- but as close to the exact results as two CPU builds of the reference are to each
+    other (93.5 % of der fits within 1e-9): the same stop reason and ||e||^2 within 1e-10 on every fit,
+    parameters within 1e-9 on at least 90 % of the fits and never further than 1e-6.  The default mode is untouched."""
+    B = 20000
+    b = synth.make_stereo19_batch_fast(B, K=64, seed=69)
+    c = lm.LmContext(0)
+    c.set_path(lm.PATH_STAGED)
+    try:
+        exact = c.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+        c.set_arith(True)
+        fast = c.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+        c.set_arith(False)
+        again = c.fit_batched(STEREO19, DER, b["p0"], b["meas"], b["off"], b["counts"], OPTS)
+    finally:
+        c.close()
+    assert np.array_equal(_bits(exact["p"]), _bits(again["p"]))  # switching back restores the exact path
+    assert not np.array_equal(_bits(exact["p"]), _bits(fast["p"]))  # (the fused kernels did run)
+    rel = np.abs(fast["p"] - exact["p"]).max(axis=1) / np.abs(exact["p"]).max(axis=1)
+    e_rel = np.abs(fast["info"][:, 1] - exact["info"][:, 1]) / exact["info"][:, 1]
+    assert (fast["info"][:, 6] == exact["info"][:, 6]).all()
+    assert e_rel.max() < 1e-10
+    assert (rel < 1e-9).mean() >= 0.90 and rel.max() < 1e-6, ((rel < 1e-9).mean(), rel.max())
