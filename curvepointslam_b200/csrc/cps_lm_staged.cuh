@@ -1583,10 +1583,49 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
             for (int q = 0; q < 6; ++q) red_add_f64(accq + q * wsn, pb[24 + q]);
           }
           }
+        } else if (seg_hi == seg_lo + 1) {
+          // the block holds the end of one contour segment and the start of the next (with contours of real lengths:
+          // one block in four, and at different rows in every lane of a warp): the two pieces belong to different
+          // curves, so the first curve's partial sums are complete when its piece ends and join the running entries
+          // right there; only the six theta/phi/z x theta/phi/z sums run on over both pieces.  Same sums in the same
+          // order as the general walk below, without its parking of 66 partial sums in the work area per piece.
+          const int mid = seg_end(g, seg_lo);
+          double pq[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+          for (int piece = 0; piece < 2; ++piece) {
+            const int p0 = piece ? mid : s_lo, p1 = piece ? blk_end : mid;
+            if (seg_lo + piece != cur_seg) enter_segment(seg_lo + piece);
+            double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
+            if (doA) {
+              double pa[36];
+#pragma unroll
+              for (int q = 0; q < 36; ++q) pa[q] = 0.0;
+              jac_pass_a(Dsa, Csa, xt, tt, p0, p1, pa, jte_cp);
+#pragma unroll
+              for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
+            }
+            if (doB) {
+              double pb[30];
+#pragma unroll
+              for (int q = 0; q < 24; ++q) pb[q] = 0.0;
+#pragma unroll
+              for (int q = 0; q < 6; ++q) pb[24 + q] = pq[q];
+              jac_pass_b(Dsa, Csa, xt, tt, p0, p1, pb, jte_q);
+#pragma unroll
+              for (int q = 0; q < 24; ++q) red_add_f64(acc + (36 + q) * wsn, pb[q]);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) pq[q] = pb[24 + q];
+            }
+          }
+          if (doB) {
+            double* accq = ws + (size_t)(kWsAcc + 120) * wsn;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) red_add_f64(accq + q * wsn, pq[q]);
+          }
         } else {
-          // the block straddles segments: its partial sums are kept per curve in the work area while the pieces are
-          // walked (a curve's rows may come in two pieces: curve 1, a short curve 2, curve 1 again), and join the
-          // running entries once, at the end of the block
+          // the block straddles three or more segments: its partial sums are kept per curve in the work area while
+          // the pieces are walked (a curve's rows come in two pieces: curve 1, a short curve 2, curve 1 again), and
+          // join the running entries once, at the end of the block
 #pragma unroll 1
           for (int q = kWsPend; q < kWsSlots; ++q) __stcg(ws + q * wsn, 0.0);
           unsigned seen = 0;
