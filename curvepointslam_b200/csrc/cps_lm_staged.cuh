@@ -1538,11 +1538,9 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
         const int s_lo = 16 * b, blk_end = min(16 * b + 16, g.nsamp);
         const int seg_lo = (s_lo >= g.b1) + (s_lo >= g.b2) + (s_lo >= g.b3);
         const int seg_hi = (blk_end - 1 >= g.b1) + (blk_end - 1 >= g.b2) + (blk_end - 1 >= g.b3);
-        if (seg_lo == seg_hi) {
-          // the block lies inside one contour segment (the usual case): partial sums start at zero in registers and join
-          // the running entries at the end of the pass (misc_core.c:118-123).  The additions are fire-and-forget
-          // reductions performed at the L2 (red.global.add.f64: the same IEEE round-to-nearest addition; one owner per
-          // address, program order per address): no load latency is exposed.
+        if (__all_sync(__activemask(), seg_lo == seg_hi)) {
+          // every lane's block lies inside one contour segment (always, for batches of equal-length contours): partial
+          // sums start at zero in registers and join the running entries at the end of the pass (misc_core.c:118-123)
           if (seg_lo != cur_seg) enter_segment(seg_lo);
           double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
 #ifdef CPS_FMA
@@ -1583,26 +1581,55 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
             for (int q = 0; q < 6; ++q) red_add_f64(accq + q * wsn, pb[24 + q]);
           }
           }
-        } else if (seg_hi == seg_lo + 1) {
-          // the block holds the end of one contour segment and the start of the next (with contours of real lengths:
-          // one block in four, and at different rows in every lane of a warp): the two pieces belong to different
-          // curves, so the first curve's partial sums are complete when its piece ends and join the running entries
-          // right there; only the six theta/phi/z x theta/phi/z sums run on over both pieces.  Same sums in the same
-          // order as the general walk below, without its parking of 66 partial sums in the work area per piece.
-          const int mid = seg_end(g, seg_lo);
+        } else if (seg_hi <= seg_lo + 1) {
+          // The block lies inside one contour segment, or holds the end of one and the start of the next (with
+          // contours of real lengths: one block in four, at different rows in every lane of a warp).  ONE code path
+          // for both, so that the lanes of a warp stay together: two pieces, the second one empty for a lane whose
+          // block does not cross a boundary.  Partial sums start at zero in registers and join the running entries
+          // when their piece ends (misc_core.c:118-123: the two pieces of a crossing block belong to different curves,
+          // so the first curve's partial sums are complete there); only the six theta/phi/z x theta/phi/z sums run on
+          // over both pieces.  The additions are fire-and-forget reductions performed at the L2 (red.global.add.f64:
+          // the same IEEE round-to-nearest addition; one owner per address, program order per address): no load
+          // latency is exposed.
+          const int mid = (seg_hi == seg_lo) ? blk_end : seg_end(g, seg_lo);
           double pq[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
           for (int piece = 0; piece < 2; ++piece) {
+            // (no lane of the warp has a second piece: batches of equal-length contours never do)
+            if (piece == 1 && !__any_sync(__activemask(), mid < blk_end)) break;
             const int p0 = piece ? mid : s_lo, p1 = piece ? blk_end : mid;
-            if (seg_lo + piece != cur_seg) enter_segment(seg_lo + piece);
-            double* acc = ws + (size_t)(kWsAcc + 60 * cur_curve) * wsn;
+            if (p0 < p1 && seg_lo + piece != cur_seg) enter_segment(seg_lo + piece);
+            double* acc = ws + (size_t)(kWsAcc + 60 * (cur_curve < 0 ? 0 : cur_curve)) * wsn;
+#ifdef CPS_FMA
+            if (doA && doB) {
+              double pa[36], pb[30];
+#pragma unroll
+              for (int q = 0; q < 36; ++q) pa[q] = 0.0;
+#pragma unroll
+              for (int q = 0; q < 24; ++q) pb[q] = 0.0;
+#pragma unroll
+              for (int q = 0; q < 6; ++q) pb[24 + q] = pq[q];
+              jac_pass_ab(Dsa, Csa, xt, tt, p0, p1, pa, pb, jte_cp, jte_q);
+              if (p0 < p1) {
+#pragma unroll
+                for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
+#pragma unroll
+                for (int q = 0; q < 24; ++q) red_add_f64(acc + (36 + q) * wsn, pb[q]);
+              }
+#pragma unroll
+              for (int q = 0; q < 6; ++q) pq[q] = pb[24 + q];
+              continue;
+            }
+#endif
             if (doA) {
               double pa[36];
 #pragma unroll
               for (int q = 0; q < 36; ++q) pa[q] = 0.0;
               jac_pass_a(Dsa, Csa, xt, tt, p0, p1, pa, jte_cp);
+              if (p0 < p1) {
 #pragma unroll
-              for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
+                for (int q = 0; q < 36; ++q) red_add_f64(acc + q * wsn, pa[q]);
+              }
             }
             if (doB) {
               double pb[30];
@@ -1611,8 +1638,10 @@ __global__ void __launch_bounds__(kJacThreads, 2) staged_jac_kernel(const Staged
 #pragma unroll
               for (int q = 0; q < 6; ++q) pb[24 + q] = pq[q];
               jac_pass_b(Dsa, Csa, xt, tt, p0, p1, pb, jte_q);
+              if (p0 < p1) {
 #pragma unroll
-              for (int q = 0; q < 24; ++q) red_add_f64(acc + (36 + q) * wsn, pb[q]);
+                for (int q = 0; q < 24; ++q) red_add_f64(acc + (36 + q) * wsn, pb[q]);
+              }
 #pragma unroll
               for (int q = 0; q < 6; ++q) pq[q] = pb[24 + q];
             }
