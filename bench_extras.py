@@ -64,7 +64,7 @@ def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, 
                         "moved_bytes": {"note": "the TMA kernel reads one tile of every mirrored pair once P's tiles are "
                                                 "exact mirrors (after any update): 12 N^2 bytes actually cross HBM",
                                         "bytes": 12 * N * N, "achieved_GBs": 12.0 * N * N / (cov_ms * 1e-3) / 1e9}},
-           "flops_tflops": 2.0 * N * N * M / (cov_ms * 1e-3) / 1e12, "launches_per_update": 3 if M <= 36 else None,
+           "flops_tflops": 2.0 * N * N * M / (cov_ms * 1e-3) / 1e12, "launches_per_update": int(tm["launches"]),
            "P_bytes": 8 * N * N, "l2": "P larger than L2" if 8 * N * N > 126e6 else "P fits L2 (72 MB): L2-resident"}
     kf.close()
     return out

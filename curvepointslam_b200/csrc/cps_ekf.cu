@@ -30,6 +30,7 @@ namespace {
 constexpr int MAXM = CPS_EKF_MAX_MEAS;
 constexpr int MAXNC = 6 + MAXM;  // compact columns of H: 6 pose columns + landmark columns
 constexpr int TILE = 64;
+constexpr int kFrontSmemMax = 225 * 1024;  // dynamic shared memory of the fused front end (M = 65 needs 209 KB)
 constexpr double kPI = 3.1415926535;  // common.h:114
 
 // constants of kalmanClass.h:17-36
@@ -366,6 +367,57 @@ __global__ void __launch_bounds__(256) ekf_gain_kernel(UpdateDesc d, const doubl
   }
 }
 
+// Gauss-Jordan steps of the fused front end with a thread's entries (at most Q of the M x M, entry e = tid + 256 q)
+// in registers from step to step.  A step is branch-free: the pivot and the entries' pivot-column and pivot-row
+// values are loaded together and the three cases of the update are selects, so the loads of a step overlap each
+// other and the reciprocal instead of forming one dependent load -> multiply -> load -> update -> store chain per
+// entry (21 us of the front end's 43 at M = 35).  Same operations on the same values as the plain loop in the kernel.
+// The matrix ping-pongs between Wa (the input) and Wb; after M steps the result is in Wb when M is odd.
+template <int Q>
+__device__ __forceinline__ void gj_register_steps(double* Wa, double* Wb, int M, int tid, int* flag, int* bad) {
+  int oi[Q], ej[Q], ei[Q];
+  double v[Q];
+  {
+    int i = tid / M, j = tid - i * M;
+    const int di = 256 / M, dj = 256 - di * M;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const bool act = tid + q * 256 < M * M;
+      ei[q] = act ? i : 0;
+      ej[q] = act ? j : 0;
+      oi[q] = ei[q] * M;
+      v[q] = act ? Wa[tid + q * 256] : 0.0;
+      i += di; j += dj;
+      if (j >= M) { j -= M; ++i; }
+    }
+  }
+  double* Wsrc = Wa;
+  double* Wdst = Wb;
+  for (int k = 0; k < M; ++k) {
+    const double piv = Wsrc[k * M + k];
+    double cik[Q], rk[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      cik[q] = Wsrc[oi[q] + k];
+      rk[q] = Wsrc[k * M + ej[q]];
+    }
+    const bool ok = (piv > 0.0) && (piv <= 1.79769313486231571e308);
+    const double ip = ok ? 1.0 / piv : 1.0;
+    if (!ok && tid == 0) { *flag = 1; *bad = 1; }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const double rkj = rk[q] * ip;
+      const double off_row = v[q] - cik[q] * rkj, in_col = -cik[q] * ip;
+      const double in_row = (ej[q] == k) ? ip : rkj;
+      const double nv = (ei[q] == k) ? in_row : ((ej[q] == k) ? in_col : off_row);
+      v[q] = nv;
+      if (tid + q * 256 < M * M) Wdst[tid + q * 256] = nv;
+    }
+    __syncthreads();
+    double* tmp = Wsrc; Wsrc = Wdst; Wdst = tmp;
+  }
+}
+
 // ---- fused front end (used whenever its tables fit shared memory: every live measurement size) ---------------
 // ekf_front_kernel, ONE block: kernel 1, then only the nc rows of T = P H^T that S needs (the rows of the compact
 // columns: an nc x nc gather of P), S = Hc Tc + R, and S^-1 by Gauss-Jordan elimination on the symmetric part of S
@@ -384,8 +436,11 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   const int tid = threadIdx.x, nt = blockDim.x;
   ekf_build_device(d, x, small, cols, land_cols);
   __syncthreads();
-  double* Hs = sh;                 // [M][nc]
-  double* Ps = Hs + M * nc;        // [nc][nc]  P restricted to the compact columns
+  // Hs rows have an odd pitch: the T loop below reads Hs[r][b] with r across the lanes, and with the natural pitch
+  // (nc = 38: 4-way, nc = 68: 8-way bank conflicts) that loop was most of this kernel at M = 65
+  const int ncp = nc | 1;
+  double* Hs = sh;                 // [M][ncp]
+  double* Ps = Hs + M * ncp;       // [nc][nc]  P restricted to the compact columns
   double* Tc = Ps + nc * nc;       // [nc][M]   rows of T at the compact columns
   double* S = Tc + nc * M;         // [M][M]
   double* W = S + M * M;           // [M][M]    elimination work matrix -> S^-1 (ping)
@@ -399,7 +454,10 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
     __device__ Walk(int e0, int step, int W_) : i(e0 / W_), j(e0 - (e0 / W_) * W_), di(step / W_), dj(step - (step / W_) * W_), W(W_) {}
     __device__ void next() { i += di; j += dj; if (j >= W) { j -= W; ++i; } }
   };
-  for (int e = tid; e < M * nc; e += nt) Hs[e] = small[SM_HC + e];
+  {
+    Walk w(tid, nt, nc);
+    for (int e = tid; e < M * nc; e += nt, w.next()) Hs[w.i * ncp + w.j] = small[SM_HC + e];
+  }
   {
     Walk w(tid, nt, nc);
     for (int e = tid; e < nc * nc; e += nt, w.next()) Ps[e] = P[(size_t)cols[w.i] * d.ld + cols[w.j]];
@@ -409,7 +467,7 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   for (int e = tid; e < nc * M; e += nt, wt.next()) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
     const int c = wt.i, r = wt.j;
     double s = 0.0;
-    for (int b = 0; b < nc; ++b) s += Ps[c * nc + b] * Hs[r * nc + b];
+    for (int b = 0; b < nc; ++b) s += Ps[c * nc + b] * Hs[r * ncp + b];
     Tc[e] = s;
   }
   __syncthreads();
@@ -418,7 +476,7 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   for (int e = tid; e < M * M; e += nt, ws.next()) {
     const int r = ws.i, q = ws.j;
     double acc = 0.0;
-    for (int c = 0; c < nc; ++c) acc += Hs[r * nc + c] * Tc[c * M + q];
+    for (int c = 0; c < nc; ++c) acc += Hs[r * ncp + c] * Tc[c * M + q];
     if (r == q) acc += small[SM_R + r];
     S[e] = acc;
   }
@@ -433,6 +491,15 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   // a step reads the matrix as it stands and writes the next one into the other buffer: one barrier per step
   double* Wsrc = W;
   double* Wdst = W2;
+  // M <= 39 (every live size; M <= 65 with more registers): a thread's entries stay in registers from step to step
+  // and a step is branch-free (gj_register_steps above)
+  if (M * M <= 6 * 256 && nt == 256) {
+    gj_register_steps<6>(W, W2, M, tid, flag, &bad);
+    Wsrc = (M & 1) ? W2 : W;
+  } else if (M * M <= 17 * 256 && nt == 256) {
+    gj_register_steps<17>(W, W2, M, tid, flag, &bad);
+    Wsrc = (M & 1) ? W2 : W;
+  } else
   for (int k = 0; k < M; ++k) {
     const double piv = Wsrc[k * M + k];
     const bool ok = (piv > 0.0) && (piv <= 1.79769313486231571e308);
@@ -465,17 +532,22 @@ __global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const doubl
                                                        double* __restrict__ x, int ldk) {
   extern __shared__ double sh[];
   const int M = d.M, nc = d.nc;
-  double* Hc = sh;                  // [M][nc]
-  double* Sinv = Hc + M * nc;       // [M][M]
-  double* S = Sinv + M * M;         // [M][M]
-  double* nu = S + M * M;           // [M]
+  // odd pitches where a matrix is read with its ROW index across the lanes (Hc in the T loop, S in the Y loop)
+  const int ncp = nc | 1, Mo = M | 1;
+  double* Hc = sh;                  // [M][ncp]
+  double* Sinv = Hc + M * ncp;      // [M][M]
+  double* S = Sinv + M * M;         // [M][Mo]
+  double* nu = S + M * Mo;          // [M]
   double* rowbuf = nu + M;          // [8 warps][nc + 2 M]
   int* scols = reinterpret_cast<int*>(rowbuf + 8 * (nc + 2 * M));
-  for (int e = threadIdx.x; e < M * nc; e += blockDim.x) Hc[e] = small[SM_HC + e];
+  for (int e = threadIdx.x; e < M * nc; e += blockDim.x) {
+    const int r = e / nc, b = e - r * nc;
+    Hc[r * ncp + b] = small[SM_HC + e];
+  }
   for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
     const int r = e / M, q = e - r * M;
     Sinv[e] = small[SM_SINV + r * MAXM + q];
-    S[e] = small[SM_S + r * MAXM + q];
+    S[r * Mo + q] = small[SM_S + r * MAXM + q];
   }
   for (int e = threadIdx.x; e < M; e += blockDim.x) nu[e] = small[SM_NU + e];
   for (int e = threadIdx.x; e < nc; e += blockDim.x) scols[e] = cols[e];
@@ -488,7 +560,7 @@ __global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const doubl
     for (int c = lane; c < nc; c += 32) pr[c] = P[(size_t)row * d.ld + scols[c]];
     __syncwarp();
     for (int r = lane; r < M; r += 32) {
-      const double* h = Hc + r * nc;
+      const double* h = Hc + r * ncp;
       double s = 0.0;
       for (int c = 0; c < nc; ++c) s += pr[c] * h[c];
       trow[r] = s;
@@ -504,7 +576,7 @@ __global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const doubl
     double dx = 0.0;
     for (int r = lane; r < M; r += 32) {
       double acc = 0.0;
-      for (int q = 0; q < M; ++q) acc += krow[q] * S[r * M + q];
+      for (int q = 0; q < M; ++q) acc += krow[q] * S[r * Mo + q];
       Yt[(size_t)r * ldk + row] = acc;
       dx += krow[r] * nu[r];
     }
@@ -939,7 +1011,12 @@ __device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1,
 // (mbarrier `done`), stores both, waits until the stores have READ shared memory, then hands the transpose buffer
 // back (`tfree`) and refills the freed stage with the pair three ahead.  The compute warps therefore never wait
 // for a store: they only wait for tiles that were requested two to three pairs earlier.
+// STAGES = depth of the P-tile ring and of the Y ring: 3 for M <= 36 (the reference's live sizes), 2 for M <= 80 (a
+// stage's Y tile grows with M and the four-warp K / Y fragments keep their padded layout, so the deeper ring no
+// longer fits the 227 KB of an SM; at those sizes a pair carries 2-3x the DMMA work and one tile in flight covers it).
 constexpr int TMA_THREADS = 288;
+constexpr int TMA2_MAX_M = 80;
+template <int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __grid_constant__ TmaMaps maps, int M,
                                                                       const double* __restrict__ Kt,
                                                                       const double* __restrict__ Yt, int ldk, int nt,
@@ -949,10 +1026,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
   const int Mp = (M + 3) & ~3;
   double* Tt = reinterpret_cast<double*>(base);                                     // 32 KB, swizzled transpose
   double* Pst = reinterpret_cast<double*>(base + TMA_TILE_BYTES);                   // [3][64][64]
-  double* Yst = reinterpret_cast<double*>(base + (1 + TMA_STAGES) * TMA_TILE_BYTES);  // [3][Mp][68]
-  double* Ks = Yst + TMA_STAGES * Mp * DSTRIDE;                                     // [Mp][68]
+  double* Yst = reinterpret_cast<double*>(base + (1 + STAGES) * TMA_TILE_BYTES);  // [3][Mp][68]
+  double* Ks = Yst + STAGES * Mp * DSTRIDE;                                     // [Mp][68]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(Ks + Mp * DSTRIDE);  // [3]
-  unsigned long long* done = full + TMA_STAGES;                                     // compute -> copy warp
+  unsigned long long* done = full + STAGES;                                     // compute -> copy warp
   unsigned long long* tfree = done + 1;                                             // copy warp -> compute
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
 
@@ -961,7 +1038,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
   const long long p_end = min(total_pairs, p_begin + per);
   if (p_begin >= p_end) return;
   if (t == 0) {
-    for (int s = 0; s < TMA_STAGES; ++s) mbar_init(full + s, 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
     mbar_init(done, 1);
     mbar_init(tfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -969,7 +1046,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
   if (t < 256)
     for (int e = t; e < (Mp - M) * DSTRIDE; e += 256) {  // padding rows of K and Y stay zero
       Ks[M * DSTRIDE + e] = 0.0;
-      for (int s = 0; s < TMA_STAGES; ++s) Yst[s * Mp * DSTRIDE + M * DSTRIDE + e] = 0.0;
+      for (int s = 0; s < STAGES; ++s) Yst[s * Mp * DSTRIDE + M * DSTRIDE + e] = 0.0;
     }
   __syncthreads();
   auto next_pair = [&](int& I, int& J) {
@@ -987,13 +1064,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
     };
     int Il = I, Jl = J;  // next pair to load
     long long pl = p_begin;
-    for (int s = 0; s < TMA_STAGES && pl < p_end; ++s, ++pl) {
+    for (int s = 0; s < STAGES && pl < p_end; ++s, ++pl) {
       issue_p(Il, Jl, s);
       next_pair(Il, Jl);
     }
     for (long long p = p_begin; p < p_end; ++p) {
       const int it = (int)(p - p_begin);
-      const int stage = it % TMA_STAGES;
+      const int stage = it % STAGES;
       mbar_wait(done, (unsigned)(it & 1));  // tile and transpose of pair p are in shared memory, fenced
       const double* pa = Pst + stage * TILE * TILE;
       if (I != J) {
@@ -1037,20 +1114,21 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
   int k_loaded = I;
   issue_k(I);
   int Iy = I, Jy = J;  // pair whose Y tile is requested next
-  issue_y(Jy, 0);
-  cp_async_commit();
-  next_pair(Iy, Jy);
-  if (p_begin + 1 < p_end) issue_y(Jy, 1);
-  cp_async_commit();
-  next_pair(Iy, Jy);
-  for (long long p = p_begin; p < p_end; ++p) {
-    const int it = (int)(p - p_begin);
-    const int stage = it % TMA_STAGES;
-    if (p + 2 < p_end) issue_y(Jy, (it + 2) % TMA_STAGES);  // that stage's Y was last read in iteration it - 1
+  // the Y tiles of the first STAGES - 1 pairs, one commit group each
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (p_begin + s < p_end) issue_y(Jy, s);
     cp_async_commit();
     next_pair(Iy, Jy);
-    cp_async_wait<2>();                                          // this thread's share of Y(p) (and of K)
-    mbar_wait(full + stage, (unsigned)((it / TMA_STAGES) & 1));  // the P tile of pair p
+  }
+  for (long long p = p_begin; p < p_end; ++p) {
+    const int it = (int)(p - p_begin);
+    const int stage = it % STAGES;
+    if (p + (STAGES - 1) < p_end) issue_y(Jy, (it + STAGES - 1) % STAGES);  // that stage's Y was last read in iteration it - 1
+    cp_async_commit();
+    next_pair(Iy, Jy);
+    cp_async_wait<STAGES - 1>();                                 // this thread's share of Y(p) (and of K)
+    mbar_wait(full + stage, (unsigned)((it / STAGES) & 1));  // the P tile of pair p
     compute_warps_sync();                                        // everybody's Y shares
     if (k_loaded != I) {
       issue_k(I);
@@ -1427,8 +1505,8 @@ int ensure_aux(cps_ekf* h, size_t bytes) {
   return CPS_OK;
 }
 
-size_t tma_smem_bytes(int Mp) {
-  return 1024 + (size_t)(1 + TMA_STAGES) * TMA_TILE_BYTES + (size_t)(TMA_STAGES + 1) * Mp * DSTRIDE * sizeof(double) + 128;
+size_t tma_smem_bytes(int Mp, int stages) {
+  return 1024 + (size_t)(1 + stages) * TMA_TILE_BYTES + (size_t)(stages + 1) * Mp * DSTRIDE * sizeof(double) + 128;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
@@ -1499,9 +1577,12 @@ int ekf_create_impl(cps_ekf* h, int device, int capacity) {
                                 2 * MAXM * DSTRIDE * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (MAXM * MAXNC + 8 * MAXNC) * (int)sizeof(double) + MAXNC * (int)sizeof(int)));
-  CPS_CUDA(cudaFuncSetAttribute(ekf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CPS_CUDA(cudaFuncSetAttribute(ekf_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes(PIPE_MAX_M)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemMax));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemMax));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel<TMA_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tma_smem_bytes(PIPE_MAX_M, TMA_STAGES)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tma_smem_bytes(TMA2_MAX_M, 2)));
   h->maps_ok = encode_maps(h);
   h->mirror_exact = true;  // P = 0
   CPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -1681,11 +1762,12 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
     CPS_CUDA(cudaMemcpyAsync(d_land, hcols, sizeof(int) * (n + n_pts), cudaMemcpyHostToDevice, st));
   CPS_CUDA(cudaEventRecord(h->ev[0], st));
   const int row_blocks = std::min((d.N + 7) / 8, h->sm_count * 8);
-  const size_t sh_front = (size_t)(2 * d.M * d.nc + d.nc * d.nc + 3 * d.M * d.M) * sizeof(double);
-  const size_t sh_rows = (size_t)(d.M * d.nc + 2 * d.M * d.M + d.M + 8 * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
+  const int ncp = d.nc | 1, Mo = d.M | 1;  // odd shared-memory pitches of the kernels' H and S tables
+  const size_t sh_front = (size_t)(d.M * ncp + d.M * d.nc + d.nc * d.nc + 3 * d.M * d.M) * sizeof(double);
+  const size_t sh_rows = (size_t)(d.M * ncp + d.M * d.M + d.M * Mo + d.M + 8 * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
   const bool no_fused = std::getenv("CPS_EKF_NO_FUSED_FRONT") != nullptr;  // A/B switch (read per call: tests flip it)
   int launches = 0;
-  if (!no_fused && sh_front <= 200 * 1024 && sh_rows <= 200 * 1024) {
+  if (!no_fused && sh_front <= (size_t)kFrontSmemMax && sh_rows <= (size_t)kFrontSmemMax) {
     ekf_front_kernel<<<1, 256, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
     ekf_rows_kernel<<<std::min(row_blocks, 2 * h->sm_count), 256, sh_rows, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_Kt, h->d_Yt, h->d_x, h->cap);
     launches = 2;
@@ -1713,11 +1795,14 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
     const int Mp = (M + 3) & ~3;
     const bool no_pipe = std::getenv("CPS_EKF_COV_NO_PIPE") != nullptr;
     const bool no_tma = std::getenv("CPS_EKF_COV_NO_TMA") != nullptr;
-    if (Mp <= PIPE_MAX_M && !no_pipe && !no_tma && h->maps_ok && h->mirror_exact && pairs >= 2LL * h->sm_count) {
+    if (Mp <= TMA2_MAX_M && !no_pipe && !no_tma && h->maps_ok && h->mirror_exact && pairs >= 2LL * h->sm_count) {
       TmaMaps maps;
       maps.full = h->map_full;
       maps.swz = h->map_swz;
-      ekf_cov_tma_kernel<<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+      if (Mp <= PIPE_MAX_M)
+        ekf_cov_tma_kernel<TMA_STAGES><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, TMA_STAGES), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+      else
+        ekf_cov_tma_kernel<2><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, 2), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
     } else if (Mp <= PIPE_MAX_M && !no_pipe && pairs >= 2LL * h->sm_count) {
       const size_t shb = (size_t)(2 * (TILE * PITCH_A + TILE * PITCH_B + Mp * DSTRIDE) + Mp * DSTRIDE) * sizeof(double);
       ekf_cov_pipe_kernel<<<h->sm_count, 256, shb, st>>>(h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);

@@ -1689,14 +1689,22 @@ extern "C" int cps_register_jacobian(void (*jacf)(double*, double*, int, int, vo
 }
 
 namespace {
+// The levmar-named entry points carry no context argument: every calling thread gets its own, released when the
+// thread ends (the main thread's goes before the static destructors, i.e. while the CUDA runtime is still up).
+struct ShimCtxHolder {
+  cps_lm_ctx* ctx = nullptr;
+  ~ShimCtxHolder() {
+    if (ctx) cps_lm_destroy(ctx);
+  }
+};
 cps_lm_ctx* shim_ctx() {
-  static thread_local cps_lm_ctx* ctx = nullptr;
-  if (!ctx) {
+  static thread_local ShimCtxHolder holder;
+  if (!holder.ctx) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (cps_lm_create(&ctx, dev) != CPS_OK) ctx = nullptr;
+    if (cps_lm_create(&holder.ctx, dev) != CPS_OK) holder.ctx = nullptr;
   }
-  return ctx;
+  return holder.ctx;
 }
 
 int shim_fit(int variant, void (*func)(double*, double*, int, int, void*),

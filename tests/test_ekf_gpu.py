@@ -288,15 +288,19 @@ def test_failed_update_leaves_the_filter_untouched():
     kf.close()
 
 
-def test_tma_half_read_kernel_is_bit_identical_to_the_two_tile_kernel(monkeypatch):
+@pytest.mark.parametrize("M_pts", [0, 10, 15])
+def test_tma_half_read_kernel_is_bit_identical_to_the_two_tile_kernel(monkeypatch, M_pts):
     """The TMA kernel reads one tile of every mirrored pair (12 N^2 bytes) because the tiles are exact mirrors after any
-    update; its P must equal, bit for bit, what the cp.async kernel that reads both tiles (16 N^2 bytes) produces.
-    N = 12 012: large enough for the persistent kernels (>= 2 pairs per SM), ragged last tile."""
+    update; its P must equal, bit for bit, what the cp.async / DMMA kernels that read both tiles (16 N^2 bytes) produce.
+    N = 12 012: large enough for the persistent kernels (>= 2 pairs per SM), ragged last tile.  M = 35 runs the
+    three-stage ring, M = 65 (4 curves + 10 points, BASELINE configs[2]) and M = 80 the two-stage ring."""
     x, G, ci, pi = ekf.make_synthetic_ekf(4000, d=3, seed=11)
     rng = np.random.default_rng(5)
     A = np.stack([np.eye(4)] * 4)
     z1 = np.concatenate([rng.normal(0, 1.0, 32), x[2:5]])
     z2 = np.concatenate([rng.normal(0, 1.0, 32), x[2:5]])
+    pts = rng.choice(len(pi), M_pts, replace=False) if M_pts else None
+    pm1, pm2 = rng.normal(0, 3.0, 3 * M_pts), rng.normal(0, 3.0, 3 * M_pts)
     res = {}
     for mode in ("tma", "two_tile"):
         if mode == "two_tile":
@@ -305,9 +309,9 @@ def test_tma_half_read_kernel_is_bit_identical_to_the_two_tile_kernel(monkeypatc
         kf.set_state(x, None, ci, pi)
         kf.set_cov_lowrank(G, 1.0 / 64.0, 0.25)
         kf.PredictKF()
-        kf.UpdateNCurvesAndPoints(z1, 4, A, [0, 1, 2, 3])
+        kf.UpdateNCurvesAndPoints(z1, 4, A, [0, 1, 2, 3], pm1 if M_pts else None, pts, M_pts)
         kf.PredictKF()
-        kf.UpdateNCurvesAndPoints(z2, 4, A, [0, 1, 2, 3])
+        kf.UpdateNCurvesAndPoints(z2, 4, A, [0, 1, 2, 3], pm2 if M_pts else None, pts, M_pts)
         res[mode] = (kf.getState(), kf.getCov())
         kf.close()
     assert np.array_equal(res["tma"][0], res["two_tile"][0])
