@@ -367,26 +367,26 @@ __global__ void __launch_bounds__(256) ekf_gain_kernel(UpdateDesc d, const doubl
   }
 }
 
-// Gauss-Jordan steps of the fused front end with a thread's entries (at most Q of the M x M, entry e = tid + 256 q)
+// Gauss-Jordan steps of the fused front end with a thread's entries (at most Q of the M x M, entry e = tid + NT q)
 // in registers from step to step.  A step is branch-free: the pivot and the entries' pivot-column and pivot-row
 // values are loaded together and the three cases of the update are selects, so the loads of a step overlap each
 // other and the reciprocal instead of forming one dependent load -> multiply -> load -> update -> store chain per
 // entry (21 us of the front end's 43 at M = 35).  Same operations on the same values as the plain loop in the kernel.
 // The matrix ping-pongs between Wa (the input) and Wb; after M steps the result is in Wb when M is odd.
-template <int Q>
+template <int Q, int NT>
 __device__ __forceinline__ void gj_register_steps(double* Wa, double* Wb, int M, int tid, int* flag, int* bad) {
   int oi[Q], ej[Q], ei[Q];
   double v[Q];
   {
     int i = tid / M, j = tid - i * M;
-    const int di = 256 / M, dj = 256 - di * M;
+    const int di = NT / M, dj = NT - di * M;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-      const bool act = tid + q * 256 < M * M;
+      const bool act = tid + q * NT < M * M;
       ei[q] = act ? i : 0;
       ej[q] = act ? j : 0;
       oi[q] = ei[q] * M;
-      v[q] = act ? Wa[tid + q * 256] : 0.0;
+      v[q] = act ? Wa[tid + q * NT] : 0.0;
       i += di; j += dj;
       if (j >= M) { j -= M; ++i; }
     }
@@ -411,7 +411,7 @@ __device__ __forceinline__ void gj_register_steps(double* Wa, double* Wb, int M,
       const double in_row = (ej[q] == k) ? ip : rkj;
       const double nv = (ei[q] == k) ? in_row : ((ej[q] == k) ? in_col : off_row);
       v[q] = nv;
-      if (tid + q * 256 < M * M) Wdst[tid + q * 256] = nv;
+      if (tid + q * NT < M * M) Wdst[tid + q * NT] = nv;
     }
     __syncthreads();
     double* tmp = Wsrc; Wsrc = Wdst; Wdst = tmp;
@@ -427,7 +427,10 @@ __device__ __forceinline__ void gj_register_steps(double* Wa, double* Wb, int M,
 // ekf_rows_kernel, one warp per state row: T_row = P_row[cols] Hc^T, K_row = T_row S^-1, Y_row = K_row S^T,
 // x_row += K_row nu -- kernels 2 and 4 in one pass, T never written to memory.
 // Same sums in the same order as kernels 1-4 for H, T, S, K, Y and x; S^-1 differs by rounding (another elimination).
-__global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const double* __restrict__ x,
+// NT threads: 256 for M <= 39 (every live size: the elimination steps are latency-bound and a barrier over eight warps
+// is cheaper), 512 above (M = 65: the T and S loops have 3.4x the entries with dot products twice as long).
+template <int NT>
+__global__ void __launch_bounds__(NT) ekf_front_kernel(UpdateDesc d, const double* __restrict__ x,
                                                         const double* __restrict__ P, double* __restrict__ small,
                                                         int* __restrict__ cols, const int* __restrict__ land_cols,
                                                         int* __restrict__ flag) {
@@ -463,22 +466,56 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
     for (int e = tid; e < nc * nc; e += nt, w.next()) Ps[e] = P[(size_t)cols[w.i] * d.ld + cols[w.j]];
   }
   __syncthreads();
+  // T and S: a thread carries four of its entries through the dot-product loop at once (four independent chains:
+  // the loops are latency-bound); every sum keeps its order
+  constexpr int ILP = 4;
   Walk wt(tid, nt, M);
-  for (int e = tid; e < nc * M; e += nt, wt.next()) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
-    const int c = wt.i, r = wt.j;
-    double s = 0.0;
-    for (int b = 0; b < nc; ++b) s += Ps[c * nc + b] * Hs[r * ncp + b];
-    Tc[e] = s;
+  for (int e0 = tid; e0 < nc * M; e0 += ILP * nt) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
+    const double* pp[ILP];
+    const double* hh[ILP];
+    double acc[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u, wt.next()) {
+      const bool act = e0 + u * nt < nc * M;
+      pp[u] = Ps + (act ? wt.i : 0) * nc;
+      hh[u] = Hs + (act ? wt.j : 0) * ncp;
+      acc[u] = 0.0;
+    }
+    for (int b = 0; b < nc; ++b) {
+#pragma unroll
+      for (int u = 0; u < ILP; ++u) acc[u] += pp[u][b] * hh[u][b];
+    }
+#pragma unroll
+    for (int u = 0; u < ILP; ++u)
+      if (e0 + u * nt < nc * M) Tc[e0 + u * nt] = acc[u];
   }
   __syncthreads();
   const Walk w0(tid, nt, M);  // the start of every [M][M] walk below
   Walk ws = w0;
-  for (int e = tid; e < M * M; e += nt, ws.next()) {
-    const int r = ws.i, q = ws.j;
-    double acc = 0.0;
-    for (int c = 0; c < nc; ++c) acc += Hs[r * ncp + c] * Tc[c * M + q];
-    if (r == q) acc += small[SM_R + r];
-    S[e] = acc;
+  for (int e0 = tid; e0 < M * M; e0 += ILP * nt) {
+    const double* hh[ILP];
+    const double* tt[ILP];
+    double acc[ILP];
+    int rr[ILP], qq[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u, ws.next()) {
+      const bool act = e0 + u * nt < M * M;
+      rr[u] = act ? ws.i : 0;
+      qq[u] = act ? ws.j : 0;
+      hh[u] = Hs + rr[u] * ncp;
+      tt[u] = Tc + qq[u];
+      acc[u] = 0.0;
+    }
+    for (int c = 0; c < nc; ++c) {
+#pragma unroll
+      for (int u = 0; u < ILP; ++u) acc[u] += hh[u][c] * tt[u][c * M];
+    }
+#pragma unroll
+    for (int u = 0; u < ILP; ++u)
+      if (e0 + u * nt < M * M) {
+        if (rr[u] == qq[u]) acc[u] += small[SM_R + rr[u]];
+        S[e0 + u * nt] = acc[u];
+      }
   }
   __syncthreads();
   Walk wc = w0;
@@ -491,13 +528,11 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   // a step reads the matrix as it stands and writes the next one into the other buffer: one barrier per step
   double* Wsrc = W;
   double* Wdst = W2;
-  // M <= 39 (every live size; M <= 65 with more registers): a thread's entries stay in registers from step to step
+  // M <= 39 (every live size; M <= 67 with 512 threads): a thread's entries stay in registers from step to step
   // and a step is branch-free (gj_register_steps above)
-  if (M * M <= 6 * 256 && nt == 256) {
-    gj_register_steps<6>(W, W2, M, tid, flag, &bad);
-    Wsrc = (M & 1) ? W2 : W;
-  } else if (M * M <= 17 * 256 && nt == 256) {
-    gj_register_steps<17>(W, W2, M, tid, flag, &bad);
+  constexpr int GJQ = NT == 256 ? 6 : 9;  // 256 threads: M <= 39; 512 threads: M <= 67
+  if (M * M <= GJQ * NT && nt == NT) {
+    gj_register_steps<GJQ, NT>(W, W2, M, tid, flag, &bad);
     Wsrc = (M & 1) ? W2 : W;
   } else
   for (int k = 0; k < M; ++k) {
@@ -526,7 +561,69 @@ __global__ void __launch_bounds__(256) ekf_front_kernel(UpdateDesc d, const doub
   }
 }
 
-__global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const double* __restrict__ P,
+// One state row of ekf_rows_kernel: T_row, K_row, Y_row and the row's share of K nu.  A lane owns the entries
+// lane, lane + 32, ... (NP = ceil(M / 32) of them) and carries their sums TOGETHER through each loop -- NP independent
+// chains per iteration instead of NP passes over one chain (the loops are latency-bound: M = 35 spent a whole second
+// pass on three entries, M = 65 three passes).  Every sum runs over the same terms in the same order as before.
+template <int NP>
+__device__ __forceinline__ void rows_one(int M, int nc, int ncp, int Mo, int lane, const double* pr, double* trow,
+                                         double* krow, const double* Hc, const double* Sinv, const double* S,
+                                         const double* nu, double* __restrict__ Kt, double* __restrict__ Yt,
+                                         size_t ldk, int row, double& dx) {
+  {
+    double a[NP];
+    const double* h[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { h[p] = Hc + min(lane + 32 * p, M - 1) * ncp; a[p] = 0.0; }
+    for (int c = 0; c < nc; ++c) {
+      const double pv = pr[c];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) a[p] += pv * h[p][c];
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (lane + 32 * p < M) trow[lane + 32 * p] = a[p];
+  }
+  __syncwarp();
+  {
+    double a[NP];
+    int q[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { q[p] = min(lane + 32 * p, M - 1); a[p] = 0.0; }
+    for (int r = 0; r < M; ++r) {
+      const double tv = trow[r];
+      const double* sr = Sinv + r * M;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) a[p] += tv * sr[q[p]];
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (lane + 32 * p < M) {
+        krow[lane + 32 * p] = a[p];
+        Kt[(size_t)(lane + 32 * p) * ldk + row] = a[p];
+      }
+  }
+  __syncwarp();
+  {
+    double a[NP];
+    const double* sr[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { sr[p] = S + min(lane + 32 * p, M - 1) * Mo; a[p] = 0.0; }
+    for (int q = 0; q < M; ++q) {
+      const double kv = krow[q];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) a[p] += kv * sr[p][q];
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (lane + 32 * p < M) {
+        Yt[(size_t)(lane + 32 * p) * ldk + row] = a[p];
+        dx += krow[lane + 32 * p] * nu[lane + 32 * p];
+      }
+  }
+}
+
+__global__ void __launch_bounds__(512) ekf_rows_kernel(UpdateDesc d, const double* __restrict__ P,
                                                        const double* __restrict__ small, const int* __restrict__ cols,
                                                        double* __restrict__ Kt, double* __restrict__ Yt,
                                                        double* __restrict__ x, int ldk) {
@@ -538,8 +635,9 @@ __global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const doubl
   double* Sinv = Hc + M * ncp;      // [M][M]
   double* S = Sinv + M * M;         // [M][Mo]
   double* nu = S + M * Mo;          // [M]
-  double* rowbuf = nu + M;          // [8 warps][nc + 2 M]
-  int* scols = reinterpret_cast<int*>(rowbuf + 8 * (nc + 2 * M));
+  const int nw = blockDim.x >> 5;   // 8 warps; 16 when the tables leave room for one block per SM only (M > 36)
+  double* rowbuf = nu + M;          // [nw warps][nc + 2 M]
+  int* scols = reinterpret_cast<int*>(rowbuf + nw * (nc + 2 * M));
   for (int e = threadIdx.x; e < M * nc; e += blockDim.x) {
     const int r = e / nc, b = e - r * nc;
     Hc[r * ncp + b] = small[SM_HC + e];
@@ -556,29 +654,15 @@ __global__ void __launch_bounds__(256) ekf_rows_kernel(UpdateDesc d, const doubl
   double* pr = rowbuf + w * (nc + 2 * M);
   double* trow = pr + nc;
   double* krow = trow + M;
-  for (int row = blockIdx.x * 8 + w; row < d.N; row += gridDim.x * 8) {
+  for (int row = blockIdx.x * nw + w; row < d.N; row += gridDim.x * nw) {
     for (int c = lane; c < nc; c += 32) pr[c] = P[(size_t)row * d.ld + scols[c]];
     __syncwarp();
-    for (int r = lane; r < M; r += 32) {
-      const double* h = Hc + r * ncp;
-      double s = 0.0;
-      for (int c = 0; c < nc; ++c) s += pr[c] * h[c];
-      trow[r] = s;
-    }
-    __syncwarp();
-    for (int q = lane; q < M; q += 32) {
-      double acc = 0.0;
-      for (int r = 0; r < M; ++r) acc += trow[r] * Sinv[r * M + q];
-      krow[q] = acc;
-      Kt[(size_t)q * ldk + row] = acc;
-    }
-    __syncwarp();
     double dx = 0.0;
-    for (int r = lane; r < M; r += 32) {
-      double acc = 0.0;
-      for (int q = 0; q < M; ++q) acc += krow[q] * S[r * Mo + q];
-      Yt[(size_t)r * ldk + row] = acc;
-      dx += krow[r] * nu[r];
+    switch ((M + 31) >> 5) {
+      case 1: rows_one<1>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
+      case 2: rows_one<2>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
+      case 3: rows_one<3>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
+      default: rows_one<4>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dx += __shfl_xor_sync(0xffffffffu, dx, o);
@@ -1577,7 +1661,8 @@ int ekf_create_impl(cps_ekf* h, int device, int capacity) {
                                 2 * MAXM * DSTRIDE * (int)sizeof(double)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_pht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (MAXM * MAXNC + 8 * MAXNC) * (int)sizeof(double) + MAXNC * (int)sizeof(int)));
-  CPS_CUDA(cudaFuncSetAttribute(ekf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemMax));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_front_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemMax));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_front_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemMax));
   CPS_CUDA(cudaFuncSetAttribute(ekf_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemMax));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel<TMA_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tma_smem_bytes(PIPE_MAX_M, TMA_STAGES)));
@@ -1764,12 +1849,20 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   const int row_blocks = std::min((d.N + 7) / 8, h->sm_count * 8);
   const int ncp = d.nc | 1, Mo = d.M | 1;  // odd shared-memory pitches of the kernels' H and S tables
   const size_t sh_front = (size_t)(d.M * ncp + d.M * d.nc + d.nc * d.nc + 3 * d.M * d.M) * sizeof(double);
-  const size_t sh_rows = (size_t)(d.M * ncp + d.M * d.M + d.M * Mo + d.M + 8 * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
+  // rows kernel: eight warps per block while two blocks fit an SM, sixteen in one block above that (M > 36)
+  auto rows_smem = [&](int nw) {
+    return (size_t)(d.M * ncp + d.M * d.M + d.M * Mo + d.M + nw * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
+  };
+  const int rows_warps = 2 * (rows_smem(8) + 1024) <= (size_t)227 * 1024 ? 8 : 16;
+  const size_t sh_rows = rows_smem(rows_warps);
+  const int rows_per_sm = rows_warps == 8 ? std::max(1, std::min(8, (int)((size_t)227 * 1024 / (sh_rows + 1024)))) : 1;
   const bool no_fused = std::getenv("CPS_EKF_NO_FUSED_FRONT") != nullptr;  // A/B switch (read per call: tests flip it)
   int launches = 0;
   if (!no_fused && sh_front <= (size_t)kFrontSmemMax && sh_rows <= (size_t)kFrontSmemMax) {
-    ekf_front_kernel<<<1, 256, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
-    ekf_rows_kernel<<<std::min(row_blocks, 2 * h->sm_count), 256, sh_rows, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_Kt, h->d_Yt, h->d_x, h->cap);
+    if (d.M * d.M <= 6 * 256) ekf_front_kernel<256><<<1, 256, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
+    else ekf_front_kernel<512><<<1, 512, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
+    const int rows_grid = std::min((d.N + rows_warps - 1) / rows_warps, h->sm_count * rows_per_sm);
+    ekf_rows_kernel<<<rows_grid, 32 * rows_warps, sh_rows, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_Kt, h->d_Yt, h->d_x, h->cap);
     launches = 2;
   } else {
     ekf_build_kernel<<<1, 128, 0, st>>>(d, h->d_x, h->d_small, h->d_cols, d_land);
