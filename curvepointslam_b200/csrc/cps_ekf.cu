@@ -33,6 +33,14 @@ constexpr int TILE = 64;
 constexpr int kFrontSmemMax = 225 * 1024;  // dynamic shared memory of the fused front end (M = 65 needs 209 KB)
 constexpr double kPI = 3.1415926535;  // common.h:114
 
+// P is symmetric to the last bit whenever the streaming covariance kernel runs (mirror_exact), and that kernel may
+// leave the tiles BELOW the diagonal tiles unwritten (cps_ekf::lower_stale): every kernel that gathers single
+// entries of P reads the copy with row <= column, which is always current (and equal to its mirror image when
+// both are).
+__device__ __forceinline__ size_t upper_index(int r, int c, int ld, int sym) {
+  return (r <= c || !sym) ? (size_t)r * ld + c : (size_t)c * ld + r;
+}
+
 // constants of kalmanClass.h:17-36
 constexpr double MEAS_COV = 0.5, PT_MEAS_COV = 5.0, PHI_MEAS_COV = 0.1, THETA_MEAS_COV = 0.1, Z_MEAS_COV = 0.2;
 constexpr double VX_COV = 0.01, VY_COV = 0.01, VZ_COV = 0.5, WX_COV = 0.01, WY_COV = 0.01, WZ_COV = 0.01;
@@ -51,6 +59,7 @@ struct UpdateDesc {
   int N, ld;      // state dimension, leading dimension of P
   int n, n_pts;   // curves and points measured
   int M, nc;      // measurement size, compact columns
+  int sym;        // P is symmetric to the last bit (cps_ekf::mirror_exact): single entries are read from the upper triangle
 };
 
 // generate_Rbe (common.h:174-186), row-major, with the reference's sign in entry [6]
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(256) ekf_pht_kernel(UpdateDesc d, const double
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double* pr = prow + w * d.nc;
   for (int row = blockIdx.x * 8 + w; row < d.N; row += gridDim.x * 8) {
-    for (int c = lane; c < d.nc; c += 32) pr[c] = P[(size_t)row * d.ld + scols[c]];
+    for (int c = lane; c < d.nc; c += 32) pr[c] = P[upper_index(row, scols[c], d.ld, d.sym)];
     __syncwarp();
     for (int r = lane; r < d.M; r += 32) {
       const double* h = Hc + r * d.nc;
@@ -463,7 +472,7 @@ __global__ void __launch_bounds__(NT) ekf_front_kernel(UpdateDesc d, const doubl
   }
   {
     Walk w(tid, nt, nc);
-    for (int e = tid; e < nc * nc; e += nt, w.next()) Ps[e] = P[(size_t)cols[w.i] * d.ld + cols[w.j]];
+    for (int e = tid; e < nc * nc; e += nt, w.next()) Ps[e] = P[upper_index(cols[w.i], cols[w.j], d.ld, d.sym)];
   }
   __syncthreads();
   // T and S: a thread carries four of its entries through the dot-product loop at once (four independent chains:
@@ -655,7 +664,7 @@ __global__ void __launch_bounds__(512) ekf_rows_kernel(UpdateDesc d, const doubl
   double* trow = pr + nc;
   double* krow = trow + M;
   for (int row = blockIdx.x * nw + w; row < d.N; row += gridDim.x * nw) {
-    for (int c = lane; c < nc; c += 32) pr[c] = P[(size_t)row * d.ld + scols[c]];
+    for (int c = lane; c < nc; c += 32) pr[c] = P[upper_index(row, scols[c], d.ld, d.sym)];
     __syncwarp();
     double dx = 0.0;
     switch ((M + 31) >> 5) {
@@ -1104,7 +1113,7 @@ template <int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __grid_constant__ TmaMaps maps, int M,
                                                                       const double* __restrict__ Kt,
                                                                       const double* __restrict__ Yt, int ldk, int nt,
-                                                                      long long total_pairs) {
+                                                                      long long total_pairs, int write_lower) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(smem_raw) + 1023) & ~(size_t)1023);
   const int Mp = (M + 3) & ~3;
@@ -1159,8 +1168,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
       const double* pa = Pst + stage * TILE * TILE;
       if (I != J) {
         tma_store_2d(&maps.full, J * TILE, I * TILE, pa);
+        if (write_lower) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, J * TILE, Tt + q * TILE * 16);
+          for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, J * TILE, Tt + q * TILE * 16);
+        }
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, I * TILE, Tt + q * TILE * 16);
@@ -1259,8 +1270,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
           const double o0 = 0.5 * (pij.x + pij.x) - acc[mi][ni][0];
           const double o1 = 0.5 * (pij.y + pij.y) - acc[mi][ni][1];
           *pp = make_double2(o0, o1);
-          Tt[swz_off(cj, ri)] = o0;
-          Tt[swz_off(cj + 1, ri)] = o1;
+          if (write_lower) {
+            Tt[swz_off(cj, ri)] = o0;
+            Tt[swz_off(cj + 1, ri)] = o1;
+          }
         }
     } else {
       // diagonal tile: entries on and above the diagonal are authoritative and mirrored, as in kernel 5c
@@ -1282,6 +1295,21 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
     if (t == 0) mbar_arrive(done);
     next_pair(I, J);
   }
+}
+
+// ---- tiles below the diagonal tiles, on demand ----------------------------------------------------------------------
+// The streaming kernel above normally writes only tile (I,J), I <= J, of every mirrored pair (8 N^2 bytes per update
+// instead of 12 N^2: cps_ekf::lower_stale).  Everything on the predict / update path reads the upper copy; an entry
+// point that hands out or walks full rows (cps_ekf_get_cov*, the two-tile fallback kernels) first rebuilds the lower
+// tiles as exact transposes with this kernel.
+__global__ void __launch_bounds__(256) ekf_mirror_lower_kernel(double* __restrict__ P, int ld) {
+  const int I = blockIdx.y, J = blockIdx.x;
+  if (I >= J) return;
+  __shared__ double tile[TILE][TILE + 1];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int r = ty; r < TILE; r += 4) tile[r][tx] = P[((size_t)I * TILE + r) * ld + (size_t)J * TILE + tx];
+  __syncthreads();
+  for (int r = ty; r < TILE; r += 4) P[((size_t)J * TILE + r) * ld + (size_t)I * TILE + tx] = tile[tx][r];
 }
 
 // ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
@@ -1589,6 +1617,19 @@ int ensure_aux(cps_ekf* h, size_t bytes) {
   return CPS_OK;
 }
 
+// Rebuilds the tiles below the diagonal tiles from their mirror images if the last updates left them unwritten.
+int ensure_lower(cps_ekf* h) {
+  if (!h->lower_stale) return CPS_OK;
+  const int nt = (h->N + TILE - 1) / TILE;
+  if (nt > 1) {
+    ekf_mirror_lower_kernel<<<dim3(nt, nt), 256, 0, h->stream>>>(h->d_P, h->cap);
+    CPS_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  h->lower_stale = false;
+  return CPS_OK;
+}
+
 size_t tma_smem_bytes(int Mp, int stages) {
   return 1024 + (size_t)(1 + stages) * TMA_TILE_BYTES + (size_t)(stages + 1) * Mp * DSTRIDE * sizeof(double) + 128;
 }
@@ -1743,6 +1784,7 @@ extern "C" int cps_ekf_set_state(cps_ekf* h, const double* x, const double* P, i
                                N, cudaMemcpyHostToDevice, h->stream));
   h->N = N;
   h->mirror_exact = (P == nullptr);  // a caller-supplied covariance need not be symmetric to the last bit
+  h->lower_stale = false;
   h->curve_inds.assign(curve_inds, curve_inds + num_curves);
   h->point_inds.assign(point_inds, point_inds + num_points);
   CPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -1760,6 +1802,7 @@ extern "C" int cps_ekf_set_cov_lowrank(cps_ekf* h, const double* G, int r, doubl
   CPS_CUDA(cudaGetLastError());
   CPS_CUDA(cudaStreamSynchronize(h->stream));
   h->mirror_exact = true;  // (i,j) and (j,i) sum the same products in the same order
+  h->lower_stale = false;
   return CPS_OK;
 }
 
@@ -1782,6 +1825,8 @@ extern "C" int cps_ekf_get_cov_block(cps_ekf* h, int r0, int c0, int nr, int nc,
   if (!h || !out || r0 < 0 || c0 < 0 || nr < 0 || nc < 0 || r0 + nr > h->N || c0 + nc > h->N) return CPS_ERR_INVALID;
   if (nr == 0 || nc == 0) return CPS_OK;
   CPS_CUDA(cudaSetDevice(h->device));
+  // a block that reaches below the diagonal tiles needs them current
+  if ((r0 + nr - 1) / TILE > c0 / TILE) { const int rc = ensure_lower(h); if (rc != CPS_OK) return rc; }
   CPS_CUDA(cudaMemcpy2DAsync(out, (size_t)nc * sizeof(double), h->d_P + (size_t)r0 * h->cap + c0,
                              (size_t)h->cap * sizeof(double), (size_t)nc * sizeof(double), nr, cudaMemcpyDeviceToHost,
                              h->stream));
@@ -1840,6 +1885,7 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   for (int k = 0; k < n_pts; ++k) hcols[n + k] = h->point_inds[point_nums[k]];
   UpdateDesc d;
   d.N = h->N; d.ld = h->cap; d.n = n; d.n_pts = n_pts; d.M = M; d.nc = 6 + 8 * n + 3 * n_pts;
+  d.sym = h->mirror_exact ? 1 : 0;
   cudaStream_t st = h->stream;
   CPS_CUDA(cudaMemcpyAsync(h->d_small + SM_IN, hz, sizeof(double) * (MAXM + 16 * (size_t)n), cudaMemcpyHostToDevice, st));
   int* d_land = h->d_cols + MAXNC;
@@ -1881,7 +1927,10 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   const int nt = (d.N + TILE - 1) / TILE;
   const long long pairs = (long long)nt * (nt + 1) / 2;
   static const bool use_cuda_cores = std::getenv("CPS_EKF_COV_CUDA_CORES") != nullptr;  // A/B switch for profiling
+  // half-written mode (default): the streaming kernel leaves the tiles below the diagonal tiles alone
+  const bool lazy_lower = std::getenv("CPS_EKF_EAGER_LOWER") == nullptr;
   if (use_cuda_cores) {
+    { const int rc = ensure_lower(h); if (rc != CPS_OK) return rc; }
     ekf_cov_kernel<<<(unsigned)pairs, 256, 2 * (size_t)M * TILE * sizeof(double), st>>>(h->d_P, h->cap, M, h->d_Kt,
                                                                                         h->d_Yt, h->cap, nt);
   } else {
@@ -1892,14 +1941,18 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
       TmaMaps maps;
       maps.full = h->map_full;
       maps.swz = h->map_swz;
+      const int write_lower = lazy_lower ? 0 : 1;
       if (Mp <= PIPE_MAX_M)
-        ekf_cov_tma_kernel<TMA_STAGES><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, TMA_STAGES), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+        ekf_cov_tma_kernel<TMA_STAGES><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, TMA_STAGES), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs, write_lower);
       else
-        ekf_cov_tma_kernel<2><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, 2), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+        ekf_cov_tma_kernel<2><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, 2), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs, write_lower);
+      if (!write_lower) h->lower_stale = true;
     } else if (Mp <= PIPE_MAX_M && !no_pipe && pairs >= 2LL * h->sm_count) {
+      { const int rc = ensure_lower(h); if (rc != CPS_OK) return rc; }
       const size_t shb = (size_t)(2 * (TILE * PITCH_A + TILE * PITCH_B + Mp * DSTRIDE) + Mp * DSTRIDE) * sizeof(double);
       ekf_cov_pipe_kernel<<<h->sm_count, 256, shb, st>>>(h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
     } else {
+      { const int rc = ensure_lower(h); if (rc != CPS_OK) return rc; }
       ekf_cov_dmma_kernel<<<(unsigned)pairs, 256, 2 * (size_t)Mp * DSTRIDE * sizeof(double), st>>>(
           h->d_P, h->cap, M, h->d_Kt, h->d_Yt, h->cap);
     }

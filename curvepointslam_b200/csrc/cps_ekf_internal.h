@@ -31,6 +31,10 @@ struct cps_ekf {
   int last_update_launches = 0;
   // true while every off-diagonal 64 x 64 tile of P is the exact mirror image of its partner (cps_ekf.cu, kernel 5d)
   bool mirror_exact = true;
+  // true while the tiles BELOW the diagonal tiles have not been rewritten by the last update(s): the streaming kernel
+  // then wrote only tile (I,J), I <= J, of every pair.  Nothing on the predict / update / gate / augmentation path reads
+  // them; ensure_lower() (cps_ekf.cu) rebuilds them for the entry points that do.
+  bool lower_stale = false;
   // TMA descriptors of P (encoded once: d_P and cap never change)
   alignas(64) CUtensorMap map_full;
   alignas(64) CUtensorMap map_swz;

@@ -28,7 +28,7 @@ struct RotArgs {
 
 __global__ void __launch_bounds__(256) gate_pack_kernel(const double* __restrict__ x, const double* __restrict__ P,
                                                         int ld, const int* __restrict__ pcols, int n_land,
-                                                        RotArgs rot, double* __restrict__ pack) {
+                                                        RotArgs rot, double* __restrict__ pack, int upper_only) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_land) return;
   const int c = pcols[j];
@@ -52,7 +52,11 @@ __global__ void __launch_bounds__(256) gate_pack_kernel(const double* __restrict
   for (int a = 0; a < 3; ++a)
     for (int b = 0; b < 9; ++b) {
       double s = 0.0;
-      for (int k = 0; k < 9; ++k) s += H[a][k] * P[(size_t)cols[k] * ld + cols[b]];
+      // upper_only (cps_ekf::lower_stale): the entry with row <= column is the current one and equals its mirror image
+      for (int k = 0; k < 9; ++k) {
+        const int r = cols[k], q = cols[b];
+        s += H[a][k] * P[(upper_only && r > q) ? (size_t)q * ld + r : (size_t)r * ld + q];
+      }
       HP[a][b] = s;
     }
   for (int a = 0; a < 3; ++a)
@@ -226,7 +230,8 @@ extern "C" int cps_gate_mahalanobis_dev(cps_ekf* h, const double* d_z, int nz, d
     CPS_CUDA(cudaMemcpyAsync(h->d_pcols, h->point_inds.data(), sizeof(int) * n_land, cudaMemcpyHostToDevice, st));
   CPS_CUDA(cudaEventRecord(h->gev[0], st));
   if (n_land) {
-    gate_pack_kernel<<<(n_land + 255) / 256, 256, 0, st>>>(h->d_x, h->d_P, h->cap, h->d_pcols, n_land, rot, h->d_pack);
+    gate_pack_kernel<<<(n_land + 255) / 256, 256, 0, st>>>(h->d_x, h->d_P, h->cap, h->d_pcols, n_land, rot, h->d_pack,
+                                                           h->lower_stale ? 1 : 0);
     h->launches++;
   }
   CPS_CUDA(cudaEventRecord(h->gev[1], st));

@@ -336,3 +336,47 @@ def test_fused_front_end_matches_the_five_kernel_path(monkeypatch):
         kf.close()
     assert out["fused"][2] == 3 and out["five"][2] == 5
     assert rel(out["fused"][0], out["five"][0]) < 1e-11 and rel(out["fused"][1], out["five"][1]) < 1e-11
+
+
+def test_half_written_covariance_is_invisible(monkeypatch):
+    """By default the streaming covariance kernel writes only tile (I,J), I <= J, of every mirrored pair (8 N^2 bytes per
+    update; cps_ekf::lower_stale) and everything on the predict / update / gate / augmentation path reads the upper
+    copy; the lower tiles are rebuilt when an entry point needs them.  Against CPS_EKF_EAGER_LOWER=1 (both tiles
+    written by every update) every observable must be the same bits: state, covariance, blocks, gate, and a sequence
+    that continues after the covariance was read back."""
+    x, G, ci, pi = ekf.make_synthetic_ekf(3000, d=3, seed=21)
+    rng = np.random.default_rng(9)
+    A = np.stack([np.eye(4)] * 4)
+    zs = [np.concatenate([rng.normal(0, 1.0, 32), x[2:5]]) for _ in range(3)]
+    pts = rng.choice(len(pi), 5, replace=False)
+    pm = rng.normal(0, 3.0, 15)
+    gz = np.stack([x[pi[k]:pi[k] + 3] for k in rng.choice(len(pi), 64, replace=False)]) + rng.normal(0, 0.3, (64, 3))
+    new_pts = rng.normal(0, 5.0, 6)
+    out = {}
+    for mode in ("lazy", "eager"):
+        if mode == "eager":
+            monkeypatch.setenv("CPS_EKF_EAGER_LOWER", "1")
+        kf = ekf.KalmanFilter(capacity=x.size + 64)
+        kf.set_state(x, None, ci, pi)
+        kf.set_cov_lowrank(G, 1.0 / 64.0, 0.25)
+        kf.PredictKF()
+        kf.UpdateNCurvesAndPoints(zs[0], 4, A, [0, 1, 2, 3])
+        kf.PredictKF()
+        kf.UpdateNCurvesAndPoints(zs[1], 4, A, [0, 1, 2, 3], pm, pts, 5)  # M = 50: the two-stage ring
+        r = {"upper_block": kf.getCovBlock(0, 64, 64, 200),    # inside the upper tiles: no rebuild needed
+             "gate": kf.gate(gz, 11.345)}
+        kf.AddNewPoints(new_pts, 2)                               # augmentation on a half-written P
+        kf.PredictKF()
+        kf.UpdatePoints(pm[:6], [len(pi), len(pi) + 1], 2)       # touches the new landmarks
+        r["lower_block"] = kf.getCovBlock(kf.N - 100, 0, 100, 70)  # below the diagonal tiles: rebuilt on demand
+        r["P1"] = kf.getCov()
+        kf.PredictKF()
+        kf.UpdateNCurvesAndPoints(zs[2], 4, A, [0, 1, 2, 3])     # the sequence goes on after the read-back
+        r["x2"], r["P2"] = kf.getState(), kf.getCov()
+        out[mode] = r
+        kf.close()
+    a, b = out["lazy"], out["eager"]
+    for k in ("upper_block", "lower_block", "P1", "x2", "P2"):
+        assert np.array_equal(a[k].view(np.int64), b[k].view(np.int64)), k
+    assert np.array_equal(a["gate"][0], b["gate"][0]) and np.array_equal(a["gate"][1].view(np.int64), b["gate"][1].view(np.int64))
+    assert np.array_equal(a["P2"], a["P2"].T) and np.array_equal(a["lower_block"], a["P1"][-100:, :70])
