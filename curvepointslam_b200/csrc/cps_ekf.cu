@@ -1079,6 +1079,30 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, c
                "r"(c1), "r"(smem_u32(src))
                : "memory");
 }
+// one contiguous run (a multiple of 16 bytes, both ends 16-byte aligned) global -> shared, completing on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// the copy warp's wait: it polls one barrier for most of a pair's duration, so it sleeps between polls instead of
+// competing with two compute warps for its scheduler's issue slots
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -1150,88 +1174,94 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
 
   if (w == 8) {
     // ---------------------------------------------------------------------------------------- copy warp
-    if (l != 0) return;
-    auto issue_p = [&](int Ia, int Ja, int stage) {
-      mbar_expect_tx(full + stage, TMA_TILE_BYTES);
-      tma_load_2d(Pst + stage * TILE * TILE, &maps.full, Ja * TILE, Ia * TILE, full + stage);
+    // lane 0 owns the TMA operations on P; all 32 lanes bring the Y_J rows of a pair (M rows of 512 bytes into the
+    // padded layout the fragment reads need) as bulk copies that complete on the same mbarrier as the P tile, so the
+    // compute warps issue no copies at all and wait on one barrier per pair
+    auto issue_pair = [&](int Ia, int Ja, int stage) {
+      if (l == 0) {
+        mbar_expect_tx(full + stage, (unsigned)(TMA_TILE_BYTES + M * TILE * 8));
+        tma_load_2d(Pst + stage * TILE * TILE, &maps.full, Ja * TILE, Ia * TILE, full + stage);
+      }
+      __syncwarp();
+      double* ys = Yst + stage * Mp * DSTRIDE;
+      for (int r = l; r < M; r += 32)
+        bulk_load_1d(ys + r * DSTRIDE, Yt + (size_t)r * ldk + (size_t)Ja * TILE, TILE * 8, full + stage);
     };
     int Il = I, Jl = J;  // next pair to load
     long long pl = p_begin;
     for (int s = 0; s < STAGES && pl < p_end; ++s, ++pl) {
-      issue_p(Il, Jl, s);
+      issue_pair(Il, Jl, s);
       next_pair(Il, Jl);
     }
     for (long long p = p_begin; p < p_end; ++p) {
       const int it = (int)(p - p_begin);
       const int stage = it % STAGES;
-      mbar_wait(done, (unsigned)(it & 1));  // tile and transpose of pair p are in shared memory, fenced
-      const double* pa = Pst + stage * TILE * TILE;
-      if (I != J) {
-        tma_store_2d(&maps.full, J * TILE, I * TILE, pa);
-        if (write_lower) {
+      mbar_wait_backoff(done, (unsigned)(it & 1));  // tile and transpose of pair p are in shared memory, fenced
+      if (l == 0) {
+        const double* pa = Pst + stage * TILE * TILE;
+        if (I != J) {
+          tma_store_2d(&maps.full, J * TILE, I * TILE, pa);
+          if (write_lower) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, J * TILE, Tt + q * TILE * 16);
+            for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, J * TILE, Tt + q * TILE * 16);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, I * TILE, Tt + q * TILE * 16);
         }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tma_store_2d(&maps.swz, I * TILE + 16 * q, I * TILE, Tt + q * TILE * 16);
+        tma_commit();
+        tma_wait_read_all();  // the stores have read the stage and the transpose buffer
+        mbar_arrive(tfree);
       }
-      tma_commit();
-      tma_wait_read_all();  // the stores have read the stage and the transpose buffer
-      mbar_arrive(tfree);
-      if (pl < p_end) {
-        issue_p(Il, Jl, stage);
+      __syncwarp();
+      if (pl < p_end) {  // the stage (P tile and Y rows: the compute warps are past the pair's products) takes the pair S ahead
+        issue_pair(Il, Jl, stage);
         next_pair(Il, Jl);
         ++pl;
       }
       next_pair(I, J);
     }
-    tma_wait_all();
+    if (l == 0) tma_wait_all();
     return;
   }
 
   // ------------------------------------------------------------------------------------------ compute warps
   const int lr = l >> 2, lc = l & 3;
   const int wr0 = (w >> 1) * 16, wc0 = (w & 1) * 32;
-  auto issue_y = [&](int Ja, int stage) {
-    double* ys = Yst + stage * Mp * DSTRIDE;
-    for (int c = t; c < M * 32; c += 256) {
-      const int r = c >> 5, cc = (c & 31) * 2;
-      cp_async16(ys + r * DSTRIDE + cc, Yt + (size_t)r * ldk + (size_t)Ja * TILE + cc);
-    }
-  };
   auto issue_k = [&](int Ia) {
     for (int c = t; c < M * 32; c += 256) {
       const int r = c >> 5, cc = (c & 31) * 2;
       cp_async16(Ks + r * DSTRIDE + cc, Kt + (size_t)r * ldk + (size_t)Ia * TILE + cc);
     }
   };
-  int k_loaded = I;
-  issue_k(I);
-  int Iy = I, Jy = J;  // pair whose Y tile is requested next
-  // the Y tiles of the first STAGES - 1 pairs, one commit group each
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (p_begin + s < p_end) issue_y(Jy, s);
+  // K_I stays the same while J advances: with at most nine k-steps (the three-stage variant, M <= 36) a thread keeps its
+  // K fragments in registers from pair to pair (two of the six shared-memory loads of a k-step)
+  constexpr int KREG = STAGES == 3 ? PIPE_MAX_M / 4 : 1;
+  double ka[KREG][2];
+  auto load_k = [&](int Ia) {
+    issue_k(Ia);
     cp_async_commit();
-    next_pair(Iy, Jy);
-  }
+    cp_async_wait<0>();
+    compute_warps_sync();
+    if (STAGES == 3) {
+#pragma unroll
+      for (int s = 0; s < KREG; ++s) {
+        const double* kr = Ks + (4 * s + lc) * DSTRIDE + wr0 + lr;
+        ka[s][0] = (4 * s < Mp) ? kr[0] : 0.0;
+        ka[s][1] = (4 * s < Mp) ? kr[8] : 0.0;
+      }
+    }
+  };
+  int k_loaded = I;
+  load_k(I);
   for (long long p = p_begin; p < p_end; ++p) {
     const int it = (int)(p - p_begin);
     const int stage = it % STAGES;
-    if (p + (STAGES - 1) < p_end) issue_y(Jy, (it + STAGES - 1) % STAGES);  // that stage's Y was last read in iteration it - 1
-    cp_async_commit();
-    next_pair(Iy, Jy);
-    cp_async_wait<STAGES - 1>();                                 // this thread's share of Y(p) (and of K)
-    mbar_wait(full + stage, (unsigned)((it / STAGES) & 1));  // the P tile of pair p
-    compute_warps_sync();                                        // everybody's Y shares
-    if (k_loaded != I) {
-      issue_k(I);
-      cp_async_commit();
-      cp_async_wait<0>();
+    if (k_loaded != I) {  // every warp is past the products of the pair before (the barrier that ends a pair)
+      load_k(I);
       k_loaded = I;
-      compute_warps_sync();
     }
+    mbar_wait(full + stage, (unsigned)((it / STAGES) & 1));  // the P tile and the Y rows of pair p
     double* pa = Pst + stage * TILE * TILE;
     const double* ys = Yst + stage * Mp * DSTRIDE;
     const bool diag = (I == J);
@@ -1241,21 +1271,33 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-    for (int ks = 0; ks < Mp; ks += 4) {
-      double a[2], b[4];
-      const double* kr = Ks + (ks + lc) * DSTRIDE + wr0 + lr;
+    auto mma_step = [&](int ks, double a0, double a1) {
+      double b[4];
       const double* yr = ys + (ks + lc) * DSTRIDE + wc0 + lr;
-      a[0] = kr[0];
-      a[1] = kr[8];
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) b[ni] = yr[8 * ni];
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
+      for (int ni = 0; ni < 4; ++ni) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[0][ni][0]), "+d"(acc[0][ni][1])
+                     : "d"(a0), "d"(b[ni]));
+      }
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
-                       : "d"(a[mi]), "d"(b[ni]));
+      for (int ni = 0; ni < 4; ++ni) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[1][ni][0]), "+d"(acc[1][ni][1])
+                     : "d"(a1), "d"(b[ni]));
+      }
+    };
+    if (STAGES == 3) {
+#pragma unroll
+      for (int s = 0; s < KREG; ++s)
+        if (4 * s < Mp) mma_step(4 * s, ka[s][0], ka[s][1]);
+    } else {
+      for (int ks = 0; ks < Mp; ks += 4) {
+        const double* kr = Ks + (ks + lc) * DSTRIDE + wr0 + lr;
+        mma_step(ks, kr[0], kr[8]);
+      }
     }
     if (it > 0) mbar_wait(tfree, (unsigned)((it - 1) & 1));  // the stores of pair p - 1 have read the transpose buffer
     if (!diag) {
@@ -1266,9 +1308,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
           const int ri = wr0 + lr + 8 * mi, cj = wc0 + 2 * lc + 8 * ni;
           double2* pp = reinterpret_cast<double2*>(pa + ri * TILE + cj);
           const double2 pij = *pp;
-          // 0.5*(p + p) - acc == p - acc bit for bit: the mirrored tile holds the same values
-          const double o0 = 0.5 * (pij.x + pij.x) - acc[mi][ni][0];
-          const double o1 = 0.5 * (pij.y + pij.y) - acc[mi][ni][1];
+          // the mirrored tile holds the same values: 0.5*(p + p) - acc == p - acc bit for bit
+          const double o0 = pij.x - acc[mi][ni][0];
+          const double o1 = pij.y - acc[mi][ni][1];
           *pp = make_double2(o0, o1);
           if (write_lower) {
             Tt[swz_off(cj, ri)] = o0;
