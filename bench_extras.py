@@ -42,7 +42,8 @@ def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, 
         pm = rng.normal(0.0, 5.0, 3 * n_point_meas) if n_point_meas else None
         kf.PredictKF()
         kf.sync()
-        tp = kf.last_timing()["total_ms"]
+        lt = kf.last_timing()
+        tp, launches_before = lt["total_ms"], lt["launches"]
         t0 = time.perf_counter()
         kf.UpdateNCurvesAndPoints(z, 4, A, [0, 1, 2, 3], pm, pts, n_point_meas)
         kf.sync()
@@ -61,10 +62,14 @@ def ekf_update_bench(device: int, L: int, n_point_meas: int = 0, reps: int = 5, 
                         "definition": "16 N^2 bytes (read P once + write P once) over the device time of the WHOLE update",
                         "cov_kernel_alone": {"achieved": 16.0 * N * N / (cov_ms * 1e-3) / 1e9,
                                              "frac": 16.0 * N * N / (cov_ms * 1e-3) / 1e9 / hbm},
-                        "moved_bytes": {"note": "the TMA kernel reads one tile of every mirrored pair once P's tiles are "
-                                                "exact mirrors (after any update): 12 N^2 bytes actually cross HBM",
-                                        "bytes": 12 * N * N, "achieved_GBs": 12.0 * N * N / (cov_ms * 1e-3) / 1e9}},
-           "flops_tflops": 2.0 * N * N * M / (cov_ms * 1e-3) / 1e12, "launches_per_update": int(tm["launches"]),
+                        "moved_bytes": {"note": "the streaming kernel reads and writes ONE tile of every mirrored pair "
+                                                "(P is symmetric to the last bit after any update; the tiles below the "
+                                                "diagonal tiles are rebuilt only when an entry point asks for them): "
+                                                "8 N^2 bytes actually cross HBM, so frac can exceed 1 on the 16 N^2 "
+                                                "definition; the kernel's own bound is achieved_GBs over the HBM peak",
+                                        "bytes": 8 * N * N, "achieved_GBs": 8.0 * N * N / (cov_ms * 1e-3) / 1e9,
+                                        "frac_of_hbm_peak": 8.0 * N * N / (cov_ms * 1e-3) / 1e9 / hbm}},
+           "flops_tflops": 2.0 * N * N * M / (cov_ms * 1e-3) / 1e12, "launches_per_update": int(tm["launches"] - launches_before),
            "P_bytes": 8 * N * N, "l2": "P larger than L2" if 8 * N * N > 126e6 else "P fits L2 (72 MB): L2-resident"}
     kf.close()
     return out

@@ -1042,8 +1042,15 @@ __global__ void __launch_bounds__(256, 1) ekf_cov_pipe_kernel(double* __restrict
 //     written into a second buffer in the 128-byte-swizzled layout of four 16-column boxes (conflict-free 8-byte
 //     stores from the DMMA accumulator layout) and leaves by four TMA stores into tile (J,I): both stores are
 //     full lines;
-//   * Y_J / K_I tiles (36 x 64, L2-resident) keep the padded layout the DMMA fragment reads need and still come
-//     by cp.async.
+//   * the Y_J rows of a pair (M x 64, L2-resident) arrive as M bulk copies of 512 bytes issued by the copy warp's
+//     32 lanes into the padded layout the DMMA fragment reads need, on the same mbarrier as the pair's P tile: the
+//     compute warps issue no copies and wait on one barrier per pair (their share of the cp.async issue loop was
+//     12 % of the kernel's instructions); K_I comes by cp.async once per tile row and, for M <= 36, its fragments
+//     stay in registers while J advances;
+//   * by default only tile (I,J), I <= J, of a pair is written (write_lower = 0): every reader on the predict /
+//     update / gate / augmentation path takes single entries from the upper copy (upper_index), and the tiles below
+//     the diagonal tiles are rebuilt by ekf_mirror_lower_kernel when an entry point needs them (cps_ekf::lower_stale):
+//     8 N^2 bytes per update instead of 12 N^2.
 constexpr int TMA_STAGES = 3;
 constexpr int TMA_TILE_BYTES = TILE * TILE * 8;
 
@@ -2049,6 +2056,7 @@ extern "C" int cps_ekf_add_first_states(cps_ekf* h, const double* z19) {
   h->launches++;
   h->N = 28;
   h->mirror_exact = true;  // a diagonal matrix
+  h->lower_stale = false;  // all of P was rewritten
   h->curve_inds = {CPS_ROBOT_STATE_SIZE, CPS_ROBOT_STATE_SIZE + 8};  // kalmanClass.cpp:307-309
   h->point_inds.clear();
   return CPS_OK;
