@@ -570,64 +570,107 @@ __global__ void __launch_bounds__(NT) ekf_front_kernel(UpdateDesc d, const doubl
   }
 }
 
-// One state row of ekf_rows_kernel: T_row, K_row, Y_row and the row's share of K nu.  A lane owns the entries
-// lane, lane + 32, ... (NP = ceil(M / 32) of them) and carries their sums TOGETHER through each loop -- NP independent
-// chains per iteration instead of NP passes over one chain (the loops are latency-bound: M = 35 spent a whole second
-// pass on three entries, M = 65 three passes).  Every sum runs over the same terms in the same order as before.
+// ROWS_R consecutive state rows of ekf_rows_kernel at once: T, K, Y rows and the rows' shares of K nu.  A lane owns
+// the entries lane, lane + 32, ... (NP = ceil(M / 32) of them) of every row and carries all NP x ROWS_R sums TOGETHER
+// through each loop: independent chains instead of passes (M = 35 spent a whole second pass on three entries), and a
+// table entry (H, S^-1, S) is read from shared memory ONCE for the ROWS_R rows -- with one row per pass the kernel ran at
+// 76 % of the shared-memory bandwidth at M = 65 (three table reads for three multiply-adds).  Every sum runs over the
+// same terms in the same order as before.  Rows past N are computed on row N - 1's data and not stored.
+constexpr int ROWS_R = 4;
 template <int NP>
-__device__ __forceinline__ void rows_one(int M, int nc, int ncp, int Mo, int lane, const double* pr, double* trow,
-                                         double* krow, const double* Hc, const double* Sinv, const double* S,
-                                         const double* nu, double* __restrict__ Kt, double* __restrict__ Yt,
-                                         size_t ldk, int row, double& dx) {
+__device__ __forceinline__ void rows_multi(int M, int nc, int ncp, int Mo, int lane, const double* pr, double* trow,
+                                           double* krow, const double* Hc, const double* Sinv, const double* S,
+                                           const double* nu, double* __restrict__ Kt, double* __restrict__ Yt,
+                                           size_t ldk, int row0, int nrows, double (&dx)[ROWS_R]) {
+  // pr [ROWS_R][nc], trow [ROWS_R][M], krow [ROWS_R][M]
   {
-    double a[NP];
+    double a[NP][ROWS_R];
     const double* h[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) { h[p] = Hc + min(lane + 32 * p, M - 1) * ncp; a[p] = 0.0; }
-    for (int c = 0; c < nc; ++c) {
-      const double pv = pr[c];
+    for (int p = 0; p < NP; ++p) {
+      h[p] = Hc + min(lane + 32 * p, M - 1) * ncp;
 #pragma unroll
-      for (int p = 0; p < NP; ++p) a[p] += pv * h[p][c];
+      for (int r = 0; r < ROWS_R; ++r) a[p][r] = 0.0;
     }
+    for (int c = 0; c < nc; ++c) {
+      double pv[ROWS_R], hv[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p)
-      if (lane + 32 * p < M) trow[lane + 32 * p] = a[p];
-  }
-  __syncwarp();
-  {
-    double a[NP];
-    int q[NP];
+      for (int r = 0; r < ROWS_R; ++r) pv[r] = pr[r * nc + c];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) { q[p] = min(lane + 32 * p, M - 1); a[p] = 0.0; }
-    for (int r = 0; r < M; ++r) {
-      const double tv = trow[r];
-      const double* sr = Sinv + r * M;
+      for (int p = 0; p < NP; ++p) hv[p] = h[p][c];
 #pragma unroll
-      for (int p = 0; p < NP; ++p) a[p] += tv * sr[q[p]];
+      for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int r = 0; r < ROWS_R; ++r) a[p][r] += pv[r] * hv[p];
     }
 #pragma unroll
     for (int p = 0; p < NP; ++p)
       if (lane + 32 * p < M) {
-        krow[lane + 32 * p] = a[p];
-        Kt[(size_t)(lane + 32 * p) * ldk + row] = a[p];
+#pragma unroll
+        for (int r = 0; r < ROWS_R; ++r) trow[r * M + lane + 32 * p] = a[p][r];
       }
   }
   __syncwarp();
   {
-    double a[NP];
-    const double* sr[NP];
+    double a[NP][ROWS_R];
+    int q[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) { sr[p] = S + min(lane + 32 * p, M - 1) * Mo; a[p] = 0.0; }
-    for (int q = 0; q < M; ++q) {
-      const double kv = krow[q];
+    for (int p = 0; p < NP; ++p) {
+      q[p] = min(lane + 32 * p, M - 1);
 #pragma unroll
-      for (int p = 0; p < NP; ++p) a[p] += kv * sr[p][q];
+      for (int r = 0; r < ROWS_R; ++r) a[p][r] = 0.0;
+    }
+    for (int k = 0; k < M; ++k) {
+      double tv[ROWS_R], sv[NP];
+#pragma unroll
+      for (int r = 0; r < ROWS_R; ++r) tv[r] = trow[r * M + k];
+      const double* sr = Sinv + k * M;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sv[p] = sr[q[p]];
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int r = 0; r < ROWS_R; ++r) a[p][r] += tv[r] * sv[p];
     }
 #pragma unroll
     for (int p = 0; p < NP; ++p)
       if (lane + 32 * p < M) {
-        Yt[(size_t)(lane + 32 * p) * ldk + row] = a[p];
-        dx += krow[lane + 32 * p] * nu[lane + 32 * p];
+#pragma unroll
+        for (int r = 0; r < ROWS_R; ++r) {
+          krow[r * M + lane + 32 * p] = a[p][r];
+          if (r < nrows) Kt[(size_t)(lane + 32 * p) * ldk + row0 + r] = a[p][r];
+        }
+      }
+  }
+  __syncwarp();
+  {
+    double a[NP][ROWS_R];
+    const double* sr[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      sr[p] = S + min(lane + 32 * p, M - 1) * Mo;
+#pragma unroll
+      for (int r = 0; r < ROWS_R; ++r) a[p][r] = 0.0;
+    }
+    for (int k = 0; k < M; ++k) {
+      double kv[ROWS_R], sv[NP];
+#pragma unroll
+      for (int r = 0; r < ROWS_R; ++r) kv[r] = krow[r * M + k];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sv[p] = sr[p][k];
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int r = 0; r < ROWS_R; ++r) a[p][r] += kv[r] * sv[p];
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (lane + 32 * p < M) {
+#pragma unroll
+        for (int r = 0; r < ROWS_R; ++r) {
+          if (r < nrows) Yt[(size_t)(lane + 32 * p) * ldk + row0 + r] = a[p][r];
+          dx[r] += krow[r * M + lane + 32 * p] * nu[lane + 32 * p];
+        }
       }
   }
 }
@@ -645,8 +688,8 @@ __global__ void __launch_bounds__(512) ekf_rows_kernel(UpdateDesc d, const doubl
   double* S = Sinv + M * M;         // [M][Mo]
   double* nu = S + M * Mo;          // [M]
   const int nw = blockDim.x >> 5;   // 8 warps; 16 when the tables leave room for one block per SM only (M > 36)
-  double* rowbuf = nu + M;          // [nw warps][nc + 2 M]
-  int* scols = reinterpret_cast<int*>(rowbuf + nw * (nc + 2 * M));
+  double* rowbuf = nu + M;          // [nw warps][ROWS_R][nc + 2 M]
+  int* scols = reinterpret_cast<int*>(rowbuf + nw * ROWS_R * (nc + 2 * M));
   for (int e = threadIdx.x; e < M * nc; e += blockDim.x) {
     const int r = e / nc, b = e - r * nc;
     Hc[r * ncp + b] = small[SM_HC + e];
@@ -660,23 +703,37 @@ __global__ void __launch_bounds__(512) ekf_rows_kernel(UpdateDesc d, const doubl
   for (int e = threadIdx.x; e < nc; e += blockDim.x) scols[e] = cols[e];
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double* pr = rowbuf + w * (nc + 2 * M);
-  double* trow = pr + nc;
-  double* krow = trow + M;
-  for (int row = blockIdx.x * nw + w; row < d.N; row += gridDim.x * nw) {
-    for (int c = lane; c < nc; c += 32) pr[c] = P[upper_index(row, scols[c], d.ld, d.sym)];
+  double* pr = rowbuf + w * ROWS_R * (nc + 2 * M);
+  double* trow = pr + ROWS_R * nc;
+  double* krow = trow + ROWS_R * M;
+  for (int row0 = (blockIdx.x * nw + w) * ROWS_R; row0 < d.N; row0 += gridDim.x * nw * ROWS_R) {
+    const int nrows = min(ROWS_R, d.N - row0);
+    for (int e = lane; e < ROWS_R * nc; e += 32) {
+      const int r = e / nc, c = e - r * nc;
+      pr[e] = P[upper_index(min(row0 + r, d.N - 1), scols[c], d.ld, d.sym)];
+    }
     __syncwarp();
-    double dx = 0.0;
+    double dx[ROWS_R];
+#pragma unroll
+    for (int r = 0; r < ROWS_R; ++r) dx[r] = 0.0;
     switch ((M + 31) >> 5) {
-      case 1: rows_one<1>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
-      case 2: rows_one<2>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
-      case 3: rows_one<3>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
-      default: rows_one<4>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row, dx); break;
+      case 1: rows_multi<1>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row0, nrows, dx); break;
+      case 2: rows_multi<2>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row0, nrows, dx); break;
+      case 3: rows_multi<3>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row0, nrows, dx); break;
+      default: rows_multi<4>(M, nc, ncp, Mo, lane, pr, trow, krow, Hc, Sinv, S, nu, Kt, Yt, (size_t)ldk, row0, nrows, dx); break;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dx += __shfl_xor_sync(0xffffffffu, dx, o);
-    if (lane == 0) {
-      double v = x[row] + dx;
+    for (int r = 0; r < ROWS_R; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dx[r] += __shfl_xor_sync(0xffffffffu, dx[r], o);
+    }
+    if (lane < nrows) {
+      const int row = row0 + lane;
+      double dxr = dx[0];
+#pragma unroll
+      for (int r = 1; r < ROWS_R; ++r)
+        if (lane == r) dxr = dx[r];
+      double v = x[row] + dxr;
       if (row >= 3 && row <= 5 && fabs(v) < 1e6) {  // kalmanClass.cpp:902-913 (bounded: a wild angle cannot spin)
         while (v > kPI) v -= 2 * kPI;
         while (v < -kPI) v += 2 * kPI;
@@ -1946,7 +2003,7 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   const size_t sh_front = (size_t)(d.M * ncp + d.M * d.nc + d.nc * d.nc + 3 * d.M * d.M) * sizeof(double);
   // rows kernel: eight warps per block while two blocks fit an SM, sixteen in one block above that (M > 36)
   auto rows_smem = [&](int nw) {
-    return (size_t)(d.M * ncp + d.M * d.M + d.M * Mo + d.M + nw * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
+    return (size_t)(d.M * ncp + d.M * d.M + d.M * Mo + d.M + nw * ROWS_R * (d.nc + 2 * d.M)) * sizeof(double) + d.nc * sizeof(int);
   };
   const int rows_warps = 2 * (rows_smem(8) + 1024) <= (size_t)227 * 1024 ? 8 : 16;
   const size_t sh_rows = rows_smem(rows_warps);
@@ -1956,7 +2013,7 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
   if (!no_fused && sh_front <= (size_t)kFrontSmemMax && sh_rows <= (size_t)kFrontSmemMax) {
     if (d.M * d.M <= 6 * 256) ekf_front_kernel<256><<<1, 256, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
     else ekf_front_kernel<512><<<1, 512, sh_front, st>>>(d, h->d_x, h->d_P, h->d_small, h->d_cols, d_land, h->d_flag);
-    const int rows_grid = std::min((d.N + rows_warps - 1) / rows_warps, h->sm_count * rows_per_sm);
+    const int rows_grid = std::min((d.N + rows_warps * ROWS_R - 1) / (rows_warps * ROWS_R), h->sm_count * rows_per_sm);
     ekf_rows_kernel<<<rows_grid, 32 * rows_warps, sh_rows, st>>>(d, h->d_P, h->d_small, h->d_cols, h->d_Kt, h->d_Yt, h->d_x, h->cap);
     launches = 2;
   } else {
