@@ -1403,6 +1403,179 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
   }
 }
 
+// ---- kernel 5e: the half-written streaming pass with TWO compute groups on alternating pairs (M <= 36) -------------
+// Kernel 5d's eight compute warps walk a pair in lockstep -- products, then the wait for the accumulators, then the
+// epilogue, then a barrier -- so the DMMA pipe idles during the epilogue and the load / store unit during the products
+// (DMMA 58 % busy, 28 % of the stall samples on the first use of the accumulators), and interleaving the two inside
+// a warp lost twice.  Here warps 0-3 take the even pairs of the CTA's range and warps 4-7 the odd ones,
+// each group a whole 64 x 64 tile (a warp: 16 rows x 64 columns, 16 DMMAs per k-step), with its own named barrier and
+// its own pairs' `done` mbarriers: while one group corrects and hands over its tile the other multiplies.  Only the
+// half-written mode (write_lower = 0 of kernel 5d): no transpose buffer -- a diagonal tile is symmetrised in place
+// in two phases (all reads, group barrier, all writes) and leaves by the same full-tile store -- which pays for a
+// 4-deep ring of P tiles and Y rows (two pairs in work, two in flight).  K_I changes once per tile row: a thread
+// keeps its K fragments in registers (nine k-steps) and reloads them from Kt (L2) when its pair's row changes, so the
+// groups may be on different tile rows.  Same sums in the same order as kernel 5d: bit-identical.
+constexpr int PP_STAGES = 4;
+__device__ __forceinline__ void group_sync(int g) {
+  if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+__global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid_constant__ TmaMaps maps, int M,
+                                                                     const double* __restrict__ Kt,
+                                                                     const double* __restrict__ Yt, int ldk, int nt,
+                                                                     long long total_pairs) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(smem_raw) + 1023) & ~(size_t)1023);
+  const int Mp = (M + 3) & ~3;
+  double* Pst = reinterpret_cast<double*>(base);                                  // [4][64][64]
+  double* Yst = reinterpret_cast<double*>(base + PP_STAGES * TMA_TILE_BYTES);     // [4][Mp][68]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(Yst + PP_STAGES * Mp * DSTRIDE);  // [4]
+  // [4] one per stage: a stage's `full` and `done` phases alternate strictly (a group can only run ahead as far as the
+  // ring has been refilled), so a parity wait can never be lapped
+  unsigned long long* done = full + PP_STAGES;
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+
+  const long long per = (total_pairs + gridDim.x - 1) / gridDim.x;
+  const long long p_begin = (long long)blockIdx.x * per;
+  const long long p_end = min(total_pairs, p_begin + per);
+  if (p_begin >= p_end) return;
+  const int n_pairs = (int)(p_end - p_begin);
+  if (t == 0) {
+    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(done + s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (t < 256)
+    for (int e = t; e < (Mp - M) * DSTRIDE; e += 256)  // padding rows of Y stay zero
+      for (int s = 0; s < PP_STAGES; ++s) Yst[s * Mp * DSTRIDE + M * DSTRIDE + e] = 0.0;
+  __syncthreads();
+  auto next_pair = [&](int& I, int& J) {
+    if (++J >= nt) { ++I; J = I; }
+  };
+  int I, J;
+  pair_from_index(p_begin, nt, I, J);
+
+  if (w == 8) {
+    // ---------------------------------------------------------------------------------------- copy warp
+    auto issue_pair = [&](int Ia, int Ja, int stage) {
+      if (l == 0) {
+        mbar_expect_tx(full + stage, (unsigned)(TMA_TILE_BYTES + M * TILE * 8));
+        tma_load_2d(Pst + stage * TILE * TILE, &maps.full, Ja * TILE, Ia * TILE, full + stage);
+      }
+      __syncwarp();
+      double* ys = Yst + stage * Mp * DSTRIDE;
+      for (int r = l; r < M; r += 32)
+        bulk_load_1d(ys + r * DSTRIDE, Yt + (size_t)r * ldk + (size_t)Ja * TILE, TILE * 8, full + stage);
+    };
+    int Il = I, Jl = J, np = 0;
+    for (; np < PP_STAGES && np < n_pairs; ++np) {
+      issue_pair(Il, Jl, np);
+      next_pair(Il, Jl);
+    }
+    for (int it = 0; it < n_pairs; ++it) {
+      const int stage = it % PP_STAGES;
+      mbar_wait_backoff(done + stage, (unsigned)((it / PP_STAGES) & 1));  // the pair's tile is corrected and fenced
+      if (l == 0) {
+        tma_store_2d(&maps.full, J * TILE, I * TILE, Pst + stage * TILE * TILE);
+        tma_commit();
+        tma_wait_read_all();  // the store has read the stage
+      }
+      __syncwarp();
+      if (np < n_pairs) {
+        issue_pair(Il, Jl, stage);
+        next_pair(Il, Jl);
+        ++np;
+      }
+      next_pair(I, J);
+    }
+    if (l == 0) tma_wait_all();
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------------ compute groups
+  const int g = w >> 2, wr0 = (w & 3) * 16;
+  const int lr = l >> 2, lc = l & 3;
+  if (g == 1) next_pair(I, J);  // the odd pairs
+  constexpr int KS = PIPE_MAX_M / 4;
+  double ka[KS][2];
+  int k_loaded = -1;
+  for (int it = g; it < n_pairs; it += 2) {
+    if (k_loaded != I) {
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int r = 4 * s + lc;
+        const double* kr = Kt + (size_t)min(r, M - 1) * ldk + (size_t)I * TILE + wr0 + lr;
+        ka[s][0] = r < M ? kr[0] : 0.0;
+        ka[s][1] = r < M ? kr[8] : 0.0;
+      }
+      k_loaded = I;
+    }
+    const int stage = it % PP_STAGES;
+    mbar_wait(full + stage, (unsigned)((it / PP_STAGES) & 1));  // the P tile and the Y rows of this pair
+    double* pa = Pst + stage * TILE * TILE;
+    const double* ys = Yst + stage * Mp * DSTRIDE;
+    double acc[2][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      if (4 * s < Mp) {
+        double b[8];
+        const double* yr = ys + (4 * s + lc) * DSTRIDE + lr;
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) b[ni] = yr[8 * ni];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                         : "d"(ka[s][mi]), "d"(b[ni]));
+      }
+    }
+    if (I != J) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          const int ri = wr0 + lr + 8 * mi, cj = 2 * lc + 8 * ni;
+          double2* pp = reinterpret_cast<double2*>(pa + ri * TILE + cj);
+          const double2 pij = *pp;
+          // the mirrored tile holds the same values: 0.5*(p + p) - acc == p - acc bit for bit
+          *pp = make_double2(pij.x - acc[mi][ni][0], pij.y - acc[mi][ni][1]);
+        }
+    } else {
+      // diagonal tile: entries on and above the diagonal are authoritative and mirrored, as in kernels 5c / 5d; every
+      // thread reads what it needs before anybody writes
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          const int ri = wr0 + lr + 8 * mi, cj = 2 * lc + 8 * ni;
+          const double2 pij = *reinterpret_cast<const double2*>(pa + ri * TILE + cj);
+          const double q0 = pa[cj * TILE + ri], q1 = pa[(cj + 1) * TILE + ri];
+          acc[mi][ni][0] = 0.5 * (pij.x + q0) - acc[mi][ni][0];
+          acc[mi][ni][1] = 0.5 * (pij.y + q1) - acc[mi][ni][1];
+        }
+      group_sync(g);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          const int ri = wr0 + lr + 8 * mi, cj = 2 * lc + 8 * ni;
+          if (cj >= ri) { pa[ri * TILE + cj] = acc[mi][ni][0]; if (cj != ri) pa[cj * TILE + ri] = acc[mi][ni][0]; }
+          if (cj + 1 >= ri) { pa[ri * TILE + cj + 1] = acc[mi][ni][1]; if (cj + 1 != ri) pa[(cj + 1) * TILE + ri] = acc[mi][ni][1]; }
+        }
+    }
+    fence_async_smem();
+    group_sync(g);
+    if ((t & 127) == 0) mbar_arrive(done + stage);
+    next_pair(I, J);
+    next_pair(I, J);
+  }
+}
+
 // ---- tiles below the diagonal tiles, on demand ----------------------------------------------------------------------
 // The streaming kernel above normally writes only tile (I,J), I <= J, of every mirrored pair (8 N^2 bytes per update
 // instead of 12 N^2: cps_ekf::lower_stale).  Everything on the predict / update path reads the upper copy; an entry
@@ -1736,6 +1909,10 @@ int ensure_lower(cps_ekf* h) {
   return CPS_OK;
 }
 
+size_t pp_smem_bytes(int Mp) {
+  return 1024 + (size_t)PP_STAGES * TMA_TILE_BYTES + (size_t)PP_STAGES * Mp * DSTRIDE * sizeof(double) + 128;
+}
+
 size_t tma_smem_bytes(int Mp, int stages) {
   return 1024 + (size_t)(1 + stages) * TMA_TILE_BYTES + (size_t)(stages + 1) * Mp * DSTRIDE * sizeof(double) + 128;
 }
@@ -1815,6 +1992,7 @@ int ekf_create_impl(cps_ekf* h, int device, int capacity) {
                                 tma_smem_bytes(PIPE_MAX_M, TMA_STAGES)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tma_smem_bytes(TMA2_MAX_M, 2)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes(PIPE_MAX_M)));
   h->maps_ok = encode_maps(h);
   h->mirror_exact = true;  // P = 0
   CPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -2048,7 +2226,10 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
       maps.full = h->map_full;
       maps.swz = h->map_swz;
       const int write_lower = lazy_lower ? 0 : 1;
-      if (Mp <= PIPE_MAX_M)
+      const bool no_pp = std::getenv("CPS_EKF_COV_NO_PINGPONG") != nullptr;  // A/B switch
+      if (Mp <= PIPE_MAX_M && lazy_lower && !no_pp)
+        ekf_cov_pp_kernel<<<h->sm_count, TMA_THREADS, pp_smem_bytes(Mp), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+      else if (Mp <= PIPE_MAX_M)
         ekf_cov_tma_kernel<TMA_STAGES><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, TMA_STAGES), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs, write_lower);
       else
         ekf_cov_tma_kernel<2><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, 2), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs, write_lower);
