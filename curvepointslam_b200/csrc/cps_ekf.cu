@@ -1415,11 +1415,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_tma_kernel(const __gri
 // 4-deep ring of P tiles and Y rows (two pairs in work, two in flight).  K_I changes once per tile row: a thread
 // keeps its K fragments in registers (nine k-steps) and reloads them from Kt (L2) when its pair's row changes, so the
 // groups may be on different tile rows.  Same sums in the same order as kernel 5d: bit-identical.
-constexpr int PP_STAGES = 4;
+// KS = k-steps a thread keeps K fragments for, NST = ring depth: <9, 4> for M <= 36, <17, 3> for M <= 68 (a stage's Y rows
+// grow with M: three stages of 32 + 37 KB; two pairs in work, one in flight -- a pair carries twice the DMMA work there).
 __device__ __forceinline__ void group_sync(int g) {
   if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
+template <int KS, int NST>
 __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid_constant__ TmaMaps maps, int M,
                                                                      const double* __restrict__ Kt,
                                                                      const double* __restrict__ Yt, int ldk, int nt,
@@ -1428,11 +1430,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(smem_raw) + 1023) & ~(size_t)1023);
   const int Mp = (M + 3) & ~3;
   double* Pst = reinterpret_cast<double*>(base);                                  // [4][64][64]
-  double* Yst = reinterpret_cast<double*>(base + PP_STAGES * TMA_TILE_BYTES);     // [4][Mp][68]
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(Yst + PP_STAGES * Mp * DSTRIDE);  // [4]
+  double* Yst = reinterpret_cast<double*>(base + NST * TMA_TILE_BYTES);     // [4][Mp][68]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(Yst + NST * Mp * DSTRIDE);  // [4]
   // [4] one per stage: a stage's `full` and `done` phases alternate strictly (a group can only run ahead as far as the
   // ring has been refilled), so a parity wait can never be lapped
-  unsigned long long* done = full + PP_STAGES;
+  unsigned long long* done = full + NST;
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
 
   const long long per = (total_pairs + gridDim.x - 1) / gridDim.x;
@@ -1441,12 +1443,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid
   if (p_begin >= p_end) return;
   const int n_pairs = (int)(p_end - p_begin);
   if (t == 0) {
-    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(done + s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(full + s, 1); mbar_init(done + s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (t < 256)
     for (int e = t; e < (Mp - M) * DSTRIDE; e += 256)  // padding rows of Y stay zero
-      for (int s = 0; s < PP_STAGES; ++s) Yst[s * Mp * DSTRIDE + M * DSTRIDE + e] = 0.0;
+      for (int s = 0; s < NST; ++s) Yst[s * Mp * DSTRIDE + M * DSTRIDE + e] = 0.0;
   __syncthreads();
   auto next_pair = [&](int& I, int& J) {
     if (++J >= nt) { ++I; J = I; }
@@ -1467,13 +1469,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid
         bulk_load_1d(ys + r * DSTRIDE, Yt + (size_t)r * ldk + (size_t)Ja * TILE, TILE * 8, full + stage);
     };
     int Il = I, Jl = J, np = 0;
-    for (; np < PP_STAGES && np < n_pairs; ++np) {
+    for (; np < NST && np < n_pairs; ++np) {
       issue_pair(Il, Jl, np);
       next_pair(Il, Jl);
     }
     for (int it = 0; it < n_pairs; ++it) {
-      const int stage = it % PP_STAGES;
-      mbar_wait_backoff(done + stage, (unsigned)((it / PP_STAGES) & 1));  // the pair's tile is corrected and fenced
+      const int stage = it % NST;
+      mbar_wait_backoff(done + stage, (unsigned)((it / NST) & 1));  // the pair's tile is corrected and fenced
       if (l == 0) {
         tma_store_2d(&maps.full, J * TILE, I * TILE, Pst + stage * TILE * TILE);
         tma_commit();
@@ -1495,7 +1497,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid
   const int g = w >> 2, wr0 = (w & 3) * 16;
   const int lr = l >> 2, lc = l & 3;
   if (g == 1) next_pair(I, J);  // the odd pairs
-  constexpr int KS = PIPE_MAX_M / 4;
   double ka[KS][2];
   int k_loaded = -1;
   for (int it = g; it < n_pairs; it += 2) {
@@ -1509,8 +1510,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ekf_cov_pp_kernel(const __grid
       }
       k_loaded = I;
     }
-    const int stage = it % PP_STAGES;
-    mbar_wait(full + stage, (unsigned)((it / PP_STAGES) & 1));  // the P tile and the Y rows of this pair
+    const int stage = it % NST;
+    mbar_wait(full + stage, (unsigned)((it / NST) & 1));  // the P tile and the Y rows of this pair
     double* pa = Pst + stage * TILE * TILE;
     const double* ys = Yst + stage * Mp * DSTRIDE;
     double acc[2][8][2];
@@ -1909,8 +1910,10 @@ int ensure_lower(cps_ekf* h) {
   return CPS_OK;
 }
 
+constexpr int PP_MAX_M = 68;  // seventeen k-steps of K fragments in registers
 size_t pp_smem_bytes(int Mp) {
-  return 1024 + (size_t)PP_STAGES * TMA_TILE_BYTES + (size_t)PP_STAGES * Mp * DSTRIDE * sizeof(double) + 128;
+  const int nst = Mp <= PIPE_MAX_M ? 4 : 3;
+  return 1024 + (size_t)nst * TMA_TILE_BYTES + (size_t)nst * Mp * DSTRIDE * sizeof(double) + 128;
 }
 
 size_t tma_smem_bytes(int Mp, int stages) {
@@ -1992,7 +1995,10 @@ int ekf_create_impl(cps_ekf* h, int device, int capacity) {
                                 tma_smem_bytes(PIPE_MAX_M, TMA_STAGES)));
   CPS_CUDA(cudaFuncSetAttribute(ekf_cov_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tma_smem_bytes(TMA2_MAX_M, 2)));
-  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes(PIPE_MAX_M)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_pp_kernel<PIPE_MAX_M / 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                pp_smem_bytes(PIPE_MAX_M)));
+  CPS_CUDA(cudaFuncSetAttribute(ekf_cov_pp_kernel<PP_MAX_M / 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                pp_smem_bytes(PP_MAX_M)));
   h->maps_ok = encode_maps(h);
   h->mirror_exact = true;  // P = 0
   CPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -2228,7 +2234,9 @@ int run_update(cps_ekf* h, const double* z, int n, const double* A, const int* c
       const int write_lower = lazy_lower ? 0 : 1;
       const bool no_pp = std::getenv("CPS_EKF_COV_NO_PINGPONG") != nullptr;  // A/B switch
       if (Mp <= PIPE_MAX_M && lazy_lower && !no_pp)
-        ekf_cov_pp_kernel<<<h->sm_count, TMA_THREADS, pp_smem_bytes(Mp), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+        ekf_cov_pp_kernel<PIPE_MAX_M / 4, 4><<<h->sm_count, TMA_THREADS, pp_smem_bytes(Mp), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
+      else if (Mp <= PP_MAX_M && lazy_lower && !no_pp)
+        ekf_cov_pp_kernel<PP_MAX_M / 4, 3><<<h->sm_count, TMA_THREADS, pp_smem_bytes(Mp), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs);
       else if (Mp <= PIPE_MAX_M)
         ekf_cov_tma_kernel<TMA_STAGES><<<h->sm_count, TMA_THREADS, tma_smem_bytes(Mp, TMA_STAGES), st>>>(maps, M, h->d_Kt, h->d_Yt, h->cap, nt, pairs, write_lower);
       else
