@@ -8,7 +8,7 @@ python bench.py --steps 5 --warmup 3 > $G/r2b_final_bench_der.json 2> $G/r2b_fin
 python bench.py --impl reference --steps 3 --warmup 1 > $G/r2b_final_bench_reference_der.json 2>/dev/null
 python scripts/ekf_bench_probe.py > $G/r2b_final_ekf.json 2> $G/r2b_final_ekf.err
 python scripts/ekfprof.py > $G/plain4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:ekf_cov_tma_kernel -s 1 -c 1 -o $G/r2b_prof_ekf_cov python scripts/ekfprof.py > $G/ncu_d.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ekf_cov_pp_kernel -s 1 -c 1 -o $G/r2b_prof_ekf_cov python scripts/ekfprof.py > $G/ncu_d.log 2>&1
 for cfg in "1000 0" "5000 0" "20000 0" "5000 10"; do
   tag=$(echo $cfg | tr ' ' '_')
   python scripts/ekfprof.py $cfg > $G/plain_ekf_$tag.log 2>&1 &&
