@@ -376,51 +376,46 @@ __global__ void __launch_bounds__(256) ekf_gain_kernel(UpdateDesc d, const doubl
   }
 }
 
-// Gauss-Jordan steps of the fused front end with a thread's entries (at most Q of the M x M, entry e = tid + NT q)
-// in registers from step to step.  A step is branch-free: the pivot and the entries' pivot-column and pivot-row
-// values are loaded together and the three cases of the update are selects, so the loads of a step overlap each
-// other and the reciprocal instead of forming one dependent load -> multiply -> load -> update -> store chain per
-// entry (21 us of the front end's 43 at M = 35).  Same operations on the same values as the plain loop in the kernel.
-// The matrix ping-pongs between Wa (the input) and Wb; after M steps the result is in Wb when M is odd.
-template <int Q, int NT>
+// Gauss-Jordan steps of the fused front end with a thread's entries in registers from step to step.  A thread owns
+// ONE column j of the M x M matrix and every RG-th row of it (RG = NT / M row groups, at most QMAX rows), so a step
+// loads the pivot, the thread's pivot-row value W[k][j] once, and one pivot-column value per owned row (the same
+// address for the lanes of a row group: a broadcast) -- the first register version loaded two values per entry and
+// spent a sixth of its work on an inactive sixth entry.  A step is branch-free: the three cases of the update are
+// selects, so the loads of a step overlap each other and the reciprocal instead of forming one dependent load ->
+// multiply -> load -> update -> store chain per entry (21 us of the front end's 43 at M = 35 in the plain loop).
+// Same operations on the same values as the plain loop in the kernel.  The matrix ping-pongs between Wa (the input)
+// and Wb; after M steps the result is in Wb when M is odd.  Requires ceil(M / (NT / M)) <= QMAX.
+template <int QMAX, int NT>
 __device__ __forceinline__ void gj_register_steps(double* Wa, double* Wb, int M, int tid, int* flag, int* bad) {
-  int oi[Q], ej[Q], ei[Q];
-  double v[Q];
-  {
-    int i = tid / M, j = tid - i * M;
-    const int di = NT / M, dj = NT - di * M;
+  const int RG = NT / M;
+  const int g = tid / M, j = tid - g * M;
+  const bool owner = g < RG;
+  const int nq = owner ? (M - g + RG - 1) / RG : 0;  // rows g, g + RG, ... below M
+  double v[QMAX];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const bool act = tid + q * NT < M * M;
-      ei[q] = act ? i : 0;
-      ej[q] = act ? j : 0;
-      oi[q] = ei[q] * M;
-      v[q] = act ? Wa[tid + q * NT] : 0.0;
-      i += di; j += dj;
-      if (j >= M) { j -= M; ++i; }
-    }
-  }
+  for (int q = 0; q < QMAX; ++q) v[q] = q < nq ? Wa[(g + RG * q) * M + j] : 0.0;
   double* Wsrc = Wa;
   double* Wdst = Wb;
   for (int k = 0; k < M; ++k) {
     const double piv = Wsrc[k * M + k];
-    double cik[Q], rk[Q];
+    const double rk = owner ? Wsrc[k * M + j] : 0.0;
+    double cik[QMAX];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      cik[q] = Wsrc[oi[q] + k];
-      rk[q] = Wsrc[k * M + ej[q]];
-    }
+    for (int q = 0; q < QMAX; ++q) cik[q] = q < nq ? Wsrc[(g + RG * q) * M + k] : 0.0;
     const bool ok = (piv > 0.0) && (piv <= 1.79769313486231571e308);
     const double ip = ok ? 1.0 / piv : 1.0;
     if (!ok && tid == 0) { *flag = 1; *bad = 1; }
+    const double rkj = rk * ip;
+    const double in_row = (j == k) ? ip : rkj;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const double rkj = rk[q] * ip;
-      const double off_row = v[q] - cik[q] * rkj, in_col = -cik[q] * ip;
-      const double in_row = (ej[q] == k) ? ip : rkj;
-      const double nv = (ei[q] == k) ? in_row : ((ej[q] == k) ? in_col : off_row);
-      v[q] = nv;
-      if (tid + q * NT < M * M) Wdst[tid + q * NT] = nv;
+    for (int q = 0; q < QMAX; ++q) {
+      if (q < nq) {
+        const int i = g + RG * q;
+        const double off_row = v[q] - cik[q] * rkj, in_col = -cik[q] * ip;
+        const double nv = (i == k) ? in_row : ((j == k) ? in_col : off_row);
+        v[q] = nv;
+        Wdst[i * M + j] = nv;
+      }
     }
     __syncthreads();
     double* tmp = Wsrc; Wsrc = Wdst; Wdst = tmp;
@@ -475,56 +470,75 @@ __global__ void __launch_bounds__(NT) ekf_front_kernel(UpdateDesc d, const doubl
     for (int e = tid; e < nc * nc; e += nt, w.next()) Ps[e] = P[upper_index(cols[w.i], cols[w.j], d.ld, d.sym)];
   }
   __syncthreads();
-  // T and S: a thread carries four of its entries through the dot-product loop at once (four independent chains:
-  // the loops are latency-bound); every sum keeps its order
-  constexpr int ILP = 4;
-  Walk wt(tid, nt, M);
-  for (int e0 = tid; e0 < nc * M; e0 += ILP * nt) {  // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
-    const double* pp[ILP];
-    const double* hh[ILP];
-    double acc[ILP];
-#pragma unroll
-    for (int u = 0; u < ILP; ++u, wt.next()) {
-      const bool act = e0 + u * nt < nc * M;
-      pp[u] = Ps + (act ? wt.i : 0) * nc;
-      hh[u] = Hs + (act ? wt.j : 0) * ncp;
-      acc[u] = 0.0;
+  // T and S: a thread owns 2 x 2 blocks of the result -- rows (a, a + half) x columns (b, b + half), so that the lanes of
+  // a warp still walk consecutive columns -- and carries the four sums through the dot-product loop together: four
+  // shared-memory loads for four multiply-adds (one entry per thread took two loads per multiply-add, and the loops
+  // were bound by the load unit of the one SM: 5 us each at M = 35, 21 us at M = 65).  Every sum keeps its order.
+  {
+    // T[cols[c]][r] = sum_b P[cols[c]][cols[b]] Hc[r][b], ascending b
+    const int ch = (nc + 1) >> 1, rh = (M + 1) >> 1;
+    int cb = tid / rh, rb = tid - cb * rh;
+    const int dcb = nt / rh, drb = nt - dcb * rh;
+    for (int bid = tid; bid < ch * rh; bid += nt) {
+      const int c0 = cb, c1 = cb + ch, r0 = rb, r1 = rb + rh;
+      const double* p0 = Ps + c0 * nc;
+      const double* p1 = Ps + min(c1, nc - 1) * nc;
+      const double* h0 = Hs + r0 * ncp;
+      const double* h1 = Hs + min(r1, M - 1) * ncp;
+      double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
+      for (int b = 0; b < nc; ++b) {
+        const double pv0 = p0[b], pv1 = p1[b], hv0 = h0[b], hv1 = h1[b];
+        a00 += pv0 * hv0;
+        a01 += pv0 * hv1;
+        a10 += pv1 * hv0;
+        a11 += pv1 * hv1;
+      }
+      Tc[c0 * M + r0] = a00;
+      if (r1 < M) Tc[c0 * M + r1] = a01;
+      if (c1 < nc) {
+        Tc[c1 * M + r0] = a10;
+        if (r1 < M) Tc[c1 * M + r1] = a11;
+      }
+      cb += dcb; rb += drb;
+      if (rb >= rh) { rb -= rh; ++cb; }
     }
-    for (int b = 0; b < nc; ++b) {
-#pragma unroll
-      for (int u = 0; u < ILP; ++u) acc[u] += pp[u][b] * hh[u][b];
-    }
-#pragma unroll
-    for (int u = 0; u < ILP; ++u)
-      if (e0 + u * nt < nc * M) Tc[e0 + u * nt] = acc[u];
   }
   __syncthreads();
   const Walk w0(tid, nt, M);  // the start of every [M][M] walk below
-  Walk ws = w0;
-  for (int e0 = tid; e0 < M * M; e0 += ILP * nt) {
-    const double* hh[ILP];
-    const double* tt[ILP];
-    double acc[ILP];
-    int rr[ILP], qq[ILP];
-#pragma unroll
-    for (int u = 0; u < ILP; ++u, ws.next()) {
-      const bool act = e0 + u * nt < M * M;
-      rr[u] = act ? ws.i : 0;
-      qq[u] = act ? ws.j : 0;
-      hh[u] = Hs + rr[u] * ncp;
-      tt[u] = Tc + qq[u];
-      acc[u] = 0.0;
-    }
-    for (int c = 0; c < nc; ++c) {
-#pragma unroll
-      for (int u = 0; u < ILP; ++u) acc[u] += hh[u][c] * tt[u][c * M];
-    }
-#pragma unroll
-    for (int u = 0; u < ILP; ++u)
-      if (e0 + u * nt < M * M) {
-        if (rr[u] == qq[u]) acc[u] += small[SM_R + rr[u]];
-        S[e0 + u * nt] = acc[u];
+  {
+    // S[r][q] = sum_c Hc[r][c] T[cols[c]][q] (+ R on the diagonal), ascending c
+    const int rh = (M + 1) >> 1;
+    int rb = tid / rh, qb = tid - rb * rh;
+    const int drb = nt / rh, dqb = nt - drb * rh;
+    for (int bid = tid; bid < rh * rh; bid += nt) {
+      const int r0 = rb, r1 = rb + rh, q0 = qb, q1 = qb + rh;
+      const double* h0 = Hs + r0 * ncp;
+      const double* h1 = Hs + min(r1, M - 1) * ncp;
+      const double* t0 = Tc + q0;
+      const double* t1 = Tc + min(q1, M - 1);
+      double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
+      for (int c = 0; c < nc; ++c) {
+        const double hv0 = h0[c], hv1 = h1[c], tv0 = t0[c * M], tv1 = t1[c * M];
+        a00 += hv0 * tv0;
+        a01 += hv0 * tv1;
+        a10 += hv1 * tv0;
+        a11 += hv1 * tv1;
       }
+      if (r0 == q0) a00 += small[SM_R + r0];
+      S[r0 * M + q0] = a00;
+      if (q1 < M) S[r0 * M + q1] = a01;  // r0 < rh <= q1: never on the diagonal
+      if (r1 < M) {
+        S[r1 * M + q0] = a10;            // q0 < rh <= r1
+        if (q1 < M) {
+          if (r1 == q1) a11 += small[SM_R + r1];
+          S[r1 * M + q1] = a11;
+        }
+      }
+      rb += drb; qb += dqb;
+      if (qb >= rh) { qb -= rh; ++rb; }
+    }
   }
   __syncthreads();
   Walk wc = w0;
@@ -539,8 +553,9 @@ __global__ void __launch_bounds__(NT) ekf_front_kernel(UpdateDesc d, const doubl
   double* Wdst = W2;
   // M <= 39 (every live size; M <= 67 with 512 threads): a thread's entries stay in registers from step to step
   // and a step is branch-free (gj_register_steps above)
-  constexpr int GJQ = NT == 256 ? 6 : 9;  // 256 threads: M <= 39; 512 threads: M <= 67
-  if (M * M <= GJQ * NT && nt == NT) {
+  constexpr int GJQ = NT == 256 ? 7 : 10;  // rows of its column a thread owns: 256 threads: M <= 39; 512 threads: M <= 67
+  const int gj_rg = NT / M;
+  if (gj_rg >= 1 && (M + gj_rg - 1) / gj_rg <= GJQ && nt == NT) {
     gj_register_steps<GJQ, NT>(W, W2, M, tid, flag, &bad);
     Wsrc = (M & 1) ? W2 : W;
   } else
