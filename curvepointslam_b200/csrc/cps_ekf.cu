@@ -1609,8 +1609,10 @@ __global__ void __launch_bounds__(256) ekf_mirror_lower_kernel(double* __restric
 
 // ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
 // Pri <- F Pri, mirrored; Prr <- F Prr F^T + Q; x[0..5] += x[6..11] DT.  F = I + DT*[0 I6; 0 0].
-__global__ void __launch_bounds__(256) ekf_predict_cross_kernel(double* __restrict__ P, int ld, int N) {
-  const int j = 12 + blockIdx.x * blockDim.x + threadIdx.x;
+// One launch: block 0 advances the 12 x 12 pose block and x, the other blocks the 12 cross rows / columns.  The two
+// parts touch disjoint entries of P (the cross part does not read x), so they need no order between them.
+__device__ __forceinline__ void ekf_predict_cross(double* __restrict__ P, int ld, int N, int block) {
+  const int j = 12 + block * blockDim.x + threadIdx.x;
   if (j >= N) return;
   double col[12];
 #pragma unroll
@@ -1624,13 +1626,16 @@ __global__ void __launch_bounds__(256) ekf_predict_cross_kernel(double* __restri
   }
 }
 
-__global__ void ekf_predict_pose_kernel(double* __restrict__ P, int ld, double* __restrict__ x) {
+__device__ __forceinline__ void ekf_predict_pose(double* __restrict__ P, int ld, double* __restrict__ x) {
   __shared__ double Prr[144], Tm[144], Q[144], F[144];
-  const int t = threadIdx.x;  // 144 threads
-  const int i = t / 12, j = t % 12;
-  F[t] = (i == j) ? 1.0 : ((j == i + 6 && i < 6) ? DT : 0.0);
-  Prr[t] = P[(size_t)i * ld + j];
-  Q[t] = 0.0;
+  const int t = threadIdx.x;  // the first 144 threads of the block work, all of them take the barriers
+  const bool act = t < 144;
+  const int i = act ? t / 12 : 0, j = act ? t % 12 : 0;
+  if (act) {
+    F[t] = (i == j) ? 1.0 : ((j == i + 6 && i < 6) ? DT : 0.0);
+    Prr[t] = P[(size_t)i * ld + j];
+    Q[t] = 0.0;
+  }
   __syncthreads();
   if (t == 0) {
     const double phi = x[3], theta = x[4], psi = x[5];
@@ -1671,12 +1676,17 @@ __global__ void ekf_predict_pose_kernel(double* __restrict__ P, int ld, double* 
   __syncthreads();
   double s = 0.0;
   for (int k = 0; k < 12; ++k) s += F[12 * i + k] * Prr[12 * k + j];
-  Tm[t] = s;
+  if (act) Tm[t] = s;
   __syncthreads();
   s = 0.0;
   for (int k = 0; k < 12; ++k) s += Tm[12 * i + k] * F[12 * j + k];
-  P[(size_t)i * ld + j] = s + Q[t];
+  if (act) P[(size_t)i * ld + j] = s + Q[t];
   if (t < 6) x[t] += x[t + 6] * DT;
+}
+
+__global__ void __launch_bounds__(256) ekf_predict_kernel(double* __restrict__ P, int ld, int N, double* __restrict__ x) {
+  if (blockIdx.x == 0) ekf_predict_pose(P, ld, x);
+  else ekf_predict_cross(P, ld, N, (int)blockIdx.x - 1);
 }
 
 // P = scale * G G^T + diag * I (benchmark-size synthetic covariances)
@@ -2148,11 +2158,7 @@ extern "C" int cps_ekf_predict(cps_ekf* h) {
   CPS_CUDA(cudaSetDevice(h->device));
   CPS_CUDA(cudaEventRecord(h->ev[0], h->stream));
   // the pose block reads x before it is advanced; the cross block does not read x
-  if (h->N > 12) {
-    ekf_predict_cross_kernel<<<(h->N - 12 + 255) / 256, 256, 0, h->stream>>>(h->d_P, h->cap, h->N);
-    h->launches++;
-  }
-  ekf_predict_pose_kernel<<<1, 144, 0, h->stream>>>(h->d_P, h->cap, h->d_x);
+  ekf_predict_kernel<<<1 + (h->N - 12 + 255) / 256, 256, 0, h->stream>>>(h->d_P, h->cap, h->N, h->d_x);
   h->launches++;
   CPS_CUDA(cudaGetLastError());
   CPS_CUDA(cudaEventRecord(h->ev[1], h->stream));
