@@ -67,6 +67,9 @@ struct cps_lm_ctx {
   long long prof_launches[4] = {0, 0, 0, 0};
   cudaEvent_t ev_last = nullptr;  // end of the last device-entry call (calls on different streams serialise on it)
   long long solve_handovers = 0;  // systems of the last staged der call that left the block-arrow solve for the dense one
+  // the staged der call about to be made holds fits of different lengths (frames entry; host entry with ragged
+  // offsets): order them by length before they enter the lists (cps_lm_staged.cuh, staged_bucket_*)
+  int bucket_hint = 0;
   long long prof_jac_evals = 0, prof_tail_fits = 0;  // Jacobian evaluations done by staged_jac_kernel; fits taken over
   std::vector<cudaEvent_t> ev_pool;
   // asynchronous device entry (cps_lm_set_async): a worker thread runs the staged shape's host loop on a private stream;
@@ -349,6 +352,12 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   const size_t o_s1 = o;   o = a256(o + sizeof(int) * B);
   const size_t o_fb = o;   o = a256(o + sizeof(int) * B);
   const size_t o_cnt = o;  o = a256(o + sizeof(unsigned int) * 8);
+  // CPS_LM_BUCKETS=0/1 overrides the callers' hint (A/B measurements)
+  bool bucket = c->bucket_hint != 0;
+  if (const char* e = std::getenv("CPS_LM_BUCKETS")) bucket = std::atoi(e) != 0;
+  const int max_chunks = (int)((B + kBucketChunk - 1) / kBucketChunk);
+  const size_t o_order = o; o = a256(o + (bucket ? sizeof(int) * B : 0));
+  const size_t o_bhist = o; o = a256(o + (bucket ? sizeof(int) * (size_t)kBucketBins * max_chunks : 0));
   if (o > sl.staged_bytes) {
     CPS_CUDA(cudaStreamSynchronize(st));
     CPS_CUDA(cudaStreamSynchronize(sl.stream));
@@ -378,6 +387,7 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
   A.force_handover = std::getenv("CPS_LM_FORCE_HANDOVER") ? std::atoi(std::getenv("CPS_LM_FORCE_HANDOVER")) : 0;
   A.init_first = 0;
   A.init_count = 0;
+  A.init_order = nullptr;
 
   auto grid_for = [&](size_t items, int per_block, int cap) {
     size_t gneed = (items + per_block - 1) / per_block;
@@ -464,6 +474,17 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
       if (P.count > 0) {
         A.init_first = P.first;
         A.init_count = P.count;
+        A.init_order = nullptr;
+        if (bucket && P.count > 64) {  // the piece's fits ordered by length (three small kernels over the offsets)
+          const int nchunks = (P.count + kBucketChunk - 1) / kBucketChunk;
+          int* bhist = (int*)(d + o_bhist);
+          int* order = (int*)(d + o_order) + P.first;
+          staged_bucket_hist_kernel<<<nchunks, 256, 0, st>>>(A, bhist, nchunks);
+          staged_bucket_scan_kernel<<<1, 1024, 0, st>>>(bhist, kBucketBins * nchunks);
+          staged_bucket_scatter_kernel<<<nchunks, 256, 0, st>>>(A, bhist, nchunks, order);
+          A.init_order = order;
+          c->launches += 3;
+        }
         span_begin(1);
         if (fma) cps_fast_launch_eval(1, grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st, &A, nxt);
         else staged_eval_kernel<true><<<grid_for((size_t)P.count, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, nxt);
@@ -1076,7 +1097,16 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const void* meas, i
     L.info = (double*)(d + o_info);
     L.ret = (int*)(d + o_ret);
     L.extra = extra ? (int*)(d + o_ext) : nullptr;
+    // ragged offsets (the longest fit at least two 32-row blocks longer than the shortest): order the fits by length
+    long long n_lo = sl.off0[1] - sl.off0[0], n_hi = n_lo;
+    for (int f = 1; f < B; ++f) {
+      const long long nn = sl.off0[f + 1] - sl.off0[f];
+      n_lo = std::min(n_lo, nn);
+      n_hi = std::max(n_hi, nn);
+    }
+    c->bucket_hint = ((n_hi + 31) / 32 - (n_lo + 31) / 32 >= 2) ? 1 : 0;
     const int rc = launch_staged_der19(c, sl, L, st, pieces);
+    c->bucket_hint = 0;
     if (rc != CPS_OK) return rc;
     CPS_CUDA(cudaMemcpyAsync(p, d + o_p, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaMemcpyAsync(info, d + o_info, sizeof(double) * (size_t)B * 10, cudaMemcpyDeviceToHost, st));
@@ -1603,6 +1633,8 @@ int fit_frames_impl(cps_lm_ctx* c, int variant, int F, const PT* pts, const long
     cps::lm_init_guess_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, d_meas, d_off, d_cnt, d_p);
     CPS_CUDA(cudaGetLastError());
     c->launches += 6;
+    c->bucket_hint = 1;  // contours of real lengths: the fits enter the staged lists ordered by length
+    struct HintReset { cps_lm_ctx* c; ~HintReset() { c->bucket_hint = 0; } } hint_reset{c};
     const int rc = fit_dev(c, sl, CPS_MODEL_STEREO19, variant, F, d_p, d_meas, nullptr, d_off, d_cnt, (int)n_max, itmax, opts,
                            d_info, d_ret, nullptr, st, CPS_LM_PATH_AUTO);
     if (rc != CPS_OK) return rc;

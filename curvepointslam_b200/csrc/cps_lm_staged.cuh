@@ -56,6 +56,7 @@ struct StagedArgs {
   int* fb_list;        // positions in the solve list whose system the block-arrow solve handed to the dense one
   int force_handover;  // test knob: > 0 hands every force_handover-th list position over regardless
   int init_first, init_count;  // range of the fit index an INIT launch covers
+  const int* init_order;       // nullptr, or [init_count] the fits of that range in the order the INIT launch takes them
 };
 
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) staged_eval_kernel(const Stag
        base += gridDim.x * kEvalThreads) {
     const unsigned int item = base + lane;
     bool have = item < total;
-    int f = have ? (INIT ? A.init_first + (int)item : A.eval_list[item]) : 0;
+    int f = have ? (INIT ? (A.init_order ? A.init_order[item] : A.init_first + (int)item) : A.eval_list[item]) : 0;
     if (f < 0) { have = false; f = 0; }  // the fit stopped in the solve
     FitGeom g;
     g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;
@@ -1153,6 +1154,68 @@ __global__ void __launch_bounds__(ARROW ? kArrowThreads : kSolveThreads, 1) stag
 
 // The host reads the list counters through pinned host memory the device writes directly (a cudaMemcpy of four
 // bytes would queue on a copy engine behind the megabytes of samples the host-buffer entry point is streaming in).
+// ---- fits of different lengths: the order in which a batch enters the lists -------------------------------------------
+// Every phase kernel gives a lane one fit and a warp walks as many 32-row blocks as its LONGEST fit has: on contours of
+// real lengths (the frames pipeline: 49 points on average, 30 to 70) a warp of 32 neighbouring fits keeps about 0.65 of
+// its lanes busy.  The lists the rounds work on are compacted from the order in which the INIT launch appended the
+// fits, so that order is chosen here: a counting sort of the batch (or of a piece of it) by the fits' number of row
+// blocks, index order kept inside a bin up to the 1 024-fit chunk a CTA scatters (neighbours in a list stay
+// neighbours in memory: a random order cost the eval kernel 3x).  Three small kernels over the offsets; per-fit results
+// do not depend on list order.
+constexpr int kBucketBins = 64;
+constexpr int kBucketChunk = 1024;
+__device__ __forceinline__ int staged_bucket_bin(const StagedArgs& A, int f) {
+  long long nb = (A.L.off[f + 1] - A.L.off[f] + 31) >> 5;
+  if (nb < 0) nb = 0;
+  return (int)(nb < kBucketBins - 1 ? nb : kBucketBins - 1);
+}
+__global__ void __launch_bounds__(256) staged_bucket_hist_kernel(const StagedArgs A, int* __restrict__ hist, int nchunks) {
+  __shared__ int h[kBucketBins];
+  if (threadIdx.x < kBucketBins) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBucketChunk; i += blockDim.x) {
+    const int item = blockIdx.x * kBucketChunk + i;
+    if (item < A.init_count) atomicAdd(&h[staged_bucket_bin(A, A.init_first + item)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kBucketBins) hist[threadIdx.x * nchunks + blockIdx.x] = h[threadIdx.x];
+}
+// exclusive scan of hist[bin][chunk] in bin-major order (one CTA of 1 024 threads)
+__global__ void __launch_bounds__(1024) staged_bucket_scan_kernel(int* __restrict__ hist, int total) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x, per = (total + 1023) / 1024;
+  const int lo = min(total, t * per), hi = min(total, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += hist[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = part[t] - s;  // exclusive prefix of this thread's run
+  for (int i = lo; i < hi; ++i) {
+    const int v = hist[i];
+    hist[i] = run;
+    run += v;
+  }
+}
+__global__ void __launch_bounds__(256) staged_bucket_scatter_kernel(const StagedArgs A, const int* __restrict__ hist,
+                                                                    int nchunks, int* __restrict__ order) {
+  __shared__ int pos[kBucketBins];
+  if (threadIdx.x < kBucketBins) pos[threadIdx.x] = hist[threadIdx.x * nchunks + blockIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBucketChunk; i += blockDim.x) {
+    const int item = blockIdx.x * kBucketChunk + i;
+    if (item < A.init_count) {
+      const int f = A.init_first + item;
+      order[atomicAdd(&pos[staged_bucket_bin(A, f)], 1)] = f;
+    }
+  }
+}
+
 // End of a round: the length of the next solve list for the host, the jac list length of the round that just ended
 // (cnt[0]: the host's estimate for the next round), and the running total of Jacobian evaluations the jac kernel has
 // performed in this call (cnt[1]).
