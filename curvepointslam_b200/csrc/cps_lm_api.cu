@@ -479,9 +479,10 @@ int launch_staged_der19(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch& L, cudaSt
           const int nchunks = (P.count + kBucketChunk - 1) / kBucketChunk;
           int* bhist = (int*)(d + o_bhist);
           int* order = (int*)(d + o_order) + P.first;
-          staged_bucket_hist_kernel<<<nchunks, 256, 0, st>>>(A, bhist, nchunks);
+          const BucketRange R{A.L.off, P.first, P.count};
+          staged_bucket_hist_kernel<<<nchunks, 256, 0, st>>>(R, bhist, nchunks);
           staged_bucket_scan_kernel<<<1, 1024, 0, st>>>(bhist, kBucketBins * nchunks);
-          staged_bucket_scatter_kernel<<<nchunks, 256, 0, st>>>(A, bhist, nchunks, order);
+          staged_bucket_scatter_kernel<<<nchunks, 256, 0, st>>>(R, bhist, nchunks, order);
           A.init_order = order;
           c->launches += 3;
         }
@@ -605,6 +606,13 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
   const size_t o_s0 = o;   o = a256(o + sizeof(int) * B);
   const size_t o_s1 = o;   o = a256(o + sizeof(int) * B);
   const size_t o_cnt = o;  o = a256(o + sizeof(unsigned int) * 4);
+  // fits of different lengths enter the lists ordered by length (cps_lm_staged.cuh, staged_bucket_*): a CTA of the build
+  // kernels walks as many rows as the longest of its 32 fits has
+  bool bucket = c->bucket_hint != 0 && B > 64;
+  if (const char* e = std::getenv("CPS_LM_BUCKETS")) bucket = std::atoi(e) != 0 && B > 64;
+  const int nchunks = (int)((B + kBucketChunk - 1) / kBucketChunk);
+  const size_t o_order = o; o = a256(o + (bucket ? sizeof(int) * B : 0));
+  const size_t o_bhist = o; o = a256(o + (bucket ? sizeof(int) * (size_t)kBucketBins * nchunks : 0));
   const size_t o_J = o;    o = a256(o + sizeof(double) * j_stride * B);
   if (o > sl.staged_bytes) {
     CPS_CUDA(cudaStreamSynchronize(st));
@@ -638,6 +646,7 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
   A.cnt = (unsigned int*)(d + o_cnt);
   A.init_first = 0;
   A.init_count = (int)B;
+  A.init_order = nullptr;
   auto grid_for = [&](size_t items, int per_block, int cap) {
     size_t gneed = (items + per_block - 1) / per_block;
     if (gneed < 1) gneed = 1;
@@ -705,6 +714,16 @@ int launch_staged_dif19_range(cps_lm_ctx* c, cps_lm_slot& sl, cps::LmLaunch L, c
   // iteration 0: validation, t, e0, loop top; every surviving fit needs its first finite-difference Jacobian
   int cur = 0, rounds = 0;
   span_begin(1);
+  if (bucket) {
+    const BucketRange R{A.L.off, 0, (int)B};
+    int* bhist = (int*)(d + o_bhist);
+    int* order = (int*)(d + o_order);
+    staged_bucket_hist_kernel<<<nchunks, 256, 0, st>>>(R, bhist, nchunks);
+    staged_bucket_scan_kernel<<<1, 1024, 0, st>>>(bhist, kBucketBins * nchunks);
+    staged_bucket_scatter_kernel<<<nchunks, 256, 0, st>>>(R, bhist, nchunks, order);
+    A.init_order = order;
+    c->launches += 3;
+  }
   dif_eval_kernel<true><<<grid_for(B, kEvalThreads, c->sm_count * eval_occ), kEvalThreads, eval_smem, st>>>(A, cur);
   span_end();
   c->launches += 1;
@@ -1097,16 +1116,7 @@ int fit_batched_host_staged(cps_lm_ctx* c, int B, double* p, const void* meas, i
     L.info = (double*)(d + o_info);
     L.ret = (int*)(d + o_ret);
     L.extra = extra ? (int*)(d + o_ext) : nullptr;
-    // ragged offsets (the longest fit at least two 32-row blocks longer than the shortest): order the fits by length
-    long long n_lo = sl.off0[1] - sl.off0[0], n_hi = n_lo;
-    for (int f = 1; f < B; ++f) {
-      const long long nn = sl.off0[f + 1] - sl.off0[f];
-      n_lo = std::min(n_lo, nn);
-      n_hi = std::max(n_hi, nn);
-    }
-    c->bucket_hint = ((n_hi + 31) / 32 - (n_lo + 31) / 32 >= 2) ? 1 : 0;
-    const int rc = launch_staged_der19(c, sl, L, st, pieces);
-    c->bucket_hint = 0;
+    const int rc = launch_staged_der19(c, sl, L, st, pieces);  // c->bucket_hint: set by fit_batched_host on ragged offsets
     if (rc != CPS_OK) return rc;
     CPS_CUDA(cudaMemcpyAsync(p, d + o_p, sizeof(double) * (size_t)B * m, cudaMemcpyDeviceToHost, st));
     CPS_CUDA(cudaMemcpyAsync(info, d + o_info, sizeof(double) * (size_t)B * 10, cudaMemcpyDeviceToHost, st));
@@ -1133,15 +1143,20 @@ int fit_batched_host(cps_lm_ctx* c, int model, int variant, int B, double* p, co
   if (B == 0) return CPS_OK;
   const int m = (model == CPS_MODEL_STEREO19) ? 19 : 8;
   const int nseg = (model == CPS_MODEL_STEREO19) ? 4 : 1;
-  long long n_max = 2;
+  long long n_max = 2, n_min = (1LL << 40);
   if (off[0] < 0) return CPS_ERR_INVALID;
   for (int f = 0; f < B; ++f) {
     const long long n = off[f + 1] - off[f];
     if (n < 0) return CPS_ERR_INVALID;
     n_max = std::max(n_max, n);
+    n_min = std::min(n_min, n);
   }
   if (n_max > (1 << 24)) return CPS_ERR_INVALID;
   CPS_CUDA(cudaSetDevice(c->device));
+  // ragged offsets (the longest fit at least two 32-row blocks longer than the shortest): the staged shapes order the
+  // fits by length before they enter their lists
+  c->bucket_hint = ((n_max + 31) / 32 - (n_min + 31) / 32 >= 2) ? 1 : 0;
+  struct HintReset { cps_lm_ctx* c; ~HintReset() { c->bucket_hint = 0; } } hint_reset{c};
   const bool staged = model == CPS_MODEL_STEREO19 && variant == CPS_LM_DER && c->path != CPS_LM_PATH_MONOLITHIC &&
                       (c->path == CPS_LM_PATH_STAGED || B >= kStagedMinFits || n_max > 40 * cps::kTileRows);
   if (staged) return fit_batched_host_staged(c, B, p, meas, pix_type, t, off, counts, n_max, itmax, opts, info, ret, extra);

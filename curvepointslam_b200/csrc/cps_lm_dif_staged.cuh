@@ -61,6 +61,7 @@ struct DifArgs {
   int* solve_list[2];
   unsigned int* cnt;    // [0] fd list, [1] upd list, [2], [3] solve lists
   int init_first, init_count;
+  const int* init_order;  // nullptr, or the fits of that range ordered by length (cps_lm_staged.cuh, staged_bucket_*)
 };
 
 __device__ __forceinline__ void dif_finish(const DifArgs& A, int f, const DifScal& s, int stop) {
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kEvalThreads, 3) dif_eval_kernel(const DifArgs
        base += gridDim.x * kEvalThreads) {
     const unsigned int item = base + lane;
     bool have = item < total;
-    int f = have ? (INIT ? A.init_first + (int)item : A.eval_list[item]) : 0;
+    int f = have ? (INIT ? (A.init_order ? A.init_order[item] : A.init_first + (int)item) : A.eval_list[item]) : 0;
     if (f < 0) { have = false; f = 0; }
     FitGeom g;
     g.n = 0; g.nsamp = 0; g.b1 = g.b2 = g.b3 = 0;

@@ -1164,18 +1164,23 @@ __global__ void __launch_bounds__(ARROW ? kArrowThreads : kSolveThreads, 1) stag
 // do not depend on list order.
 constexpr int kBucketBins = 64;
 constexpr int kBucketChunk = 1024;
-__device__ __forceinline__ int staged_bucket_bin(const StagedArgs& A, int f) {
-  long long nb = (A.L.off[f + 1] - A.L.off[f] + 31) >> 5;
+__device__ __forceinline__ int staged_bucket_bin(const long long* __restrict__ off, int f) {
+  long long nb = (off[f + 1] - off[f] + 31) >> 5;
   if (nb < 0) nb = 0;
   return (int)(nb < kBucketBins - 1 ? nb : kBucketBins - 1);
 }
-__global__ void __launch_bounds__(256) staged_bucket_hist_kernel(const StagedArgs A, int* __restrict__ hist, int nchunks) {
+// the range of the fit index being ordered (shared by the der and the dif launchers)
+struct BucketRange {
+  const long long* off;
+  int init_first, init_count;
+};
+__global__ void __launch_bounds__(256) staged_bucket_hist_kernel(const BucketRange A, int* __restrict__ hist, int nchunks) {
   __shared__ int h[kBucketBins];
   if (threadIdx.x < kBucketBins) h[threadIdx.x] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < kBucketChunk; i += blockDim.x) {
     const int item = blockIdx.x * kBucketChunk + i;
-    if (item < A.init_count) atomicAdd(&h[staged_bucket_bin(A, A.init_first + item)], 1);
+    if (item < A.init_count) atomicAdd(&h[staged_bucket_bin(A.off, A.init_first + item)], 1);
   }
   __syncthreads();
   if (threadIdx.x < kBucketBins) hist[threadIdx.x * nchunks + blockIdx.x] = h[threadIdx.x];
@@ -1202,7 +1207,7 @@ __global__ void __launch_bounds__(1024) staged_bucket_scan_kernel(int* __restric
     run += v;
   }
 }
-__global__ void __launch_bounds__(256) staged_bucket_scatter_kernel(const StagedArgs A, const int* __restrict__ hist,
+__global__ void __launch_bounds__(256) staged_bucket_scatter_kernel(const BucketRange A, const int* __restrict__ hist,
                                                                     int nchunks, int* __restrict__ order) {
   __shared__ int pos[kBucketBins];
   if (threadIdx.x < kBucketBins) pos[threadIdx.x] = hist[threadIdx.x * nchunks + blockIdx.x];
@@ -1211,7 +1216,7 @@ __global__ void __launch_bounds__(256) staged_bucket_scatter_kernel(const Staged
     const int item = blockIdx.x * kBucketChunk + i;
     if (item < A.init_count) {
       const int f = A.init_first + item;
-      order[atomicAdd(&pos[staged_bucket_bin(A, f)], 1)] = f;
+      order[atomicAdd(&pos[staged_bucket_bin(A.off, f)], 1)] = f;
     }
   }
 }
