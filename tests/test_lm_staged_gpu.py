@@ -387,3 +387,35 @@ def test_fused_arithmetic_mode_distribution():
     assert (fast["info"][:, 6] == exact["info"][:, 6]).all()
     assert e_rel.max() < 1e-10
     assert (rel < 1e-9).mean() >= 0.90 and rel.max() < 1e-6, ((rel < 1e-9).mean(), rel.max())
+
+
+@pytest.mark.parametrize("variant", [DER, 1])
+def test_length_ordered_list_entry_is_invisible(monkeypatch, variant):
+    """Fits of different lengths enter the staged lists ordered by their number of row blocks (a device counting sort
+    over 1 024-fit chunks: csrc/cps_lm_staged.cuh, staged_bucket_*) so that the lanes of a warp walk fits of similar
+    length; per-fit results do not depend on list order.  3 000 fits of 4 x 5..101 points (three chunks, every bin from
+    2 to 26 row blocks, some fits refused): CPS_LM_BUCKETS=0 (index order) and =1 give the same bits, and the oracle's."""
+    rng = np.random.default_rng(23)
+    counts = rng.integers(5, 102, size=(3000, 4)).astype(np.int32)
+    counts[7] = (1, 1, 1, 1)      # n < m: refused by the INIT pass whatever the order
+    counts[2048] = (3, 2, 3, 2)   # the unblocked small-problem loop
+    b = synth.make_stereo19_batch(3000, seed=64, counts=counts, round_pixels=True)
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CPS_LM_BUCKETS", flag)
+        c = lm.LmContext(0)
+        c.set_path(lm.PATH_STAGED)
+        try:
+            out.append(c.fit_batched(STEREO19, variant, b["p0"], b["meas"], b["off"], b["counts"], OPTS, itmax=40))
+        finally:
+            c.close()
+    assert_same_fit(out[0], out[1])
+    assert out[1]["ret"][7] == -1
+    sample = np.arange(0, 3000, 7)
+    sub = synth.make_stereo19_batch(3000, seed=64, counts=counts, round_pixels=True)
+    off = sub["off"]
+    meas = np.concatenate([sub["meas"][off[f]:off[f + 1]] for f in sample])
+    off_s = np.concatenate([[0], np.cumsum([off[f + 1] - off[f] for f in sample])]).astype(np.int64)
+    cpu = oracle().fit_batch(STEREO19, variant, sub["p0"][sample], meas, off_s, counts[sample], OPTS, itmax=40, nthreads=8)
+    got = {k: out[1][k][sample] for k in ("p", "info", "ret", "extra")}
+    assert_same_fit(got, cpu)
