@@ -1607,6 +1607,16 @@ __global__ void __launch_bounds__(256) ekf_mirror_lower_kernel(double* __restric
   for (int r = ty; r < TILE; r += 4) P[((size_t)J * TILE + r) * ld + (size_t)I * TILE + tx] = tile[tx][r];
 }
 
+// A block of P for cps_ekf_get_cov_block while the lower tiles are stale: every entry from the copy with row <= column.
+__global__ void __launch_bounds__(256) ekf_gather_block_kernel(const double* __restrict__ P, int ld, int r0, int c0,
+                                                               int nr, int nc, double* __restrict__ out) {
+  const long long total = (long long)nr * nc;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / nc), j = (int)(e - (long long)i * nc);
+    out[e] = P[upper_index(r0 + i, c0 + j, ld, 1)];
+  }
+}
+
 // ---- PredictKF (kalmanClass.cpp:161-272): only the 12 pose rows/columns of P change ----------------------
 // Pri <- F Pri, mirrored; Prr <- F Prr F^T + Q; x[0..5] += x[6..11] DT.  F = I + DT*[0 I6; 0 0].
 // One launch: block 0 advances the 12 x 12 pose block and x, the other blocks the 12 cross rows / columns.  The two
@@ -2140,8 +2150,21 @@ extern "C" int cps_ekf_get_cov_block(cps_ekf* h, int r0, int c0, int nr, int nc,
   if (!h || !out || r0 < 0 || c0 < 0 || nr < 0 || nc < 0 || r0 + nr > h->N || c0 + nc > h->N) return CPS_ERR_INVALID;
   if (nr == 0 || nc == 0) return CPS_OK;
   CPS_CUDA(cudaSetDevice(h->device));
-  // a block that reaches below the diagonal tiles needs them current
-  if ((r0 + nr - 1) / TILE > c0 / TILE) { const int rc = ensure_lower(h); if (rc != CPS_OK) return rc; }
+  // a block that reaches below the diagonal tiles while they are stale: a small one is gathered from the upper copies
+  // (a per-frame read of a landmark's 3 x 3 block must not cost a pass over P), a large one has them rebuilt first
+  if (h->lower_stale && (r0 + nr - 1) / TILE > c0 / TILE) {
+    if ((long long)nr * nc <= (1LL << 20)) {
+      { const int rc = ensure_aux(h, sizeof(double) * (size_t)nr * nc); if (rc != CPS_OK) return rc; }
+      const int grid = (int)std::min<long long>(((long long)nr * nc + 255) / 256, 1024);
+      ekf_gather_block_kernel<<<grid, 256, 0, h->stream>>>(h->d_P, h->cap, r0, c0, nr, nc, h->d_aux);
+      CPS_CUDA(cudaGetLastError());
+      h->launches++;
+      CPS_CUDA(cudaMemcpyAsync(out, h->d_aux, sizeof(double) * (size_t)nr * nc, cudaMemcpyDeviceToHost, h->stream));
+      return cps_ekf_sync(h);
+    }
+    const int rc = ensure_lower(h);
+    if (rc != CPS_OK) return rc;
+  }
   CPS_CUDA(cudaMemcpy2DAsync(out, (size_t)nc * sizeof(double), h->d_P + (size_t)r0 * h->cap + c0,
                              (size_t)h->cap * sizeof(double), (size_t)nc * sizeof(double), nr, cudaMemcpyDeviceToHost,
                              h->stream));

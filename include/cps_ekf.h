@@ -49,7 +49,8 @@ int cps_ekf_dims(cps_ekf *h, int *N, int *num_curves, int *num_points);
 int cps_ekf_get_state(cps_ekf *h, double *x_out);                                         /* [N]      */
 /* The full symmetric matrix / any block of it.  Between updates only the 64 x 64 tiles on and above the diagonal tiles
    are kept current on the device (an update then moves 8 N^2 bytes instead of 12 N^2); a read that reaches below them
-   first rebuilds the mirror images (one extra pass over P on the handle's stream, only when asked). */
+   gathers a small block (up to 2^20 entries) from the upper copies, and for a larger one first rebuilds the mirror images
+   (one extra pass over P on the handle's stream, only when asked). */
 int cps_ekf_get_cov(cps_ekf *h, double *P_out);                                           /* [N*N]    */
 int cps_ekf_get_cov_block(cps_ekf *h, int r0, int c0, int nr, int nc, double *out);       /* [nr*nc]  */
 
